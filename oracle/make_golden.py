@@ -1,0 +1,102 @@
+"""Pin the oracle against the UNMODIFIED reference and write tests/golden/*.npz.
+
+Runs only in the build container (needs /root/reference, which does not travel to the GPU box).
+The reference's hot path imports once three path-irrelevant, absent packages are stubbed in
+``sys.modules``.  Nothing is copied from the reference: it is imported, fed
+the oracle's seeded weights through ``load_state_dict(strict=True)`` (which also proves the
+name/shape structure of ``oracle.make_state_dict``), run, and compared.
+
+    python oracle/make_golden.py            # asserts bit-exactness, rewrites the fixtures
+"""
+import os
+import sys
+import types
+
+import numpy as np
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+sys.path.insert(0, ROOT)
+sys.dont_write_bytecode = True
+
+from oracle import sgmse_oracle as O  # noqa: E402
+
+
+def import_reference():
+    for name in ("matplotlib", "matplotlib.pyplot", "pydub"):
+        sys.modules.setdefault(name, types.ModuleType(name))
+    sys.modules["matplotlib"].pyplot = sys.modules["matplotlib.pyplot"]
+    sys.modules["pydub"].AudioSegment = object
+    sys.path.insert(0, "/root/reference")
+    from src.models.components.sgmse.model_wrapper import ScoreModel  # type: ignore
+    from src.models.components.sgmse.backbones.ncsnpp import NCSNpp  # type: ignore
+    from src.models.components.sgmse.backbones.ncsnpp_utils import up_or_down_sampling as UD  # type: ignore
+
+    return ScoreModel, NCSNpp, UD
+
+
+def main():
+    torch.set_num_threads(os.cpu_count())
+    ScoreModel, NCSNpp, UD = import_reference()
+    out_dir = os.path.join(ROOT, "tests", "golden")
+    os.makedirs(out_dir, exist_ok=True)
+
+    # ---- 1. step schedule: bit patterns of linspace(1, .03, N) and G_i ------------------------
+    sched = {}
+    for N in (3, 30, 50, 60):
+        ts, G = O.step_coefficients(N)
+        ref_ts = torch.linspace(1, 3e-2, N)
+        assert torch.equal(ts, ref_ts)
+        sched[f"t_{N}"] = ts.numpy().view(np.uint32)
+        sched[f"G_{N}"] = G.numpy().view(np.uint32)
+    sched["std1"] = O.ouve_std(torch.ones(1)).numpy().view(np.uint32)
+    np.savez(os.path.join(out_dir, "schedule.npz"), **sched)
+    print("schedule ok")
+
+    # ---- 2. FIR resampling vs the reference functions ----------------------------------------
+    g = torch.Generator().manual_seed(5)
+    x = torch.randn(2, 3, 8, 10, generator=g)
+    assert torch.equal(O.fir_upsample_2d(x), UD.upsample_2d(x, (1, 3, 3, 1), factor=2))
+    assert torch.equal(O.fir_downsample_2d(x), UD.downsample_2d(x, (1, 3, 3, 1), factor=2))
+    np.savez(os.path.join(out_dir, "fir.npz"), x=x.numpy(), up=O.fir_upsample_2d(x).numpy(),
+             down=O.fir_downsample_2d(x).numpy())
+    print("fir ok")
+
+    # ---- 3. TINY network forward vs reference NCSNpp with the same kwargs ---------------------
+    cfg = O.TINY
+    sd = O.make_state_dict(cfg, seed=11)
+    ref_net = NCSNpp(nf=cfg.nf, ch_mult=cfg.ch_mult, num_res_blocks=cfg.num_res_blocks, attn_resolutions=(0,)).eval()
+    ref_net.load_state_dict(sd, strict=True)
+    g = torch.Generator().manual_seed(3)
+    xin = torch.randn(2, 2, 16, 24, dtype=torch.complex64, generator=g)
+    tt = torch.tensor([0.9, 0.31])
+    with torch.no_grad():
+        r = ref_net(xin, tt)
+        o = O.ncsnpp_forward(sd, cfg, xin, tt)
+    assert torch.equal(r, o), float((r - o).abs().max())
+    np.savez(os.path.join(out_dir, "tiny_forward.npz"), x=xin.numpy(), t=tt.numpy(), out=r.numpy())
+    print("tiny forward ok")
+
+    # ---- 4. full sample(): NCSNppLarge, B=2, 0.4 s clips (61 frames -> padded to 64), N=3 ------
+    sdL = O.make_state_dict(O.LARGE, seed=7)
+    m = ScoreModel(backbone="ncsnpplarge", sde="ouve", t_eps=3e-2, mode="regen-joint-training", condition="noisy",
+                   loss_type="mse", n_fft=1022, hop_length=160, num_frames=512, window="hann", spec_factor=0.15,
+                   spec_abs_exponent=0.5, sde_input="noisy").eval()
+    m.score_net.load_state_dict(sdL, strict=True)
+    B, L, N, seed = 2, 9600, 3, 42
+    y = O.synthetic_clips(B, L)
+    torch.manual_seed(seed)
+    ref = m.sample({"perturbed": y.clone()}, N=N)["enhanced"]
+    mine, xm, Y = O.sample(sdL, y, N, seed=seed, return_spec=True)
+    d = float((ref - mine).abs().max())
+    print("sample max|ref-oracle| =", d)
+    assert d == 0.0
+    np.savez_compressed(os.path.join(out_dir, "sample_large_T64_N3.npz"), y=y.numpy(), enhanced=ref.numpy(),
+                        xmean_re=xm.real[:, 0, ::16, ::4].numpy(), xmean_im=xm.imag[:, 0, ::16, ::4].numpy(),
+                        B=B, L=L, N=N, seed=seed, weight_seed=7)
+    print("sample ok; goldens written to", out_dir)
+
+
+if __name__ == "__main__":
+    main()
