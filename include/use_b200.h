@@ -1,0 +1,143 @@
+/* use_b200 -- C ABI of the B200-native SGMSE sampling path (libuse_b200.so).
+ *
+ * Plain pointers and sizes only; no torch types.  Every function returns 0 on success and a non-zero
+ * code on failure, with a message retrievable through use_last_error() (the reference surfaces native
+ * failures as Python RuntimeError through TORCH_CHECK, op/upfirdn2d.cpp:8-10; the Python host layer maps
+ * non-zero codes to RuntimeError the same way).  Inputs are borrowed and never mutated; outputs and all
+ * scratch memory are caller-provided (the reference allocates outputs with the input's options inside
+ * the op, upfirdn2d_kernel.cu:242-243 -- here the caller's allocator, torch's, stays the only one).
+ * All work is enqueued on the cudaStream_t passed as `stream` (the reference launches on the current
+ * stream of the current device, upfirdn2d_kernel.cu:213-215) and the functions are re-entrant per
+ * stream for distinct engines.
+ *
+ * What each entry point replaces in /root/reference (paths relative to src/models/components/sgmse/):
+ *   use_upfirdn2d_f32        backbones/ncsnpp_utils/op/upfirdn2d.cpp:12-23 (pybind `upfirdn2d`), the
+ *                            reference's only native FFI on the path; kernels op/upfirdn2d_kernel.cu:107-207
+ *   use_engine_*             construction of NCSNpp (backbones/ncsnpp.py:42-316) + load of its state_dict
+ *   use_score_forward        ScoreModel.forward / forward_score (model_wrapper.py:135-145) -> NCSNpp.forward
+ *                            (backbones/ncsnpp.py:324-501)
+ *   use_pc_sample            sampling.get_pc_sampler().pc_sampler (sampling/__init__.py:59-71) with
+ *                            ReverseDiffusionPredictor (sampling/predictors.py:61-68), NoneCorrector
+ *                            (sampling/correctors.py:101-111), RSDE.discretize (sdes.py:159-173)
+ *   use_stft / use_istft     ScoreModel.stft + spec_fwd + pad_spec / spec_back + istft
+ *                            (model_wrapper.py:92-122, util/other.py:128-135)
+ *   use_op_*                 single kernels, exported for the parity tests
+ */
+#ifndef USE_B200_H_
+#define USE_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+#if defined(__GNUC__)
+#pragma GCC visibility push(default)
+#endif
+
+#define USE_B200_ABI_VERSION 1
+
+#define USE_DTYPE_F32 0  /* fp32 storage, TF32 tensor-core math (PyTorch's own GPU default for conv) */
+#define USE_DTYPE_BF16 1 /* bf16 storage + bf16 tensor-core math, fp32 accumulate / statistics / SDE state */
+
+typedef struct use_engine use_engine;
+
+typedef struct use_config {
+  int nf;               /* base width (NCSNppLarge: 128) */
+  int num_levels;       /* len(ch_mult) (7) */
+  int ch_mult[8];       /* (1,1,2,2,2,2,2) */
+  int num_res_blocks;   /* 2 */
+  int input_channels;   /* 4 = [Re x, Im x, Re Y, Im Y] */
+  int act_dtype;        /* USE_DTYPE_* */
+  int n_fft, hop;       /* 1022, 160 */
+  float spec_factor;    /* 0.15 */
+  float spec_abs_exponent; /* 0.5 */
+  float theta;          /* OUVE stiffness 1.5 */
+} use_config;
+
+int use_abi_version(void);
+const char* use_last_error(void);
+
+/* ---- engine lifetime and weights ------------------------------------------------------------- */
+use_engine* use_engine_create(const use_config* cfg);
+void use_engine_destroy(use_engine* e);
+/* Register one state_dict tensor (host fp32, key relative to score_net, e.g. "all_modules.4.Conv_0.weight"). */
+int use_engine_set_weight(use_engine* e, const char* name, const float* host, const int64_t* shape, int ndim);
+/* Validate that every tensor of the architecture is present and pack them (host side); returns the number of
+ * device bytes the packed blob needs through *bytes. */
+int use_engine_pack(use_engine* e, size_t* bytes);
+/* Copy the packed blob into caller-allocated device memory (kept by the engine until destroy). */
+int use_engine_upload(use_engine* e, void* dev_weights, size_t bytes, void* stream);
+/* Workspace (device bytes) a forward / sample over B spectrograms of F x T (T % 2^(levels-1) == 0) needs. */
+int use_engine_workspace_bytes(use_engine* e, int B, int F, int T, size_t* bytes);
+
+/* Instrumentation: kernels launched so far by this engine; per-op-class CUDA-event timing of network evaluations
+ * (events on the launch stream, one pair per op; enable only outside timed regions). */
+long long use_engine_launch_count(use_engine* e);
+int use_engine_set_profiling(use_engine* e, int on);
+int use_engine_get_profile(use_engine* e, char* json, size_t cap);
+
+/* ---- the hot path ------------------------------------------------------------------------------ */
+/* score = -net(cat[x, Y], t).  x, Y, score: device complex64 [B][F][T] (interleaved re, im).
+ * t_host [B] and gfp_host [B][2*nf] = [sin(2 pi W log t), cos(..)] are HOST arrays (the Fourier features are
+ * evaluated by the host layer with torch so the embedding is bit-identical to the reference's). */
+int use_score_forward(use_engine* e, int B, int F, int T, const void* x, const void* Y, const float* t_host,
+                      const float* gfp_host, void* score, void* workspace, size_t workspace_bytes, void* stream);
+
+/* N reverse-diffusion predictor steps.  Y: device complex64 [B][F][T]; x_mean (out) same shape: the
+ * noise-free mean of the last step (denoise=True).  x_state: device scratch of the same shape.
+ * t_host[N], G_host[N] (= g(t_i) sqrt(1/N)), gfp_host[N][2*nf]: the float32 step schedule, host arrays.
+ * noise: device complex64 [N+1][B][F][T] explicit draws (prior, then one per step) or NULL for the in-kernel
+ * Philox stream keyed by (seed, step, clip0 + b).  */
+int use_pc_sample(use_engine* e, int B, int F, int T, const void* Y, void* x_state, void* x_mean, int N,
+                  const float* t_host, const float* G_host, const float* gfp_host, float prior_std, const void* noise,
+                  uint64_t seed, uint32_t clip0, void* workspace, size_t workspace_bytes, void* stream);
+
+/* y: device float [B][L] -> Y: device complex64 [B][n_fft/2+1][Tp], frames >= 1 + L/hop zero (pad_spec).
+ * window [n_fft] and twiddle [n_fft] (cos, sin of 2 pi i / n_fft, interleaved) are device arrays. */
+int use_stft(use_engine* e, int B, int L, int Tp, const float* y, void* Y, const float* window, const float* twiddle,
+             void* stream);
+/* X: device complex64 [B][F][Tp] -> y device float [B][L].  frames_scratch: device float [B][Tp][n_fft].
+ * envelope: device float [n_fft + hop (Tp-1)] = overlap-added squared window. */
+int use_istft(use_engine* e, int B, int L, int Tp, const void* X, float* y, float* frames_scratch, const float* window,
+              const float* twiddle, const float* envelope, void* stream);
+
+/* ---- the reference's native op -------------------------------------------------------------------- */
+/* upfirdn2d over [major][in_h][in_w][minor] fp32 (op/upfirdn2d.cpp:12-23 argument order). */
+int use_upfirdn2d_f32(const float* in, float* out, int major, int in_h, int in_w, int minor, const float* kernel,
+                      int kh, int kw, int up_x, int up_y, int down_x, int down_y, int pad_x0, int pad_x1, int pad_y0,
+                      int pad_y1, void* stream);
+
+/* ---- single kernels (parity tests) ----------------------------------------------------------------- */
+int use_op_gn_stats(int dtype, const void* x, double* stats, int B, int HW, int C, void* stream);
+int use_op_gn_apply(int dtype, const void* x0, const double* stats0, int C0, const void* x1, const double* stats1, int C1,
+                    const float* gamma, const float* beta, float eps, int fir, int do_silu, int as_operand, void* out_act,
+                    void* out_raw, int B, int Hin, int Win, void* stream);
+/* tcgen05 implicit-GEMM convolution; up to 3 segments summed into one accumulator.
+ * seg_act[i]: act tensor [B][H][W][seg_ctensor[i]], channel window [seg_c0, seg_c0+seg_c);
+ * seg_w[i]: packed weights [taps][N][seg_cw[i]] in act dtype, window starting at seg_wc0[i]. */
+int use_op_conv_tc(int dtype, int nseg, const void* const* seg_act, const int* seg_ctensor, const int* seg_c0,
+                   const int* seg_c, const void* const* seg_w, const int* seg_cw, const int* seg_wc0, const int* seg_taps,
+                   int B, int H, int W, int N, const float* bias, int bias_bstride, const void* res, float scale, void* out,
+                   void* stream);
+int use_op_conv_ref(int dtype, const void* x, const float* w, const float* bias, int bias_bstride, const void* res,
+                    float scale, void* out, int B, int H, int W, int Cin, int Cout, int ksize, void* stream);
+int use_op_conv_in4(int dtype, const float* x, const float* w, const float* bias, void* out, int B, int H, int W, int N,
+                    void* stream);
+int use_op_conv_out4(int dtype, const void* a, const float* w, const float* bias, const float* prev, float* out, int B,
+                     int H, int W, int C, void* stream);
+int use_op_combine(int dtype, const void* h, const float* pyr, const float* w, const float* bias, void* out, int B, int HW,
+                   int C, void* stream);
+int use_op_fir4_down(const float* x, float* out, int B, int Hin, int Win, void* stream);
+int use_op_philox(void* z, uint64_t seed, uint32_t step, uint32_t clip0, int B, size_t per_clip, void* stream);
+/* pack fp32 OIHW conv weights into the tcgen05 layout [taps][O][I] of the act dtype (host -> host). */
+int use_pack_conv_weight(int dtype, const float* w_oihw, int O, int I, int ksize, void* out);
+
+#if defined(__GNUC__)
+#pragma GCC visibility pop
+#endif
+#ifdef __cplusplus
+}
+#endif
+#endif /* USE_B200_H_ */

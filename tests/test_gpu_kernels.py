@@ -1,0 +1,318 @@
+"""Per-kernel parity on the B200, called through the C ABI (libuse_b200.so); torch CPU float64 is the checker.
+
+Operands are rounded to what the tensor core consumes (bf16 / TF32) BEFORE the reference computation, so the
+remaining difference is fp32 accumulation order (+ the output rounding of bf16 storage): tolerances are tight
+enough that any layout / descriptor / swizzle / pipeline-phase bug shows up as O(1) errors.
+"""
+import ctypes as C
+
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as Fnn
+
+from use_b200 import _lib
+from oracle import sgmse_oracle as O
+from util import (BF16, F32, act_tensor, describe_mismatch, from_act, int_array, pack_weight, ptr_array, rel_l2, stream,
+                  to_operand)
+
+pytestmark = pytest.mark.gpu
+
+OUT_TOL = {F32: 2e-5, BF16: 6e-3}  # relative-to-max tolerance on act-dtype outputs
+
+
+def _sync():
+    torch.cuda.synchronize()
+
+
+def run_conv_tc(dt, segs, B, H, W, N, bias, res=None, scale=1.0):
+    """segs: list of (x_nchw fp32 already operand-rounded, w_oihw fp32 already rounded, ks).  One weight tensor per
+    segment here (wc0 = 0); the concat-window form is covered by test_conv_tc_weight_window."""
+    L = _lib.lib()
+    acts, ws, ct, c0, cc, cw, wc0, taps, keep = [], [], [], [], [], [], [], [], []
+    for x, w, ks in segs:
+        a = act_tensor(x, dt)
+        pw = pack_weight(L, w, dt)
+        keep += [a, pw]
+        acts.append(a.data_ptr()); ws.append(pw.data_ptr())
+        ct.append(x.shape[1]); c0.append(0); cc.append(x.shape[1]); cw.append(w.shape[1]); wc0.append(0); taps.append(ks * ks)
+    out = torch.empty(B, H, W, N, device="cuda", dtype=torch.bfloat16 if dt == BF16 else torch.float32)
+    bias_d = bias.to("cuda", torch.float32).contiguous()
+    bstride = N if bias.dim() == 2 else 0
+    res_d = act_tensor(res, dt) if res is not None else None
+    rc = L.use_op_conv_tc(dt, len(segs), ptr_array(acts), int_array(ct), int_array(c0), int_array(cc), ptr_array(ws),
+                          int_array(cw), int_array(wc0), int_array(taps), B, H, W, N, bias_d.data_ptr(), bstride,
+                          res_d.data_ptr() if res_d is not None else None, float(scale), out.data_ptr(), stream())
+    assert rc == 0, L.use_last_error()
+    _sync()
+    return from_act(out)
+
+
+def ref_conv(dt, segs, bias, res=None, scale=1.0):
+    acc = None
+    for x, w, ks in segs:
+        y = Fnn.conv2d(x.double(), w.double(), padding=ks // 2)
+        acc = y if acc is None else acc + y
+    acc = acc + (bias.double()[:, :, None, None] if bias.dim() == 2 else bias.double()[None, :, None, None])
+    if res is not None:
+        acc = acc + to_operand(res, dt).double() if dt == BF16 else acc + res.double()
+    return (acc * scale).float()
+
+
+def make_seg(g, dt, B, Cin, Cout, H, W, ks):
+    x = to_operand(torch.randn(B, Cin, H, W, generator=g), dt)
+    w = to_operand(torch.randn(Cout, Cin, ks, ks, generator=g) / np.sqrt(Cin * ks * ks), dt)
+    return (x, w, ks)
+
+
+CONV_CASES = [
+    # name, B, H, W, N, [(Cin, ks), ...], per-sample bias, residual
+    ("1x1_single_chunk", 1, 32, 8, 128, [(64, 1)], False, False),
+    ("1x1_multi_chunk", 1, 32, 8, 128, [(256, 1)], False, False),
+    ("3x3_one_tile", 1, 32, 8, 128, [(64, 3)], False, False),
+    ("3x3_c128", 1, 32, 16, 128, [(128, 3)], False, False),
+    ("3x3_ragged_edges", 2, 20, 10, 128, [(128, 3)], True, False),
+    ("3x3_n256", 2, 16, 24, 256, [(128, 3)], True, False),
+    ("3x3_n256_small_level", 1, 8, 10, 256, [(256, 3)], False, True),
+    ("3x3_n64", 1, 16, 24, 64, [(64, 3)], False, False),
+    ("resblock_tail_3seg", 1, 32, 16, 128, [(128, 3), (128, 1), (64, 1)], False, False),
+    ("residual_scale", 2, 32, 8, 128, [(128, 3)], True, True),
+    ("persistent_many_tiles", 2, 128, 160, 128, [(128, 3)], False, True),
+    ("persistent_many_tiles_n256", 3, 64, 80, 256, [(256, 3), (256, 1)], True, False),
+]
+
+
+@pytest.mark.parametrize("dt", [F32, BF16], ids=["tf32", "bf16"])
+@pytest.mark.parametrize("case", CONV_CASES, ids=[c[0] for c in CONV_CASES])
+def test_conv_tc(case, dt):
+    name, B, H, W, N, seg_spec, per_sample, with_res = case
+    g = torch.Generator().manual_seed(hash(name) % 1000)
+    segs = [make_seg(g, dt, B, cin, N, H, W, ks) for cin, ks in seg_spec]
+    bias = torch.randn(B, N, generator=g) if per_sample else torch.randn(N, generator=g)
+    res = torch.randn(B, N, H, W, generator=g) if with_res else None
+    scale = 0.70710678 if (with_res or len(segs) > 1) else 1.0
+    got = run_conv_tc(dt, segs, B, H, W, N, bias, res, scale)
+    ref = ref_conv(dt, segs, bias, res, scale)
+    tol = OUT_TOL[dt] * float(ref.abs().max())
+    assert float((got - ref).abs().max()) <= tol, f"{name}: " + describe_mismatch(got, ref)
+
+
+@pytest.mark.parametrize("dt", [F32, BF16], ids=["tf32", "bf16"])
+def test_conv_tc_weight_window(dt):
+    """Two activation tensors against channel windows of ONE weight tensor (Conv_2 over cat[h, skip])."""
+    L = _lib.lib()
+    g = torch.Generator().manual_seed(5)
+    B, H, W, N, C0, C1 = 1, 32, 16, 128, 128, 64
+    x0 = to_operand(torch.randn(B, C0, H, W, generator=g), dt)
+    x1 = to_operand(torch.randn(B, C1, H, W, generator=g), dt)
+    w = to_operand(torch.randn(N, C0 + C1, 1, 1, generator=g) / np.sqrt(C0 + C1), dt)
+    bias = torch.randn(N, generator=g)
+    a0, a1, pw = act_tensor(x0, dt), act_tensor(x1, dt), pack_weight(L, w, dt)
+    out = torch.empty(B, H, W, N, device="cuda", dtype=a0.dtype)
+    bd = bias.cuda()
+    rc = L.use_op_conv_tc(dt, 2, ptr_array([a0.data_ptr(), a1.data_ptr()]), int_array([C0, C1]), int_array([0, 0]),
+                          int_array([C0, C1]), ptr_array([pw.data_ptr(), pw.data_ptr()]), int_array([C0 + C1, C0 + C1]),
+                          int_array([0, C0]), int_array([1, 1]), B, H, W, N, bd.data_ptr(), 0, None, 1.0, out.data_ptr(),
+                          stream())
+    assert rc == 0, L.use_last_error()
+    _sync()
+    ref = Fnn.conv2d(torch.cat([x0, x1], 1).double(), w.double()).float() + bias[None, :, None, None]
+    got = from_act(out)
+    assert float((got - ref).abs().max()) <= OUT_TOL[dt] * float(ref.abs().max()), describe_mismatch(got, ref)
+
+
+@pytest.mark.parametrize("dt", [F32, BF16], ids=["fp32", "bf16"])
+def test_conv_ref_matches_torch(dt):
+    L = _lib.lib()
+    g = torch.Generator().manual_seed(1)
+    B, H, W, Cin, Cout = 2, 9, 7, 8, 5
+    x = to_operand(torch.randn(B, Cin, H, W, generator=g), dt)
+    w = torch.randn(Cout, Cin, 3, 3, generator=g)
+    bias = torch.randn(Cout, generator=g)
+    a = act_tensor(x, dt)
+    out = torch.empty(B, H, W, Cout, device="cuda", dtype=a.dtype)
+    wd, bd = w.cuda(), bias.cuda()
+    assert L.use_op_conv_ref(dt, a.data_ptr(), wd.data_ptr(), bd.data_ptr(), 0, None, 1.0, out.data_ptr(), B, H, W, Cin,
+                             Cout, 3, stream()) == 0
+    _sync()
+    ref = Fnn.conv2d(x.double(), w.double(), bias.double(), padding=1).float()
+    assert float((from_act(out) - ref).abs().max()) <= OUT_TOL[dt] * float(ref.abs().max())
+
+
+def _gn_ref(x, gamma, beta, silu):
+    C = x.shape[1]
+    y = Fnn.group_norm(x.double(), min(C // 4, 32), gamma.double(), beta.double(), eps=1e-6)
+    return (Fnn.silu(y) if silu else y).float()
+
+
+@pytest.mark.parametrize("dt", [F32, BF16], ids=["fp32", "bf16"])
+@pytest.mark.parametrize("C0,C1,fir", [(128, 0, 0), (64, 0, 0), (256, 128, 0), (128, 64, 0), (128, 0, 1), (128, 0, 2),
+                                       (256, 0, 1)])
+def test_groupnorm_silu_fir(dt, C0, C1, fir):
+    """gn_stats + gn_apply vs torch group_norm -> SiLU -> FIR resample (layerspp.py:283-298)."""
+    L = _lib.lib()
+    g = torch.Generator().manual_seed(C0 + 7 * C1 + fir)
+    B, H, W = 2, 12, 20
+    x0 = to_operand(1.5 * torch.randn(B, C0, H, W, generator=g) + 0.3, dt) if dt == BF16 else 1.5 * torch.randn(B, C0, H, W, generator=g) + 0.3
+    srcs = [x0]
+    if C1:
+        x1 = 0.7 * torch.randn(B, C1, H, W, generator=g) - 0.2
+        srcs.append(to_operand(x1, dt) if dt == BF16 else x1)
+    Ct = C0 + C1
+    gamma, beta = 1 + 0.1 * torch.randn(Ct, generator=g), 0.1 * torch.randn(Ct, generator=g)
+    acts = [act_tensor(s, dt) for s in srcs]
+    stats = [torch.zeros(B, s.shape[1], 2, dtype=torch.float64, device="cuda") for s in srcs]
+    for a, st, s in zip(acts, stats, srcs):
+        assert L.use_op_gn_stats(dt, a.data_ptr(), st.data_ptr(), B, H * W, s.shape[1], stream()) == 0
+    _sync()
+    # statistics themselves
+    for st, s in zip(stats, srcs):
+        ref_sum = s.double().sum(dim=(2, 3))
+        ref_sq = (s.double() ** 2).sum(dim=(2, 3))
+        assert torch.allclose(st[..., 0].cpu(), ref_sum, rtol=1e-5, atol=1e-3)
+        assert torch.allclose(st[..., 1].cpu(), ref_sq, rtol=1e-5, atol=1e-3)
+    Ho, Wo = (H // 2, W // 2) if fir == 1 else ((H * 2, W * 2) if fir == 2 else (H, W))
+    out = torch.empty(B, Ho, Wo, Ct, device="cuda", dtype=acts[0].dtype)
+    raw = torch.empty_like(out) if fir else None
+    gd, bd = gamma.cuda(), beta.cuda()
+    rc = L.use_op_gn_apply(dt, acts[0].data_ptr(), stats[0].data_ptr(), C0, acts[1].data_ptr() if C1 else None,
+                           stats[1].data_ptr() if C1 else None, C1, gd.data_ptr(), bd.data_ptr(), 1e-6, fir, 1, 0,
+                           out.data_ptr(), raw.data_ptr() if fir else None, B, H, W, stream())
+    assert rc == 0, L.use_last_error()
+    _sync()
+    xcat = torch.cat(srcs, 1)
+    ref = _gn_ref(xcat, gamma, beta, True)
+    ref_raw = xcat
+    if fir == 1:
+        ref, ref_raw = O.fir_downsample_2d(ref), O.fir_downsample_2d(ref_raw)
+    elif fir == 2:
+        ref, ref_raw = O.fir_upsample_2d(ref), O.fir_upsample_2d(ref_raw)
+    tol = (1e-5 if dt == F32 else 6e-3) * float(ref.abs().max())
+    got = from_act(out)
+    assert float((got - ref).abs().max()) <= tol, describe_mismatch(got, ref)
+    if fir:
+        gr = from_act(raw)
+        assert float((gr - ref_raw).abs().max()) <= (1e-5 if dt == F32 else 6e-3) * float(ref_raw.abs().max()), \
+            describe_mismatch(gr, ref_raw)
+
+
+def test_gn_apply_operand_rounding_fp32():
+    """as_operand=1 in fp32 mode stores TF32-representable values (low 13 mantissa bits clear)."""
+    L = _lib.lib()
+    B, H, W, Cc = 1, 4, 4, 64
+    x = torch.randn(B, Cc, H, W)
+    a = act_tensor(x, F32)
+    st = torch.zeros(B, Cc, 2, dtype=torch.float64, device="cuda")
+    L.use_op_gn_stats(F32, a.data_ptr(), st.data_ptr(), B, H * W, Cc, stream())
+    out = torch.empty_like(a)
+    gd, bd = torch.ones(Cc, device="cuda"), torch.zeros(Cc, device="cuda")
+    assert L.use_op_gn_apply(F32, a.data_ptr(), st.data_ptr(), Cc, None, None, 0, gd.data_ptr(), bd.data_ptr(), 1e-6, 0, 1,
+                             1, out.data_ptr(), None, B, H, W, stream()) == 0
+    _sync()
+    assert int((out.view(torch.int32) & 0x1FFF).abs().max()) == 0
+
+
+@pytest.mark.parametrize("dt", [F32, BF16], ids=["fp32", "bf16"])
+def test_conv_in4(dt):
+    L = _lib.lib()
+    g = torch.Generator().manual_seed(2)
+    B, H, W, N = 2, 16, 24, 128
+    x = torch.randn(B, 4, H, W, generator=g)
+    w = torch.randn(N, 4, 3, 3, generator=g) / 6
+    bias = torch.randn(N, generator=g)
+    xd = x.permute(0, 2, 3, 1).contiguous().cuda()
+    out = torch.empty(B, H, W, N, device="cuda", dtype=torch.bfloat16 if dt == BF16 else torch.float32)
+    wd, bd = w.cuda(), bias.cuda()
+    assert L.use_op_conv_in4(dt, xd.data_ptr(), wd.data_ptr(), bd.data_ptr(), out.data_ptr(), B, H, W, N, stream()) == 0
+    _sync()
+    ref = Fnn.conv2d(x.double(), w.double(), bias.double(), padding=1).float()
+    got = from_act(out)
+    assert float((got - ref).abs().max()) <= OUT_TOL[dt] * float(ref.abs().max()), describe_mismatch(got, ref)
+
+
+@pytest.mark.parametrize("dt", [F32, BF16], ids=["fp32", "bf16"])
+@pytest.mark.parametrize("with_prev", [False, True])
+def test_conv_out4(dt, with_prev):
+    """pyramid conv3x3 C->4 (+ FIR-up of the previous pyramid): ncsnpp.py:440-461."""
+    L = _lib.lib()
+    g = torch.Generator().manual_seed(3)
+    B, H, W, Cc = 2, 16, 20, 128
+    a = to_operand(torch.randn(B, Cc, H, W, generator=g), dt) if dt == BF16 else torch.randn(B, Cc, H, W, generator=g)
+    w = torch.randn(4, Cc, 3, 3, generator=g) / np.sqrt(9 * Cc)
+    bias = torch.randn(4, generator=g)
+    prev = torch.randn(B, 4, H // 2, W // 2, generator=g)
+    ad = act_tensor(a, dt)
+    wd, bd = w.cuda(), bias.cuda()
+    pd = prev.permute(0, 2, 3, 1).contiguous().cuda()
+    out = torch.empty(B, H, W, 4, device="cuda")
+    assert L.use_op_conv_out4(dt, ad.data_ptr(), wd.data_ptr(), bd.data_ptr(), pd.data_ptr() if with_prev else None,
+                              out.data_ptr(), B, H, W, Cc, stream()) == 0
+    _sync()
+    ref = Fnn.conv2d(a.double(), w.double(), bias.double(), padding=1).float()
+    if with_prev:
+        ref = ref + O.fir_upsample_2d(prev)
+    got = out.permute(0, 3, 1, 2).cpu()
+    assert float((got - ref).abs().max()) <= 2e-5 * float(ref.abs().max()), describe_mismatch(got, ref)
+
+
+@pytest.mark.parametrize("dt", [F32, BF16], ids=["fp32", "bf16"])
+def test_combine_and_fir4(dt):
+    L = _lib.lib()
+    g = torch.Generator().manual_seed(4)
+    B, H, W, Cc = 2, 16, 24, 128
+    pyr = torch.randn(B, 4, H, W, generator=g)
+    pd = pyr.permute(0, 2, 3, 1).contiguous().cuda()
+    pdown = torch.empty(B, H // 2, W // 2, 4, device="cuda")
+    assert L.use_op_fir4_down(pd.data_ptr(), pdown.data_ptr(), B, H, W, stream()) == 0
+    _sync()
+    ref_down = O.fir_downsample_2d(pyr)
+    assert float((pdown.permute(0, 3, 1, 2).cpu() - ref_down).abs().max()) < 1e-5
+    h = to_operand(torch.randn(B, Cc, H // 2, W // 2, generator=g), dt) if dt == BF16 else torch.randn(B, Cc, H // 2, W // 2, generator=g)
+    w = torch.randn(Cc, 4, 1, 1, generator=g) / 2
+    bias = torch.randn(Cc, generator=g)
+    hd = act_tensor(h, dt)
+    wd, bd = w.cuda(), bias.cuda()
+    assert L.use_op_combine(dt, hd.data_ptr(), pdown.data_ptr(), wd.data_ptr(), bd.data_ptr(), hd.data_ptr(), B,
+                            (H // 2) * (W // 2), Cc, stream()) == 0
+    _sync()
+    ref = Fnn.conv2d(ref_down.double(), w.double(), bias.double()).float() + h
+    got = from_act(hd)
+    assert float((got - ref).abs().max()) <= OUT_TOL[dt] * float(ref.abs().max()), describe_mismatch(got, ref)
+
+
+@pytest.mark.parametrize("up,down,pad", [(2, 1, (2, 1)), (1, 2, (1, 1)), (1, 1, (0, 0)), (2, 2, (1, 0))])
+def test_upfirdn2d_abi(up, down, pad):
+    """The reference's native op seam (op/upfirdn2d.cpp:12-23) against its CPU semantics."""
+    L = _lib.lib()
+    g = torch.Generator().manual_seed(6)
+    x = torch.randn(3, 2, 9, 11, generator=g)  # [N, C, H, W] -> planes [N*C, H, W, 1]
+    k = torch.tensor(O._setup_kernel((1, 3, 3, 1)) * (up**2))
+    ref = O._upfirdn2d(x, k, up, down, pad[0], pad[1])
+    oh, ow = ref.shape[-2:]
+    xd, kd = x.reshape(-1, 9, 11, 1).contiguous().cuda(), k.cuda()
+    out = torch.empty(6, oh, ow, 1, device="cuda")
+    assert L.use_upfirdn2d_f32(xd.data_ptr(), out.data_ptr(), 6, 9, 11, 1, kd.data_ptr(), 4, 4, up, up, down, down, pad[0],
+                               pad[1], pad[0], pad[1], stream()) == 0
+    _sync()
+    assert float((out.reshape(3, 2, oh, ow).cpu() - ref).abs().max()) < 1e-5
+
+
+def test_philox_complex_normal_statistics():
+    """In-kernel noise: complex standard normal (Re, Im ~ N(0, 1/2)), independent across step / clip streams."""
+    L = _lib.lib()
+    B, per = 4, 1 << 18
+    z = torch.empty(B, per, dtype=torch.complex64, device="cuda")
+    assert L.use_op_philox(z.data_ptr(), 1234, 3, 10, B, per, stream()) == 0
+    z2 = torch.empty_like(z)
+    assert L.use_op_philox(z2.data_ptr(), 1234, 4, 10, B, per, stream()) == 0
+    z3 = torch.empty(2, per, dtype=torch.complex64, device="cuda")
+    assert L.use_op_philox(z3.data_ptr(), 1234, 3, 12, 2, per, stream()) == 0  # clips 12, 13 = rows 2, 3 of z
+    _sync()
+    zr = torch.view_as_real(z).double().cpu()
+    n = zr.numel()
+    assert abs(float(zr.mean())) < 5 / np.sqrt(n)
+    assert abs(float(zr.var()) - 0.5) < 5 * 0.5 * np.sqrt(2 / n)
+    assert abs(float((zr**4).mean()) - 3 * 0.25) < 0.01                       # kurtosis of N(0, 1/2)
+    assert abs(float((zr[..., 0] * zr[..., 1]).mean())) < 5 * 0.5 / np.sqrt(n / 2)  # Re / Im uncorrelated
+    assert abs(float((zr * torch.view_as_real(z2).double().cpu()).mean())) < 5 * 0.5 / np.sqrt(n)
+    assert torch.equal(z[2:], z3)  # shard invariance: stream depends on the global clip index only

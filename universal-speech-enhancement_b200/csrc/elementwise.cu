@@ -1,0 +1,556 @@
+// Bandwidth-bound kernels of the score network: GroupNorm statistics, normalise + SiLU (+ FIR resample),
+// Combine, the 4-channel input / pyramid convolutions and the FIR of the input pyramid.
+// Reference semantics: nn.GroupNorm(min(C/4,32), eps=1e-6) + SiLU (layerspp.py:255-271,283,304),
+// upsample_2d / downsample_2d with k=[1,3,3,1] (up_or_down_sampling.py:202-264), Combine "sum"
+// (layerspp.py:50-55), input conv / pyramid convs (ncsnpp.py:214,377-381,440-461).
+#include <algorithm>
+
+#include "common.cuh"
+#include "kernels.h"
+
+namespace use {
+
+#define DISPATCH_DT(dt, ...)                \
+  do {                                      \
+    if ((dt) == kBF16) {                    \
+      using T = __nv_bfloat16;              \
+      __VA_ARGS__                           \
+    } else {                                \
+      using T = float;                      \
+      __VA_ARGS__                           \
+    }                                       \
+  } while (0)
+
+// ------------------------------------------------------------------------------------------------
+// GroupNorm statistics: per sample and per CHANNEL sum and sum of squares (double atomics).
+// Channels (not groups) so that a GroupNorm over a channel concat whose group boundary straddles the
+// two sources (384 = 256 + 128 channels, 12 per group) can be assembled from per-tensor partials.
+// ------------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(256) gn_stats_kernel(const T* __restrict__ x, double* __restrict__ stats, int HW, int C,
+                                                        int pix_per_block) {
+  constexpr int V = Vec<T>::N;
+  extern __shared__ float sred[];  // [C][2]
+  for (int i = threadIdx.x; i < C * 2; i += blockDim.x) sred[i] = 0.f;
+  __syncthreads();
+  const int b = blockIdx.y;
+  const int vp = C / V;                 // vectors per pixel
+  const int p0 = blockIdx.x * pix_per_block;
+  const int p1 = min(HW, p0 + pix_per_block);
+  const T* base = x + (static_cast<size_t>(b) * HW) * C;
+  // thread -> fixed vector column v (when blockDim % vp == 0) so partial sums stay in registers
+  if (blockDim.x % vp == 0) {
+    const int rp = blockDim.x / vp;
+    const int v = threadIdx.x % vp;
+    float s[V], ss[V];
+#pragma unroll
+    for (int i = 0; i < V; ++i) s[i] = ss[i] = 0.f;
+    for (int p = p0 + threadIdx.x / vp; p < p1; p += rp) {
+      float f[V];
+      Vec<T>::load(base + static_cast<size_t>(p) * C + v * V, f);
+#pragma unroll
+      for (int i = 0; i < V; ++i) { s[i] += f[i]; ss[i] += f[i] * f[i]; }
+    }
+#pragma unroll
+    for (int i = 0; i < V; ++i) {
+      atomicAdd(&sred[(v * V + i) * 2], s[i]);
+      atomicAdd(&sred[(v * V + i) * 2 + 1], ss[i]);
+    }
+  } else {
+    const long long nvec = static_cast<long long>(p1 - p0) * vp;
+    for (long long i = threadIdx.x; i < nvec; i += blockDim.x) {
+      const int v = static_cast<int>(i % vp);
+      float f[V];
+      Vec<T>::load(base + (static_cast<size_t>(p0) + i / vp) * C + v * V, f);
+#pragma unroll
+      for (int j = 0; j < V; ++j) {
+        atomicAdd(&sred[(v * V + j) * 2], f[j]);
+        atomicAdd(&sred[(v * V + j) * 2 + 1], f[j] * f[j]);
+      }
+    }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < C * 2; i += blockDim.x)
+    atomicAdd(&stats[static_cast<size_t>(b) * C * 2 + i], static_cast<double>(sred[i]));
+}
+
+void launch_gn_stats(int dt, const void* x, double* stats, int B, int HW, int C, cudaStream_t st) {
+  const int ppb = 1024;
+  dim3 grid((HW + ppb - 1) / ppb, B);
+  DISPATCH_DT(dt, { gn_stats_kernel<T><<<grid, 256, C * 2 * sizeof(float), st>>>((const T*)x, stats, HW, C, ppb); });
+}
+
+// ------------------------------------------------------------------------------------------------
+// normalise + affine + SiLU (+ FIR x2 up / down) over a (possibly concatenated) input.
+// ------------------------------------------------------------------------------------------------
+template <typename T>
+struct GnSrcT {
+  const T* x;
+  const double* stats;
+  int C;
+};
+
+template <typename T, int FIR>
+__global__ void __launch_bounds__(256) gn_apply_kernel(GnSrcT<T> s0, GnSrcT<T> s1, const float* __restrict__ gamma,
+                                                        const float* __restrict__ beta, float eps, int do_silu, int as_operand,
+                                                        T* __restrict__ out_act, T* __restrict__ out_raw, int Hin, int Win,
+                                                        int vec_per_block) {
+  constexpr int V = Vec<T>::N;
+  extern __shared__ float saff[];  // scale[Ct], shift[Ct]
+  const int Ct = s0.C + s1.C;
+  const int G = min(Ct / 4, 32);
+  const int cpg = Ct / G;
+  const int b = blockIdx.y;
+  const double cnt = static_cast<double>(Hin) * Win * cpg;
+  for (int c = threadIdx.x; c < Ct; c += blockDim.x) {
+    const int g = c / cpg;
+    double sum = 0.0, sq = 0.0;
+    for (int cc = g * cpg; cc < (g + 1) * cpg; ++cc) {  // channel index in the concatenation
+      const double* st = (cc < s0.C) ? s0.stats + (static_cast<size_t>(b) * s0.C + cc) * 2
+                                     : s1.stats + (static_cast<size_t>(b) * s1.C + (cc - s0.C)) * 2;
+      sum += st[0];
+      sq += st[1];
+    }
+    const double mean = sum / cnt;
+    double var = sq / cnt - mean * mean;
+    if (var < 0.0) var = 0.0;
+    const float rstd = static_cast<float>(1.0 / sqrt(var + static_cast<double>(eps)));
+    const float sc = gamma[c] * rstd;
+    saff[c] = sc;
+    saff[Ct + c] = beta[c] - static_cast<float>(mean) * sc;
+  }
+  __syncthreads();
+
+  const int Hout = FIR == 1 ? Hin / 2 : (FIR == 2 ? Hin * 2 : Hin);
+  const int Wout = FIR == 1 ? Win / 2 : (FIR == 2 ? Win * 2 : Win);
+  const int vpp = Ct / V;
+  const long long total = static_cast<long long>(Hout) * Wout * vpp;
+  const long long i0 = static_cast<long long>(blockIdx.x) * vec_per_block;
+  const long long i1 = min(total, i0 + vec_per_block);
+  for (long long i = i0 + threadIdx.x; i < i1; i += blockDim.x) {
+    const int cv = static_cast<int>(i % vpp);
+    const long long pix = i / vpp;
+    const int c = cv * V;
+    const bool first = c < s0.C;
+    const T* src = first ? s0.x : s1.x;
+    const int Cs = first ? s0.C : s1.C;
+    const int cs = first ? c : c - s0.C;
+    float sc[V], sh[V];
+#pragma unroll
+    for (int j = 0; j < V; ++j) { sc[j] = saff[c + j]; sh[j] = saff[Ct + c + j]; }
+    const T* sb = src + static_cast<size_t>(b) * Hin * Win * Cs + cs;
+    float acc[V], raw[V];
+    if constexpr (FIR == 0) {
+      float f[V];
+      Vec<T>::load(sb + static_cast<size_t>(pix) * Cs, f);
+#pragma unroll
+      for (int j = 0; j < V; ++j) {
+        const float n = f[j] * sc[j] + sh[j];
+        acc[j] = do_silu ? silu(n) : n;
+      }
+    } else {
+      const int ox = static_cast<int>(pix % Wout), oy = static_cast<int>(pix / Wout);
+#pragma unroll
+      for (int j = 0; j < V; ++j) acc[j] = raw[j] = 0.f;
+      if constexpr (FIR == 1) {
+        // out[oy][ox] = sum_{a,b<4} k[a]k[b] in[2oy+a-1][2ox+b-1],  k = [1,3,3,1]/8, zero outside
+        const float k1[4] = {0.125f, 0.375f, 0.375f, 0.125f};
+#pragma unroll
+        for (int a = 0; a < 4; ++a) {
+          const int iy = 2 * oy + a - 1;
+          if (iy < 0 || iy >= Hin) continue;
+#pragma unroll
+          for (int bb = 0; bb < 4; ++bb) {
+            const int ix = 2 * ox + bb - 1;
+            if (ix < 0 || ix >= Win) continue;
+            float f[V];
+            Vec<T>::load(sb + (static_cast<size_t>(iy) * Win + ix) * Cs, f);
+            const float kw = k1[a] * k1[bb];
+#pragma unroll
+            for (int j = 0; j < V; ++j) {
+              const float n = f[j] * sc[j] + sh[j];
+              acc[j] += kw * (do_silu ? silu(n) : n);
+              raw[j] += kw * f[j];
+            }
+          }
+        }
+      } else {
+        // per axis: out[2m] = (in[m-1] + 3 in[m]) / 4 ; out[2m+1] = (3 in[m] + in[m+1]) / 4, zero outside
+        const int my = oy >> 1, mx = ox >> 1;
+        const int ya = (oy & 1) ? my : my - 1, yb = ya + 1;
+        const int xa = (ox & 1) ? mx : mx - 1, xb = xa + 1;
+        const float wya = (oy & 1) ? 0.75f : 0.25f, wyb = 1.0f - wya;
+        const float wxa = (ox & 1) ? 0.75f : 0.25f, wxb = 1.0f - wxa;
+        const int ys[2] = {ya, yb};
+        const int xs[2] = {xa, xb};
+        const float wy[2] = {wya, wyb};
+        const float wx[2] = {wxa, wxb};
+#pragma unroll
+        for (int a = 0; a < 2; ++a) {
+          if (ys[a] < 0 || ys[a] >= Hin) continue;
+#pragma unroll
+          for (int bb = 0; bb < 2; ++bb) {
+            if (xs[bb] < 0 || xs[bb] >= Win) continue;
+            float f[V];
+            Vec<T>::load(sb + (static_cast<size_t>(ys[a]) * Win + xs[bb]) * Cs, f);
+            const float kw = wy[a] * wx[bb];
+#pragma unroll
+            for (int j = 0; j < V; ++j) {
+              const float n = f[j] * sc[j] + sh[j];
+              acc[j] += kw * (do_silu ? silu(n) : n);
+              raw[j] += kw * f[j];
+            }
+          }
+        }
+      }
+    }
+    const size_t o = (static_cast<size_t>(b) * Hout * Wout + pix) * Ct + c;
+    if (as_operand) Vec<T>::store_operand(out_act + o, acc);
+    else Vec<T>::store(out_act + o, acc);
+    if constexpr (FIR != 0) {
+      if (out_raw != nullptr) Vec<T>::store_operand(out_raw + o, raw);
+    }
+  }
+}
+
+void launch_gn_apply(int dt, GnSrc s0, GnSrc s1, const float* gamma, const float* beta, float eps, int fir, bool do_silu,
+                     bool as_operand, void* out_act, void* out_raw, int B, int Hin, int Win, cudaStream_t st) {
+  const int Ct = s0.C + s1.C;
+  const int Hout = fir == 1 ? Hin / 2 : (fir == 2 ? Hin * 2 : Hin);
+  const int Wout = fir == 1 ? Win / 2 : (fir == 2 ? Win * 2 : Win);
+  DISPATCH_DT(dt, {
+    constexpr int V = Vec<T>::N;
+    const long long total = static_cast<long long>(Hout) * Wout * (Ct / V);
+    const int vpb = 256 * 16;
+    dim3 grid(static_cast<unsigned>((total + vpb - 1) / vpb), B);
+    GnSrcT<T> a{(const T*)s0.x, s0.stats, s0.C};
+    GnSrcT<T> c{(const T*)s1.x, s1.stats, s1.C};
+    const size_t sm = 2 * Ct * sizeof(float);
+    if (fir == 0)
+      gn_apply_kernel<T, 0><<<grid, 256, sm, st>>>(a, c, gamma, beta, eps, do_silu, as_operand, (T*)out_act, (T*)out_raw, Hin, Win, vpb);
+    else if (fir == 1)
+      gn_apply_kernel<T, 1><<<grid, 256, sm, st>>>(a, c, gamma, beta, eps, do_silu, as_operand, (T*)out_act, (T*)out_raw, Hin, Win, vpb);
+    else
+      gn_apply_kernel<T, 2><<<grid, 256, sm, st>>>(a, c, gamma, beta, eps, do_silu, as_operand, (T*)out_act, (T*)out_raw, Hin, Win, vpb);
+  });
+}
+
+// ------------------------------------------------------------------------------------------------
+// input convolution: 3x3 pad 1, 4 -> N channels.  fp32 NHWC4 input, act-dtype output.
+// ------------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(256) conv_in4_kernel(const float* __restrict__ x, const float* __restrict__ w,
+                                                        const float* __restrict__ bias, T* __restrict__ out, int H, int W,
+                                                        int N, long long total) {
+  constexpr int V = Vec<T>::N;
+  extern __shared__ float sw[];  // [36][N] (tap*4+ci major), then bias [N]
+  for (int i = threadIdx.x; i < 36 * N; i += blockDim.x) {
+    const int co = i % N, k = i / N;  // k = tap*4 + ci
+    const int tap = k >> 2, ci = k & 3;
+    sw[i] = w[(co * 4 + ci) * 9 + tap];
+  }
+  for (int i = threadIdx.x; i < N; i += blockDim.x) sw[36 * N + i] = bias[i];
+  __syncthreads();
+  const int vpp = N / V;
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int cv = static_cast<int>(i % vpp);
+    const long long pix = i / vpp;  // over B*H*W
+    const int xw = static_cast<int>(pix % W);
+    const int yh = static_cast<int>((pix / W) % H);
+    const long long b = pix / (static_cast<long long>(W) * H);
+    float acc[V];
+#pragma unroll
+    for (int j = 0; j < V; ++j) acc[j] = sw[36 * N + cv * V + j];
+#pragma unroll
+    for (int r = 0; r < 3; ++r) {
+      const int iy = yh + r - 1;
+      if (iy < 0 || iy >= H) continue;
+#pragma unroll
+      for (int s = 0; s < 3; ++s) {
+        const int ix = xw + s - 1;
+        if (ix < 0 || ix >= W) continue;
+        const float4 in = __ldg(reinterpret_cast<const float4*>(x) + (b * H + iy) * W + ix);
+        const float iv[4] = {in.x, in.y, in.z, in.w};
+        const int tap = r * 3 + s;
+#pragma unroll
+        for (int ci = 0; ci < 4; ++ci) {
+          const float* wr = sw + (tap * 4 + ci) * N + cv * V;
+#pragma unroll
+          for (int j = 0; j < V; ++j) acc[j] += iv[ci] * wr[j];
+        }
+      }
+    }
+    Vec<T>::store(out + pix * N + cv * V, acc);
+  }
+}
+
+void launch_conv_in4(int dt, const float* x, const float* w, const float* bias, void* out, int B, int H, int W, int N,
+                     cudaStream_t st) {
+  DISPATCH_DT(dt, {
+    constexpr int V = Vec<T>::N;
+    const long long total = static_cast<long long>(B) * H * W * (N / V);
+    const int blocks = static_cast<int>(std::min<long long>((total + 255) / 256, 148LL * 32));
+    conv_in4_kernel<T><<<blocks, 256, (37 * N) * sizeof(float), st>>>(x, w, bias, (T*)out, H, W, N, total);
+  });
+}
+
+// ------------------------------------------------------------------------------------------------
+// pyramid convolution: 3x3 pad 1, C -> 4 channels (fp32 out), optional + FIR-upsample(prev pyramid).
+// One thread = PX horizontally adjacent pixels x 4 outputs; weights [tap][c][4] in shared memory.
+// ------------------------------------------------------------------------------------------------
+template <typename T, int PX>
+__global__ void __launch_bounds__(128) conv_out4_kernel(const T* __restrict__ a, const float* __restrict__ w,
+                                                         const float* __restrict__ bias, const float* __restrict__ prev,
+                                                         float* __restrict__ out, int H, int W, int C, long long total) {
+  constexpr int V = Vec<T>::N;
+  extern __shared__ float4 sw4[];  // [9][C] float4 over the 4 output channels
+  for (int i = threadIdx.x; i < 9 * C; i += blockDim.x) {
+    const int c = i % C, tap = i / C;
+    sw4[i] = make_float4(w[(0 * C + c) * 9 + tap], w[(1 * C + c) * 9 + tap], w[(2 * C + c) * 9 + tap],
+                         w[(3 * C + c) * 9 + tap]);
+  }
+  __syncthreads();
+  const int wq = (W + PX - 1) / PX;
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int xq = static_cast<int>(i % wq) * PX;
+    const int yh = static_cast<int>((i / wq) % H);
+    const long long b = i / (static_cast<long long>(wq) * H);
+    float acc[PX][4];
+#pragma unroll
+    for (int p = 0; p < PX; ++p) {
+      acc[p][0] = bias[0]; acc[p][1] = bias[1]; acc[p][2] = bias[2]; acc[p][3] = bias[3];
+    }
+    for (int r = 0; r < 3; ++r) {
+      const int iy = yh + r - 1;
+      if (iy < 0 || iy >= H) continue;
+      const T* row = a + ((b * H + iy) * W) * C;
+      for (int c = 0; c < C; c += V) {
+        // input columns xq-1 .. xq+PX
+        float f[PX + 2][V];
+#pragma unroll
+        for (int q = 0; q < PX + 2; ++q) {
+          const int ix = xq + q - 1;
+          if (ix >= 0 && ix < W) {
+            Vec<T>::load(row + static_cast<size_t>(ix) * C + c, f[q]);
+          } else {
+#pragma unroll
+            for (int j = 0; j < V; ++j) f[q][j] = 0.f;
+          }
+        }
+#pragma unroll
+        for (int s = 0; s < 3; ++s) {
+          const float4* wr = sw4 + (r * 3 + s) * C + c;
+#pragma unroll
+          for (int j = 0; j < V; ++j) {
+            const float4 ww = wr[j];
+#pragma unroll
+            for (int p = 0; p < PX; ++p) {
+              const float v = f[p + s][j];
+              acc[p][0] += v * ww.x; acc[p][1] += v * ww.y; acc[p][2] += v * ww.z; acc[p][3] += v * ww.w;
+            }
+          }
+        }
+      }
+    }
+#pragma unroll
+    for (int p = 0; p < PX; ++p) {
+      const int ox = xq + p;
+      if (ox >= W) continue;
+      if (prev != nullptr) {
+        const int Hp = H / 2, Wp = W / 2;
+        const int my = yh >> 1, mx = ox >> 1;
+        const int ya = (yh & 1) ? my : my - 1, xa = (ox & 1) ? mx : mx - 1;
+        const float wya = (yh & 1) ? 0.75f : 0.25f, wxa = (ox & 1) ? 0.75f : 0.25f;
+#pragma unroll
+        for (int dy = 0; dy < 2; ++dy) {
+          const int yy = ya + dy;
+          if (yy < 0 || yy >= Hp) continue;
+#pragma unroll
+          for (int dx = 0; dx < 2; ++dx) {
+            const int xx = xa + dx;
+            if (xx < 0 || xx >= Wp) continue;
+            const float kw = (dy ? 1.f - wya : wya) * (dx ? 1.f - wxa : wxa);
+            const float4 pv = __ldg(reinterpret_cast<const float4*>(prev) + (b * Hp + yy) * Wp + xx);
+            acc[p][0] += kw * pv.x; acc[p][1] += kw * pv.y; acc[p][2] += kw * pv.z; acc[p][3] += kw * pv.w;
+          }
+        }
+      }
+      reinterpret_cast<float4*>(out)[(b * H + yh) * W + ox] = make_float4(acc[p][0], acc[p][1], acc[p][2], acc[p][3]);
+    }
+  }
+}
+
+void launch_conv_out4(int dt, const void* a, const float* w, const float* bias, const float* prev, float* out, int B,
+                      int H, int W, int C, cudaStream_t st) {
+  constexpr int PX = 4;
+  const long long total = static_cast<long long>(B) * H * ((W + PX - 1) / PX);
+  const int blocks = static_cast<int>(std::min<long long>((total + 127) / 128, 148LL * 16));
+  DISPATCH_DT(dt, {
+    auto kern = conv_out4_kernel<T, PX>;
+    const size_t sm = static_cast<size_t>(9) * C * sizeof(float4);
+    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(sm));
+    kern<<<blocks, 128, sm, st>>>((const T*)a, w, bias, prev, out, H, W, C, total);
+  });
+}
+
+// ------------------------------------------------------------------------------------------------
+// Combine(sum): out = h + bias + W[C][4] . pyr
+// ------------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(256) combine_kernel(const T* __restrict__ h, const float* __restrict__ pyr,
+                                                       const float* __restrict__ w, const float* __restrict__ bias,
+                                                       T* __restrict__ out, int C, long long total) {
+  constexpr int V = Vec<T>::N;
+  const int vpp = C / V;
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int cv = static_cast<int>(i % vpp);
+    const long long pix = i / vpp;
+    const float4 pv = __ldg(reinterpret_cast<const float4*>(pyr) + pix);
+    float f[V];
+    Vec<T>::load(h + pix * C + cv * V, f);
+#pragma unroll
+    for (int j = 0; j < V; ++j) {
+      const int c = cv * V + j;
+      const float4 ww = __ldg(reinterpret_cast<const float4*>(w) + c);
+      // same association as conv2d then "+ h": (bias + w.p) + h
+      f[j] = (bias[c] + ww.x * pv.x + ww.y * pv.y + ww.z * pv.z + ww.w * pv.w) + f[j];
+    }
+    Vec<T>::store(out + pix * C + cv * V, f);
+  }
+}
+
+void launch_combine(int dt, const void* h, const float* pyr, const float* w, const float* bias, void* out, int B, int HW,
+                    int C, cudaStream_t st) {
+  DISPATCH_DT(dt, {
+    constexpr int V = Vec<T>::N;
+    const long long total = static_cast<long long>(B) * HW * (C / V);
+    const int blocks = static_cast<int>(std::min<long long>((total + 255) / 256, 148LL * 32));
+    combine_kernel<T><<<blocks, 256, 0, st>>>((const T*)h, pyr, w, bias, (T*)out, C, total);
+  });
+}
+
+// ------------------------------------------------------------------------------------------------
+// FIR downsample of the 4-channel fp32 input pyramid
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) fir4_down_kernel(const float4* __restrict__ x, float4* __restrict__ out, int Hin,
+                                                         int Win, long long total) {
+  const int Ho = Hin / 2, Wo = Win / 2;
+  const float k1[4] = {0.125f, 0.375f, 0.375f, 0.125f};
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int ox = static_cast<int>(i % Wo), oy = static_cast<int>((i / Wo) % Ho);
+    const long long b = i / (static_cast<long long>(Wo) * Ho);
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int a = 0; a < 4; ++a) {
+      const int iy = 2 * oy + a - 1;
+      if (iy < 0 || iy >= Hin) continue;
+#pragma unroll
+      for (int bb = 0; bb < 4; ++bb) {
+        const int ix = 2 * ox + bb - 1;
+        if (ix < 0 || ix >= Win) continue;
+        const float kw = k1[a] * k1[bb];
+        const float4 v = __ldg(x + (b * Hin + iy) * Win + ix);
+        acc.x += kw * v.x; acc.y += kw * v.y; acc.z += kw * v.z; acc.w += kw * v.w;
+      }
+    }
+    out[i] = acc;
+  }
+}
+
+void launch_fir4_down(const float* x, float* out, int B, int Hin, int Win, cudaStream_t st) {
+  const long long total = static_cast<long long>(B) * (Hin / 2) * (Win / 2);
+  const int blocks = static_cast<int>(std::min<long long>((total + 255) / 256, 148LL * 32));
+  fir4_down_kernel<<<blocks, 256, 0, st>>>((const float4*)x, (float4*)out, Hin, Win, total);
+}
+
+// ------------------------------------------------------------------------------------------------
+// generic direct convolution: verification of the tcgen05 path only (slow by construction)
+// ------------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void conv_ref_kernel(const T* __restrict__ x, const float* __restrict__ w, const float* __restrict__ bias,
+                                int bias_bstride, const T* __restrict__ res, float scale, T* __restrict__ out, int H, int W,
+                                int Cin, int Cout, int ks, long long total) {
+  const int pad = ks / 2;
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int co = static_cast<int>(i % Cout);
+    const long long pix = i / Cout;
+    const int xw = static_cast<int>(pix % W), yh = static_cast<int>((pix / W) % H);
+    const long long b = pix / (static_cast<long long>(W) * H);
+    float acc = 0.f;
+    for (int r = 0; r < ks; ++r) {
+      const int iy = yh + r - pad;
+      if (iy < 0 || iy >= H) continue;
+      for (int s = 0; s < ks; ++s) {
+        const int ix = xw + s - pad;
+        if (ix < 0 || ix >= W) continue;
+        const T* px = x + ((b * H + iy) * W + ix) * Cin;
+        const float* pw = w + (static_cast<size_t>(co) * Cin) * ks * ks + r * ks + s;
+        for (int ci = 0; ci < Cin; ++ci) acc += static_cast<float>(px[ci]) * pw[static_cast<size_t>(ci) * ks * ks];
+      }
+    }
+    acc += bias[b * bias_bstride + co];
+    if (res != nullptr) acc += static_cast<float>(res[i]);
+    out[i] = static_cast<T>(acc * scale);
+  }
+}
+
+void launch_conv_ref(int dt, const void* x, const float* w, const float* bias, int bias_bstride, const void* res,
+                     float scale, void* out, int B, int H, int W, int Cin, int Cout, int ksize, cudaStream_t st) {
+  const long long total = static_cast<long long>(B) * H * W * Cout;
+  const int blocks = static_cast<int>(std::min<long long>((total + 255) / 256, 148LL * 64));
+  DISPATCH_DT(dt, {
+    conv_ref_kernel<T><<<blocks, 256, 0, st>>>((const T*)x, w, bias, bias_bstride, (const T*)res, scale, (T*)out, H, W, Cin,
+                                               Cout, ksize, total);
+  });
+}
+
+// ------------------------------------------------------------------------------------------------
+// upfirdn2d, the reference's own native op (op/upfirdn2d.cpp:12-23, semantics of upfirdn2d_native,
+// op/upfirdn2d.py:173-208): zero-insert upsample, pad (negative pads crop), FIR with the flipped kernel,
+// decimate.  Generic gather formulation over [major][H][W][minor]; the network itself uses the fused
+// normalise+FIR kernel above, this entry point exists for callers of the reference's FFI seam.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) upfirdn2d_kernel(const float* __restrict__ in, float* __restrict__ out,
+                                                         const float* __restrict__ kernel, int in_h, int in_w, int minor,
+                                                         int kh, int kw, int up_x, int up_y, int down_x, int down_y,
+                                                         int pad_x0, int pad_y0, int out_h, int out_w, long long total) {
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int mi = static_cast<int>(i % minor);
+    const int ox = static_cast<int>((i / minor) % out_w);
+    const int oy = static_cast<int>((i / minor / out_w) % out_h);
+    const long long mj = i / minor / out_w / out_h;
+    float acc = 0.f;
+    for (int ky = 0; ky < kh; ++ky) {
+      const int uy = oy * down_y + ky - pad_y0;
+      if (uy < 0 || uy >= in_h * up_y || uy % up_y) continue;
+      const int iy = uy / up_y;
+      for (int kx = 0; kx < kw; ++kx) {
+        const int ux = ox * down_x + kx - pad_x0;
+        if (ux < 0 || ux >= in_w * up_x || ux % up_x) continue;
+        const int ix = ux / up_x;
+        acc += in[((mj * in_h + iy) * in_w + ix) * minor + mi] * kernel[(kh - 1 - ky) * kw + (kw - 1 - kx)];
+      }
+    }
+    out[i] = acc;
+  }
+}
+
+void launch_upfirdn2d(const float* in, float* out, int major, int in_h, int in_w, int minor, const float* kernel, int kh,
+                      int kw, int up_x, int up_y, int down_x, int down_y, int pad_x0, int pad_x1, int pad_y0, int pad_y1,
+                      cudaStream_t st) {
+  const int out_h = (in_h * up_y + pad_y0 + pad_y1 - kh) / down_y + 1;
+  const int out_w = (in_w * up_x + pad_x0 + pad_x1 - kw) / down_x + 1;
+  const long long total = static_cast<long long>(major) * out_h * out_w * minor;
+  if (total <= 0) return;
+  const int blocks = static_cast<int>(std::min<long long>((total + 255) / 256, 148LL * 32));
+  upfirdn2d_kernel<<<blocks, 256, 0, st>>>(in, out, kernel, in_h, in_w, minor, kh, kw, up_x, up_y, down_x, down_y, pad_x0,
+                                           pad_y0, out_h, out_w, total);
+}
+
+}  // namespace use

@@ -1,0 +1,1021 @@
+// Host runtime of the score network: weight packing, workspace planning, the launch program of one
+// NCSN++ evaluation and the reverse-diffusion loop.  Mirrors the module list the reference builds in
+// NCSNpp.__init__ (backbones/ncsnpp.py:186-316) and the dataflow of NCSNpp.forward (:324-501); every
+// tensor is NHWC, ResBlocks follow layerspp.py:282-314.
+#include <math.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <functional>
+#include <map>
+#include <memory>
+#include <string>
+#include <vector>
+
+#include "../../include/use_b200.h"
+#include "kernels.h"
+
+namespace use {
+
+static thread_local char g_err[1024] = "";
+static int fail(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+  return 1;
+}
+static int cuda_check(const char* what) {
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return fail("%s: CUDA error %d (%s)", what, (int)e, cudaGetErrorString(e));
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// host-side number formats
+// ---------------------------------------------------------------------------------------------
+static inline uint16_t f32_to_bf16(float f) {
+  uint32_t u;
+  memcpy(&u, &f, 4);
+  if ((u & 0x7f800000u) == 0x7f800000u) return (uint16_t)(u >> 16);
+  u += 0x7fffu + ((u >> 16) & 1u);
+  return (uint16_t)(u >> 16);
+}
+static inline float f32_to_tf32(float f) {
+  uint32_t u;
+  memcpy(&u, &f, 4);
+  if ((u & 0x7f800000u) != 0x7f800000u) {
+    u += 0xfffu + ((u >> 13) & 1u);
+    u &= ~0x1fffu;
+  }
+  float r;
+  memcpy(&r, &u, 4);
+  return r;
+}
+
+static void pack_conv_weight(int dt, const float* w, int O, int I, int ks, void* out) {
+  const int taps = ks * ks;
+  for (int tap = 0; tap < taps; ++tap)
+    for (int o = 0; o < O; ++o)
+      for (int i = 0; i < I; ++i) {
+        const float v = w[((size_t)o * I + i) * taps + tap];
+        const size_t idx = ((size_t)tap * O + o) * I + i;
+        if (dt == kBF16) ((uint16_t*)out)[idx] = f32_to_bf16(v);
+        else ((float*)out)[idx] = f32_to_tf32(v);
+      }
+}
+
+// ---------------------------------------------------------------------------------------------
+// architecture plan (same order as the reference's all_modules list)
+// ---------------------------------------------------------------------------------------------
+enum Kind { K_GFP, K_LINEAR, K_CONV3, K_RB, K_COMBINE, K_ATTN, K_GN };
+struct Mod {
+  Kind kind;
+  int cin = 0, cout = 0;
+  bool up = false, down = false;
+};
+
+struct HostTensor {
+  std::vector<float> data;
+  std::vector<int64_t> shape;
+};
+
+struct RbW {  // device offsets (bytes into the weight blob)
+  size_t gn0_g, gn0_b, gn1_g, gn1_b, w0, w1, w2, bias1;
+  int dense_off;  // row offset inside the stacked Dense_0 matrix
+  bool has_conv2;
+};
+
+struct Arena {
+  // first-fit offset allocator with coalescing; used both for the dry run (peak) and the real build
+  std::vector<std::pair<size_t, size_t>> free_;  // (offset, size)
+  std::map<size_t, size_t> live_;
+  size_t top = 0, peak = 0;
+  static size_t up(size_t n) { return (n + 1023) & ~size_t(1023); }
+  size_t alloc(size_t n) {
+    n = up(n ? n : 1);
+    for (size_t i = 0; i < free_.size(); ++i) {
+      if (free_[i].second >= n) {
+        size_t off = free_[i].first;
+        if (free_[i].second == n) free_.erase(free_.begin() + i);
+        else { free_[i].first += n; free_[i].second -= n; }
+        live_[off] = n;
+        return off;
+      }
+    }
+    size_t off = top;
+    top += n;
+    if (top > peak) peak = top;
+    live_[off] = n;
+    return off;
+  }
+  void release(size_t off) {
+    auto it = live_.find(off);
+    if (it == live_.end()) return;
+    size_t n = it->second;
+    live_.erase(it);
+    if (off + n == top) {
+      top = off;
+      // absorb trailing free blocks
+      bool again = true;
+      while (again) {
+        again = false;
+        for (size_t i = 0; i < free_.size(); ++i)
+          if (free_[i].first + free_[i].second == top) { top = free_[i].first; free_.erase(free_.begin() + i); again = true; break; }
+      }
+      return;
+    }
+    free_.push_back({off, n});
+    // coalesce neighbours
+    bool merged = true;
+    while (merged) {
+      merged = false;
+      for (size_t i = 0; i < free_.size() && !merged; ++i)
+        for (size_t j = 0; j < free_.size() && !merged; ++j)
+          if (i != j && free_[i].first + free_[i].second == free_[j].first) {
+            free_[i].second += free_[j].second;
+            free_.erase(free_.begin() + j);
+            merged = true;
+          }
+    }
+  }
+};
+
+struct Act {  // activation tensor of the current program (batch implied)
+  size_t off = 0;
+  int C = 0, H = 0, W = 0;
+  size_t stats_off = (size_t)-1;  // offset into the stats region or -1
+  bool valid = false;
+};
+
+enum OpTag { TAG_CONV_TC = 0, TAG_GN_STATS, TAG_GN_APPLY, TAG_SMALL_CONV, TAG_ATTN, TAG_OTHER, TAG_COUNT };
+static const char* kTagNames[TAG_COUNT] = {"conv_tc", "gn_stats", "gn_apply", "small_conv", "attn", "other"};
+
+struct Op {
+  std::function<void(cudaStream_t)> fn;
+  int tag;
+  int launches;
+  double flops;  // algorithmic FLOPs of this op
+  double bytes;  // algorithmic HBM bytes of this op (each operand / result once)
+};
+
+struct Program {
+  int B = 0, F = 0, T = 0;
+  std::vector<Op> ops;
+  std::vector<TcConvPlan*> plans;
+  size_t stats_bytes = 0;
+  size_t pyramid_off = 0;  // final fp32 [B][F][T][4]
+  char* base = nullptr;
+  ~Program() {
+    for (auto* p : plans) tc_conv_plan_destroy(p);
+  }
+};
+
+}  // namespace use
+
+using namespace use;
+
+struct use_engine {
+  use_config cfg;
+  int dt;
+  std::vector<Mod> mods;
+  std::map<std::string, HostTensor> host_w;
+  // packed blob
+  std::vector<uint8_t> blob;
+  std::map<int, RbW> rbw;                         // module index -> ResBlock weight offsets
+  std::map<std::string, size_t> off;              // misc named offsets
+  int dense_rows = 0;
+  char* dev_w = nullptr;
+  int num_sms = 148;
+  std::map<std::string, std::unique_ptr<Program>> programs;  // keyed by "B,F,T,base"
+  // fixed head of the workspace (byte offsets)
+  struct Head { size_t xr, t, gfp, temb, dense, stats, arena; } head;
+  // instrumentation
+  long long launches = 0;
+  bool profiling = false;
+  double prof_ms[8] = {0}, prof_flops[8] = {0}, prof_bytes[8] = {0}, prof_top_flops = 0, prof_top_ms = 0;
+  long long prof_launches[8] = {0};
+};
+
+namespace use {
+
+static void build_mods(use_engine* e) {
+  const use_config& c = e->cfg;
+  auto& m = e->mods;
+  m.clear();
+  const int nf = c.nf, L = c.num_levels;
+  m.push_back({K_GFP});
+  m.push_back({K_LINEAR, 2 * nf, 4 * nf});
+  m.push_back({K_LINEAR, 4 * nf, 4 * nf});
+  m.push_back({K_CONV3, c.input_channels, nf});
+  std::vector<int> hs{nf};
+  int in_ch = nf;
+  for (int l = 0; l < L; ++l) {
+    for (int r = 0; r < c.num_res_blocks; ++r) {
+      int out_ch = nf * c.ch_mult[l];
+      m.push_back({K_RB, in_ch, out_ch});
+      in_ch = out_ch;
+      hs.push_back(in_ch);
+    }
+    if (l != L - 1) {
+      Mod d{K_RB, in_ch, in_ch};
+      d.down = true;
+      m.push_back(d);
+      m.push_back({K_COMBINE, c.input_channels, in_ch});
+      hs.push_back(in_ch);
+    }
+  }
+  in_ch = hs.back();
+  m.push_back({K_RB, in_ch, in_ch});
+  m.push_back({K_ATTN, in_ch, in_ch});
+  m.push_back({K_RB, in_ch, in_ch});
+  for (int l = L - 1; l >= 0; --l) {
+    for (int r = 0; r < c.num_res_blocks + 1; ++r) {
+      int out_ch = nf * c.ch_mult[l];
+      m.push_back({K_RB, in_ch + hs.back(), out_ch});
+      hs.pop_back();
+      in_ch = out_ch;
+    }
+    m.push_back({K_GN, in_ch, in_ch});
+    m.push_back({K_CONV3, in_ch, c.input_channels});
+    if (l != 0) {
+      Mod u{K_RB, in_ch, in_ch};
+      u.up = true;
+      m.push_back(u);
+    }
+  }
+}
+
+static const HostTensor* getw(use_engine* e, const std::string& name, std::vector<int64_t> shape) {
+  auto it = e->host_w.find(name);
+  if (it == e->host_w.end()) { fail("missing weight '%s'", name.c_str()); return nullptr; }
+  if (it->second.shape != shape) {
+    std::string s;
+    for (auto d : it->second.shape) s += std::to_string(d) + ",";
+    fail("weight '%s' has shape [%s], which does not match the architecture", name.c_str(), s.c_str());
+    return nullptr;
+  }
+  return &it->second;
+}
+
+struct BlobWriter {
+  std::vector<uint8_t>& b;
+  size_t put(const void* p, size_t n) {
+    size_t off = (b.size() + 255) & ~size_t(255);
+    b.resize(off + n);
+    memcpy(b.data() + off, p, n);
+    return off;
+  }
+  size_t reserve(size_t n) {
+    size_t off = (b.size() + 255) & ~size_t(255);
+    b.resize(off + n);
+    return off;
+  }
+};
+
+static int pack_all(use_engine* e) {
+  const use_config& c = e->cfg;
+  const int dt = e->dt, nf = c.nf, D = 4 * nf;
+  const size_t es = act_size(dt);
+  e->blob.clear();
+  e->rbw.clear();
+  e->off.clear();
+  BlobWriter bw{e->blob};
+  auto P = [&](int i) { return "all_modules." + std::to_string(i); };
+  auto putf = [&](const std::string& key, const std::string& name, std::vector<int64_t> shape) -> int {
+    const HostTensor* t = getw(e, name, shape);
+    if (!t) return 1;
+    e->off[key] = bw.put(t->data.data(), t->data.size() * 4);
+    return 0;
+  };
+  auto put_conv_tc = [&](const std::string& name, int O, int I, int ks, size_t* off) -> int {
+    const HostTensor* t = getw(e, name, {O, I, ks, ks});
+    if (!t) return 1;
+    *off = bw.reserve((size_t)ks * ks * O * I * es);
+    pack_conv_weight(dt, t->data.data(), O, I, ks, e->blob.data() + *off);
+    return 0;
+  };
+  if (putf("gfp.W", P(0) + ".W", {nf})) return 1;
+  if (putf("l1.w", P(1) + ".weight", {D, 2 * nf}) || putf("l1.b", P(1) + ".bias", {D})) return 1;
+  if (putf("l2.w", P(2) + ".weight", {D, D}) || putf("l2.b", P(2) + ".bias", {D})) return 1;
+  if (putf("out.w", "output_layer.weight", {2, c.input_channels, 1, 1}) || putf("out.b", "output_layer.bias", {2})) return 1;
+  // stacked Dense_0 matrix + base bias (conv0 bias + dense bias)
+  int rows = 0;
+  for (auto& m : e->mods) if (m.kind == K_RB) rows += m.cout;
+  e->dense_rows = rows;
+  std::vector<float> dW((size_t)rows * D), dbase(rows);
+  int row = 0;
+  for (size_t i = 0; i < e->mods.size(); ++i) {
+    const Mod& m = e->mods[i];
+    const std::string p = P((int)i);
+    switch (m.kind) {
+      case K_GFP: case K_LINEAR: break;
+      case K_CONV3: {
+        if (putf(p + ".w", p + ".weight", {m.cout, m.cin, 3, 3}) || putf(p + ".b", p + ".bias", {m.cout})) return 1;
+        break;
+      }
+      case K_GN: {
+        if (putf(p + ".g", p + ".weight", {m.cin}) || putf(p + ".b", p + ".bias", {m.cin})) return 1;
+        break;
+      }
+      case K_COMBINE: {
+        if (putf(p + ".w", p + ".Conv_0.weight", {m.cout, m.cin, 1, 1}) || putf(p + ".b", p + ".Conv_0.bias", {m.cout})) return 1;
+        break;
+      }
+      case K_ATTN: {
+        if (putf(p + ".g", p + ".GroupNorm_0.weight", {m.cin}) || putf(p + ".gb", p + ".GroupNorm_0.bias", {m.cin})) return 1;
+        for (int j = 0; j < 4; ++j) {
+          const std::string n = p + ".NIN_" + std::to_string(j);
+          if (putf(n + ".W", n + ".W", {m.cin, m.cin}) || putf(n + ".b", n + ".b", {m.cin})) return 1;
+        }
+        break;
+      }
+      case K_RB: {
+        RbW r{};
+        r.has_conv2 = (m.cin != m.cout) || m.up || m.down;
+        const HostTensor *g0 = getw(e, p + ".GroupNorm_0.weight", {m.cin}), *b0 = getw(e, p + ".GroupNorm_0.bias", {m.cin});
+        const HostTensor *g1 = getw(e, p + ".GroupNorm_1.weight", {m.cout}), *b1 = getw(e, p + ".GroupNorm_1.bias", {m.cout});
+        const HostTensor *c0b = getw(e, p + ".Conv_0.bias", {m.cout}), *c1b = getw(e, p + ".Conv_1.bias", {m.cout});
+        const HostTensor *dw = getw(e, p + ".Dense_0.weight", {m.cout, D}), *db = getw(e, p + ".Dense_0.bias", {m.cout});
+        if (!g0 || !b0 || !g1 || !b1 || !c0b || !c1b || !dw || !db) return 1;
+        r.gn0_g = bw.put(g0->data.data(), m.cin * 4);
+        r.gn0_b = bw.put(b0->data.data(), m.cin * 4);
+        r.gn1_g = bw.put(g1->data.data(), m.cout * 4);
+        r.gn1_b = bw.put(b1->data.data(), m.cout * 4);
+        if (put_conv_tc(p + ".Conv_0.weight", m.cout, m.cin, 3, &r.w0)) return 1;
+        if (put_conv_tc(p + ".Conv_1.weight", m.cout, m.cout, 3, &r.w1)) return 1;
+        std::vector<float> bias1(c1b->data);
+        if (r.has_conv2) {
+          if (put_conv_tc(p + ".Conv_2.weight", m.cout, m.cin, 1, &r.w2)) return 1;
+          const HostTensor* c2b = getw(e, p + ".Conv_2.bias", {m.cout});
+          if (!c2b) return 1;
+          for (int k = 0; k < m.cout; ++k) bias1[k] += c2b->data[k];
+        }
+        r.bias1 = bw.put(bias1.data(), m.cout * 4);
+        r.dense_off = row;
+        memcpy(&dW[(size_t)row * D], dw->data.data(), (size_t)m.cout * D * 4);
+        for (int k = 0; k < m.cout; ++k) dbase[row + k] = c0b->data[k] + db->data[k];
+        row += m.cout;
+        e->rbw[(int)i] = r;
+        break;
+      }
+    }
+  }
+  e->off["dense.W"] = bw.put(dW.data(), dW.size() * 4);
+  e->off["dense.base"] = bw.put(dbase.data(), dbase.size() * 4);
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// program construction
+// ---------------------------------------------------------------------------------------------
+struct Builder {
+  use_engine* e;
+  Program* prog;   // nullptr on the dry run
+  int B, F, T;
+  Arena arena;
+  size_t stats_top = 0;
+  char* base;      // workspace base (nullptr on the dry run)
+  bool dry;
+  int err = 0;
+  const float kInvSqrt2 = 0.70710678118654752440f;
+
+  size_t es() const { return act_size(e->dt); }
+  char* ws(size_t off) const { return base + e->head.arena + off; }
+  char* wt(size_t off) const { return e->dev_w + off; }
+  const float* wf(const std::string& k) const { return (const float*)(e->dev_w + e->off.at(k)); }
+  double* stats_ptr(size_t off) const { return (double*)(base + e->head.stats + off); }
+
+  Act new_act(int C, int H, int W) {
+    Act a;
+    a.C = C; a.H = H; a.W = W;
+    a.off = arena.alloc((size_t)B * H * W * C * es());
+    a.valid = true;
+    return a;
+  }
+  size_t new_f32(size_t n) { return arena.alloc(n * 4); }
+  void free_act(Act& a) {
+    if (a.valid) arena.release(a.off);
+    a.valid = false;
+  }
+  void emit(std::function<void(cudaStream_t)> f, int tag = TAG_OTHER, int launches = 1, double flops = 0, double bytes = 0) {
+    if (!dry) prog->ops.push_back(Op{std::move(f), tag, launches, flops, bytes});
+  }
+  void ensure_stats(Act& a) {
+    if (a.stats_off != (size_t)-1) return;
+    a.stats_off = stats_top;
+    stats_top += (size_t)B * a.C * 2 * sizeof(double);
+    if (dry) return;
+    const int dt = e->dt, Bn = B, HW = a.H * a.W, C = a.C;
+    const void* x = ws(a.off);
+    double* st = stats_ptr(a.stats_off);
+    emit([=](cudaStream_t s) { launch_gn_stats(dt, x, st, Bn, HW, C, s); }, TAG_GN_STATS, 1, 3.0 * Bn * HW * C,
+         (double)Bn * HW * C * es());
+  }
+  void gn_apply(Act& s0, Act* s1, size_t gamma_off, size_t beta_off, int fir, bool silu, bool operand, Act& out, Act* raw) {
+    ensure_stats(s0);
+    if (s1) ensure_stats(*s1);
+    if (dry) return;
+    GnSrc a{ws(s0.off), stats_ptr(s0.stats_off), s0.C};
+    GnSrc b{nullptr, nullptr, 0};
+    if (s1) b = GnSrc{ws(s1->off), stats_ptr(s1->stats_off), s1->C};
+    const float* g = (const float*)wt(gamma_off);
+    const float* bt = (const float*)wt(beta_off);
+    void* o = ws(out.off);
+    void* r = raw ? ws(raw->off) : nullptr;
+    const int dt = e->dt, Bn = B, H = s0.H, W = s0.W;
+    {
+      const double nin = (double)Bn * H * W * (s0.C + (s1 ? s1->C : 0));
+      const double nout = fir == 1 ? nin / 4 : (fir == 2 ? nin * 4 : nin);
+      emit([=](cudaStream_t s) { launch_gn_apply(dt, a, b, g, bt, 1e-6f, fir, silu, operand, o, r, Bn, H, W, s); },
+           TAG_GN_APPLY, 1, 8.0 * nout, (nin + nout * (raw ? 2 : 1)) * es());
+    }
+  }
+  void conv_tc(const TcConvDesc& d) {
+    if (dry) return;
+    char msg[512];
+    TcConvPlan* p = tc_conv_plan_create(e->dt, d, e->num_sms, msg, sizeof(msg));
+    if (!p) { err = fail("%s", msg); return; }
+    prog->plans.push_back(p);
+    double k = 0, cin = 0;
+    for (int i = 0; i < d.nseg; ++i) { k += (double)d.seg[i].taps * d.seg[i].C; cin += d.seg[i].C; }
+    const double px = (double)d.B * d.H * d.W;
+    emit([=](cudaStream_t s) { tc_conv_launch(p, s); }, TAG_CONV_TC, 1, 2.0 * px * d.N * k,
+         (px * (cin + d.N * (d.res ? 2 : 1))) * es());
+  }
+
+  // ResnetBlockBigGANpp.forward (layerspp.py:282-314).  x1 != nullptr: input is cat[x0, x1].
+  Act resblock(int idx, Act& x0, Act* x1) {
+    const Mod& m = e->mods[idx];
+    const RbW& w = e->rbw.at(idx);
+    const int Cin = m.cin, Cout = m.cout;
+    const int fir = m.down ? 1 : (m.up ? 2 : 0);
+    const int Ho = m.down ? x0.H / 2 : (m.up ? x0.H * 2 : x0.H);
+    const int Wo = m.down ? x0.W / 2 : (m.up ? x0.W * 2 : x0.W);
+    Act a0 = new_act(Cin, Ho, Wo);
+    Act raw;
+    if (fir) raw = new_act(Cin, Ho, Wo);
+    gn_apply(x0, x1, w.gn0_g, w.gn0_b, fir, true, true, a0, fir ? &raw : nullptr);
+    Act h1 = new_act(Cout, Ho, Wo);
+    {
+      TcConvDesc d{};
+      d.nseg = 1;
+      d.seg[0] = TcSegDesc{dry ? nullptr : ws(a0.off), Cin, 0, Cin, dry ? nullptr : wt(w.w0), Cin, 0, 9};
+      d.B = B; d.H = Ho; d.W = Wo; d.N = Cout;
+      d.out = dry ? nullptr : ws(h1.off);
+      d.bias = dry ? nullptr : (const float*)(base + e->head.dense) + w.dense_off;
+      d.bias_bstride = e->dense_rows;
+      d.res = nullptr;
+      d.scale = 1.0f;
+      conv_tc(d);
+    }
+    free_act(a0);
+    Act a1 = new_act(Cout, Ho, Wo);
+    gn_apply(h1, nullptr, w.gn1_g, w.gn1_b, 0, true, true, a1, nullptr);
+    free_act(h1);
+    Act out = new_act(Cout, Ho, Wo);
+    {
+      TcConvDesc d{};
+      d.seg[0] = TcSegDesc{dry ? nullptr : ws(a1.off), Cout, 0, Cout, dry ? nullptr : wt(w.w1), Cout, 0, 9};
+      d.nseg = 1;
+      d.res = nullptr;
+      if (w.has_conv2) {
+        if (fir) {
+          d.seg[1] = TcSegDesc{dry ? nullptr : ws(raw.off), Cin, 0, Cin, dry ? nullptr : wt(w.w2), Cin, 0, 1};
+          d.nseg = 2;
+        } else {
+          d.seg[1] = TcSegDesc{dry ? nullptr : ws(x0.off), x0.C, 0, x0.C, dry ? nullptr : wt(w.w2), Cin, 0, 1};
+          d.nseg = 2;
+          if (x1) {
+            d.seg[2] = TcSegDesc{dry ? nullptr : ws(x1->off), x1->C, 0, x1->C, dry ? nullptr : wt(w.w2), Cin, x0.C, 1};
+            d.nseg = 3;
+          }
+        }
+      } else {
+        d.res = dry ? nullptr : ws(x0.off);
+      }
+      d.B = B; d.H = Ho; d.W = Wo; d.N = Cout;
+      d.out = dry ? nullptr : ws(out.off);
+      d.bias = dry ? nullptr : (const float*)wt(w.bias1);
+      d.bias_bstride = 0;
+      d.scale = kInvSqrt2;
+      conv_tc(d);
+    }
+    free_act(a1);
+    if (fir) free_act(raw);
+    return out;
+  }
+
+  // AttnBlockpp.forward (layerspp.py:77-93), all fp32 internally
+  Act attn(int idx, Act& x) {
+    const std::string p = "all_modules." + std::to_string(idx);
+    const int C = x.C, Pn = x.H * x.W, M = B * Pn;
+    Act hn = new_act(C, x.H, x.W);
+    gn_apply(x, nullptr, e->off.at(p + ".g"), e->off.at(p + ".gb"), 0, false, false, hn, nullptr);
+    const size_t n = (size_t)M * C;
+    size_t hf = new_f32(n), q = new_f32(n), k = new_f32(n), v = new_f32(n), att = new_f32(n), proj = new_f32(n);
+    Act out = new_act(C, x.H, x.W);
+    if (!dry) {
+      const int dt = e->dt, Bn = B;
+      const void* hnp = ws(hn.off);
+      float *hfp = (float*)ws(hf), *qp = (float*)ws(q), *kp = (float*)ws(k), *vp = (float*)ws(v), *ap = (float*)ws(att),
+            *pp = (float*)ws(proj);
+      const float *W0 = wf(p + ".NIN_0.W"), *b0 = wf(p + ".NIN_0.b"), *W1 = wf(p + ".NIN_1.W"), *b1 = wf(p + ".NIN_1.b");
+      const float *W2 = wf(p + ".NIN_2.W"), *b2 = wf(p + ".NIN_2.b"), *W3 = wf(p + ".NIN_3.W"), *b3 = wf(p + ".NIN_3.b");
+      const void* xp = ws(x.off);
+      void* op = ws(out.off);
+      const float sc = kInvSqrt2;
+      emit([=](cudaStream_t s) {
+        launch_act_to_f32(dt, hnp, hfp, n, s);
+        launch_linear(hfp, W0, b0, qp, M, C, C, s);
+        launch_linear(hfp, W1, b1, kp, M, C, C, s);
+        launch_linear(hfp, W2, b2, vp, M, C, C, s);
+        launch_attn_core(qp, kp, vp, ap, Bn, Pn, C, s);
+        launch_linear(ap, W3, b3, pp, M, C, C, s);
+        launch_add_scale(dt, xp, pp, sc, op, n, s);
+      }, TAG_ATTN, 7, 8.0 * M * C * C + 4.0 * Bn * Pn * Pn * C, 0);
+    }
+    free_act(hn);
+    arena.release(hf); arena.release(q); arena.release(k); arena.release(v); arena.release(att); arena.release(proj);
+    return out;
+  }
+
+  void build() {
+    const use_config& c = e->cfg;
+    const int L = c.num_levels;
+    const int dt = e->dt, Bn = B;
+    int idx = 3;
+    // input conv (ncsnpp.py:381); the input pyramid level 0 is the packed network input itself
+    std::vector<Act> hs;
+    const float* xr = dry ? nullptr : (const float*)(base + e->head.xr);
+    {
+      Act h0 = new_act(c.nf, F, T);
+      if (!dry) {
+        const float *w = wf("all_modules.3.w"), *b = wf("all_modules.3.b");
+        void* o = ws(h0.off);
+        const int H = F, W = T, N = c.nf;
+        emit([=](cudaStream_t s) { launch_conv_in4(dt, xr, w, b, o, Bn, H, W, N, s); }, TAG_SMALL_CONV, 1,
+             2.0 * Bn * H * W * N * 36, (double)Bn * H * W * (16 + N * es()));
+      }
+      hs.push_back(h0);
+      idx = 4;
+    }
+    size_t pyr_off = (size_t)-1;  // fp32 input pyramid of the current level (arena), level 0 = xr
+    int pH = F, pW = T;
+    for (int l = 0; l < L; ++l) {
+      for (int r = 0; r < c.num_res_blocks; ++r) {
+        Act h = resblock(idx++, hs.back(), nullptr);
+        hs.push_back(h);
+      }
+      if (l != L - 1) {
+        Act h = resblock(idx++, hs.back(), nullptr);
+        // input_pyramid = FIR-down(input_pyramid); h = Conv1x1(input_pyramid) + h  (ncsnpp.py:404-406)
+        size_t np = new_f32((size_t)B * (pH / 2) * (pW / 2) * 4);
+        if (!dry) {
+          const float* src = (pyr_off == (size_t)-1) ? xr : (const float*)ws(pyr_off);
+          float* dst = (float*)ws(np);
+          const int H = pH, W = pW;
+          const std::string p = "all_modules." + std::to_string(idx);
+          const float *cw = wf(p + ".w"), *cb = wf(p + ".b");
+          void* hp = ws(h.off);
+          const int HW = h.H * h.W, C = h.C;
+          emit([=](cudaStream_t s) {
+            launch_fir4_down(src, dst, Bn, H, W, s);
+            launch_combine(dt, hp, dst, cw, cb, hp, Bn, HW, C, s);
+          }, TAG_SMALL_CONV, 2, 2.0 * Bn * HW * C * 4, 2.0 * Bn * HW * C * es());
+        }
+        if (pyr_off != (size_t)-1) arena.release(pyr_off);
+        pyr_off = np;
+        pH /= 2; pW /= 2;
+        idx++;
+        hs.push_back(h);
+      }
+    }
+    if (pyr_off != (size_t)-1) arena.release(pyr_off);
+    // bottleneck
+    Act h = resblock(idx++, hs.back(), nullptr);
+    {
+      Act a = attn(idx++, h);
+      free_act(h);
+      h = a;
+    }
+    {
+      Act r = resblock(idx++, h, nullptr);
+      free_act(h);
+      h = r;
+    }
+    // up path
+    size_t opyr = (size_t)-1;  // fp32 output pyramid [B][H][W][4]
+    for (int l = L - 1; l >= 0; --l) {
+      for (int r = 0; r < c.num_res_blocks + 1; ++r) {
+        Act skip = hs.back();
+        hs.pop_back();
+        Act o = resblock(idx++, h, &skip);
+        free_act(h);
+        free_act(skip);
+        h = o;
+      }
+      // pyramid: GN -> SiLU -> conv3x3 C->4 (+ FIR-up of the previous pyramid)   (ncsnpp.py:440-461)
+      {
+        const std::string pg = "all_modules." + std::to_string(idx), pc = "all_modules." + std::to_string(idx + 1);
+        Act a = new_act(h.C, h.H, h.W);
+        gn_apply(h, nullptr, e->off.at(pg + ".g"), e->off.at(pg + ".b"), 0, true, false, a, nullptr);
+        size_t np = new_f32((size_t)B * h.H * h.W * 4);
+        if (!dry) {
+          const void* ap = ws(a.off);
+          const float *w = wf(pc + ".w"), *b = wf(pc + ".b");
+          const float* prev = (opyr == (size_t)-1) ? nullptr : (const float*)ws(opyr);
+          float* o = (float*)ws(np);
+          const int H = h.H, W = h.W, C = h.C;
+          emit([=](cudaStream_t s) { launch_conv_out4(dt, ap, w, b, prev, o, Bn, H, W, C, s); }, TAG_SMALL_CONV, 1,
+               2.0 * Bn * H * W * C * 36, (double)Bn * H * W * (C * es() + 16));
+        }
+        free_act(a);
+        if (opyr != (size_t)-1) arena.release(opyr);
+        opyr = np;
+        idx += 2;
+      }
+      if (l != 0) {
+        Act u = resblock(idx++, h, nullptr);
+        free_act(h);
+        h = u;
+      }
+    }
+    free_act(h);
+    if (!dry) prog->pyramid_off = e->head.arena + opyr;
+    if (!dry) prog->stats_bytes = stats_top;
+    if ((size_t)idx != e->mods.size() || !hs.empty()) err = fail("internal: module walk mismatch (%d of %zu)", idx, e->mods.size());
+  }
+};
+
+static size_t align_up(size_t n, size_t a) { return (n + a - 1) / a * a; }
+
+// lays out the fixed head of the workspace and returns total bytes (dry run of the arena)
+static int plan_workspace(use_engine* e, int B, int F, int T, size_t* total, size_t* stats_bytes) {
+  const use_config& c = e->cfg;
+  if (F % (1 << (c.num_levels - 1)) || T % (1 << (c.num_levels - 1)))
+    return fail("spectrogram %dx%d is not divisible by 2^%d", F, T, c.num_levels - 1);
+  Builder b{e, nullptr, B, F, T};
+  b.base = nullptr;
+  b.dry = true;
+  // provisional head so pointer arithmetic on the dry run stays defined
+  e->head = {};
+  b.build();
+  if (b.err) return 1;
+  size_t off = 0;
+  e->head.xr = off; off = align_up(off + (size_t)B * F * T * 4 * 4, 1024);
+  e->head.t = off; off = align_up(off + (size_t)B * 4, 1024);
+  e->head.gfp = off; off = align_up(off + (size_t)B * 2 * c.nf * 4, 1024);
+  e->head.temb = off; off = align_up(off + (size_t)B * 4 * c.nf * 4, 1024);
+  e->head.dense = off; off = align_up(off + (size_t)B * e->dense_rows * 4, 1024);
+  e->head.stats = off; off = align_up(off + b.stats_top, 1024);
+  e->head.arena = off;
+  *total = off + b.arena.peak;
+  if (stats_bytes) *stats_bytes = b.stats_top;
+  return 0;
+}
+
+static Program* get_program(use_engine* e, int B, int F, int T, void* workspace, size_t workspace_bytes) {
+  char key[128];
+  snprintf(key, sizeof(key), "%d,%d,%d,%p", B, F, T, workspace);
+  size_t need = 0;
+  if (plan_workspace(e, B, F, T, &need, nullptr)) return nullptr;
+  if (workspace_bytes < need) {
+    fail("workspace too small: %zu bytes given, %zu needed for B=%d F=%d T=%d", workspace_bytes, need, B, F, T);
+    return nullptr;
+  }
+  auto it = e->programs.find(key);
+  if (it != e->programs.end()) return it->second.get();
+  if (!e->dev_w) { fail("weights not uploaded"); return nullptr; }
+  if (e->programs.size() > 8) e->programs.clear();
+  std::unique_ptr<Program> p(new Program());
+  p->B = B; p->F = F; p->T = T; p->base = (char*)workspace;
+  Builder b{e, p.get(), B, F, T};
+  b.base = (char*)workspace;
+  b.dry = false;
+  b.build();
+  if (b.err) return nullptr;
+  Program* raw = p.get();
+  e->programs[key] = std::move(p);
+  return raw;
+}
+
+// one network evaluation: t / gfp already in the workspace head; xr packed
+static void run_network(use_engine* e, Program* p, cudaStream_t st) {
+  char* base = p->base;
+  const int nf = e->cfg.nf;
+  cudaMemsetAsync(base + e->head.stats, 0, p->stats_bytes, st);
+  launch_temb_mlp((const float*)(base + e->head.gfp), (const float*)(e->dev_w + e->off.at("l1.w")),
+                  (const float*)(e->dev_w + e->off.at("l1.b")), (const float*)(e->dev_w + e->off.at("l2.w")),
+                  (const float*)(e->dev_w + e->off.at("l2.b")), (float*)(base + e->head.temb), p->B, nf, st);
+  launch_dense_all((const float*)(base + e->head.temb), (const float*)(e->dev_w + e->off.at("dense.W")),
+                   (const float*)(e->dev_w + e->off.at("dense.base")), (float*)(base + e->head.dense), p->B,
+                   e->dense_rows, 4 * nf, st);
+  e->launches += 2;
+  if (!e->profiling) {
+    for (auto& op : p->ops) { op.fn(st); e->launches += op.launches; }
+    return;
+  }
+  // profiling pass: one event pair per op, on the launch stream (never used inside a timed bench step)
+  std::vector<cudaEvent_t> ev(p->ops.size() + 1);
+  for (auto& x : ev) cudaEventCreate(&x);
+  for (size_t i = 0; i < p->ops.size(); ++i) {
+    cudaEventRecord(ev[i], st);
+    p->ops[i].fn(st);
+    e->launches += p->ops[i].launches;
+  }
+  cudaEventRecord(ev.back(), st);
+  cudaStreamSynchronize(st);
+  for (size_t i = 0; i < p->ops.size(); ++i) {
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, ev[i], ev[i + 1]);
+    const Op& o = p->ops[i];
+    e->prof_ms[o.tag] += ms;
+    e->prof_flops[o.tag] += o.flops;
+    e->prof_bytes[o.tag] += o.bytes;
+    e->prof_launches[o.tag] += o.launches;
+    if (o.tag == TAG_CONV_TC && o.flops > e->prof_top_flops) { e->prof_top_flops = o.flops; e->prof_top_ms = ms; }
+  }
+  for (auto& x : ev) cudaEventDestroy(x);
+}
+
+}  // namespace use
+
+// =================================================================================================
+// C ABI
+// =================================================================================================
+extern "C" {
+
+int use_abi_version(void) { return USE_B200_ABI_VERSION; }
+const char* use_last_error(void) { return g_err; }
+
+use_engine* use_engine_create(const use_config* cfg) {
+  if (!cfg) { fail("null config"); return nullptr; }
+  if (cfg->num_levels < 1 || cfg->num_levels > 8 || cfg->nf <= 0 || cfg->input_channels != 4 ||
+      (cfg->act_dtype != USE_DTYPE_F32 && cfg->act_dtype != USE_DTYPE_BF16)) {
+    fail("unsupported config (levels=%d nf=%d input_channels=%d dtype=%d)", cfg->num_levels, cfg->nf,
+         cfg->input_channels, cfg->act_dtype);
+    return nullptr;
+  }
+  use_engine* e = new use_engine();
+  e->cfg = *cfg;
+  e->dt = cfg->act_dtype;
+  build_mods(e);
+  for (auto& m : e->mods) {
+    if (m.kind == K_RB) {
+      const int ck = 128 / (int)act_size(e->dt);
+      if (!tc_conv_supported(e->dt, m.cout) || m.cin % ck) {
+        fail("architecture not supported by the tcgen05 conv path: ResBlock %d -> %d channels", m.cin, m.cout);
+        delete e;
+        return nullptr;
+      }
+    }
+  }
+  int dev = 0;
+  if (cudaGetDevice(&dev) == cudaSuccess) {
+    int sms = 0;
+    if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && sms > 0) e->num_sms = sms;
+  }
+  cudaGetLastError();
+  return e;
+}
+
+void use_engine_destroy(use_engine* e) { delete e; }
+
+int use_engine_set_weight(use_engine* e, const char* name, const float* host, const int64_t* shape, int ndim) {
+  if (!e || !name || !host) return fail("null argument");
+  HostTensor t;
+  size_t n = 1;
+  for (int i = 0; i < ndim; ++i) { t.shape.push_back(shape[i]); n *= (size_t)shape[i]; }
+  t.data.assign(host, host + n);
+  e->host_w[name] = std::move(t);
+  return 0;
+}
+
+int use_engine_pack(use_engine* e, size_t* bytes) {
+  if (!e) return fail("null engine");
+  if (pack_all(e)) return 1;
+  if (bytes) *bytes = e->blob.size();
+  return 0;
+}
+
+int use_engine_upload(use_engine* e, void* dev_weights, size_t bytes, void* stream) {
+  if (!e || !dev_weights) return fail("null argument");
+  if (e->blob.empty()) return fail("use_engine_pack has not been called");
+  if (bytes < e->blob.size()) return fail("weight buffer too small: %zu < %zu", bytes, e->blob.size());
+  cudaStream_t st = (cudaStream_t)stream;
+  cudaMemcpyAsync(dev_weights, e->blob.data(), e->blob.size(), cudaMemcpyHostToDevice, st);
+  cudaStreamSynchronize(st);
+  e->dev_w = (char*)dev_weights;
+  e->programs.clear();
+  return cuda_check("use_engine_upload");
+}
+
+int use_engine_workspace_bytes(use_engine* e, int B, int F, int T, size_t* bytes) {
+  if (!e || !bytes) return fail("null argument");
+  if (e->dense_rows == 0) return fail("use_engine_pack has not been called");
+  return plan_workspace(e, B, F, T, bytes, nullptr);
+}
+
+static int stage_head(use_engine* e, Program* p, const float* t_host, const float* gfp_host, cudaStream_t st) {
+  char* base = p->base;
+  cudaMemcpyAsync(base + e->head.t, t_host, (size_t)p->B * 4, cudaMemcpyHostToDevice, st);
+  cudaMemcpyAsync(base + e->head.gfp, gfp_host, (size_t)p->B * 2 * e->cfg.nf * 4, cudaMemcpyHostToDevice, st);
+  return 0;
+}
+
+int use_score_forward(use_engine* e, int B, int F, int T, const void* x, const void* Y, const float* t_host,
+                      const float* gfp_host, void* score, void* workspace, size_t workspace_bytes, void* stream) {
+  if (!e || !x || !Y || !t_host || !gfp_host || !score || !workspace) return fail("null argument");
+  Program* p = get_program(e, B, F, T, workspace, workspace_bytes);
+  if (!p) return 1;
+  cudaStream_t st = (cudaStream_t)stream;
+  stage_head(e, p, t_host, gfp_host, st);
+  const size_t per = (size_t)F * T;
+  launch_pack_input((const float2*)x, (const float2*)Y, (float*)(p->base + e->head.xr), per * B, st);
+  run_network(e, p, st);
+  StepArgs a{};
+  a.pyramid = (const float*)(p->base + p->pyramid_off);
+  a.t = (const float*)(p->base + e->head.t);
+  a.ow = (const float*)(e->dev_w + e->off.at("out.w"));
+  a.ob = (const float*)(e->dev_w + e->off.at("out.b"));
+  a.score = (float2*)score;
+  a.x = nullptr;
+  a.B = B;
+  a.per_clip = per;
+  launch_final_step(a, st);
+  e->launches += 2;
+  return cuda_check("use_score_forward");
+}
+
+int use_pc_sample(use_engine* e, int B, int F, int T, const void* Y, void* x_state, void* x_mean, int N,
+                  const float* t_host, const float* G_host, const float* gfp_host, float prior_std, const void* noise,
+                  uint64_t seed, uint32_t clip0, void* workspace, size_t workspace_bytes, void* stream) {
+  if (!e || !Y || !x_state || !x_mean || !t_host || !G_host || !gfp_host || !workspace) return fail("null argument");
+  if (N < 1) return fail("N must be >= 1");
+  Program* p = get_program(e, B, F, T, workspace, workspace_bytes);
+  if (!p) return 1;
+  cudaStream_t st = (cudaStream_t)stream;
+  const size_t per = (size_t)F * T, n = per * B;
+  const float2* z = (const float2*)noise;
+  // x_0 = Y + z_0 * std(1)   (sdes.py:248-254)
+  launch_prior((const float2*)Y, z, (float2*)x_state, prior_std, seed, clip0, B, per, st);
+  const int nf2 = 2 * e->cfg.nf;
+  std::vector<float> tb(B), gb((size_t)B * nf2);
+  for (int i = 0; i < N; ++i) {
+    // vec_t = ones(B) * t_i: the schedule is batch-uniform; the embedding is still evaluated per sample
+    for (int b = 0; b < B; ++b) {
+      tb[b] = t_host[i];
+      memcpy(&gb[(size_t)b * nf2], gfp_host + (size_t)i * nf2, nf2 * 4);
+    }
+    cudaStreamSynchronize(st);  // staging buffers are reused; the loop is GPU-bound by orders of magnitude
+    stage_head(e, p, tb.data(), gb.data(), st);
+    launch_pack_input((const float2*)x_state, (const float2*)Y, (float*)(p->base + e->head.xr), n, st);
+    run_network(e, p, st);
+    StepArgs a{};
+    a.pyramid = (const float*)(p->base + p->pyramid_off);
+    a.t = (const float*)(p->base + e->head.t);
+    a.ow = (const float*)(e->dev_w + e->off.at("out.w"));
+    a.ob = (const float*)(e->dev_w + e->off.at("out.b"));
+    a.score = nullptr;
+    a.x = (const float2*)x_state;
+    a.Y = (const float2*)Y;
+    a.z = z ? z + (size_t)(i + 1) * n : nullptr;
+    a.x_mean = (float2*)x_mean;
+    a.x_next = (float2*)x_state;
+    a.theta = e->cfg.theta;
+    a.dt = 1.0f / (float)N;
+    a.G = G_host[i];
+    a.seed = seed;
+    a.step = (unsigned)i;
+    a.clip0 = clip0;
+    a.B = B;
+    a.per_clip = per;
+    launch_final_step(a, st);
+    e->launches += 2;
+  }
+  e->launches += 1;
+  return cuda_check("use_pc_sample");
+}
+
+long long use_engine_launch_count(use_engine* e) { return e ? e->launches : -1; }
+
+int use_engine_set_profiling(use_engine* e, int on) {
+  if (!e) return fail("null engine");
+  e->profiling = on != 0;
+  for (int i = 0; i < 8; ++i) e->prof_ms[i] = e->prof_flops[i] = e->prof_bytes[i] = 0, e->prof_launches[i] = 0;
+  e->prof_top_flops = e->prof_top_ms = 0;
+  return 0;
+}
+
+int use_engine_get_profile(use_engine* e, char* json, size_t cap) {
+  if (!e || !json) return fail("null argument");
+  size_t n = 0;
+  n += snprintf(json + n, cap - n, "{");
+  for (int i = 0; i < TAG_COUNT; ++i)
+    n += snprintf(json + n, n < cap ? cap - n : 0, "%s\"%s\": {\"ms\": %.6f, \"flops\": %.6e, \"bytes\": %.6e, \"launches\": %lld}",
+                  i ? ", " : "", kTagNames[i], e->prof_ms[i], e->prof_flops[i], e->prof_bytes[i], e->prof_launches[i]);
+  n += snprintf(json + n, n < cap ? cap - n : 0, ", \"top_conv\": {\"ms\": %.6f, \"flops\": %.6e}}", e->prof_top_ms, e->prof_top_flops);
+  return n < cap ? 0 : fail("profile buffer too small");
+}
+
+int use_stft(use_engine* e, int B, int L, int Tp, const float* y, void* Y, const float* window, const float* twiddle,
+             void* stream) {
+  if (!e || !y || !Y || !window || !twiddle) return fail("null argument");
+  const int T = 1 + L / e->cfg.hop;
+  if (Tp < T) return fail("Tp=%d smaller than the frame count %d", Tp, T);
+  if (L <= e->cfg.n_fft / 2) return fail("clip too short for reflect padding: L=%d", L);
+  launch_stft(y, (float2*)Y, window, (const float2*)twiddle, B, L, e->cfg.n_fft, e->cfg.hop, T, Tp, e->cfg.spec_factor,
+              e->cfg.spec_abs_exponent, (cudaStream_t)stream);
+  return cuda_check("use_stft");
+}
+
+int use_istft(use_engine* e, int B, int L, int Tp, const void* X, float* y, float* frames_scratch, const float* window,
+              const float* twiddle, const float* envelope, void* stream) {
+  if (!e || !X || !y || !frames_scratch || !window || !twiddle || !envelope) return fail("null argument");
+  if (L + e->cfg.n_fft / 2 > e->cfg.n_fft + e->cfg.hop * (Tp - 1)) return fail("requested length %d exceeds the signal", L);
+  launch_istft((const float2*)X, frames_scratch, y, window, (const float2*)twiddle, envelope, B, L, e->cfg.n_fft,
+               e->cfg.hop, Tp, e->cfg.spec_factor, e->cfg.spec_abs_exponent, (cudaStream_t)stream);
+  return cuda_check("use_istft");
+}
+
+int use_upfirdn2d_f32(const float* in, float* out, int major, int in_h, int in_w, int minor, const float* kernel,
+                      int kh, int kw, int up_x, int up_y, int down_x, int down_y, int pad_x0, int pad_x1, int pad_y0,
+                      int pad_y1, void* stream) {
+  if (!in || !out || !kernel) return fail("null argument");
+  if (up_x < 1 || up_y < 1 || down_x < 1 || down_y < 1 || kh < 1 || kw < 1) return fail("invalid upfirdn2d factors");
+  launch_upfirdn2d(in, out, major, in_h, in_w, minor, kernel, kh, kw, up_x, up_y, down_x, down_y, pad_x0, pad_x1, pad_y0,
+                   pad_y1, (cudaStream_t)stream);
+  return cuda_check("use_upfirdn2d_f32");
+}
+
+// ---- single-kernel exports ----------------------------------------------------------------------
+int use_op_gn_stats(int dtype, const void* x, double* stats, int B, int HW, int C, void* stream) {
+  launch_gn_stats(dtype, x, stats, B, HW, C, (cudaStream_t)stream);
+  return cuda_check("use_op_gn_stats");
+}
+int use_op_gn_apply(int dtype, const void* x0, const double* stats0, int C0, const void* x1, const double* stats1, int C1,
+                    const float* gamma, const float* beta, float eps, int fir, int do_silu, int as_operand, void* out_act,
+                    void* out_raw, int B, int Hin, int Win, void* stream) {
+  launch_gn_apply(dtype, GnSrc{x0, stats0, C0}, GnSrc{x1, stats1, C1}, gamma, beta, eps, fir, do_silu != 0, as_operand != 0,
+                  out_act, out_raw, B, Hin, Win, (cudaStream_t)stream);
+  return cuda_check("use_op_gn_apply");
+}
+int use_op_conv_tc(int dtype, int nseg, const void* const* seg_act, const int* seg_ctensor, const int* seg_c0,
+                   const int* seg_c, const void* const* seg_w, const int* seg_cw, const int* seg_wc0, const int* seg_taps,
+                   int B, int H, int W, int N, const float* bias, int bias_bstride, const void* res, float scale, void* out,
+                   void* stream) {
+  if (nseg < 1 || nseg > 3) return fail("nseg must be 1..3");
+  TcConvDesc d{};
+  d.nseg = nseg;
+  for (int i = 0; i < nseg; ++i)
+    d.seg[i] = TcSegDesc{seg_act[i], seg_ctensor[i], seg_c0[i], seg_c[i], seg_w[i], seg_cw[i], seg_wc0[i], seg_taps[i]};
+  d.B = B; d.H = H; d.W = W; d.N = N;
+  d.out = out; d.bias = bias; d.bias_bstride = bias_bstride; d.res = res; d.scale = scale;
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  char msg[512];
+  TcConvPlan* p = tc_conv_plan_create(dtype, d, sms, msg, sizeof(msg));
+  if (!p) return fail("%s", msg);
+  tc_conv_launch(p, (cudaStream_t)stream);
+  cudaStreamSynchronize((cudaStream_t)stream);  // the plan (tensor maps live in kernel params) can go now
+  tc_conv_plan_destroy(p);
+  return cuda_check("use_op_conv_tc");
+}
+int use_op_conv_ref(int dtype, const void* x, const float* w, const float* bias, int bias_bstride, const void* res,
+                    float scale, void* out, int B, int H, int W, int Cin, int Cout, int ksize, void* stream) {
+  launch_conv_ref(dtype, x, w, bias, bias_bstride, res, scale, out, B, H, W, Cin, Cout, ksize, (cudaStream_t)stream);
+  return cuda_check("use_op_conv_ref");
+}
+int use_op_conv_in4(int dtype, const float* x, const float* w, const float* bias, void* out, int B, int H, int W, int N,
+                    void* stream) {
+  launch_conv_in4(dtype, x, w, bias, out, B, H, W, N, (cudaStream_t)stream);
+  return cuda_check("use_op_conv_in4");
+}
+int use_op_conv_out4(int dtype, const void* a, const float* w, const float* bias, const float* prev, float* out, int B,
+                     int H, int W, int C, void* stream) {
+  launch_conv_out4(dtype, a, w, bias, prev, out, B, H, W, C, (cudaStream_t)stream);
+  return cuda_check("use_op_conv_out4");
+}
+int use_op_combine(int dtype, const void* h, const float* pyr, const float* w, const float* bias, void* out, int B, int HW,
+                   int C, void* stream) {
+  launch_combine(dtype, h, pyr, w, bias, out, B, HW, C, (cudaStream_t)stream);
+  return cuda_check("use_op_combine");
+}
+int use_op_fir4_down(const float* x, float* out, int B, int Hin, int Win, void* stream) {
+  launch_fir4_down(x, out, B, Hin, Win, (cudaStream_t)stream);
+  return cuda_check("use_op_fir4_down");
+}
+int use_op_philox(void* z, uint64_t seed, uint32_t step, uint32_t clip0, int B, size_t per_clip, void* stream) {
+  launch_philox_fill((float2*)z, seed, step, clip0, B, per_clip, (cudaStream_t)stream);
+  return cuda_check("use_op_philox");
+}
+int use_pack_conv_weight(int dtype, const float* w_oihw, int O, int I, int ksize, void* out) {
+  if (!w_oihw || !out) return fail("null argument");
+  pack_conv_weight(dtype, w_oihw, O, I, ksize, out);
+  return 0;
+}
+
+}  // extern "C"

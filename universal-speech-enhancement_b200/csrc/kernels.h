@@ -1,0 +1,133 @@
+// Host-side launchers of every CUDA kernel on the path.  All pointers are device pointers, all tensors
+// are NHWC ("channels last"), all launches go to the given stream and never allocate.
+// act dtype code: 0 = fp32 storage / TF32 MMA, 1 = bf16 storage / bf16 MMA.
+#pragma once
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace use {
+
+enum ActDtype { kF32 = 0, kBF16 = 1 };
+inline size_t act_size(int dt) { return dt == kBF16 ? 2 : 4; }
+
+// ---- GroupNorm ---------------------------------------------------------------------------------
+// stats: double [B][C][2] (sum, sum of squares per channel), must be zero on entry.
+void launch_gn_stats(int dt, const void* x, double* stats, int B, int HW, int C, cudaStream_t st);
+
+struct GnSrc {
+  const void* x;        // act [B][Hin][Win][C]
+  const double* stats;  // [B][C][2]
+  int C;
+};
+// out_act = FIR(silu?(groupnorm(cat[s0,s1])))  (fir: 0 none, 1 down x2, 2 up x2), written as an MMA operand
+// (TF32-rounded in fp32 mode) when as_operand
+// out_raw (optional, fir != 0 only) = FIR(cat[s0,s1]) un-normalised.
+void launch_gn_apply(int dt, GnSrc s0, GnSrc s1, const float* gamma, const float* beta, float eps, int fir, bool do_silu,
+                     bool as_operand, void* out_act, void* out_raw, int B, int Hin, int Win, cudaStream_t st);
+
+// ---- small / bandwidth-bound convolutions ---------------------------------------------------------
+// 3x3 pad 1, C_in = 4 (fp32 NHWC input) -> N channels of act dtype.  w: [N][4][3][3] fp32, bias [N].
+void launch_conv_in4(int dt, const float* x, const float* w, const float* bias, void* out, int B, int H, int W, int N,
+                     cudaStream_t st);
+// 3x3 pad 1, C channels (act dtype, already normalised) -> 4 fp32 channels; w: [4][C][3][3] fp32.
+// If prev != nullptr adds FIR-upsample-x2(prev) where prev is fp32 [B][H/2][W/2][4].
+void launch_conv_out4(int dt, const void* a, const float* w, const float* bias, const float* prev, float* out, int B,
+                      int H, int W, int C, cudaStream_t st);
+// out = h + bias + conv1x1_{4->C}(pyr): Combine(method="sum").  w: [C][4] fp32.  In place allowed.
+void launch_combine(int dt, const void* h, const float* pyr, const float* w, const float* bias, void* out, int B, int HW,
+                    int C, cudaStream_t st);
+// FIR [1,3,3,1] downsample x2 of an fp32 4-channel map.
+void launch_fir4_down(const float* x, float* out, int B, int Hin, int Win, cudaStream_t st);
+void launch_upfirdn2d(const float* in, float* out, int major, int in_h, int in_w, int minor, const float* kernel, int kh,
+                      int kw, int up_x, int up_y, int down_x, int down_y, int pad_x0, int pad_x1, int pad_y0, int pad_y1,
+                      cudaStream_t st);
+// generic direct convolution (debug / verification of the tcgen05 kernel; never on the hot path)
+void launch_conv_ref(int dt, const void* x, const float* w, const float* bias, int bias_bstride, const void* res,
+                     float scale, void* out, int B, int H, int W, int Cin, int Cout, int ksize, cudaStream_t st);
+
+// ---- network input / output, SDE arithmetic -------------------------------------------------------
+// xr[b][f][t][:] = 2*[Re x, Im x, Re Y, Im Y] - 1
+void launch_pack_input(const float2* x, const float2* Y, float* xr, size_t n, cudaStream_t st);
+
+struct StepArgs {
+  const float* pyramid;  // fp32 [B][F][T][4]
+  const float* t;        // [B] time value of each sample (divides the pyramid: scale_by_sigma)
+  const float* ow;       // output_layer weight [2][4]
+  const float* ob;       // output_layer bias [2]
+  float2* score;         // optional out: -net(x)   (ScoreModel.forward)
+  // fused ReverseDiffusionPredictor step (all optional as a group; enabled when x != nullptr)
+  const float2* x;
+  const float2* Y;
+  const float2* z;       // explicit noise or nullptr -> Philox
+  float2* x_mean;
+  float2* x_next;
+  float theta, dt, G;
+  unsigned long long seed;
+  unsigned int step;
+  unsigned int clip0;    // global index of sample 0 (shard-invariant RNG streams)
+  int B;
+  size_t per_clip;       // F*T
+};
+void launch_final_step(const StepArgs& a, cudaStream_t st);
+// x0 = Y + z * std   (z explicit or Philox, step = 0xffffffff stream)
+void launch_prior(const float2* Y, const float2* z, float2* x0, float std, unsigned long long seed, unsigned int clip0,
+                  int B, size_t per_clip, cudaStream_t st);
+// fill z with the Philox complex normal stream of (seed, step, clip0 + b) -- test hook for the RNG
+void launch_philox_fill(float2* z, unsigned long long seed, unsigned int step, unsigned int clip0, int B,
+                        size_t per_clip, cudaStream_t st);
+
+// ---- time embedding ---------------------------------------------------------------------------------
+// gfp [B][2*nf] (host-computed Fourier features) -> silu(Linear(silu(Linear(gfp)))) [B][4*nf]
+void launch_temb_mlp(const float* gfp, const float* w1, const float* b1, const float* w2, const float* b2, float* out,
+                     int B, int nf, cudaStream_t st);
+// out[b][n] = base[n] + sum_k W[n][k] * temb[b][k]  for all rows of all ResBlocks at once
+void launch_dense_all(const float* temb, const float* W, const float* base, float* out, int B, int rows, int K,
+                      cudaStream_t st);
+
+// ---- attention block (bottleneck only) ----------------------------------------------------------------
+// out[m][n] = sum_k in[m][k] * W[k][n] + b[n], fp32
+void launch_linear(const float* in, const float* W, const float* b, float* out, int M, int K, int N, cudaStream_t st);
+// act -> fp32 group-normalised (no SiLU) rows
+void launch_attn_core(const float* q, const float* k, const float* v, float* out, int B, int P, int C, cudaStream_t st);
+// out_act = (x + h + 0) * scale with h fp32 [rows][C]
+void launch_add_scale(int dt, const void* x, const float* h, float scale, void* out, size_t n, cudaStream_t st);
+void launch_act_to_f32(int dt, const void* x, float* out, size_t n, cudaStream_t st);
+
+// ---- STFT front / back end ------------------------------------------------------------------------------
+// y [B][L] -> Y complex [B][F][Tp] with spectral compression (|S|^e e^{j angle} * factor), zero for frames >= T
+void launch_stft(const float* y, float2* Y, const float* window, const float2* twiddle, int B, int L, int n_fft, int hop,
+                 int T, int Tp, float factor, float exponent, cudaStream_t st);
+// X complex [B][F][Tp] -> y [B][L]; frames scratch fp32 [B][Tp][n_fft]
+void launch_istft(const float2* X, float* frames, float* y, const float* window, const float2* twiddle,
+                  const float* inv_env, int B, int L, int n_fft, int hop, int Tp, float factor, float exponent,
+                  cudaStream_t st);
+
+// ---- tcgen05 convolution ----------------------------------------------------------------------------------
+struct TcSegDesc {
+  const void* act;   // act tensor [B][H][W][C_tensor]
+  int C_tensor;      // channels of the tensor (row pitch)
+  int c0, C;         // channel window used by this segment
+  const void* w;     // packed weights [taps][N][Cw_total] (act dtype)
+  int Cw_total;      // total input channels of the weight tensor
+  int wc0;           // first weight channel used by this segment
+  int taps;          // 9 or 1
+};
+struct TcConvDesc {
+  TcSegDesc seg[3];
+  int nseg;
+  int B, H, W, N;
+  void* out;
+  const float* bias;
+  int bias_bstride;
+  const void* res;
+  float scale;
+};
+struct TcConvPlan;  // opaque: tensor maps + launch geometry
+// Build (host) the launch plan; returns nullptr and fills err on failure.
+TcConvPlan* tc_conv_plan_create(int dt, const TcConvDesc& d, int num_sms, char* err, int errlen);
+void tc_conv_plan_destroy(TcConvPlan* p);
+void tc_conv_launch(const TcConvPlan* p, cudaStream_t st);
+bool tc_conv_supported(int dt, int N);
+
+}  // namespace use

@@ -1,0 +1,124 @@
+// SDE arithmetic of the sampler, fused with the network's output head.
+// Reference: NCSNpp.forward tail (ncsnpp.py:483-500: h / t, output_layer 1x1 4->2, view_as_complex),
+// ScoreModel.forward_score sign (model_wrapper.py:137), RSDE.discretize + OUVESDE.sde (sdes.py:75-92,
+// 159-173,216-224), ReverseDiffusionPredictor.update_fn (predictors.py:61-68), OUVESDE.prior_sampling
+// (sdes.py:248-254).  In-kernel noise: Philox4x32-10 + Box-Muller, one stream per (seed, step, global clip
+// index, element) so results do not depend on how clips are sharded over GPUs.
+#include <algorithm>
+
+#include "common.cuh"
+#include "kernels.h"
+
+namespace use {
+
+__device__ __forceinline__ void philox4x32_10(uint32_t (&c)[4], uint32_t k0, uint32_t k1) {
+#pragma unroll
+  for (int i = 0; i < 10; ++i) {
+    const uint32_t hi0 = __umulhi(0xD2511F53u, c[0]), lo0 = 0xD2511F53u * c[0];
+    const uint32_t hi1 = __umulhi(0xCD9E8D57u, c[2]), lo1 = 0xCD9E8D57u * c[2];
+    const uint32_t n0 = hi1 ^ c[1] ^ k0, n1 = lo1, n2 = hi0 ^ c[3] ^ k1, n3 = lo0;
+    c[0] = n0; c[1] = n1; c[2] = n2; c[3] = n3;
+    k0 += 0x9E3779B9u;
+    k1 += 0xBB67AE85u;
+  }
+}
+
+// complex standard normal (Re, Im each variance 1/2): what torch.randn_like(complex64) draws
+__device__ __forceinline__ float2 philox_cnormal(unsigned long long seed, uint32_t step, uint32_t clip, uint64_t elem) {
+  uint32_t c[4] = {static_cast<uint32_t>(elem), static_cast<uint32_t>(elem >> 32), step, clip};
+  philox4x32_10(c, static_cast<uint32_t>(seed), static_cast<uint32_t>(seed >> 32));
+  const float u1 = (static_cast<float>(c[0] >> 8) + 0.5f) * (1.0f / 16777216.0f);  // (0,1)
+  const float u2 = (static_cast<float>(c[1] >> 8) + 0.5f) * (1.0f / 16777216.0f);
+  const float r = sqrtf(-logf(u1));  // sqrt(-2 ln u1) / sqrt(2)
+  float sn, cs;
+  sincospif(2.0f * u2, &sn, &cs);
+  return make_float2(r * cs, r * sn);
+}
+
+__global__ void __launch_bounds__(256) pack_input_kernel(const float2* __restrict__ x, const float2* __restrict__ Y,
+                                                          float4* __restrict__ xr, size_t n) {
+  for (size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n;
+       i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const float2 a = x[i], b = Y[i];
+    xr[i] = make_float4(2.f * a.x - 1.0f, 2.f * a.y - 1.0f, 2.f * b.x - 1.0f, 2.f * b.y - 1.0f);
+  }
+}
+
+void launch_pack_input(const float2* x, const float2* Y, float* xr, size_t n, cudaStream_t st) {
+  const int blocks = static_cast<int>(std::min<size_t>((n + 255) / 256, 148 * 32));
+  pack_input_kernel<<<blocks, 256, 0, st>>>(x, Y, reinterpret_cast<float4*>(xr), n);
+}
+
+__global__ void __launch_bounds__(256) final_step_kernel(StepArgs a) {
+  const size_t n = a.per_clip * a.B;
+  const float w00 = a.ow[0], w01 = a.ow[1], w02 = a.ow[2], w03 = a.ow[3];
+  const float w10 = a.ow[4], w11 = a.ow[5], w12 = a.ow[6], w13 = a.ow[7];
+  const float b0 = a.ob[0], b1 = a.ob[1];
+  const float G2 = a.G * a.G;
+  for (size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n;
+       i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const int b = static_cast<int>(i / a.per_clip);
+    const float t = a.t[b];
+    float4 p = __ldg(reinterpret_cast<const float4*>(a.pyramid) + i);
+    p.x /= t; p.y /= t; p.z /= t; p.w /= t;
+    const float ore = b0 + w00 * p.x + w01 * p.y + w02 * p.z + w03 * p.w;
+    const float oim = b1 + w10 * p.x + w11 * p.y + w12 * p.z + w13 * p.w;
+    const float2 score = make_float2(-ore, -oim);
+    if (a.score != nullptr) a.score[i] = score;
+    if (a.x != nullptr) {
+      const float2 x = a.x[i], Y = a.Y[i];
+      float2 z;
+      if (a.z != nullptr) z = a.z[i];
+      else z = philox_cnormal(a.seed, a.step, a.clip0 + b, i - static_cast<size_t>(b) * a.per_clip);
+      // f = theta (Y - x) dt ; rev_f = f - G^2 score ; x_mean = x - rev_f ; x = x_mean + G z
+      const float fre = (a.theta * (Y.x - x.x)) * a.dt, fim = (a.theta * (Y.y - x.y)) * a.dt;
+      const float rre = fre - G2 * score.x, rim = fim - G2 * score.y;
+      const float2 xm = make_float2(x.x - rre, x.y - rim);
+      a.x_mean[i] = xm;
+      a.x_next[i] = make_float2(xm.x + a.G * z.x, xm.y + a.G * z.y);
+    }
+  }
+}
+
+void launch_final_step(const StepArgs& a, cudaStream_t st) {
+  const size_t n = a.per_clip * a.B;
+  const int blocks = static_cast<int>(std::min<size_t>((n + 255) / 256, 148 * 16));
+  final_step_kernel<<<blocks, 256, 0, st>>>(a);
+}
+
+__global__ void __launch_bounds__(256) prior_kernel(const float2* __restrict__ Y, const float2* __restrict__ z,
+                                                     float2* __restrict__ x0, float std, unsigned long long seed,
+                                                     unsigned int clip0, size_t per_clip, size_t n) {
+  for (size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n;
+       i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const uint32_t b = static_cast<uint32_t>(i / per_clip);
+    const float2 zz = z ? z[i] : philox_cnormal(seed, 0xffffffffu, clip0 + b, i - static_cast<size_t>(b) * per_clip);
+    const float2 y = Y[i];
+    x0[i] = make_float2(y.x + zz.x * std, y.y + zz.y * std);
+  }
+}
+
+void launch_prior(const float2* Y, const float2* z, float2* x0, float std, unsigned long long seed, unsigned int clip0,
+                  int B, size_t per_clip, cudaStream_t st) {
+  const size_t n = per_clip * B;
+  const int blocks = static_cast<int>(std::min<size_t>((n + 255) / 256, 148 * 16));
+  prior_kernel<<<blocks, 256, 0, st>>>(Y, z, x0, std, seed, clip0, per_clip, n);
+}
+
+__global__ void __launch_bounds__(256) philox_fill_kernel(float2* z, unsigned long long seed, unsigned int step,
+                                                           unsigned int clip0, size_t per_clip, size_t n) {
+  for (size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n;
+       i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const uint32_t b = static_cast<uint32_t>(i / per_clip);
+    z[i] = philox_cnormal(seed, step, clip0 + b, i - static_cast<size_t>(b) * per_clip);
+  }
+}
+
+void launch_philox_fill(float2* z, unsigned long long seed, unsigned int step, unsigned int clip0, int B,
+                        size_t per_clip, cudaStream_t st) {
+  const size_t n = per_clip * B;
+  const int blocks = static_cast<int>(std::min<size_t>((n + 255) / 256, 148 * 16));
+  philox_fill_kernel<<<blocks, 256, 0, st>>>(z, seed, step, clip0, per_clip, n);
+}
+
+}  // namespace use

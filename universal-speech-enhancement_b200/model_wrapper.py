@@ -1,0 +1,251 @@
+"""ScoreModel: the reference's model wrapper, executed by the B200 engine.
+
+Drop-in for /root/reference/src/models/components/sgmse/model_wrapper.py:23-329 on the predict path:
+same constructor kwargs (configs/model/SGMSE_Large.yaml:3-17), same ``sample(batch, sampler_type, N,
+corrector_steps, snr) -> batch`` (adds ``batch["enhanced"]``, float32 [B, L] on the input device), same
+``forward(x, t, score_conditioning, sde_input)``, ``stft / istft / spec_fwd / spec_back``,
+``get_pc_sampler`` and an ``enhance(y, N=30, ...)`` convenience with the semantics of the legacy
+``StochasticRegenerationModel.enhance`` (/root/reference/src/models/components/sgmse/model.py:933-1010).
+
+Everything numerical runs in libuse_b200.so; the host layer only stages pointers and the float32 step
+schedule.  Additions over the reference (all defaulting to reference behaviour): ``dtype`` ("fp32": fp32
+storage + TF32 tensor-core convolutions, PyTorch's own GPU default; "bf16": bf16 score network with fp32
+SDE state), ``micro_batch`` (memory control, like the reference's ``minibatch`` argument
+model_wrapper.py:220-236), ``noise`` / ``seed`` for reproducible sampling.
+"""
+from __future__ import annotations
+
+import time
+from math import ceil
+from typing import Optional
+
+import numpy as np
+import torch
+import torch.nn as nn
+
+from . import _lib, sampling
+from .backbones import BackboneRegistry
+from .sdes import SDERegistry
+
+
+def get_window(window_type, window_length):
+    if window_type == "sqrthann":
+        return torch.sqrt(torch.hann_window(window_length, periodic=True))
+    if window_type == "hann":
+        return torch.hann_window(window_length, periodic=True)
+    raise NotImplementedError(f"Window type {window_type} not implemented!")
+
+
+def pad_spec(Y):
+    """Zero-pad the frame axis to a multiple of 64 (util/other.py:128-135)."""
+    T = Y.size(3)
+    num_pad = 64 - T % 64 if T % 64 != 0 else 0
+    return torch.nn.functional.pad(Y, (0, num_pad, 0, 0))
+
+
+class ScoreModel(nn.Module):
+    def __init__(self, backbone: str = "ncsnpp", sde: str = "ouve", t_eps: float = 3e-2, mode="regen-joint-training",
+                 condition="both", loss_type: str = "mse", n_fft=510, hop_length=128, num_frames=256, window="hann",
+                 spec_factor=0.15, spec_abs_exponent=0.5, sde_input="denoised", predictor="reverse_diffusion",
+                 corrector="none", dtype: str = "fp32", micro_batch: Optional[int] = None, N: Optional[int] = None,
+                 sampler_type: Optional[str] = None):
+        super().__init__()
+        if condition != "noisy" or sde_input != "noisy":
+            raise NotImplementedError(
+                "ScoreModel(B200): only condition='noisy', sde_input='noisy' (configs/model/SGMSE_Large.yaml) is on "
+                "the accelerated path; 'both'/'denoised' belong to the GAN-refiner pipeline (SURVEY.md section 8f)")
+        self.score_net = BackboneRegistry.get_by_name(backbone)(input_channels=4, compute_dtype=dtype)
+        self.sde = SDERegistry.get_by_name(sde)()
+        self.t_eps = t_eps
+        self.condition, self.mode, self.loss_type = condition, mode, loss_type
+        self.n_fft, self.hop_length, self.num_frames = n_fft, hop_length, num_frames
+        self.window_type = window
+        self.window = get_window(window, n_fft)
+        self.spec_factor, self.spec_abs_exponent = spec_factor, spec_abs_exponent
+        self.target_len = (num_frames - 1) * hop_length
+        self.sde_input = sde_input
+        self.predictor, self.corrector = predictor, corrector
+        self.dtype_name = dtype
+        self.micro_batch = micro_batch
+        self.default_N = N                      # None -> the reference's hard-coded 50 (model_wrapper.py:266)
+        self.default_sampler_type = sampler_type
+        self.score_net._spec = dict(n_fft=n_fft, hop_length=hop_length, spec_factor=spec_factor,
+                                    spec_abs_exponent=spec_abs_exponent)
+        self.score_net._theta = float(getattr(self.sde, "theta", 1.5))
+        self._tables = {}
+
+    # ---- device tables (window, twiddles, OLA envelope) -------------------------------------------
+    def _dev_tables(self, device, Tp: int):
+        key = (str(device), Tp)
+        tb = self._tables.get(key)
+        if tb is None:
+            n = self.n_fft
+            k = torch.arange(n, dtype=torch.float64)
+            ang = 2.0 * np.pi * k / n
+            tw = torch.stack([torch.cos(ang), torch.sin(ang)], dim=1).to(torch.float32)
+            w64 = self.window.to(torch.float64)
+            env = torch.zeros(n + self.hop_length * (Tp - 1), dtype=torch.float64)
+            for f in range(Tp):
+                env[f * self.hop_length: f * self.hop_length + n] += w64 * w64
+            tb = dict(window=self.window.to(device=device, dtype=torch.float32).contiguous(),
+                      twiddle=tw.contiguous().to(device), env=env.to(torch.float32).to(device))
+            self._tables = {key: tb}
+        return tb
+
+    def _engine(self, device):
+        return self.score_net.engine(device, self.dtype_name)
+
+    # ---- transforms (same call surface as the reference; executed by the CUDA kernels) ------------
+    def spec_fwd(self, spec):
+        if self.spec_abs_exponent != 1:
+            e = self.spec_abs_exponent
+            spec = spec.abs() ** e * torch.exp(1j * spec.angle())
+        return spec * self.spec_factor
+
+    def spec_back(self, spec):
+        spec = spec / self.spec_factor
+        if self.spec_abs_exponent != 1:
+            e = self.spec_abs_exponent
+            spec = spec.abs() ** (1 / e) * torch.exp(1j * spec.angle())
+        return spec
+
+    def stft_compressed(self, y: torch.Tensor) -> torch.Tensor:
+        """pad_spec(spec_fwd(stft(y))) fused: float [B, L] (CUDA) -> complex64 [B, F, Tp]."""
+        if not y.is_cuda:
+            raise RuntimeError("ScoreModel(B200) runs on CUDA tensors only; there is no CPU path")
+        y = y.to(torch.float32).contiguous()
+        B, L = y.shape
+        T = 1 + L // self.hop_length
+        Tp = int(ceil(T / 64) * 64)
+        F = self.n_fft // 2 + 1
+        eng = self._engine(y.device)
+        tb = self._dev_tables(y.device, Tp)
+        Y = torch.empty(B, F, Tp, dtype=torch.complex64, device=y.device)
+        with torch.cuda.device(y.device):
+            _lib.check(eng.L.use_stft(eng.h, B, L, Tp, y.data_ptr(), Y.data_ptr(), tb["window"].data_ptr(),
+                                      tb["twiddle"].data_ptr(), _lib.stream_ptr()), "use_stft")
+        return Y
+
+    def istft_decompressed(self, X: torch.Tensor, length: int) -> torch.Tensor:
+        """istft(spec_back(X), length) fused: complex64 [B, F, Tp] -> float [B, length]."""
+        X = X.contiguous()
+        B, F, Tp = X.shape
+        eng = self._engine(X.device)
+        tb = self._dev_tables(X.device, Tp)
+        out = torch.empty(B, length, dtype=torch.float32, device=X.device)
+        frames = torch.empty(B, Tp, self.n_fft, dtype=torch.float32, device=X.device)
+        with torch.cuda.device(X.device):
+            _lib.check(eng.L.use_istft(eng.h, B, length, Tp, X.data_ptr(), out.data_ptr(), frames.data_ptr(),
+                                       tb["window"].data_ptr(), tb["twiddle"].data_ptr(), tb["env"].data_ptr(),
+                                       _lib.stream_ptr()), "use_istft")
+        return out
+
+    def stft(self, sig):
+        """Uncompressed STFT, complex [B, F, T] (API parity; = spec_back of the fused kernel's output)."""
+        T = 1 + sig.shape[-1] // self.hop_length
+        return self.spec_back(self.stft_compressed(sig)[..., :T])
+
+    def istft(self, spec, length=None):
+        T = spec.shape[-1]
+        Tp = int(ceil(T / 64) * 64)
+        X = torch.nn.functional.pad(self.spec_fwd(spec), (0, Tp - T))
+        if length is None:
+            length = self.hop_length * (T - 1)
+        return self.istft_decompressed(X, length)
+
+    # ---- score network -----------------------------------------------------------------------------
+    def forward_score(self, x, t, score_conditioning, sde_input):
+        """score = -score_net(cat[x, Y], t)  (model_wrapper.py:135-141); x, Y complex [B,1,F,T]."""
+        if len(score_conditioning) != 1:
+            raise NotImplementedError("exactly one conditioning tensor (condition='noisy') is supported")
+        Y = score_conditioning[0]
+        s = self._engine(x.device).score(x[:, 0], Y[:, 0], t)
+        return s.unsqueeze(1)
+
+    def forward(self, x, t, score_conditioning, sde_input):
+        return self.forward_score(x, t, score_conditioning, sde_input)
+
+    # ---- samplers ----------------------------------------------------------------------------------
+    def _fused_pc_sample(self, sde, y, eps, noise=None, seed=None, clip0=0):
+        """y: complex [B,1,F,T].  One C call for prior + N predictor steps."""
+        ts, G, std1 = sde.step_tables(sde.N, eps)
+        if seed is None:
+            seed = int(torch.randint(0, 2**31 - 1, (1,)).item())  # consumes the global RNG like randn_like would
+        nz = noise[:, :, 0] if noise is not None else None
+        mb = self.micro_batch or y.shape[0]
+        outs = []
+        for s in range(0, y.shape[0], mb):
+            Yc = y[s:s + mb, 0]
+            nc = nz[:, s:s + mb].contiguous() if nz is not None else None
+            outs.append(self._engine(y.device).pc_sample(Yc, ts, G, std1, noise=nc, seed=seed, clip0=clip0 + s))
+        return torch.cat(outs, dim=0).unsqueeze(1) if len(outs) > 1 else outs[0].unsqueeze(1)
+
+    def get_pc_sampler(self, predictor_name, corrector_name, y, N=None, minibatch=None, **kwargs):
+        N = self.sde.N if N is None else N
+        sde = self.sde.copy()
+        sde.N = N
+        kwargs = {"eps": self.t_eps, **kwargs}
+        if minibatch is None:
+            return sampling.get_pc_sampler(predictor_name, corrector_name, sde=sde, score_fn=self, y=y, **kwargs)
+        M = y.shape[0]
+
+        def batched_sampling_fn():
+            samples, ns = [], []
+            for i in range(int(ceil(M / minibatch))):
+                y_mini = y[i * minibatch:(i + 1) * minibatch]
+                kw = dict(kwargs)
+                if kw.get("conditioning") is not None:
+                    kw["conditioning"] = [y_mini if c is y else c[i * minibatch:(i + 1) * minibatch]
+                                          for c in kw["conditioning"]]
+                sample, n = sampling.get_pc_sampler(predictor_name, corrector_name, sde=sde, score_fn=self, y=y_mini,
+                                                    **kw)()
+                samples.append(sample)
+                ns.append(n)
+            return torch.cat(samples, dim=0), ns
+
+        return batched_sampling_fn
+
+    def get_ode_sampler(self, y, N=None, minibatch=1, **kwargs):
+        raise NotImplementedError("the ODE (RK45) sampler is not on the accelerated path (SURVEY.md section 8f, rank 3)")
+
+    @torch.no_grad()
+    def sample(self, batch, sampler_type=None, N=None, corrector_steps=1, snr=0.5, noise=None, seed=None, clip0=0):
+        """ScoreModel.sample (model_wrapper.py:262-329)."""
+        sampler_type = sampler_type or self.default_sampler_type or "pc"
+        N = N if N is not None else (self.default_N if self.default_N is not None else 50)
+        y = batch["perturbed"]
+        T_orig = y.size(1)
+        Y = self.stft_compressed(y).unsqueeze(1)          # = pad_spec(spec_fwd(stft(y)).unsqueeze(1))
+        score_conditioning = [Y]
+        if sampler_type != "pc":
+            raise NotImplementedError(f"{sampler_type} is not a valid sampler type on the accelerated path (use 'pc')")
+        sampler = self.get_pc_sampler(self.predictor, self.corrector, Y, N=N, corrector_steps=corrector_steps, snr=snr,
+                                      intermediate=False, conditioning=score_conditioning, noise=noise, seed=seed,
+                                      clip0=clip0)
+        sample, nfe = sampler()
+        batch["enhanced"] = self.istft_decompressed(sample.squeeze(1), T_orig)
+        return batch
+
+    @torch.no_grad()
+    def enhance(self, y, sampler_type="pc", predictor="reverse_diffusion", corrector="none", N=30, corrector_steps=1,
+                snr=0.5, timeit=False, return_stft=False, sr=24000, **kwargs):
+        """One-call enhancement of ``y`` [1, L] (or [B, L]): peak-normalise, sample, rescale (model.py:933-1010)."""
+        start = time.time()
+        dev = y.device if y.is_cuda else torch.device("cuda", torch.cuda.current_device())
+        y = y.to(dev, torch.float32)
+        norm_factor = y.abs().max().item()
+        y = y / norm_factor
+        T_orig = y.size(1)
+        Y = self.stft_compressed(y).unsqueeze(1)
+        if sampler_type != "pc":
+            raise NotImplementedError("only the 'pc' sampler is on the accelerated path")
+        sample, nfe = self.get_pc_sampler(predictor, corrector, Y, N=N, corrector_steps=corrector_steps, snr=snr,
+                                          intermediate=False, conditioning=[Y], **kwargs)()
+        if return_stft:
+            return sample.squeeze(), Y.squeeze(), T_orig, norm_factor
+        x_hat = self.istft_decompressed(sample.squeeze(1), T_orig) * norm_factor
+        x_hat = x_hat.squeeze().cpu()
+        if timeit:
+            rtf = (time.time() - start) / (x_hat.shape[-1] / sr)
+            return x_hat, nfe, rtf
+        return x_hat
