@@ -110,7 +110,11 @@ int use_upfirdn2d_f32(const float* in, float* out, int major, int in_h, int in_w
                       int pad_y1, void* stream);
 
 /* ---- single kernels (parity tests) ----------------------------------------------------------------- */
-int use_op_gn_stats(int dtype, const void* x, double* stats, int B, int HW, int C, void* stream);
+/* per-channel sum / sum of squares, double [B][C][2]; bitwise deterministic.  scratch: use_op_gn_stats_scratch_bytes
+ * device bytes; tickets: device uint32 [B], zero on entry (left zero). */
+size_t use_op_gn_stats_scratch_bytes(int B, int HW, int C);
+int use_op_gn_stats(int dtype, const void* x, double* stats, void* scratch, void* tickets, int B, int HW, int C,
+                    void* stream);
 int use_op_gn_apply(int dtype, const void* x0, const double* stats0, int C0, const void* x1, const double* stats1, int C1,
                     const float* gamma, const float* beta, float eps, int fir, int do_silu, int as_operand, void* out_act,
                     void* out_raw, int B, int Hin, int Win, void* stream);

@@ -164,7 +164,9 @@ def test_large_score_forward(dtype):
 def test_full_size_properties_bf16():
     """BASELINE shape (4 s @ 24 kHz -> 512 x 640) where the oracle is too slow: size-independent properties.
     (1) shard invariance: clips sampled together == clips sampled alone with their global clip index (Philox streams
-    are keyed by clip index), (2) determinism of the seed, (3) finite output of the right shape."""
+    are keyed by clip index), (2) determinism of the seed, (3) finite output of the right shape.  Quantisation (bf16 / TF32 operand rounding) amplifies ANY ulp-level
+    run-to-run difference to the rounding-noise floor within a few layers, so this only holds because no kernel uses
+    floating-point atomics."""
     m, _ = large_model("bf16")
     y = O.synthetic_clips(2, 96000).cuda()
     a = m.sample({"perturbed": y}, N=2, seed=5)["enhanced"]
@@ -172,7 +174,9 @@ def test_full_size_properties_bf16():
     b1 = m.sample({"perturbed": y[1:2]}, N=2, seed=5, clip0=1)["enhanced"]
     e = rel_l2(b1.cpu(), a[1:2].cpu())
     record("shard_invariance_rel_l2_bf16", e)
-    assert e < 1e-3, e  # identical noise; only the fp32 atomics order of the GroupNorm statistics may differ
+    assert torch.equal(b1, a[1:2]), e  # every kernel is deterministic and batch-invariant: BIT-identical
+    a2 = m.sample({"perturbed": y}, N=2, seed=5)["enhanced"]
+    assert torch.equal(a, a2)  # same seed, same result
     c = m.sample({"perturbed": y}, N=2, seed=6)["enhanced"]
     assert rel_l2(c.cpu(), a.cpu()) > 1e-3  # a different seed gives a different sample
 

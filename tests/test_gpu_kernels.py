@@ -139,6 +139,34 @@ def test_conv_ref_matches_torch(dt):
     assert float((from_act(out) - ref).abs().max()) <= OUT_TOL[dt] * float(ref.abs().max())
 
 
+def gn_stats(L, dt, a, B, HW, Cc):
+    st = torch.empty(B, Cc, 2, dtype=torch.float64, device="cuda")
+    scratch = torch.empty(max(1, L.use_op_gn_stats_scratch_bytes(B, HW, Cc)), dtype=torch.uint8, device="cuda")
+    tickets = torch.zeros(B, dtype=torch.int32, device="cuda")
+    assert L.use_op_gn_stats(dt, a.data_ptr(), st.data_ptr(), scratch.data_ptr(), tickets.data_ptr(), B, HW, Cc,
+                             stream()) == 0, L.use_last_error()
+    torch.cuda.synchronize()
+    assert int(tickets.abs().max()) == 0  # tickets are handed back zeroed
+    return st
+
+
+def test_gn_stats_deterministic_and_batch_invariant():
+    """No floating-point atomics: repeated launches and different batch sizes give bit-identical statistics."""
+    L = _lib.lib()
+    g = torch.Generator().manual_seed(0)
+    B, H, W, Cc = 3, 96, 80, 128  # 7680 pixels -> 4 partial blocks per sample
+    x = torch.randn(B, Cc, H, W, generator=g)
+    for dt in (F32, BF16):
+        a = act_tensor(x, dt)
+        s1 = gn_stats(L, dt, a, B, H * W, Cc)
+        s2 = gn_stats(L, dt, a, B, H * W, Cc)
+        assert torch.equal(s1, s2)
+        s3 = gn_stats(L, dt, a[1:2].contiguous(), 1, H * W, Cc)
+        assert torch.equal(s1[1:2], s3)
+        ref = to_operand(x, dt).double().sum(dim=(2, 3)) if dt == BF16 else x.double().sum(dim=(2, 3))
+        assert torch.allclose(s1[..., 0].cpu(), ref, rtol=1e-5, atol=1e-2)
+
+
 def _gn_ref(x, gamma, beta, silu):
     C = x.shape[1]
     y = Fnn.group_norm(x.double(), min(C // 4, 32), gamma.double(), beta.double(), eps=1e-6)
@@ -161,9 +189,7 @@ def test_groupnorm_silu_fir(dt, C0, C1, fir):
     Ct = C0 + C1
     gamma, beta = 1 + 0.1 * torch.randn(Ct, generator=g), 0.1 * torch.randn(Ct, generator=g)
     acts = [act_tensor(s, dt) for s in srcs]
-    stats = [torch.zeros(B, s.shape[1], 2, dtype=torch.float64, device="cuda") for s in srcs]
-    for a, st, s in zip(acts, stats, srcs):
-        assert L.use_op_gn_stats(dt, a.data_ptr(), st.data_ptr(), B, H * W, s.shape[1], stream()) == 0
+    stats = [gn_stats(L, dt, a, B, H * W, s.shape[1]) for a, s in zip(acts, srcs)]
     _sync()
     # statistics themselves
     for st, s in zip(stats, srcs):
@@ -202,8 +228,7 @@ def test_gn_apply_operand_rounding_fp32():
     B, H, W, Cc = 1, 4, 4, 64
     x = torch.randn(B, Cc, H, W)
     a = act_tensor(x, F32)
-    st = torch.zeros(B, Cc, 2, dtype=torch.float64, device="cuda")
-    L.use_op_gn_stats(F32, a.data_ptr(), st.data_ptr(), B, H * W, Cc, stream())
+    st = gn_stats(L, F32, a, B, H * W, Cc)
     out = torch.empty_like(a)
     gd, bd = torch.ones(Cc, device="cuda"), torch.zeros(Cc, device="cuda")
     assert L.use_op_gn_apply(F32, a.data_ptr(), st.data_ptr(), Cc, None, None, 0, gd.data_ptr(), bd.data_ptr(), 1e-6, 0, 1,

@@ -22,62 +22,90 @@ namespace use {
   } while (0)
 
 // ------------------------------------------------------------------------------------------------
-// GroupNorm statistics: per sample and per CHANNEL sum and sum of squares (double atomics).
+// GroupNorm statistics: per sample and per CHANNEL sum and sum of squares.
 // Channels (not groups) so that a GroupNorm over a channel concat whose group boundary straddles the
 // two sources (384 = 256 + 128 channels, 12 per group) can be assembled from per-tensor partials.
+// BITWISE DETERMINISTIC and independent of the batch size: no floating-point atomics anywhere.  Every
+// block reduces a fixed pixel range in a fixed order and publishes a double partial; the block that
+// takes the last ticket of its sample sums the partials in block order.  (Any run-to-run ulp difference
+// would be amplified to the bf16 / TF32 rounding-noise floor within a few layers, which would break
+// "clips sampled alone == clips sampled in a batch".)
 // ------------------------------------------------------------------------------------------------
+constexpr int kGnPixPerBlock = 2048;
+
 template <typename T>
-__global__ void __launch_bounds__(256) gn_stats_kernel(const T* __restrict__ x, double* __restrict__ stats, int HW, int C,
-                                                        int pix_per_block) {
+__global__ void __launch_bounds__(256) gn_stats_kernel(const T* __restrict__ x, double* __restrict__ stats,
+                                                        double* __restrict__ partials, unsigned int* __restrict__ tickets,
+                                                        int HW, int C) {
   constexpr int V = Vec<T>::N;
-  extern __shared__ float sred[];  // [C][2]
-  for (int i = threadIdx.x; i < C * 2; i += blockDim.x) sred[i] = 0.f;
-  __syncthreads();
-  const int b = blockIdx.y;
-  const int vp = C / V;                 // vectors per pixel
-  const int p0 = blockIdx.x * pix_per_block;
-  const int p1 = min(HW, p0 + pix_per_block);
+  extern __shared__ float sred[];  // [rows][C][2]
+  __shared__ unsigned int s_ticket;
+  const int b = blockIdx.y, nblk = gridDim.x;
+  const int vp = C / V;  // vectors per pixel
+  const int p0 = blockIdx.x * kGnPixPerBlock;
+  const int p1 = min(HW, p0 + kGnPixPerBlock);
   const T* base = x + (static_cast<size_t>(b) * HW) * C;
-  // thread -> fixed vector column v (when blockDim % vp == 0) so partial sums stay in registers
-  if (blockDim.x % vp == 0) {
-    const int rp = blockDim.x / vp;
-    const int v = threadIdx.x % vp;
+  // thread -> fixed vector column v and pixel row r; rows = number of pixel rows processed concurrently
+  const int rows = max(1, static_cast<int>(blockDim.x) / vp);
+  const int nact = rows * min(vp, static_cast<int>(blockDim.x));
+  for (int v0 = 0; v0 < vp; v0 += blockDim.x) {  // vp > blockDim only for very wide tensors
+    const int v = v0 + (threadIdx.x % min(vp, static_cast<int>(blockDim.x)));
+    const int r = threadIdx.x / min(vp, static_cast<int>(blockDim.x));
     float s[V], ss[V];
 #pragma unroll
     for (int i = 0; i < V; ++i) s[i] = ss[i] = 0.f;
-    for (int p = p0 + threadIdx.x / vp; p < p1; p += rp) {
-      float f[V];
-      Vec<T>::load(base + static_cast<size_t>(p) * C + v * V, f);
+    if (threadIdx.x < nact && v < vp) {
+      for (int p = p0 + r; p < p1; p += rows) {
+        float f[V];
+        Vec<T>::load(base + static_cast<size_t>(p) * C + v * V, f);
 #pragma unroll
-      for (int i = 0; i < V; ++i) { s[i] += f[i]; ss[i] += f[i] * f[i]; }
-    }
+        for (int i = 0; i < V; ++i) { s[i] += f[i]; ss[i] += f[i] * f[i]; }
+      }
 #pragma unroll
-    for (int i = 0; i < V; ++i) {
-      atomicAdd(&sred[(v * V + i) * 2], s[i]);
-      atomicAdd(&sred[(v * V + i) * 2 + 1], ss[i]);
-    }
-  } else {
-    const long long nvec = static_cast<long long>(p1 - p0) * vp;
-    for (long long i = threadIdx.x; i < nvec; i += blockDim.x) {
-      const int v = static_cast<int>(i % vp);
-      float f[V];
-      Vec<T>::load(base + (static_cast<size_t>(p0) + i / vp) * C + v * V, f);
-#pragma unroll
-      for (int j = 0; j < V; ++j) {
-        atomicAdd(&sred[(v * V + j) * 2], f[j]);
-        atomicAdd(&sred[(v * V + j) * 2 + 1], f[j] * f[j]);
+      for (int i = 0; i < V; ++i) {
+        sred[(r * C + v * V + i) * 2] = s[i];
+        sred[(r * C + v * V + i) * 2 + 1] = ss[i];
       }
     }
   }
   __syncthreads();
-  for (int i = threadIdx.x; i < C * 2; i += blockDim.x)
-    atomicAdd(&stats[static_cast<size_t>(b) * C * 2 + i], static_cast<double>(sred[i]));
+  double* mine = partials + (static_cast<size_t>(b) * nblk + blockIdx.x) * C * 2;
+  for (int i = threadIdx.x; i < C * 2; i += blockDim.x) {
+    double acc = 0.0;
+    for (int r = 0; r < rows; ++r) acc += static_cast<double>(sred[r * C * 2 + i]);
+    mine[i] = acc;
+  }
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) s_ticket = atomicAdd(&tickets[b], 1u);
+  __syncthreads();
+  if (s_ticket == static_cast<unsigned>(nblk - 1)) {
+    __threadfence();
+    const double* pb = partials + static_cast<size_t>(b) * nblk * C * 2;
+    for (int i = threadIdx.x; i < C * 2; i += blockDim.x) {
+      double acc = 0.0;
+      for (int k = 0; k < nblk; ++k) acc += __ldcg(pb + static_cast<size_t>(k) * C * 2 + i);
+      stats[static_cast<size_t>(b) * C * 2 + i] = acc;
+    }
+    if (threadIdx.x == 0) tickets[b] = 0;  // ready for the next launch that shares the scratch
+  }
 }
 
-void launch_gn_stats(int dt, const void* x, double* stats, int B, int HW, int C, cudaStream_t st) {
-  const int ppb = 1024;
-  dim3 grid((HW + ppb - 1) / ppb, B);
-  DISPATCH_DT(dt, { gn_stats_kernel<T><<<grid, 256, C * 2 * sizeof(float), st>>>((const T*)x, stats, HW, C, ppb); });
+size_t gn_stats_scratch_bytes(int B, int HW, int C) {
+  const size_t nblk = (HW + kGnPixPerBlock - 1) / kGnPixPerBlock;
+  return static_cast<size_t>(B) * nblk * C * 2 * sizeof(double);
+}
+
+void launch_gn_stats(int dt, const void* x, double* stats, double* partials, unsigned int* tickets, int B, int HW, int C,
+                     cudaStream_t st) {
+  dim3 grid((HW + kGnPixPerBlock - 1) / kGnPixPerBlock, B);
+  DISPATCH_DT(dt, {
+    constexpr int V = Vec<T>::N;
+    const int vp = C / V;
+    const int rows = vp >= 256 ? 1 : 256 / vp;
+    gn_stats_kernel<T><<<grid, 256, static_cast<size_t>(rows) * C * 2 * sizeof(float), st>>>((const T*)x, stats, partials,
+                                                                                            tickets, HW, C);
+  });
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -208,7 +236,10 @@ __global__ void __launch_bounds__(256) gn_apply_kernel(GnSrcT<T> s0, GnSrcT<T> s
     if (as_operand) Vec<T>::store_operand(out_act + o, acc);
     else Vec<T>::store(out_act + o, acc);
     if constexpr (FIR != 0) {
-      if (out_raw != nullptr) Vec<T>::store_operand(out_raw + o, raw);
+      if (out_raw != nullptr) {
+        if (as_operand) Vec<T>::store_operand(out_raw + o, raw);
+        else Vec<T>::store(out_raw + o, raw);
+      }
     }
   }
 }

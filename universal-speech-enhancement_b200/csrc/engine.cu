@@ -7,6 +7,7 @@
 #include <stdio.h>
 #include <string.h>
 
+#include <algorithm>
 #include <functional>
 #include <map>
 #include <memory>
@@ -190,7 +191,7 @@ struct use_engine {
   int num_sms = 148;
   std::map<std::string, std::unique_ptr<Program>> programs;  // keyed by "B,F,T,base"
   // fixed head of the workspace (byte offsets)
-  struct Head { size_t xr, t, gfp, temb, dense, stats, arena; } head;
+  struct Head { size_t xr, t, gfp, temb, dense, stats, gn_scratch, tickets, arena; } head;
   // instrumentation
   long long launches = 0;
   bool profiling = false;
@@ -376,6 +377,7 @@ struct Builder {
   int B, F, T;
   Arena arena;
   size_t stats_top = 0;
+  size_t gn_scratch_max = 0;
   char* base;      // workspace base (nullptr on the dry run)
   bool dry;
   int err = 0;
@@ -406,11 +408,14 @@ struct Builder {
     if (a.stats_off != (size_t)-1) return;
     a.stats_off = stats_top;
     stats_top += (size_t)B * a.C * 2 * sizeof(double);
+    gn_scratch_max = std::max(gn_scratch_max, gn_stats_scratch_bytes(B, a.H * a.W, a.C));
     if (dry) return;
     const int dt = e->dt, Bn = B, HW = a.H * a.W, C = a.C;
     const void* x = ws(a.off);
     double* st = stats_ptr(a.stats_off);
-    emit([=](cudaStream_t s) { launch_gn_stats(dt, x, st, Bn, HW, C, s); }, TAG_GN_STATS, 1, 3.0 * Bn * HW * C,
+    double* scratch = (double*)(base + e->head.gn_scratch);
+    unsigned int* tickets = (unsigned int*)(base + e->head.tickets);
+    emit([=](cudaStream_t s) { launch_gn_stats(dt, x, st, scratch, tickets, Bn, HW, C, s); }, TAG_GN_STATS, 1, 3.0 * Bn * HW * C,
          (double)Bn * HW * C * es());
   }
   void gn_apply(Act& s0, Act* s1, size_t gamma_off, size_t beta_off, int fir, bool silu, bool operand, Act& out, Act* raw) {
@@ -670,6 +675,8 @@ static int plan_workspace(use_engine* e, int B, int F, int T, size_t* total, siz
   e->head.temb = off; off = align_up(off + (size_t)B * 4 * c.nf * 4, 1024);
   e->head.dense = off; off = align_up(off + (size_t)B * e->dense_rows * 4, 1024);
   e->head.stats = off; off = align_up(off + b.stats_top, 1024);
+  e->head.gn_scratch = off; off = align_up(off + b.gn_scratch_max, 1024);
+  e->head.tickets = off; off = align_up(off + (size_t)B * 4, 1024);
   e->head.arena = off;
   *total = off + b.arena.peak;
   if (stats_bytes) *stats_bytes = b.stats_top;
@@ -705,7 +712,7 @@ static Program* get_program(use_engine* e, int B, int F, int T, void* workspace,
 static void run_network(use_engine* e, Program* p, cudaStream_t st) {
   char* base = p->base;
   const int nf = e->cfg.nf;
-  cudaMemsetAsync(base + e->head.stats, 0, p->stats_bytes, st);
+  cudaMemsetAsync(base + e->head.tickets, 0, (size_t)p->B * 4, st);
   launch_temb_mlp((const float*)(base + e->head.gfp), (const float*)(e->dev_w + e->off.at("l1.w")),
                   (const float*)(e->dev_w + e->off.at("l1.b")), (const float*)(e->dev_w + e->off.at("l2.w")),
                   (const float*)(e->dev_w + e->off.at("l2.b")), (float*)(base + e->head.temb), p->B, nf, st);
@@ -951,8 +958,11 @@ int use_upfirdn2d_f32(const float* in, float* out, int major, int in_h, int in_w
 }
 
 // ---- single-kernel exports ----------------------------------------------------------------------
-int use_op_gn_stats(int dtype, const void* x, double* stats, int B, int HW, int C, void* stream) {
-  launch_gn_stats(dtype, x, stats, B, HW, C, (cudaStream_t)stream);
+size_t use_op_gn_stats_scratch_bytes(int B, int HW, int C) { return gn_stats_scratch_bytes(B, HW, C); }
+int use_op_gn_stats(int dtype, const void* x, double* stats, void* scratch, void* tickets, int B, int HW, int C,
+                    void* stream) {
+  if (!x || !stats || !scratch || !tickets) return fail("null argument");
+  launch_gn_stats(dtype, x, stats, (double*)scratch, (unsigned int*)tickets, B, HW, C, (cudaStream_t)stream);
   return cuda_check("use_op_gn_stats");
 }
 int use_op_gn_apply(int dtype, const void* x0, const double* stats0, int C0, const void* x1, const double* stats1, int C1,

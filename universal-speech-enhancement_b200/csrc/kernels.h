@@ -12,8 +12,11 @@ enum ActDtype { kF32 = 0, kBF16 = 1 };
 inline size_t act_size(int dt) { return dt == kBF16 ? 2 : 4; }
 
 // ---- GroupNorm ---------------------------------------------------------------------------------
-// stats: double [B][C][2] (sum, sum of squares per channel), must be zero on entry.
-void launch_gn_stats(int dt, const void* x, double* stats, int B, int HW, int C, cudaStream_t st);
+// stats: double [B][C][2] (sum, sum of squares per channel), overwritten.  Deterministic (no fp atomics):
+// `partials` is scratch of gn_stats_scratch_bytes(B, HW, C) bytes, `tickets` [B] uint32 zero on entry (left zero).
+size_t gn_stats_scratch_bytes(int B, int HW, int C);
+void launch_gn_stats(int dt, const void* x, double* stats, double* partials, unsigned int* tickets, int B, int HW, int C,
+                     cudaStream_t st);
 
 struct GnSrc {
   const void* x;        // act [B][Hin][Win][C]
