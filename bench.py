@@ -225,8 +225,16 @@ def main():
 
         buf = ctypes.create_string_buffer(4096)
         eng.L.use_engine_get_profile(eng.h, buf, 4096)
-        eng.L.use_engine_set_profiling(eng.h, 0)
         prof = json.loads(buf.value.decode())
+        big = ctypes.create_string_buffer(1 << 18)
+        eng.L.use_engine_get_profile_ops(eng.h, big, 1 << 18)
+        eng.L.use_engine_set_profiling(eng.h, 0)
+        try:
+            os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
+            with open(os.path.join(ROOT, "gpurun_out", f"profile_ops_{args.dtype}_b{B}.csv"), "w") as f:
+                f.write("tag,ms,flops,bytes\n" + big.value.decode())
+        except OSError:
+            pass
 
     if rank != 0:
         if world > 1:

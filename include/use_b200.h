@@ -77,6 +77,7 @@ int use_engine_workspace_bytes(use_engine* e, int B, int F, int T, size_t* bytes
 long long use_engine_launch_count(use_engine* e);
 int use_engine_set_profiling(use_engine* e, int on);
 int use_engine_get_profile(use_engine* e, char* json, size_t cap);
+int use_engine_get_profile_ops(use_engine* e, char* csv, size_t cap);
 
 /* ---- the hot path ------------------------------------------------------------------------------ */
 /* score = -net(cat[x, Y], t).  x, Y, score: device complex64 [B][F][T] (interleaved re, im).
@@ -120,11 +121,14 @@ int use_op_gn_apply(int dtype, const void* x0, const double* stats0, int C0, con
                     void* out_raw, int B, int Hin, int Win, void* stream);
 /* tcgen05 implicit-GEMM convolution; up to 3 segments summed into one accumulator.
  * seg_act[i]: act tensor [B][H][W][seg_ctensor[i]], channel window [seg_c0, seg_c0+seg_c);
- * seg_w[i]: packed weights [taps][N][seg_cw[i]] in act dtype, window starting at seg_wc0[i]. */
+ * seg_w[i]: packed weights [taps][N][seg_cw[i]] in act dtype, window starting at seg_wc0[i].
+ * stats (optional): double [B][N][2] GroupNorm statistics of `out`, produced by the epilogue (deterministic);
+ * needs stats_scratch of use_op_conv_tc_stats_scratch_bytes() device bytes. */
 int use_op_conv_tc(int dtype, int nseg, const void* const* seg_act, const int* seg_ctensor, const int* seg_c0,
                    const int* seg_c, const void* const* seg_w, const int* seg_cw, const int* seg_wc0, const int* seg_taps,
                    int B, int H, int W, int N, const float* bias, int bias_bstride, const void* res, float scale, void* out,
-                   void* stream);
+                   double* stats, void* stats_scratch, void* stream);
+size_t use_op_conv_tc_stats_scratch_bytes(int dtype, int B, int H, int W, int N);
 int use_op_conv_ref(int dtype, const void* x, const float* w, const float* bias, int bias_bstride, const void* res,
                     float scale, void* out, int B, int H, int W, int Cin, int Cout, int ksize, void* stream);
 int use_op_conv_in4(int dtype, const float* x, const float* w, const float* bias, void* out, int B, int H, int W, int N,

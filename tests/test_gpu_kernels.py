@@ -25,7 +25,7 @@ def _sync():
     torch.cuda.synchronize()
 
 
-def run_conv_tc(dt, segs, B, H, W, N, bias, res=None, scale=1.0):
+def run_conv_tc(dt, segs, B, H, W, N, bias, res=None, scale=1.0, want_stats=False):
     """segs: list of (x_nchw fp32 already operand-rounded, w_oihw fp32 already rounded, ks).  One weight tensor per
     segment here (wc0 = 0); the concat-window form is covered by test_conv_tc_weight_window."""
     L = _lib.lib()
@@ -40,11 +40,18 @@ def run_conv_tc(dt, segs, B, H, W, N, bias, res=None, scale=1.0):
     bias_d = bias.to("cuda", torch.float32).contiguous()
     bstride = N if bias.dim() == 2 else 0
     res_d = act_tensor(res, dt) if res is not None else None
+    stats = scratch = None
+    if want_stats:
+        stats = torch.empty(B, N, 2, dtype=torch.float64, device="cuda")
+        scratch = torch.empty(L.use_op_conv_tc_stats_scratch_bytes(dt, B, H, W, N), dtype=torch.uint8, device="cuda")
     rc = L.use_op_conv_tc(dt, len(segs), ptr_array(acts), int_array(ct), int_array(c0), int_array(cc), ptr_array(ws),
                           int_array(cw), int_array(wc0), int_array(taps), B, H, W, N, bias_d.data_ptr(), bstride,
-                          res_d.data_ptr() if res_d is not None else None, float(scale), out.data_ptr(), stream())
+                          res_d.data_ptr() if res_d is not None else None, float(scale), out.data_ptr(),
+                          stats.data_ptr() if want_stats else None, scratch.data_ptr() if want_stats else None, stream())
     assert rc == 0, L.use_last_error()
     _sync()
+    if want_stats:
+        return from_act(out), stats.cpu()
     return from_act(out)
 
 
@@ -98,6 +105,23 @@ def test_conv_tc(case, dt):
 
 
 @pytest.mark.parametrize("dt", [F32, BF16], ids=["tf32", "bf16"])
+@pytest.mark.parametrize("shape", [(2, 40, 20, 128, 128), (2, 24, 10, 256, 128), (1, 128, 160, 128, 128)])
+def test_conv_tc_fused_groupnorm_stats(dt, shape):
+    """The epilogue's per-channel sum / sum of squares of the STORED output (ragged tiles masked), bit-reproducible."""
+    B, H, W, N, Cin = shape
+    g = torch.Generator().manual_seed(17)
+    segs = [make_seg(g, dt, B, Cin, N, H, W, 3)]
+    bias = torch.randn(B, N, generator=g)
+    got, stats = run_conv_tc(dt, segs, B, H, W, N, bias, None, 1.0, want_stats=True)
+    got2, stats2 = run_conv_tc(dt, segs, B, H, W, N, bias, None, 1.0, want_stats=True)
+    assert torch.equal(stats, stats2) and torch.equal(got, got2)
+    ref_sum = got.double().sum(dim=(2, 3))
+    ref_sq = (got.double() ** 2).sum(dim=(2, 3))
+    assert torch.allclose(stats[..., 0], ref_sum, rtol=2e-5, atol=2e-3), describe_mismatch(stats[..., 0], ref_sum)
+    assert torch.allclose(stats[..., 1], ref_sq, rtol=2e-5, atol=2e-3), describe_mismatch(stats[..., 1], ref_sq)
+
+
+@pytest.mark.parametrize("dt", [F32, BF16], ids=["tf32", "bf16"])
 def test_conv_tc_weight_window(dt):
     """Two activation tensors against channel windows of ONE weight tensor (Conv_2 over cat[h, skip])."""
     L = _lib.lib()
@@ -113,7 +137,7 @@ def test_conv_tc_weight_window(dt):
     rc = L.use_op_conv_tc(dt, 2, ptr_array([a0.data_ptr(), a1.data_ptr()]), int_array([C0, C1]), int_array([0, 0]),
                           int_array([C0, C1]), ptr_array([pw.data_ptr(), pw.data_ptr()]), int_array([C0 + C1, C0 + C1]),
                           int_array([0, C0]), int_array([1, 1]), B, H, W, N, bd.data_ptr(), 0, None, 1.0, out.data_ptr(),
-                          stream())
+                          None, None, stream())
     assert rc == 0, L.use_last_error()
     _sync()
     ref = Fnn.conv2d(torch.cat([x0, x1], 1).double(), w.double()).float() + bias[None, :, None, None]

@@ -11,6 +11,7 @@ from __future__ import annotations
 import functools
 import importlib
 import os
+import re
 from typing import Any, Dict, List, Optional
 
 import yaml
@@ -43,6 +44,20 @@ def instantiate(node: Any, **overrides):
     if node.get("_partial_", False):
         return functools.partial(fn, **kwargs)
     return fn(**kwargs)
+
+
+_SCI = re.compile(r"^[+-]?(\d+\.?\d*|\.\d+)[eE][+-]?\d+$")
+
+
+def _fix_scalars(node):
+    """PyYAML reads `3e-2` / `5e-4` as strings (YAML 1.1 wants a dot); OmegaConf reads floats.  Follow OmegaConf."""
+    if isinstance(node, dict):
+        return {k: _fix_scalars(v) for k, v in node.items()}
+    if isinstance(node, list):
+        return [_fix_scalars(v) for v in node]
+    if isinstance(node, str) and _SCI.match(node):
+        return float(node)
+    return node
 
 
 def _set(cfg: dict, dotted: str, value):
@@ -84,4 +99,4 @@ def compose(config_dir: str, config_name: str = "predict.yaml", overrides: Optio
     cfg.update(root)
     for k, v in leaf:
         _set(cfg, k, v)
-    return cfg
+    return _fix_scalars(cfg)

@@ -1,5 +1,6 @@
 // Host side of the tcgen05 convolution: TMA tensor-map construction and launch.
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <mutex>
@@ -30,10 +31,22 @@ static EncodeTiledFn get_encode() {
 
 struct TcConvPlan {
   ConvParams params;
-  int dt, N, nsub;
+  int dt, N, nsub, mc;
   int grid, threads, smem;
   const void* kernel;
 };
+
+// CTA-pair weight multicast (cluster of 2) is OFF by default: measured on B200 it does not pay (bf16, batch 8:
+// 25.3 ms of convolutions per evaluation with it, 24.0 ms without) because the C_out = 128 layers are bound by the
+// shared-memory read bandwidth of single-CTA M128xN128 MMAs, not by L2 -> SM weight traffic.  USE_B200_CONV_MC=2
+// enables it for A/B measurements.
+static int multicast_width() {
+  static int mc = [] {
+    const char* v = getenv("USE_B200_CONV_MC");
+    return (v && v[0] == '2') ? 2 : 1;
+  }();
+  return mc;
+}
 
 static bool encode_act(CUtensorMap* m, int dt, const void* base, int B, int H, int W, int Ct, int rows, char* err,
                        int errlen) {
@@ -55,14 +68,15 @@ static bool encode_act(CUtensorMap* m, int dt, const void* base, int B, int H, i
   return true;
 }
 
-static bool encode_w(CUtensorMap* m, int dt, const void* base, int taps, int N, int Ctot, char* err, int errlen) {
+static bool encode_w(CUtensorMap* m, int dt, const void* base, int taps, int N, int Ctot, int box_rows, char* err,
+                     int errlen) {
   EncodeTiledFn enc = get_encode();
   if (!enc) { snprintf(err, errlen, "cuTensorMapEncodeTiled unavailable"); return false; }
   const cuuint64_t es = act_size(dt);
   const cuuint32_t ck = 128 / es;
   cuuint64_t dims[3] = {(cuuint64_t)Ctot, (cuuint64_t)N, (cuuint64_t)taps};
   cuuint64_t strides[2] = {Ctot * es, (cuuint64_t)N * Ctot * es};
-  cuuint32_t box[3] = {ck, (cuuint32_t)N, 1};
+  cuuint32_t box[3] = {ck, (cuuint32_t)box_rows, 1};
   cuuint32_t estr[3] = {1, 1, 1};
   CUresult r = enc(m, dt == kBF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3,
                    const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
@@ -77,32 +91,40 @@ static bool encode_w(CUtensorMap* m, int dt, const void* base, int taps, int N, 
 template <typename T, int N, int NSUB>
 static void fill_kernel(TcConvPlan* p) {
   using C = ConvCfg<T, N, NSUB>;
-  p->kernel = reinterpret_cast<const void*>(&conv_tc_kernel<T, N, NSUB>);
+  if (p->mc == 2) {
+    p->kernel = reinterpret_cast<const void*>(&conv_tc_kernel<T, N, NSUB, 2>);
+    cudaFuncSetAttribute(conv_tc_kernel<T, N, NSUB, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES);
+  } else {
+    p->kernel = reinterpret_cast<const void*>(&conv_tc_kernel<T, N, NSUB, 1>);
+    cudaFuncSetAttribute(conv_tc_kernel<T, N, NSUB, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES);
+  }
   p->threads = C::THREADS;
   p->smem = C::SMEM_BYTES;
   p->nsub = NSUB;
-  cudaFuncSetAttribute(conv_tc_kernel<T, N, NSUB>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES);
 }
 
-bool tc_conv_supported(int dt, int N) { return N == 64 || N == 128 || N == 256; }
+bool tc_conv_supported(int dt, int N) { return N == 32 || N == 64 || N == 128 || N == 256; }
 
 TcConvPlan* tc_conv_plan_create(int dt, const TcConvDesc& d, int num_sms, char* err, int errlen) {
-  if (!tc_conv_supported(dt, d.N)) {
-    snprintf(err, errlen, "tcgen05 conv: unsupported C_out=%d", d.N);
+  if (!tc_conv_supported(dt, d.N) || ((d.N == 32) != (d.out4 != nullptr))) {
+    snprintf(err, errlen, "tcgen05 conv: unsupported C_out=%d (out4 %s)", d.N, d.out4 ? "set" : "unset");
     return nullptr;
   }
   TcConvPlan* p = new TcConvPlan();
   memset(&p->params, 0, sizeof(p->params));
   p->dt = dt;
   p->N = d.N;
+  p->mc = (d.N >= 64) ? multicast_width() : 1;  // the 32-wide pyramid head has 4 KB weight tiles: not worth pairing
   if (dt == kBF16) {
     if (d.N == 256) fill_kernel<__nv_bfloat16, 256, 1>(p);
     else if (d.N == 128) fill_kernel<__nv_bfloat16, 128, 2>(p);
-    else fill_kernel<__nv_bfloat16, 64, 2>(p);
+    else if (d.N == 64) fill_kernel<__nv_bfloat16, 64, 2>(p);
+    else fill_kernel<__nv_bfloat16, 32, 2>(p);
   } else {
     if (d.N == 256) fill_kernel<float, 256, 1>(p);
     else if (d.N == 128) fill_kernel<float, 128, 2>(p);
-    else fill_kernel<float, 64, 2>(p);
+    else if (d.N == 64) fill_kernel<float, 64, 2>(p);
+    else fill_kernel<float, 32, 2>(p);
   }
   const int ck = 128 / (int)act_size(dt);
   const int tile_h = 16 * p->nsub;
@@ -118,7 +140,8 @@ TcConvPlan* tc_conv_plan_create(int dt, const TcConvDesc& d, int num_sms, char* 
     }
     const int rows = s.taps == 9 ? tile_h + 2 : tile_h;
     if (!encode_act(&P.seg[i].tmA, dt, s.act, d.B, d.H, d.W, s.C_tensor, rows, err, errlen) ||
-        !encode_w(&P.seg[i].tmW, dt, s.w, s.taps, d.N, s.Cw_total, err, errlen)) {
+        !encode_w(&P.seg[i].tmW, dt, s.w, s.taps, d.N, s.Cw_total, d.N, err, errlen) ||
+        !encode_w(&P.seg[i].tmWh, dt, s.w, s.taps, d.N, s.Cw_total, d.N / 2, err, errlen)) {
       delete p;
       return nullptr;
     }
@@ -132,15 +155,72 @@ TcConvPlan* tc_conv_plan_create(int dt, const TcConvDesc& d, int num_sms, char* 
   P.tiles_h = (d.H + tile_h - 1) / tile_h;
   P.ntiles = P.tiles_w * P.tiles_h * d.B;
   P.out = d.out; P.bias = d.bias; P.bias_bstride = d.bias_bstride; P.res = d.res; P.scale = d.scale;
-  p->grid = P.ntiles < num_sms ? P.ntiles : num_sms;
+  P.stats_partial = d.stats_partial;
+  P.out4 = d.out4; P.prev4 = d.prev4;
+  const int units = (P.ntiles + p->mc - 1) / p->mc;           // tile groups
+  const int max_groups = num_sms / p->mc;
+  p->grid = (units < max_groups ? units : max_groups) * p->mc;  // a multiple of the cluster width
   return p;
 }
 
 void tc_conv_plan_destroy(TcConvPlan* p) { delete p; }
 
+int tc_conv_tiles_per_image(int dt, int N, int H, int W) {
+  const int tile_h = (N == 256) ? 16 : 32;  // NSUB = 1 for N = 256, 2 otherwise (see tc_conv_plan_create)
+  return ((W + 7) / 8) * ((H + tile_h - 1) / tile_h);
+}
+
+// grid (kFinalizeSlices, B), block 256
+__global__ void __launch_bounds__(256) gn_finalize_kernel(const float* __restrict__ partial, double* __restrict__ stats,
+                                                           double* __restrict__ slices, unsigned int* __restrict__ tickets,
+                                                           int tiles, int N) {
+  __shared__ unsigned int s_ticket;
+  const int b = blockIdx.y, sl = blockIdx.x, ns = gridDim.x;
+  const int per = (tiles + ns - 1) / ns;
+  const int t0 = sl * per, t1 = min(tiles, t0 + per);
+  const float* pb = partial + static_cast<size_t>(b) * tiles * N * 2;
+  double* mine = slices + (static_cast<size_t>(b) * ns + sl) * N * 2;
+  for (int i = threadIdx.x; i < N * 2; i += blockDim.x) {
+    double acc = 0.0;
+    for (int t = t0; t < t1; ++t) acc += static_cast<double>(__ldcg(pb + static_cast<size_t>(t) * N * 2 + i));
+    mine[i] = acc;
+  }
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) s_ticket = atomicAdd(&tickets[b], 1u);
+  __syncthreads();
+  if (s_ticket == static_cast<unsigned>(ns - 1)) {
+    __threadfence();
+    const double* sb = slices + static_cast<size_t>(b) * ns * N * 2;
+    for (int i = threadIdx.x; i < N * 2; i += blockDim.x) {
+      double acc = 0.0;
+      for (int k = 0; k < ns; ++k) acc += __ldcg(sb + static_cast<size_t>(k) * N * 2 + i);
+      stats[static_cast<size_t>(b) * N * 2 + i] = acc;
+    }
+    if (threadIdx.x == 0) tickets[b] = 0;
+  }
+}
+
+void launch_gn_finalize(const float* partial, double* stats, double* slices, unsigned int* tickets, int B,
+                        int tiles_per_img, int N, cudaStream_t st) {
+  gn_finalize_kernel<<<dim3(kFinalizeSlices, B), 256, 0, st>>>(partial, stats, slices, tickets, tiles_per_img, N);
+}
+
 void tc_conv_launch(const TcConvPlan* p, cudaStream_t st) {
   void* args[1] = {const_cast<ConvParams*>(&p->params)};
-  cudaLaunchKernel(p->kernel, dim3(p->grid), dim3(p->threads), args, p->smem, st);
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(p->grid);
+  cfg.blockDim = dim3(p->threads);
+  cfg.dynamicSmemBytes = p->smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = p->mc;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  cudaLaunchKernelExC(&cfg, p->kernel, args);
 }
 
 }  // namespace use

@@ -24,6 +24,7 @@ namespace use {
 struct alignas(64) ConvSeg {
   CUtensorMap tmA;  // rank 4 {C, W, H, B}, box {CK, 8, rows, 1}; rows = 16*NSUB+2 (3x3) or 16*NSUB (1x1)
   CUtensorMap tmW;  // rank 3 {C_total, N, taps}, box {CK, N, 1}
+  CUtensorMap tmWh; // same tensor, box {CK, N/2, 1}: the half each CTA of a pair loads and multicasts
   int nchunks;      // channels of this segment / CK
   int taps;         // 9 or 1
   int wc0;          // first weight channel of this segment inside tmW (concatenated inputs)
@@ -40,6 +41,10 @@ struct alignas(64) ConvParams {
   int bias_bstride;   // N (per-sample bias incl. the time-embedding term) or 0
   const void* res;    // optional residual, T [B][H][W][N]
   float scale;        // out = (acc + bias [+ res]) * scale
+  float* stats_partial;  // optional [B][tiles_per_img][N][2]: per-tile column sums / sums of squares of `out`
+  // "pyramid head" mode (N = 32, only output channels 0..3 are real): fp32 [B][H][W][4] = acc + bias (+ FIR-up(prev4))
+  float* out4;
+  const float* prev4;    // optional fp32 [B][H/2][W/2][4]
 };
 
 template <typename T, int N, int NSUB>
@@ -51,19 +56,25 @@ struct ConvCfg {
   static constexpr int A_SLOT = A_ROWS * 1024;
   static constexpr int B_TILE = N * 128;
   static constexpr int A_SLOTS = 3;
-  static constexpr int B_SLOTS = (N == 256) ? 5 : (N == 128 ? 7 : 8);
+  static constexpr int B_SLOTS = (N == 256) ? 5 : (N == 128 ? 7 : 8);  // N <= 64: 8 slots
   static constexpr int ACC_COLS = NSUB * N;
   static constexpr int TMEM_COLS = (2 * ACC_COLS < 32) ? 32 : 2 * ACC_COLS;
   static constexpr int EPI_WARPS = 4 * NSUB;
   static constexpr int THREADS = 64 + 32 * EPI_WARPS;
   static constexpr int NBARS = 2 * A_SLOTS + 2 * B_SLOTS + 4;
-  static constexpr int SMEM_BYTES = 1024 + A_SLOTS * A_SLOT + B_SLOTS * B_TILE + NBARS * 8 + 16;
+  static constexpr int STAT_BYTES = EPI_WARPS * N * 2 * 4;  // per-warp column statistics of the current tile
+  static constexpr int SMEM_BYTES = 1024 + A_SLOTS * A_SLOT + B_SLOTS * B_TILE + STAT_BYTES + NBARS * 8 + 16;
   static_assert(TMEM_COLS <= 512 && (TMEM_COLS & (TMEM_COLS - 1)) == 0, "TMEM columns must be a power of two <= 512");
   static_assert(SMEM_BYTES <= 232448, "shared memory budget");
   static_assert(N % 32 == 0 && N <= 256, "N");
 };
 
-template <typename T, int N, int NSUB>
+// MC = 2: CTA pairs (cluster of 2).  Both CTAs of a pair walk their own tiles through the same weight-tile
+// sequence; each loads HALF of every weight tile and multicasts it into both CTAs' shared memory, which halves the
+// L2 -> SM weight traffic (the binding resource of the C_out = 128 layers: 295 KB of weights per 256-pixel tile).
+// A weight slot is recycled only when the MMAs of BOTH CTAs have released it (b_empty counts 2 arrivals, one of
+// them a multicast tcgen05.commit from the peer).
+template <typename T, int N, int NSUB, int MC>
 __global__ void __launch_bounds__(ConvCfg<T, N, NSUB>::THREADS, 1) conv_tc_kernel(const __grid_constant__ ConvParams p) {
   using C = ConvCfg<T, N, NSUB>;
   constexpr bool kBf16 = DT<T>::kIsBf16;
@@ -71,7 +82,8 @@ __global__ void __launch_bounds__(ConvCfg<T, N, NSUB>::THREADS, 1) conv_tc_kerne
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* sA = smem;
   uint8_t* sB = sA + C::A_SLOTS * C::A_SLOT;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sB + C::B_SLOTS * C::B_TILE);
+  float* stat_s = reinterpret_cast<float*>(sB + C::B_SLOTS * C::B_TILE);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sB + C::B_SLOTS * C::B_TILE + C::STAT_BYTES);
   uint64_t* a_full = bars;
   uint64_t* a_empty = a_full + C::A_SLOTS;
   uint64_t* b_full = a_empty + C::A_SLOTS;
@@ -87,9 +99,10 @@ __global__ void __launch_bounds__(ConvCfg<T, N, NSUB>::THREADS, 1) conv_tc_kerne
     for (int i = 0; i < p.nseg; ++i) {
       prefetch_tmap(&p.seg[i].tmA);
       prefetch_tmap(&p.seg[i].tmW);
+      prefetch_tmap(&p.seg[i].tmWh);
     }
     for (int i = 0; i < C::A_SLOTS; ++i) { mbar_init(&a_full[i], 1); mbar_init(&a_empty[i], 1); }
-    for (int i = 0; i < C::B_SLOTS; ++i) { mbar_init(&b_full[i], 1); mbar_init(&b_empty[i], 1); }
+    for (int i = 0; i < C::B_SLOTS; ++i) { mbar_init(&b_full[i], 1); mbar_init(&b_empty[i], MC); }
     for (int i = 0; i < 2; ++i) { mbar_init(&t_full[i], 1); mbar_init(&t_empty[i], C::EPI_WARPS); }
     fence_barrier_init();
   }
@@ -99,17 +112,23 @@ __global__ void __launch_bounds__(ConvCfg<T, N, NSUB>::THREADS, 1) conv_tc_kerne
   }
   tc_fence_before();
   __syncthreads();
+  if constexpr (MC > 1) cluster_sync_all();  // the peer's barriers are initialised before anything targets them
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
   const int tiles_per_img = p.tiles_w * p.tiles_h;
+  const uint32_t crank = MC > 1 ? cluster_ctarank() : 0u;
+  const int g0 = blockIdx.x / MC, gstep = gridDim.x / MC;  // tile groups of MC consecutive tiles
+  // Both CTAs of a pair run the same number of iterations; a CTA whose tile index falls past the end processes a
+  // "ghost" tile (loads are zero-filled out of bounds, nothing is stored) to keep the weight pipeline in lockstep.
 
   if (warp == 0) {
     // ================================ TMA producer ================================
     if (lane == 0) {
       uint32_t ai = 0, bi = 0;  // running slot counters
-      for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x) {
-        const int b = tile / tiles_per_img;
+      for (int g = g0; g * MC < p.ntiles; g += gstep) {
+        const int tile = g * MC + crank;
+        const int b = tile / tiles_per_img;  // == p.B for a ghost tile: every TMA box is out of bounds -> zeros
         const int rem = tile - b * tiles_per_img;
         const int th = rem / p.tiles_w;
         const int w0 = (rem - th * p.tiles_w) * C::TILE_W;
@@ -131,7 +150,11 @@ __global__ void __launch_bounds__(ConvCfg<T, N, NSUB>::THREADS, 1) conv_tc_kerne
                 const uint32_t bs = bi % C::B_SLOTS, bph = (bi / C::B_SLOTS) & 1;
                 mbar_wait(&b_empty[bs], bph ^ 1);
                 mbar_arrive_expect_tx(&b_full[bs], C::B_TILE);
-                tma_load_3d(sB + bs * C::B_TILE, &S.tmW, &b_full[bs], S.wc0 + kc * C::CK, 0, k3 ? (r * 3 + s) : 0);
+                if constexpr (MC > 1)
+                  tma_load_3d_mc(sB + bs * C::B_TILE + crank * (C::B_TILE / 2), &S.tmWh, &b_full[bs], S.wc0 + kc * C::CK,
+                                 crank * (N / 2), k3 ? (r * 3 + s) : 0, uint16_t(3));
+                else
+                  tma_load_3d(sB + bs * C::B_TILE, &S.tmW, &b_full[bs], S.wc0 + kc * C::CK, 0, k3 ? (r * 3 + s) : 0);
                 ++bi;
               }
             }
@@ -145,7 +168,7 @@ __global__ void __launch_bounds__(ConvCfg<T, N, NSUB>::THREADS, 1) conv_tc_kerne
       constexpr uint32_t idesc = umma_idesc(kBf16 ? 1 : 2, 128, N);
       const uint32_t sA_addr = smem_u32(sA), sB_addr = smem_u32(sB);
       uint32_t ai = 0, bi = 0, ti = 0;
-      for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x, ++ti) {
+      for (int g = g0; g * MC < p.ntiles; g += gstep, ++ti) {
         const uint32_t acs = ti & 1, acph = (ti >> 1) & 1;
         mbar_wait(&t_empty[acs], acph ^ 1);
         tc_fence_after();
@@ -171,7 +194,8 @@ __global__ void __launch_bounds__(ConvCfg<T, N, NSUB>::THREADS, 1) conv_tc_kerne
                   }
                 }
                 first = false;
-                umma_commit(&b_empty[bs]);
+                if constexpr (MC > 1) umma_commit_mc(&b_empty[bs], uint16_t(3));
+                else umma_commit(&b_empty[bs]);
                 ++bi;
               }
               umma_commit(&a_empty[as]);
@@ -192,57 +216,143 @@ __global__ void __launch_bounds__(ConvCfg<T, N, NSUB>::THREADS, 1) conv_tc_kerne
     T* out = reinterpret_cast<T*>(p.out);
     const T* res = reinterpret_cast<const T*>(p.res);
     uint32_t ti = 0;
-    for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x, ++ti) {
-      const int b = tile / tiles_per_img;
-      const int rem = tile - b * tiles_per_img;
+    for (int g = g0; g * MC < p.ntiles; g += gstep, ++ti) {
+      const int tile = g * MC + crank;
+      const bool ghost = tile >= p.ntiles;
+      const int b = ghost ? 0 : tile / tiles_per_img;
+      const int rem = tile - (tile / tiles_per_img) * tiles_per_img;
       const int th = rem / p.tiles_w;
       const int w = (rem - th * p.tiles_w) * C::TILE_W + wl;
       const int h = th * C::TILE_H + hl;
-      const bool valid = (h < p.H) && (w < p.W);
+      const bool valid = !ghost && (h < p.H) && (w < p.W);
       const size_t pix = (static_cast<size_t>(b) * p.H + h) * p.W + w;
       const float* bias = p.bias + static_cast<size_t>(b) * p.bias_bstride;
       const uint32_t acs = ti & 1, acph = (ti >> 1) & 1;
       mbar_wait(&t_full[acs], acph);
       tc_fence_after();
       const uint32_t trow = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + acs * C::ACC_COLS + sub * N;
+      if (p.out4 != nullptr) {
+        // pyramid head: 4 real output channels, fp32, + FIR-upsampled previous pyramid (ncsnpp.py:440-461)
+        uint32_t r[32];
+        tmem_ld32(trow, r);
+        tmem_ld_wait();
+        if (valid) {
+          float4 o = make_float4(__uint_as_float(r[0]) + bias[0], __uint_as_float(r[1]) + bias[1],
+                                 __uint_as_float(r[2]) + bias[2], __uint_as_float(r[3]) + bias[3]);
+          if (p.prev4 != nullptr) {
+            const int Hp = p.H >> 1, Wp = p.W >> 1;
+            const int my = h >> 1, mx = w >> 1;
+            const int ya = (h & 1) ? my : my - 1, xa = (w & 1) ? mx : mx - 1;
+            const float wya = (h & 1) ? 0.75f : 0.25f, wxa = (w & 1) ? 0.75f : 0.25f;
+#pragma unroll
+            for (int dy = 0; dy < 2; ++dy) {
+              const int yy = ya + dy;
+              if (yy < 0 || yy >= Hp) continue;
+#pragma unroll
+              for (int dx = 0; dx < 2; ++dx) {
+                const int xx = xa + dx;
+                if (xx < 0 || xx >= Wp) continue;
+                const float kw = (dy ? 1.f - wya : wya) * (dx ? 1.f - wxa : wxa);
+                const float4 pv = __ldg(reinterpret_cast<const float4*>(p.prev4) + (static_cast<size_t>(b) * Hp + yy) * Wp + xx);
+                o.x += kw * pv.x; o.y += kw * pv.y; o.z += kw * pv.z; o.w += kw * pv.w;
+              }
+            }
+          }
+          reinterpret_cast<float4*>(p.out4)[pix] = o;
+        }
+      } else
 #pragma unroll 1
       for (int c0 = 0; c0 < N; c0 += 32) {
         uint32_t r[32];
         tmem_ld32(trow + c0, r);
         tmem_ld_wait();
+        constexpr int V = DT<T>::kVec;
+        float f[32];
+#pragma unroll
+        for (int j = 0; j < 32; j += 4) {
+          const float4 bb = __ldg(reinterpret_cast<const float4*>(bias + c0 + j));
+          f[j] = __uint_as_float(r[j]) + bb.x;
+          f[j + 1] = __uint_as_float(r[j + 1]) + bb.y;
+          f[j + 2] = __uint_as_float(r[j + 2]) + bb.z;
+          f[j + 3] = __uint_as_float(r[j + 3]) + bb.w;
+        }
+        if (res != nullptr && valid) {
+#pragma unroll
+          for (int j = 0; j < 32; j += V) {
+            float rr[V];
+            Vec<T>::load(res + pix * N + c0 + j, rr);
+#pragma unroll
+            for (int q = 0; q < V; ++q) f[j + q] += rr[q];
+          }
+        }
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          f[j] *= p.scale;
+          if constexpr (kBf16) f[j] = __bfloat162float(__float2bfloat16_rn(f[j]));  // the value that is stored
+        }
         if (valid) {
-          constexpr int V = DT<T>::kVec;
 #pragma unroll
           for (int j = 0; j < 32; j += V) {
             float v[V];
 #pragma unroll
-            for (int q = 0; q < V; q += 4) {
-              const float4 bb = __ldg(reinterpret_cast<const float4*>(bias + c0 + j + q));
-              v[q] = __uint_as_float(r[j + q]) + bb.x;
-              v[q + 1] = __uint_as_float(r[j + q + 1]) + bb.y;
-              v[q + 2] = __uint_as_float(r[j + q + 2]) + bb.z;
-              v[q + 3] = __uint_as_float(r[j + q + 3]) + bb.w;
-            }
-            if (res != nullptr) {
-              float rr[V];
-              Vec<T>::load(res + pix * N + c0 + j, rr);
-#pragma unroll
-              for (int q = 0; q < V; ++q) v[q] += rr[q];
-            }
-#pragma unroll
-            for (int q = 0; q < V; ++q) v[q] *= p.scale;
+            for (int q = 0; q < V; ++q) v[q] = f[j + q];
             Vec<T>::store(out + pix * N + c0 + j, v);
           }
+        }
+        if (p.stats_partial != nullptr) {
+          // column sums over this warp's 32 rows by recursive halving (31 shuffles): lane j ends with column c0 + j
+          float a[32];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) a[j] = valid ? f[j] : 0.f;
+#pragma unroll
+          for (int off = 16; off >= 1; off >>= 1) {
+            const bool hi = (lane & off) != 0;
+#pragma unroll
+            for (int j = 0; j < off; ++j) {
+              const float send = hi ? a[j] : a[j + off];
+              const float keep = hi ? a[j + off] : a[j];
+              a[j] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+            }
+          }
+          const float colsum = a[0];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) a[j] = valid ? f[j] * f[j] : 0.f;
+#pragma unroll
+          for (int off = 16; off >= 1; off >>= 1) {
+            const bool hi = (lane & off) != 0;
+#pragma unroll
+            for (int j = 0; j < off; ++j) {
+              const float send = hi ? a[j] : a[j + off];
+              const float keep = hi ? a[j + off] : a[j];
+              a[j] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+            }
+          }
+          stat_s[(ew * N + c0 + lane) * 2] = colsum;
+          stat_s[(ew * N + c0 + lane) * 2 + 1] = a[0];
         }
       }
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&t_empty[acs]);
+      if (p.stats_partial != nullptr) {
+        // combine the epilogue warps of this tile in a fixed order (deterministic) and publish the tile partial
+        constexpr int ET = 32 * C::EPI_WARPS;
+        asm volatile("bar.sync 1, %0;" ::"r"(ET) : "memory");
+        float* dst = p.stats_partial + static_cast<size_t>(tile) * N * 2;  // tile = b * tiles_per_img + rem
+        for (int i = threadIdx.x - 64; i < N * 2 && !ghost; i += ET) {
+          float acc = 0.f;
+#pragma unroll
+          for (int w = 0; w < C::EPI_WARPS; ++w) acc += stat_s[w * N * 2 + i];
+          dst[i] = acc;
+        }
+        asm volatile("bar.sync 1, %0;" ::"r"(ET) : "memory");
+      }
     }
   }
 
   tc_fence_before();
   __syncthreads();
+  if constexpr (MC > 1) cluster_sync_all();  // no CTA leaves while its peer may still multicast into it
   if (warp == 1) tmem_dealloc(tmem_base, C::TMEM_COLS);
 }
 

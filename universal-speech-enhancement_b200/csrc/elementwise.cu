@@ -118,31 +118,49 @@ struct GnSrcT {
   int C;
 };
 
+__device__ __forceinline__ float silu_fast(float x) { return __fdividef(x, 1.0f + __expf(-x)); }
+// x * sigmoid(x) = x * (0.5 + 0.5 tanh(x/2)): ONE MUFU op.  tanh.approx has ~2^-11 relative error, invisible after the
+// bf16 rounding of the result (2^-9) but not acceptable for the fp32 path, which keeps the exp + rcp form.
+__device__ __forceinline__ float silu_tanh(float x) {
+  float t;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(0.5f * x));
+  return x * fmaf(0.5f, t, 0.5f);
+}
+template <typename T> __device__ __forceinline__ float silu_act(float x) {
+  if constexpr (DT<T>::kIsBf16) return silu_tanh(x);
+  else return silu_fast(x);
+}
+
+// One thread owns a fixed 16-byte channel vector (scale / shift live in registers) and walks over pixels;
+// consecutive threads cover consecutive vectors of the same pixel, so every warp access is a contiguous run.
+constexpr int kGnMaxWorkPerBlock = 256;  // work items (pixels / 2x2 blocks) per block; shrunk for small tensors
+
 template <typename T, int FIR>
 __global__ void __launch_bounds__(256) gn_apply_kernel(GnSrcT<T> s0, GnSrcT<T> s1, const float* __restrict__ gamma,
                                                         const float* __restrict__ beta, float eps, int do_silu, int as_operand,
                                                         T* __restrict__ out_act, T* __restrict__ out_raw, int Hin, int Win,
-                                                        int vec_per_block) {
+                                                        int work_per_block) {
   constexpr int V = Vec<T>::N;
   extern __shared__ float saff[];  // scale[Ct], shift[Ct]
   const int Ct = s0.C + s1.C;
   const int G = min(Ct / 4, 32);
   const int cpg = Ct / G;
   const int b = blockIdx.y;
-  const double cnt = static_cast<double>(Hin) * Win * cpg;
+  const double inv_cnt = 1.0 / (static_cast<double>(Hin) * Win * cpg);
   for (int c = threadIdx.x; c < Ct; c += blockDim.x) {
     const int g = c / cpg;
     double sum = 0.0, sq = 0.0;
     for (int cc = g * cpg; cc < (g + 1) * cpg; ++cc) {  // channel index in the concatenation
-      const double* st = (cc < s0.C) ? s0.stats + (static_cast<size_t>(b) * s0.C + cc) * 2
-                                     : s1.stats + (static_cast<size_t>(b) * s1.C + (cc - s0.C)) * 2;
-      sum += st[0];
-      sq += st[1];
+      const double2 st = __ldg(reinterpret_cast<const double2*>(
+          (cc < s0.C) ? s0.stats + (static_cast<size_t>(b) * s0.C + cc) * 2
+                      : s1.stats + (static_cast<size_t>(b) * s1.C + (cc - s0.C)) * 2));
+      sum += st.x;
+      sq += st.y;
     }
-    const double mean = sum / cnt;
-    double var = sq / cnt - mean * mean;
+    const double mean = sum * inv_cnt;
+    double var = sq * inv_cnt - mean * mean;  // biased variance, like nn.GroupNorm
     if (var < 0.0) var = 0.0;
-    const float rstd = static_cast<float>(1.0 / sqrt(var + static_cast<double>(eps)));
+    const float rstd = rsqrtf(static_cast<float>(var) + eps);
     const float sc = gamma[c] * rstd;
     saff[c] = sc;
     saff[Ct + c] = beta[c] - static_cast<float>(mean) * sc;
@@ -152,93 +170,158 @@ __global__ void __launch_bounds__(256) gn_apply_kernel(GnSrcT<T> s0, GnSrcT<T> s
   const int Hout = FIR == 1 ? Hin / 2 : (FIR == 2 ? Hin * 2 : Hin);
   const int Wout = FIR == 1 ? Win / 2 : (FIR == 2 ? Win * 2 : Win);
   const int vpp = Ct / V;
-  const long long total = static_cast<long long>(Hout) * Wout * vpp;
-  const long long i0 = static_cast<long long>(blockIdx.x) * vec_per_block;
-  const long long i1 = min(total, i0 + vec_per_block);
-  for (long long i = i0 + threadIdx.x; i < i1; i += blockDim.x) {
-    const int cv = static_cast<int>(i % vpp);
-    const long long pix = i / vpp;
-    const int c = cv * V;
-    const bool first = c < s0.C;
-    const T* src = first ? s0.x : s1.x;
-    const int Cs = first ? s0.C : s1.C;
-    const int cs = first ? c : c - s0.C;
-    float sc[V], sh[V];
+  const int rows = blockDim.x / vpp;  // blockDim.x is a multiple of vpp (host guarantees it)
+  const int cv = threadIdx.x % vpp, prow = threadIdx.x / vpp;
+  const int c = cv * V;
+  const bool first = c < s0.C;
+  const int Cs = first ? s0.C : s1.C;
+  const T* sb = (first ? s0.x + c : s1.x + (c - s0.C)) + static_cast<size_t>(b) * Hin * Win * Cs;
+  float sc[V], sh[V];
 #pragma unroll
-    for (int j = 0; j < V; ++j) { sc[j] = saff[c + j]; sh[j] = saff[Ct + c + j]; }
-    const T* sb = src + static_cast<size_t>(b) * Hin * Win * Cs + cs;
-    float acc[V], raw[V];
-    if constexpr (FIR == 0) {
-      float f[V];
-      Vec<T>::load(sb + static_cast<size_t>(pix) * Cs, f);
+  for (int j = 0; j < V; ++j) { sc[j] = saff[c + j]; sh[j] = saff[Ct + c + j]; }
+  const int npix = Hout * Wout;
+  // work items: output pixels (FIR 0), input pixels (FIR 2: one 2x2 output block each), 2x2 output blocks (FIR 1)
+  const int nwork = FIR == 0 ? npix : (FIR == 2 ? Hin * Win : ((Hout + 1) / 2) * ((Wout + 1) / 2));
+  const int p0 = blockIdx.x * work_per_block;
+  const int p1 = min(nwork, p0 + work_per_block);
+  T* oa = out_act + static_cast<size_t>(b) * npix * Ct + c;
+  T* orw = (FIR != 0 && out_raw != nullptr) ? out_raw + static_cast<size_t>(b) * npix * Ct + c : nullptr;
+
+  if constexpr (FIR == 0) {
+    constexpr int U = 4;  // independent 16-byte loads in flight per thread
+    for (int p = p0 + prow; p < p1; p += rows * U) {
+      float f[U][V];
 #pragma unroll
-      for (int j = 0; j < V; ++j) {
-        const float n = f[j] * sc[j] + sh[j];
-        acc[j] = do_silu ? silu(n) : n;
+      for (int u = 0; u < U; ++u) {
+        const int pp = p + u * rows;
+        if (pp < p1) Vec<T>::load(sb + static_cast<size_t>(pp) * Cs, f[u]);
       }
-    } else {
-      const int ox = static_cast<int>(pix % Wout), oy = static_cast<int>(pix / Wout);
 #pragma unroll
-      for (int j = 0; j < V; ++j) acc[j] = raw[j] = 0.f;
-      if constexpr (FIR == 1) {
-        // out[oy][ox] = sum_{a,b<4} k[a]k[b] in[2oy+a-1][2ox+b-1],  k = [1,3,3,1]/8, zero outside
-        const float k1[4] = {0.125f, 0.375f, 0.375f, 0.125f};
+      for (int u = 0; u < U; ++u) {
+        const int pp = p + u * rows;
+        if (pp < p1) {
 #pragma unroll
-        for (int a = 0; a < 4; ++a) {
-          const int iy = 2 * oy + a - 1;
-          if (iy < 0 || iy >= Hin) continue;
-#pragma unroll
-          for (int bb = 0; bb < 4; ++bb) {
-            const int ix = 2 * ox + bb - 1;
-            if (ix < 0 || ix >= Win) continue;
-            float f[V];
-            Vec<T>::load(sb + (static_cast<size_t>(iy) * Win + ix) * Cs, f);
-            const float kw = k1[a] * k1[bb];
-#pragma unroll
-            for (int j = 0; j < V; ++j) {
-              const float n = f[j] * sc[j] + sh[j];
-              acc[j] += kw * (do_silu ? silu(n) : n);
-              raw[j] += kw * f[j];
-            }
+          for (int j = 0; j < V; ++j) {
+            const float n = fmaf(f[u][j], sc[j], sh[j]);
+            f[u][j] = do_silu ? silu_act<T>(n) : n;
           }
-        }
-      } else {
-        // per axis: out[2m] = (in[m-1] + 3 in[m]) / 4 ; out[2m+1] = (3 in[m] + in[m+1]) / 4, zero outside
-        const int my = oy >> 1, mx = ox >> 1;
-        const int ya = (oy & 1) ? my : my - 1, yb = ya + 1;
-        const int xa = (ox & 1) ? mx : mx - 1, xb = xa + 1;
-        const float wya = (oy & 1) ? 0.75f : 0.25f, wyb = 1.0f - wya;
-        const float wxa = (ox & 1) ? 0.75f : 0.25f, wxb = 1.0f - wxa;
-        const int ys[2] = {ya, yb};
-        const int xs[2] = {xa, xb};
-        const float wy[2] = {wya, wyb};
-        const float wx[2] = {wxa, wxb};
-#pragma unroll
-        for (int a = 0; a < 2; ++a) {
-          if (ys[a] < 0 || ys[a] >= Hin) continue;
-#pragma unroll
-          for (int bb = 0; bb < 2; ++bb) {
-            if (xs[bb] < 0 || xs[bb] >= Win) continue;
-            float f[V];
-            Vec<T>::load(sb + (static_cast<size_t>(ys[a]) * Win + xs[bb]) * Cs, f);
-            const float kw = wy[a] * wx[bb];
-#pragma unroll
-            for (int j = 0; j < V; ++j) {
-              const float n = f[j] * sc[j] + sh[j];
-              acc[j] += kw * (do_silu ? silu(n) : n);
-              raw[j] += kw * f[j];
-            }
-          }
+          if (as_operand) Vec<T>::store_operand(oa + static_cast<size_t>(pp) * Ct, f[u]);
+          else Vec<T>::store(oa + static_cast<size_t>(pp) * Ct, f[u]);
         }
       }
     }
-    const size_t o = (static_cast<size_t>(b) * Hout * Wout + pix) * Ct + c;
-    if (as_operand) Vec<T>::store_operand(out_act + o, acc);
-    else Vec<T>::store(out_act + o, acc);
-    if constexpr (FIR != 0) {
-      if (out_raw != nullptr) {
-        if (as_operand) Vec<T>::store_operand(out_raw + o, raw);
-        else Vec<T>::store(out_raw + o, raw);
+  } else if constexpr (FIR == 2) {
+    // x2 upsample: each thread produces the 2x2 output block of input pixel (m, n) from its 3x3 neighbourhood
+    // (9 normalise+SiLU evaluations per 4 outputs instead of 16).  Per axis:
+    //   out[2m] = (in[m-1] + 3 in[m]) / 4 ; out[2m+1] = (3 in[m] + in[m+1]) / 4, zero outside.
+    for (int p = p0 + prow; p < p1; p += rows) {   // p indexes INPUT pixels here (grid sized by the host accordingly)
+      const int m = p / Win, n = p - m * Win;
+      float ea[2][V], oa2[2][V], er[2][V], orr[2][V];  // [0]: output column 2n, [1]: output column 2n+1; e = row 2m, o = row 2m+1
+#pragma unroll
+      for (int j = 0; j < V; ++j) ea[0][j] = ea[1][j] = oa2[0][j] = oa2[1][j] = er[0][j] = er[1][j] = orr[0][j] = orr[1][j] = 0.f;
+#pragma unroll
+      for (int dc = -1; dc <= 1; ++dc) {
+        const int xx = n + dc;
+        if (xx < 0 || xx >= Win) continue;
+        float ve[V], vo[V], re[V], ro[V];  // vertical combinations for this input column
+#pragma unroll
+        for (int j = 0; j < V; ++j) ve[j] = vo[j] = re[j] = ro[j] = 0.f;
+#pragma unroll
+        for (int dr = -1; dr <= 1; ++dr) {
+          const int yy = m + dr;
+          if (yy < 0 || yy >= Hin) continue;
+          float f[V];
+          Vec<T>::load(sb + (static_cast<size_t>(yy) * Win + xx) * Cs, f);
+          const float we = dr == -1 ? 0.25f : (dr == 0 ? 0.75f : 0.f);
+          const float wo = dr == -1 ? 0.f : (dr == 0 ? 0.75f : 0.25f);
+#pragma unroll
+          for (int j = 0; j < V; ++j) {
+            const float nn = fmaf(f[j], sc[j], sh[j]);
+            const float a = do_silu ? silu_act<T>(nn) : nn;
+            ve[j] += we * a; vo[j] += wo * a;
+            re[j] += we * f[j]; ro[j] += wo * f[j];
+          }
+        }
+        const float w0 = dc == -1 ? 0.25f : (dc == 0 ? 0.75f : 0.f);   // weight into output column 2n
+        const float w1 = dc == -1 ? 0.f : (dc == 0 ? 0.75f : 0.25f);   // weight into output column 2n+1
+#pragma unroll
+        for (int j = 0; j < V; ++j) {
+          ea[0][j] += w0 * ve[j]; ea[1][j] += w1 * ve[j];
+          oa2[0][j] += w0 * vo[j]; oa2[1][j] += w1 * vo[j];
+          er[0][j] += w0 * re[j]; er[1][j] += w1 * re[j];
+          orr[0][j] += w0 * ro[j]; orr[1][j] += w1 * ro[j];
+        }
+      }
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const size_t o = (static_cast<size_t>(2 * m + (q >> 1)) * Wout + 2 * n + (q & 1)) * Ct;
+        const float(&va)[V] = (q >> 1) ? oa2[q & 1] : ea[q & 1];
+        const float(&vr)[V] = (q >> 1) ? orr[q & 1] : er[q & 1];
+        if (as_operand) Vec<T>::store_operand(oa + o, va);
+        else Vec<T>::store(oa + o, va);
+        if (orw != nullptr) {
+          if (as_operand) Vec<T>::store_operand(orw + o, vr);
+          else Vec<T>::store(orw + o, vr);
+        }
+      }
+    }
+  } else {
+    // x2 downsample: out[i][j] = sum_{a,b<4} k[a]k[b] in[2i+a-1][2j+b-1], k = [1,3,3,1]/8, zero outside.
+    // Each thread produces a 2x2 output block from a 6x6 input window, separably (36 normalise+SiLU evaluations
+    // per 4 outputs instead of 64).  p indexes 2x2 output blocks.
+    const int bw2 = (Wout + 1) / 2;
+    const float k1[4] = {0.125f, 0.375f, 0.375f, 0.125f};
+    for (int p = p0 + prow; p < p1; p += rows) {
+      const int I = p / bw2, J = p - I * bw2;
+      float acc[4][V], raw[4][V];
+#pragma unroll
+      for (int q = 0; q < 4; ++q)
+#pragma unroll
+        for (int j = 0; j < V; ++j) acc[q][j] = raw[q][j] = 0.f;
+#pragma unroll
+      for (int cc = 0; cc < 6; ++cc) {
+        const int ix = 4 * J - 1 + cc;
+        if (ix < 0 || ix >= Win) continue;
+        float va[2][V], vr[2][V];  // vertical FIR for output rows 2I and 2I+1 at this input column
+#pragma unroll
+        for (int j = 0; j < V; ++j) va[0][j] = va[1][j] = vr[0][j] = vr[1][j] = 0.f;
+#pragma unroll
+        for (int rr = 0; rr < 6; ++rr) {
+          const int iy = 4 * I - 1 + rr;
+          if (iy < 0 || iy >= Hin) continue;
+          float f[V];
+          Vec<T>::load(sb + (static_cast<size_t>(iy) * Win + ix) * Cs, f);
+          const float w0 = rr < 4 ? k1[rr] : 0.f;       // tap of output row 2I
+          const float w1 = rr >= 2 ? k1[rr - 2] : 0.f;  // tap of output row 2I+1
+#pragma unroll
+          for (int j = 0; j < V; ++j) {
+            const float nn = fmaf(f[j], sc[j], sh[j]);
+            const float a = do_silu ? silu_act<T>(nn) : nn;
+            va[0][j] += w0 * a; va[1][j] += w1 * a;
+            vr[0][j] += w0 * f[j]; vr[1][j] += w1 * f[j];
+          }
+        }
+        const float h0 = cc < 4 ? k1[cc] : 0.f;
+        const float h1 = cc >= 2 ? k1[cc - 2] : 0.f;
+#pragma unroll
+        for (int j = 0; j < V; ++j) {
+          acc[0][j] += h0 * va[0][j]; acc[1][j] += h1 * va[0][j];
+          acc[2][j] += h0 * va[1][j]; acc[3][j] += h1 * va[1][j];
+          raw[0][j] += h0 * vr[0][j]; raw[1][j] += h1 * vr[0][j];
+          raw[2][j] += h0 * vr[1][j]; raw[3][j] += h1 * vr[1][j];
+        }
+      }
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const int oy = 2 * I + (q >> 1), ox = 2 * J + (q & 1);
+        if (oy >= Hout || ox >= Wout) continue;
+        const size_t o = (static_cast<size_t>(oy) * Wout + ox) * Ct;
+        if (as_operand) Vec<T>::store_operand(oa + o, acc[q]);
+        else Vec<T>::store(oa + o, acc[q]);
+        if (orw != nullptr) {
+          if (as_operand) Vec<T>::store_operand(orw + o, raw[q]);
+          else Vec<T>::store(orw + o, raw[q]);
+        }
       }
     }
   }
@@ -251,18 +334,24 @@ void launch_gn_apply(int dt, GnSrc s0, GnSrc s1, const float* gamma, const float
   const int Wout = fir == 1 ? Win / 2 : (fir == 2 ? Win * 2 : Win);
   DISPATCH_DT(dt, {
     constexpr int V = Vec<T>::N;
-    const long long total = static_cast<long long>(Hout) * Wout * (Ct / V);
-    const int vpb = 256 * 16;
-    dim3 grid(static_cast<unsigned>((total + vpb - 1) / vpb), B);
+    const int vpp = Ct / V;
+    const int threads = vpp >= 256 ? vpp : (256 / vpp) * vpp;  // a multiple of vpp (<= 1024 for Ct <= 4096)
+    const int nwork = fir == 0 ? Hout * Wout : (fir == 2 ? Hin * Win : ((Hout + 1) / 2) * ((Wout + 1) / 2));
+    // enough blocks for >= ~8 waves of 148 SMs when the tensor allows it, at most kGnMaxWorkPerBlock items per block
+    const int rows = threads / vpp;
+    long long wpb = (static_cast<long long>(nwork) * B + 148 * 8 - 1) / (148 * 8);
+    wpb = std::max<long long>(rows, std::min<long long>(kGnMaxWorkPerBlock, (wpb + rows - 1) / rows * rows));
+    const int work_per_block = static_cast<int>(wpb);
+    dim3 grid((nwork + work_per_block - 1) / work_per_block, B);
     GnSrcT<T> a{(const T*)s0.x, s0.stats, s0.C};
     GnSrcT<T> c{(const T*)s1.x, s1.stats, s1.C};
     const size_t sm = 2 * Ct * sizeof(float);
     if (fir == 0)
-      gn_apply_kernel<T, 0><<<grid, 256, sm, st>>>(a, c, gamma, beta, eps, do_silu, as_operand, (T*)out_act, (T*)out_raw, Hin, Win, vpb);
+      gn_apply_kernel<T, 0><<<grid, threads, sm, st>>>(a, c, gamma, beta, eps, do_silu, as_operand, (T*)out_act, (T*)out_raw, Hin, Win, work_per_block);
     else if (fir == 1)
-      gn_apply_kernel<T, 1><<<grid, 256, sm, st>>>(a, c, gamma, beta, eps, do_silu, as_operand, (T*)out_act, (T*)out_raw, Hin, Win, vpb);
+      gn_apply_kernel<T, 1><<<grid, threads, sm, st>>>(a, c, gamma, beta, eps, do_silu, as_operand, (T*)out_act, (T*)out_raw, Hin, Win, work_per_block);
     else
-      gn_apply_kernel<T, 2><<<grid, 256, sm, st>>>(a, c, gamma, beta, eps, do_silu, as_operand, (T*)out_act, (T*)out_raw, Hin, Win, vpb);
+      gn_apply_kernel<T, 2><<<grid, threads, sm, st>>>(a, c, gamma, beta, eps, do_silu, as_operand, (T*)out_act, (T*)out_raw, Hin, Win, work_per_block);
   });
 }
 

@@ -191,12 +191,14 @@ struct use_engine {
   int num_sms = 148;
   std::map<std::string, std::unique_ptr<Program>> programs;  // keyed by "B,F,T,base"
   // fixed head of the workspace (byte offsets)
-  struct Head { size_t xr, t, gfp, temb, dense, stats, gn_scratch, tickets, arena; } head;
+  struct Head { size_t xr, xpad, t, gfp, temb, dense, stats, gn_scratch, tickets, conv_part, fin_slices, arena; } head;
   // instrumentation
   long long launches = 0;
   bool profiling = false;
   double prof_ms[8] = {0}, prof_flops[8] = {0}, prof_bytes[8] = {0}, prof_top_flops = 0, prof_top_ms = 0;
   long long prof_launches[8] = {0};
+  struct ProfOp { int tag; float ms; double flops, bytes; };
+  std::vector<ProfOp> prof_ops;
 };
 
 namespace use {
@@ -314,6 +316,30 @@ static int pack_all(use_engine* e) {
       case K_GFP: case K_LINEAR: break;
       case K_CONV3: {
         if (putf(p + ".w", p + ".weight", {m.cout, m.cin, 3, 3}) || putf(p + ".b", p + ".bias", {m.cout})) return 1;
+        if (m.cin == c.input_channels && tc_conv_supported(dt, m.cout) && m.cout != 32) {
+          // input conv 4 -> nf: tcgen05 layout with the input channels zero-padded to one 128-byte chunk
+          const int ck = 128 / (int)es;
+          const HostTensor* t = getw(e, p + ".weight", {m.cout, m.cin, 3, 3});
+          std::vector<float> wp((size_t)m.cout * ck * 9, 0.f);
+          for (int o = 0; o < m.cout; ++o)
+            for (int ci = 0; ci < m.cin; ++ci)
+              for (int tap = 0; tap < 9; ++tap) wp[((size_t)o * ck + ci) * 9 + tap] = t->data[((size_t)o * m.cin + ci) * 9 + tap];
+          size_t off = bw.reserve((size_t)9 * m.cout * ck * es);
+          pack_conv_weight(dt, wp.data(), m.cout, ck, 3, e->blob.data() + off);
+          e->off[p + ".wtc"] = off;
+        }
+        if (m.cout == c.input_channels && m.cin % (128 / (int)es) == 0) {
+          // pyramid head C -> 4: tcgen05 layout with the output channels zero-padded to 32
+          const HostTensor* t = getw(e, p + ".weight", {m.cout, m.cin, 3, 3});
+          const HostTensor* tb = getw(e, p + ".bias", {m.cout});
+          std::vector<float> wp((size_t)32 * m.cin * 9, 0.f), bp(32, 0.f);
+          memcpy(wp.data(), t->data.data(), t->data.size() * 4);
+          memcpy(bp.data(), tb->data.data(), tb->data.size() * 4);
+          size_t off = bw.reserve((size_t)9 * 32 * m.cin * es);
+          pack_conv_weight(dt, wp.data(), 32, m.cin, 3, e->blob.data() + off);
+          e->off[p + ".wtc"] = off;
+          e->off[p + ".btc"] = bw.put(bp.data(), 32 * 4);
+        }
         break;
       }
       case K_GN: {
@@ -378,6 +404,8 @@ struct Builder {
   Arena arena;
   size_t stats_top = 0;
   size_t gn_scratch_max = 0;
+  size_t conv_part_max = 0;  // bytes of the largest per-tile statistics scratch any conv needs
+  int fin_nmax = 0;
   char* base;      // workspace base (nullptr on the dry run)
   bool dry;
   int err = 0;
@@ -437,7 +465,17 @@ struct Builder {
            TAG_GN_APPLY, 1, 8.0 * nout, (nin + nout * (raw ? 2 : 1)) * es());
     }
   }
-  void conv_tc(const TcConvDesc& d) {
+  // stat_target: the conv's output tensor when the epilogue should also produce its GroupNorm statistics
+  void conv_tc(TcConvDesc d, Act* stat_target = nullptr) {
+    int tiles = 0;
+    if (stat_target) {
+      tiles = tc_conv_tiles_per_image(e->dt, d.N, d.H, d.W);
+      conv_part_max = std::max(conv_part_max, (size_t)B * tiles * d.N * 2 * sizeof(float));
+      fin_nmax = std::max(fin_nmax, d.N);
+      stat_target->stats_off = stats_top;
+      stats_top += (size_t)B * d.N * 2 * sizeof(double);
+      if (!dry) d.stats_partial = (float*)(base + e->head.conv_part);
+    }
     if (dry) return;
     char msg[512];
     TcConvPlan* p = tc_conv_plan_create(e->dt, d, e->num_sms, msg, sizeof(msg));
@@ -448,6 +486,15 @@ struct Builder {
     const double px = (double)d.B * d.H * d.W;
     emit([=](cudaStream_t s) { tc_conv_launch(p, s); }, TAG_CONV_TC, 1, 2.0 * px * d.N * k,
          (px * (cin + d.N * (d.res ? 2 : 1))) * es());
+    if (stat_target) {
+      const float* part = d.stats_partial;
+      double* st = stats_ptr(stat_target->stats_off);
+      double* slices = (double*)(base + e->head.fin_slices);
+      unsigned int* tickets = (unsigned int*)(base + e->head.tickets);
+      const int Bn = B, N = d.N;
+      emit([=](cudaStream_t s) { launch_gn_finalize(part, st, slices, tickets, Bn, tiles, N, s); }, TAG_GN_STATS, 1, 0,
+           (double)Bn * tiles * N * 8);
+    }
   }
 
   // ResnetBlockBigGANpp.forward (layerspp.py:282-314).  x1 != nullptr: input is cat[x0, x1].
@@ -473,7 +520,7 @@ struct Builder {
       d.bias_bstride = e->dense_rows;
       d.res = nullptr;
       d.scale = 1.0f;
-      conv_tc(d);
+      conv_tc(d, &h1);
     }
     free_act(a0);
     Act a1 = new_act(Cout, Ho, Wo);
@@ -505,7 +552,7 @@ struct Builder {
       d.bias = dry ? nullptr : (const float*)wt(w.bias1);
       d.bias_bstride = 0;
       d.scale = kInvSqrt2;
-      conv_tc(d);
+      conv_tc(d, m.down ? nullptr : &out);  // a down block's output is modified by Combine before any GroupNorm
     }
     free_act(a1);
     if (fir) free_act(raw);
@@ -556,7 +603,18 @@ struct Builder {
     const float* xr = dry ? nullptr : (const float*)(base + e->head.xr);
     {
       Act h0 = new_act(c.nf, F, T);
-      if (!dry) {
+      if (e->off.count("all_modules.3.wtc")) {
+        const int ck = 128 / (int)es();
+        TcConvDesc d{};
+        d.nseg = 1;
+        d.seg[0] = TcSegDesc{dry ? nullptr : base + e->head.xpad, ck, 0, ck, dry ? nullptr : wt(e->off.at("all_modules.3.wtc")), ck, 0, 9};
+        d.B = B; d.H = F; d.W = T; d.N = c.nf;
+        d.out = dry ? nullptr : ws(h0.off);
+        d.bias = dry ? nullptr : wf("all_modules.3.b");
+        d.bias_bstride = 0;
+        d.scale = 1.0f;
+        conv_tc(d, &h0);
+      } else if (!dry) {
         const float *w = wf("all_modules.3.w"), *b = wf("all_modules.3.b");
         void* o = ws(h0.off);
         const int H = F, W = T, N = c.nf;
@@ -625,9 +683,22 @@ struct Builder {
       {
         const std::string pg = "all_modules." + std::to_string(idx), pc = "all_modules." + std::to_string(idx + 1);
         Act a = new_act(h.C, h.H, h.W);
-        gn_apply(h, nullptr, e->off.at(pg + ".g"), e->off.at(pg + ".b"), 0, true, false, a, nullptr);
+        const bool head_tc = e->off.count(pc + ".wtc") != 0;
+        gn_apply(h, nullptr, e->off.at(pg + ".g"), e->off.at(pg + ".b"), 0, true, head_tc, a, nullptr);
         size_t np = new_f32((size_t)B * h.H * h.W * 4);
-        if (!dry) {
+        if (head_tc) {
+          TcConvDesc d{};
+          d.nseg = 1;
+          d.seg[0] = TcSegDesc{dry ? nullptr : ws(a.off), h.C, 0, h.C, dry ? nullptr : wt(e->off.at(pc + ".wtc")), h.C, 0, 9};
+          d.B = B; d.H = h.H; d.W = h.W; d.N = 32;
+          d.out = nullptr;
+          d.bias = dry ? nullptr : (const float*)wt(e->off.at(pc + ".btc"));
+          d.bias_bstride = 0;
+          d.scale = 1.0f;
+          d.out4 = dry ? (float*)1 : (float*)ws(np);
+          d.prev4 = (dry || opyr == (size_t)-1) ? nullptr : (const float*)ws(opyr);
+          conv_tc(d);
+        } else if (!dry) {
           const void* ap = ws(a.off);
           const float *w = wf(pc + ".w"), *b = wf(pc + ".b");
           const float* prev = (opyr == (size_t)-1) ? nullptr : (const float*)ws(opyr);
@@ -670,6 +741,7 @@ static int plan_workspace(use_engine* e, int B, int F, int T, size_t* total, siz
   if (b.err) return 1;
   size_t off = 0;
   e->head.xr = off; off = align_up(off + (size_t)B * F * T * 4 * 4, 1024);
+  e->head.xpad = off; off = align_up(off + (size_t)B * F * T * 128, 1024);
   e->head.t = off; off = align_up(off + (size_t)B * 4, 1024);
   e->head.gfp = off; off = align_up(off + (size_t)B * 2 * c.nf * 4, 1024);
   e->head.temb = off; off = align_up(off + (size_t)B * 4 * c.nf * 4, 1024);
@@ -677,6 +749,8 @@ static int plan_workspace(use_engine* e, int B, int F, int T, size_t* total, siz
   e->head.stats = off; off = align_up(off + b.stats_top, 1024);
   e->head.gn_scratch = off; off = align_up(off + b.gn_scratch_max, 1024);
   e->head.tickets = off; off = align_up(off + (size_t)B * 4, 1024);
+  e->head.conv_part = off; off = align_up(off + b.conv_part_max, 1024);
+  e->head.fin_slices = off; off = align_up(off + (size_t)B * kFinalizeSlices * 2 * b.fin_nmax * sizeof(double), 1024);
   e->head.arena = off;
   *total = off + b.arena.peak;
   if (stats_bytes) *stats_bytes = b.stats_top;
@@ -743,6 +817,7 @@ static void run_network(use_engine* e, Program* p, cudaStream_t st) {
     e->prof_bytes[o.tag] += o.bytes;
     e->prof_launches[o.tag] += o.launches;
     if (o.tag == TAG_CONV_TC && o.flops > e->prof_top_flops) { e->prof_top_flops = o.flops; e->prof_top_ms = ms; }
+    if (e->prof_ops.size() < 4096) e->prof_ops.push_back({o.tag, ms, o.flops, o.bytes});
   }
   for (auto& x : ev) cudaEventDestroy(x);
 }
@@ -840,7 +915,7 @@ int use_score_forward(use_engine* e, int B, int F, int T, const void* x, const v
   cudaStream_t st = (cudaStream_t)stream;
   stage_head(e, p, t_host, gfp_host, st);
   const size_t per = (size_t)F * T;
-  launch_pack_input((const float2*)x, (const float2*)Y, (float*)(p->base + e->head.xr), per * B, st);
+  launch_pack_input(e->dt, (const float2*)x, (const float2*)Y, (float*)(p->base + e->head.xr), p->base + e->head.xpad, per * B, st);
   run_network(e, p, st);
   StepArgs a{};
   a.pyramid = (const float*)(p->base + p->pyramid_off);
@@ -878,7 +953,7 @@ int use_pc_sample(use_engine* e, int B, int F, int T, const void* Y, void* x_sta
     }
     cudaStreamSynchronize(st);  // staging buffers are reused; the loop is GPU-bound by orders of magnitude
     stage_head(e, p, tb.data(), gb.data(), st);
-    launch_pack_input((const float2*)x_state, (const float2*)Y, (float*)(p->base + e->head.xr), n, st);
+    launch_pack_input(e->dt, (const float2*)x_state, (const float2*)Y, (float*)(p->base + e->head.xr), p->base + e->head.xpad, n, st);
     run_network(e, p, st);
     StepArgs a{};
     a.pyramid = (const float*)(p->base + p->pyramid_off);
@@ -913,6 +988,19 @@ int use_engine_set_profiling(use_engine* e, int on) {
   e->profiling = on != 0;
   for (int i = 0; i < 8; ++i) e->prof_ms[i] = e->prof_flops[i] = e->prof_bytes[i] = 0, e->prof_launches[i] = 0;
   e->prof_top_flops = e->prof_top_ms = 0;
+  e->prof_ops.clear();
+  return 0;
+}
+
+/* CSV "tag,ms,flops,bytes" per op of the profiled evaluations, in launch order */
+int use_engine_get_profile_ops(use_engine* e, char* csv, size_t cap) {
+  if (!e || !csv) return fail("null argument");
+  size_t n = 0;
+  for (auto& o : e->prof_ops) {
+    if (n + 96 >= cap) break;
+    n += snprintf(csv + n, cap - n, "%s,%.5f,%.4e,%.4e\n", kTagNames[o.tag], o.ms, o.flops, o.bytes);
+  }
+  if (n < cap) csv[n] = 0;
   return 0;
 }
 
@@ -975,14 +1063,24 @@ int use_op_gn_apply(int dtype, const void* x0, const double* stats0, int C0, con
 int use_op_conv_tc(int dtype, int nseg, const void* const* seg_act, const int* seg_ctensor, const int* seg_c0,
                    const int* seg_c, const void* const* seg_w, const int* seg_cw, const int* seg_wc0, const int* seg_taps,
                    int B, int H, int W, int N, const float* bias, int bias_bstride, const void* res, float scale, void* out,
-                   void* stream) {
+                   double* stats, void* stats_scratch, void* stream) {
   if (nseg < 1 || nseg > 3) return fail("nseg must be 1..3");
+  if (stats && !stats_scratch) return fail("stats requested without scratch");
   TcConvDesc d{};
   d.nseg = nseg;
   for (int i = 0; i < nseg; ++i)
     d.seg[i] = TcSegDesc{seg_act[i], seg_ctensor[i], seg_c0[i], seg_c[i], seg_w[i], seg_cw[i], seg_wc0[i], seg_taps[i]};
   d.B = B; d.H = H; d.W = W; d.N = N;
   d.out = out; d.bias = bias; d.bias_bstride = bias_bstride; d.res = res; d.scale = scale;
+  // scratch layout: tickets [B] u32 (zeroed here) | slices | per-tile partials
+  const int tiles = tc_conv_tiles_per_image(dtype, N, H, W);
+  char* sc = (char*)stats_scratch;
+  const size_t off_slices = ((size_t)B * 4 + 255) & ~size_t(255);
+  const size_t off_part = off_slices + (size_t)B * kFinalizeSlices * 2 * N * sizeof(double);
+  if (stats) {
+    cudaMemsetAsync(sc, 0, (size_t)B * 4, (cudaStream_t)stream);
+    d.stats_partial = (float*)(sc + off_part);
+  }
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
@@ -990,9 +1088,16 @@ int use_op_conv_tc(int dtype, int nseg, const void* const* seg_act, const int* s
   TcConvPlan* p = tc_conv_plan_create(dtype, d, sms, msg, sizeof(msg));
   if (!p) return fail("%s", msg);
   tc_conv_launch(p, (cudaStream_t)stream);
+  if (stats)
+    launch_gn_finalize(d.stats_partial, stats, (double*)(sc + off_slices), (unsigned int*)sc, B, tiles, N, (cudaStream_t)stream);
   cudaStreamSynchronize((cudaStream_t)stream);  // the plan (tensor maps live in kernel params) can go now
   tc_conv_plan_destroy(p);
   return cuda_check("use_op_conv_tc");
+}
+size_t use_op_conv_tc_stats_scratch_bytes(int dtype, int B, int H, int W, int N) {
+  const int tiles = tc_conv_tiles_per_image(dtype, N, H, W);
+  return (((size_t)B * 4 + 255) & ~size_t(255)) + (size_t)B * kFinalizeSlices * 2 * N * sizeof(double) +
+         (size_t)B * tiles * N * 2 * sizeof(float);
 }
 int use_op_conv_ref(int dtype, const void* x, const float* w, const float* bias, int bias_bstride, const void* res,
                     float scale, void* out, int B, int H, int W, int Cin, int Cout, int ksize, void* stream) {

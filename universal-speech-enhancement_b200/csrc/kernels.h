@@ -50,8 +50,9 @@ void launch_conv_ref(int dt, const void* x, const float* w, const float* bias, i
                      float scale, void* out, int B, int H, int W, int Cin, int Cout, int ksize, cudaStream_t st);
 
 // ---- network input / output, SDE arithmetic -------------------------------------------------------
-// xr[b][f][t][:] = 2*[Re x, Im x, Re Y, Im Y] - 1
-void launch_pack_input(const float2* x, const float2* Y, float* xr, size_t n, cudaStream_t st);
+// xr[b][f][t][:] = 2*[Re x, Im x, Re Y, Im Y] - 1 (fp32 x4); xpad (optional): the same 4 values as act-dtype MMA
+// operands zero-padded to one 128-byte channel chunk per pixel (input of the tcgen05 input convolution)
+void launch_pack_input(int dt, const float2* x, const float2* Y, float* xr, void* xpad, size_t n, cudaStream_t st);
 
 struct StepArgs {
   const float* pyramid;  // fp32 [B][F][T][4]
@@ -125,6 +126,9 @@ struct TcConvDesc {
   int bias_bstride;
   const void* res;
   float scale;
+  float* stats_partial;  // optional scratch [B][tiles_per_img][N][2] floats, see tc_conv_stats_scratch_bytes
+  float* out4;           // pyramid-head mode (N must be 32): fp32 [B][H][W][4] output instead of `out`
+  const float* prev4;    // optional previous pyramid level, fp32 [B][H/2][W/2][4], FIR-upsampled and added
 };
 struct TcConvPlan;  // opaque: tensor maps + launch geometry
 // Build (host) the launch plan; returns nullptr and fills err on failure.
@@ -132,5 +136,11 @@ TcConvPlan* tc_conv_plan_create(int dt, const TcConvDesc& d, int num_sms, char* 
 void tc_conv_plan_destroy(TcConvPlan* p);
 void tc_conv_launch(const TcConvPlan* p, cudaStream_t st);
 bool tc_conv_supported(int dt, int N);
+int tc_conv_tiles_per_image(int dt, int N, int H, int W);
+// Sum the per-tile partials written by the conv epilogue in tile order (double accumulation) into stats [B][N][2].
+// slices: double scratch [B][kFinalizeSlices][2N]; tickets [B] zero on entry (left zero).  Deterministic.
+constexpr int kFinalizeSlices = 8;
+void launch_gn_finalize(const float* partial, double* stats, double* slices, unsigned int* tickets, int B,
+                        int tiles_per_img, int N, cudaStream_t st);
 
 }  // namespace use

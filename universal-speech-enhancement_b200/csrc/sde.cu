@@ -35,18 +35,36 @@ __device__ __forceinline__ float2 philox_cnormal(unsigned long long seed, uint32
   return make_float2(r * cs, r * sn);
 }
 
+// xr: fp32 [n][4] (input pyramid level 0).  xpad (optional): act dtype [n][128 B of channels], channels 0..3 = the
+// same values as MMA operands, the rest zero -- the tcgen05 input convolution reads it as one K chunk.
+template <typename T>
 __global__ void __launch_bounds__(256) pack_input_kernel(const float2* __restrict__ x, const float2* __restrict__ Y,
-                                                          float4* __restrict__ xr, size_t n) {
-  for (size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n;
+                                                          float4* __restrict__ xr, T* __restrict__ xpad, size_t n) {
+  constexpr int V = Vec<T>::N;
+  constexpr int VPP = 8;  // 16-byte vectors per padded pixel (128 B)
+  for (size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n * VPP;
        i += static_cast<size_t>(gridDim.x) * blockDim.x) {
-    const float2 a = x[i], b = Y[i];
-    xr[i] = make_float4(2.f * a.x - 1.0f, 2.f * a.y - 1.0f, 2.f * b.x - 1.0f, 2.f * b.y - 1.0f);
+    const size_t pix = i / VPP;
+    const int v = static_cast<int>(i % VPP);
+    float f[V];
+#pragma unroll
+    for (int j = 0; j < V; ++j) f[j] = 0.f;
+    if (v == 0) {
+      const float2 a = x[pix], b = Y[pix];
+      const float4 o = make_float4(2.f * a.x - 1.0f, 2.f * a.y - 1.0f, 2.f * b.x - 1.0f, 2.f * b.y - 1.0f);
+      xr[pix] = o;
+      f[0] = o.x; f[1] = o.y; f[2] = o.z; f[3] = o.w;
+    }
+    if (xpad != nullptr) Vec<T>::store_operand(xpad + pix * (VPP * V) + v * V, f);
   }
 }
 
-void launch_pack_input(const float2* x, const float2* Y, float* xr, size_t n, cudaStream_t st) {
-  const int blocks = static_cast<int>(std::min<size_t>((n + 255) / 256, 148 * 32));
-  pack_input_kernel<<<blocks, 256, 0, st>>>(x, Y, reinterpret_cast<float4*>(xr), n);
+void launch_pack_input(int dt, const float2* x, const float2* Y, float* xr, void* xpad, size_t n, cudaStream_t st) {
+  const int blocks = static_cast<int>(std::min<size_t>((n * 8 + 255) / 256, 148 * 32));
+  if (dt == kBF16)
+    pack_input_kernel<__nv_bfloat16><<<blocks, 256, 0, st>>>(x, Y, reinterpret_cast<float4*>(xr), (__nv_bfloat16*)xpad, n);
+  else
+    pack_input_kernel<float><<<blocks, 256, 0, st>>>(x, Y, reinterpret_cast<float4*>(xr), (float*)xpad, n);
 }
 
 __global__ void __launch_bounds__(256) final_step_kernel(StepArgs a) {
