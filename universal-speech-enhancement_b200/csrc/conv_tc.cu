@@ -88,15 +88,29 @@ static bool encode_w(CUtensorMap* m, int dt, const void* base, int taps, int N, 
   return true;
 }
 
+// swap-AB variant of the C_out = 128 kernel (see conv_tc.cuh); USE_B200_CONV_SWAP=0 selects the pixel-major one.
+static bool swap_ab_enabled() {
+  static bool on = [] {
+    const char* v = getenv("USE_B200_CONV_SWAP");
+    return !(v && v[0] == '0');
+  }();
+  return on;
+}
+
 template <typename T, int N, int NSUB>
 static void fill_kernel(TcConvPlan* p) {
   using C = ConvCfg<T, N, NSUB>;
   if (p->mc == 2) {
-    p->kernel = reinterpret_cast<const void*>(&conv_tc_kernel<T, N, NSUB, 2>);
-    cudaFuncSetAttribute(conv_tc_kernel<T, N, NSUB, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES);
+    p->kernel = reinterpret_cast<const void*>(&conv_tc_kernel<T, N, NSUB, 2, false>);
+    cudaFuncSetAttribute(conv_tc_kernel<T, N, NSUB, 2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES);
+  } else if (N == 128 && NSUB == 2 && swap_ab_enabled()) {
+    if constexpr (N == 128 && NSUB == 2) {
+      p->kernel = reinterpret_cast<const void*>(&conv_tc_kernel<T, N, NSUB, 1, true>);
+      cudaFuncSetAttribute(conv_tc_kernel<T, N, NSUB, 1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES);
+    }
   } else {
-    p->kernel = reinterpret_cast<const void*>(&conv_tc_kernel<T, N, NSUB, 1>);
-    cudaFuncSetAttribute(conv_tc_kernel<T, N, NSUB, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES);
+    p->kernel = reinterpret_cast<const void*>(&conv_tc_kernel<T, N, NSUB, 1, false>);
+    cudaFuncSetAttribute(conv_tc_kernel<T, N, NSUB, 1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES);
   }
   p->threads = C::THREADS;
   p->smem = C::SMEM_BYTES;

@@ -74,9 +74,18 @@ struct ConvCfg {
 // L2 -> SM weight traffic (the binding resource of the C_out = 128 layers: 295 KB of weights per 256-pixel tile).
 // A weight slot is recycled only when the MMAs of BOTH CTAs have released it (b_empty counts 2 arrivals, one of
 // them a multicast tcgen05.commit from the peer).
-template <typename T, int N, int NSUB, int MC>
+//
+// SWAP (C_out = 128 only): "swap-AB".  A single-CTA M128 x N128 MMA reads 4 KB (A) + 4 KB (B) of shared memory per 64
+// cycles = the 128 B/clk shared-memory limit, which capped these layers (80 % of the FLOPs) near 70 % of the tensor
+// peak.  With the roles swapped -- weights [128 c_out x K] as the M operand, the 256 pixels of the tile as the N
+// operand -- one MMA reads 4 + 8 KB per 128 cycles (96 B/clk, the profile of the C_out = 256 layers).  The accumulator
+// is then channel-major (TMEM lane = output channel, column = pixel); the epilogue transposes 8x8 blocks across lanes
+// with shuffles so that every thread still stores 16-byte NHWC vectors, and per-channel GroupNorm statistics become
+// in-register sums.
+template <typename T, int N, int NSUB, int MC, bool SWAP>
 __global__ void __launch_bounds__(ConvCfg<T, N, NSUB>::THREADS, 1) conv_tc_kernel(const __grid_constant__ ConvParams p) {
   using C = ConvCfg<T, N, NSUB>;
+  static_assert(!SWAP || (N == 128 && NSUB == 2 && MC == 1), "swap-AB is built for C_out = 128, 256-pixel tiles");
   constexpr bool kBf16 = DT<T>::kIsBf16;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -165,7 +174,7 @@ __global__ void __launch_bounds__(ConvCfg<T, N, NSUB>::THREADS, 1) conv_tc_kerne
   } else if (warp == 1) {
     // ================================ MMA issuer ================================
     if (lane == 0) {
-      constexpr uint32_t idesc = umma_idesc(kBf16 ? 1 : 2, 128, N);
+      constexpr uint32_t idesc = SWAP ? umma_idesc(kBf16 ? 1 : 2, 128, 128 * NSUB) : umma_idesc(kBf16 ? 1 : 2, 128, N);
       const uint32_t sA_addr = smem_u32(sA), sB_addr = smem_u32(sB);
       uint32_t ai = 0, bi = 0, ti = 0;
       for (int g = g0; g * MC < p.ntiles; g += gstep, ++ti) {
@@ -184,13 +193,23 @@ __global__ void __launch_bounds__(ConvCfg<T, N, NSUB>::THREADS, 1) conv_tc_kerne
                 const uint32_t bs = bi % C::B_SLOTS, bph = (bi / C::B_SLOTS) & 1;
                 mbar_wait(&b_full[bs], bph);
                 tc_fence_after();
-#pragma unroll
-                for (int sub = 0; sub < NSUB; ++sub) {
+                if constexpr (SWAP) {
+                  // D[c_out][pixel] += W[c_out][K] * X[pixel][K]^T : M operand = weight tile, N operand = 256 pixel rows
 #pragma unroll
                   for (int k = 0; k < 4; ++k) {
-                    const uint64_t ad = umma_desc_sw128(sA_addr + as * C::A_SLOT + (sub * 16 + r) * 1024 + k * 32);
-                    const uint64_t bd = umma_desc_sw128(sB_addr + bs * C::B_TILE + k * 32);
-                    umma_ss<kBf16>(tmem_base + acs * C::ACC_COLS + sub * N, ad, bd, idesc, (first && k == 0) ? 0u : 1u);
+                    const uint64_t wd = umma_desc_sw128(sB_addr + bs * C::B_TILE + k * 32);
+                    const uint64_t xd = umma_desc_sw128(sA_addr + as * C::A_SLOT + r * 1024 + k * 32);
+                    umma_ss<kBf16>(tmem_base + acs * C::ACC_COLS, wd, xd, idesc, (first && k == 0) ? 0u : 1u);
+                  }
+                } else {
+#pragma unroll
+                  for (int sub = 0; sub < NSUB; ++sub) {
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                      const uint64_t ad = umma_desc_sw128(sA_addr + as * C::A_SLOT + (sub * 16 + r) * 1024 + k * 32);
+                      const uint64_t bd = umma_desc_sw128(sB_addr + bs * C::B_TILE + k * 32);
+                      umma_ss<kBf16>(tmem_base + acs * C::ACC_COLS + sub * N, ad, bd, idesc, (first && k == 0) ? 0u : 1u);
+                    }
                   }
                 }
                 first = false;
@@ -228,8 +247,132 @@ __global__ void __launch_bounds__(ConvCfg<T, N, NSUB>::THREADS, 1) conv_tc_kerne
       const size_t pix = (static_cast<size_t>(b) * p.H + h) * p.W + w;
       const float* bias = p.bias + static_cast<size_t>(b) * p.bias_bstride;
       const uint32_t acs = ti & 1, acph = (ti >> 1) & 1;
+      if (res != nullptr && !ghost) {
+        // pull this thread's share of the residual tile into L2 while the MMAs of the tile are still running
+        const int tw0p = (rem - th * p.tiles_w) * C::TILE_W, th0p = th * C::TILE_H;
+        constexpr int ET = 32 * C::EPI_WARPS;
+        constexpr int row_bytes = N * static_cast<int>(sizeof(T));  // one pixel
+        constexpr int SEGS = (row_bytes + 127) / 128;
+        for (int i = threadIdx.x - 64; i < C::TILE_H * C::TILE_W * SEGS; i += ET) {
+          const int pixl = i / SEGS, seg = i % SEGS;
+          const int hh = th0p + (pixl >> 3), ww = tw0p + (pixl & 7);
+          if (hh < p.H && ww < p.W) {
+            const char* a = reinterpret_cast<const char*>(res) +
+                            ((static_cast<size_t>(b) * p.H + hh) * p.W + ww) * row_bytes + seg * 128;
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(a));
+          }
+        }
+      }
       mbar_wait(&t_full[acs], acph);
       tc_fence_after();
+      if constexpr (SWAP) {
+        // channel-major accumulator: this thread = output channel quad*32 + lane; warp half `sub` owns pixel columns
+        // [128*sub, 128*sub + 128) of the 256-pixel tile
+        const int tw0 = (rem - th * p.tiles_w) * C::TILE_W;
+        const int th0 = th * C::TILE_H;
+        const int grp = lane >> 3, l8 = lane & 7;
+        const int cb = quad * 32 + grp * 8;  // first of the 8 channels this thread stores after the transposition
+        const float bias_c = __ldg(bias + quad * 32 + lane);
+        const uint32_t tcol = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + acs * C::ACC_COLS + sub * 128;
+        float s8[8], q8[8];
+#pragma unroll
+        for (int m8 = 0; m8 < 8; ++m8) s8[m8] = q8[m8] = 0.f;
+        constexpr int RV = 8 / DT<T>::kVec;  // 16-byte vectors per 8 channels
+#pragma unroll 1
+        for (int ch = 0; ch < 4; ++ch) {
+          // residual vectors of this chunk: issued before the TMEM load and the transposition so their latency overlaps
+          uint4 rq[4][RV];
+          if (res != nullptr) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              const int n = sub * 128 + ch * 32 + 8 * i + l8;
+              const int hh = th0 + (n >> 3), ww = tw0 + l8;
+              const bool ok = !ghost && (hh < p.H) && (ww < p.W);
+              const size_t px = (static_cast<size_t>(b) * p.H + hh) * p.W + ww;
+#pragma unroll
+              for (int j = 0; j < RV; ++j)
+                rq[i][j] = ok ? __ldg(reinterpret_cast<const uint4*>(res + px * N + cb) + j) : make_uint4(0, 0, 0, 0);
+            }
+          }
+          uint32_t r[32];
+          tmem_ld32(tcol + ch * 32, r);
+          tmem_ld_wait();
+          float v[32];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]) + bias_c;
+          // 8x8 transposes across the 8 lanes of a group: afterwards v[8i+m8] = (channel cb+m8, pixel 8i + l8)
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+#pragma unroll
+            for (int st = 4; st >= 1; st >>= 1) {
+              const bool up = (l8 & st) != 0;
+#pragma unroll
+              for (int k = 0; k < 8; ++k) {
+                if ((k & st) == 0) {
+                  const float lo = v[8 * i + k], hi = v[8 * i + (k | st)];
+                  const float recv = __shfl_xor_sync(0xffffffffu, up ? lo : hi, st);
+                  v[8 * i + k] = up ? recv : lo;
+                  v[8 * i + (k | st)] = up ? hi : recv;
+                }
+              }
+            }
+          }
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const int n = sub * 128 + ch * 32 + 8 * i + l8;  // pixel column: row n >> 3 of the tile, w = l8
+            const int hh = th0 + (n >> 3), ww = tw0 + l8;
+            const bool ok = !ghost && (hh < p.H) && (ww < p.W);
+            const size_t px = (static_cast<size_t>(b) * p.H + hh) * p.W + ww;
+            float o[8];
+#pragma unroll
+            for (int m8 = 0; m8 < 8; ++m8) o[m8] = v[8 * i + m8];
+            constexpr int V = DT<T>::kVec;
+            if (res != nullptr) {
+#pragma unroll
+              for (int j = 0; j < RV; ++j) {
+                float rr[V];
+                Vec<T>::unpack(rq[i][j], rr);
+#pragma unroll
+                for (int q = 0; q < V; ++q) o[j * V + q] += rr[q];
+              }
+            }
+#pragma unroll
+            for (int m8 = 0; m8 < 8; ++m8) {
+              o[m8] *= p.scale;
+              if constexpr (kBf16) o[m8] = __bfloat162float(__float2bfloat16_rn(o[m8]));
+            }
+            if (ok) {
+#pragma unroll
+              for (int j = 0; j < 8; j += V) {
+                float vv[V];
+#pragma unroll
+                for (int q = 0; q < V; ++q) vv[q] = o[j + q];
+                Vec<T>::store(out + px * N + cb + j, vv);
+              }
+#pragma unroll
+              for (int m8 = 0; m8 < 8; ++m8) { s8[m8] += o[m8]; q8[m8] += o[m8] * o[m8]; }
+            }
+          }
+        }
+        if (p.stats_partial != nullptr) {
+          // the 8 lanes of a group hold the same 8 channels for different pixels: recursive halving, lane l8 keeps
+          // channel cb + l8
+#pragma unroll
+          for (int st = 4; st >= 1; st >>= 1) {
+            const bool up = (l8 & st) != 0;
+#pragma unroll
+            for (int k = 0; k < st; ++k) {
+              const float ks = up ? s8[k + st] : s8[k], ss = up ? s8[k] : s8[k + st];
+              s8[k] = ks + __shfl_xor_sync(0xffffffffu, ss, st);
+              const float kq = up ? q8[k + st] : q8[k], sq = up ? q8[k] : q8[k + st];
+              q8[k] = kq + __shfl_xor_sync(0xffffffffu, sq, st);
+            }
+          }
+          // stat_s layout in this mode: [half = sub][N][2]
+          stat_s[(sub * N + cb + l8) * 2] = s8[0];
+          stat_s[(sub * N + cb + l8) * 2 + 1] = q8[0];
+        }
+      } else {
       const uint32_t trow = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + acs * C::ACC_COLS + sub * N;
       if (p.out4 != nullptr) {
         // pyramid head: 4 real output channels, fp32, + FIR-upsampled previous pyramid (ncsnpp.py:440-461)
@@ -263,10 +406,15 @@ __global__ void __launch_bounds__(ConvCfg<T, N, NSUB>::THREADS, 1) conv_tc_kerne
       } else
 #pragma unroll 1
       for (int c0 = 0; c0 < N; c0 += 32) {
+        constexpr int V = DT<T>::kVec;
+        uint4 rq[32 / V];
+        if (res != nullptr && valid) {
+#pragma unroll
+          for (int j = 0; j < 32 / V; ++j) rq[j] = __ldg(reinterpret_cast<const uint4*>(res + pix * N + c0) + j);
+        }
         uint32_t r[32];
         tmem_ld32(trow + c0, r);
         tmem_ld_wait();
-        constexpr int V = DT<T>::kVec;
         float f[32];
 #pragma unroll
         for (int j = 0; j < 32; j += 4) {
@@ -280,7 +428,7 @@ __global__ void __launch_bounds__(ConvCfg<T, N, NSUB>::THREADS, 1) conv_tc_kerne
 #pragma unroll
           for (int j = 0; j < 32; j += V) {
             float rr[V];
-            Vec<T>::load(res + pix * N + c0 + j, rr);
+            Vec<T>::unpack(rq[j / V], rr);
 #pragma unroll
             for (int q = 0; q < V; ++q) f[j + q] += rr[q];
           }
@@ -331,6 +479,7 @@ __global__ void __launch_bounds__(ConvCfg<T, N, NSUB>::THREADS, 1) conv_tc_kerne
           stat_s[(ew * N + c0 + lane) * 2 + 1] = a[0];
         }
       }
+      }  // !SWAP
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&t_empty[acs]);
@@ -341,8 +490,12 @@ __global__ void __launch_bounds__(ConvCfg<T, N, NSUB>::THREADS, 1) conv_tc_kerne
         float* dst = p.stats_partial + static_cast<size_t>(tile) * N * 2;  // tile = b * tiles_per_img + rem
         for (int i = threadIdx.x - 64; i < N * 2 && !ghost; i += ET) {
           float acc = 0.f;
+          if constexpr (SWAP) {
+            acc = stat_s[i] + stat_s[N * 2 + i];  // the two pixel halves
+          } else {
 #pragma unroll
-          for (int w = 0; w < C::EPI_WARPS; ++w) acc += stat_s[w * N * 2 + i];
+            for (int w = 0; w < C::EPI_WARPS; ++w) acc += stat_s[w * N * 2 + i];
+          }
           dst[i] = acc;
         }
         asm volatile("bar.sync 1, %0;" ::"r"(ET) : "memory");

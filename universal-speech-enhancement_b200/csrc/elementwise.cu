@@ -327,11 +327,151 @@ __global__ void __launch_bounds__(256) gn_apply_kernel(GnSrcT<T> s0, GnSrcT<T> s
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// Shared-memory tiled normalise + SiLU + FIR x2 (single source): every input element is loaded and activated ONCE
+// per block (halo overlap 1.27x down / 1.56x up instead of 9x / 2.25x SiLU evaluations per output in the direct form),
+// then the 16-tap (down) or 4-tap (up) filter runs out of shared memory for both the activated and the raw tensor.
+// Block = one output tile x 32 channels x one sample.  Down: 8x8 outputs from an 18x18 window; up: 16x16 from 10x10.
+// ------------------------------------------------------------------------------------------------
+constexpr int kFirCh = 32;
+
+template <typename T, int FIR>
+__global__ void __launch_bounds__(256) gn_apply_fir_tiled_kernel(GnSrcT<T> s0, const float* __restrict__ gamma,
+                                                                  const float* __restrict__ beta, float eps, int do_silu,
+                                                                  int as_operand, T* __restrict__ out_act,
+                                                                  T* __restrict__ out_raw, int Hin, int Win) {
+  constexpr int V = Vec<T>::N;
+  constexpr int TO = FIR == 1 ? 8 : 16;        // output tile edge
+  constexpr int WIN = FIR == 1 ? 18 : 10;      // input window edge
+  constexpr int VPC = kFirCh / V;              // 16-byte vectors per pixel of the channel chunk
+  extern __shared__ float sm[];
+  float* sa = sm;                              // activated  [WIN*WIN][32]
+  float* sr = sm + WIN * WIN * kFirCh;         // raw        [WIN*WIN][32]
+  float* saff = sr + WIN * WIN * kFirCh;       // scale[32], shift[32]
+  const int C = s0.C;
+  const int G = min(C / 4, 32), cpg = C / G;
+  const int b = blockIdx.z, c0 = blockIdx.y * kFirCh;
+  const int Hout = FIR == 1 ? Hin / 2 : Hin * 2, Wout = FIR == 1 ? Win / 2 : Win * 2;
+  const int tiles_x = (Wout + TO - 1) / TO;
+  const int oy0 = (blockIdx.x / tiles_x) * TO, ox0 = (blockIdx.x % tiles_x) * TO;
+  if (threadIdx.x < kFirCh) {
+    const int c = c0 + threadIdx.x, g = c / cpg;
+    const double inv_cnt = 1.0 / (static_cast<double>(Hin) * Win * cpg);
+    double sum = 0.0, sq = 0.0;
+    for (int cc = g * cpg; cc < (g + 1) * cpg; ++cc) {
+      const double2 st = __ldg(reinterpret_cast<const double2*>(s0.stats + (static_cast<size_t>(b) * C + cc) * 2));
+      sum += st.x;
+      sq += st.y;
+    }
+    const double mean = sum * inv_cnt;
+    double var = sq * inv_cnt - mean * mean;
+    if (var < 0.0) var = 0.0;
+    const float rstd = rsqrtf(static_cast<float>(var) + eps);
+    const float sc = gamma[c] * rstd;
+    saff[threadIdx.x] = sc;
+    saff[kFirCh + threadIdx.x] = beta[c] - static_cast<float>(mean) * sc;
+  }
+  __syncthreads();
+  // ---- load + activate the input window (zero outside the image: the FIR pads the ACTIVATED tensor with zeros) ----
+  const int iy0 = FIR == 1 ? 2 * oy0 - 1 : oy0 / 2 - 1, ix0 = FIR == 1 ? 2 * ox0 - 1 : ox0 / 2 - 1;
+  const T* src = s0.x + static_cast<size_t>(b) * Hin * Win * C + c0;
+  for (int it = threadIdx.x; it < WIN * WIN * VPC; it += blockDim.x) {
+    const int v = it % VPC, pw = it / VPC;
+    const int iy = iy0 + pw / WIN, ix = ix0 + pw % WIN;
+    float f[V], a[V];
+    if (iy >= 0 && iy < Hin && ix >= 0 && ix < Win) {
+      Vec<T>::load(src + (static_cast<size_t>(iy) * Win + ix) * C + v * V, f);
+#pragma unroll
+      for (int j = 0; j < V; ++j) {
+        const float n = fmaf(f[j], saff[v * V + j], saff[kFirCh + v * V + j]);
+        a[j] = do_silu ? silu_act<T>(n) : n;
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < V; ++j) f[j] = a[j] = 0.f;
+    }
+#pragma unroll
+    for (int j = 0; j < V; j += 4) {
+      *reinterpret_cast<float4*>(sa + pw * kFirCh + v * V + j) = make_float4(a[j], a[j + 1], a[j + 2], a[j + 3]);
+      *reinterpret_cast<float4*>(sr + pw * kFirCh + v * V + j) = make_float4(f[j], f[j + 1], f[j + 2], f[j + 3]);
+    }
+  }
+  __syncthreads();
+  // ---- FIR out of shared memory: one item = (output pixel, 4-channel quad) ----
+  const float k1[4] = {0.125f, 0.375f, 0.375f, 0.125f};
+  for (int it = threadIdx.x; it < TO * TO * (kFirCh / 4); it += blockDim.x) {
+    const int q = it % (kFirCh / 4), pl = it / (kFirCh / 4);
+    const int ty = pl / TO, tx = pl % TO;
+    const int oy = oy0 + ty, ox = ox0 + tx;
+    if (oy >= Hout || ox >= Wout) continue;
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f), raw = acc;
+    if constexpr (FIR == 1) {
+#pragma unroll
+      for (int a = 0; a < 4; ++a) {
+#pragma unroll
+        for (int bb = 0; bb < 4; ++bb) {
+          const float kw = k1[a] * k1[bb];
+          const int pw = (2 * ty + a) * WIN + 2 * tx + bb;
+          const float4 va = *reinterpret_cast<const float4*>(sa + pw * kFirCh + q * 4);
+          const float4 vr = *reinterpret_cast<const float4*>(sr + pw * kFirCh + q * 4);
+          acc.x += kw * va.x; acc.y += kw * va.y; acc.z += kw * va.z; acc.w += kw * va.w;
+          raw.x += kw * vr.x; raw.y += kw * vr.y; raw.z += kw * vr.z; raw.w += kw * vr.w;
+        }
+      }
+    } else {
+      // per axis: out[2m] = (in[m-1] + 3 in[m]) / 4 ; out[2m+1] = (3 in[m] + in[m+1]) / 4 ; window row 0 = m0 - 1
+      const int ry = (ty >> 1) + (ty & 1), rx = (tx >> 1) + (tx & 1);  // first of the two window rows / cols used
+      const float wy0 = (ty & 1) ? 0.75f : 0.25f, wx0 = (tx & 1) ? 0.75f : 0.25f;
+#pragma unroll
+      for (int a = 0; a < 2; ++a) {
+#pragma unroll
+        for (int bb = 0; bb < 2; ++bb) {
+          const float kw = (a ? 1.0f - wy0 : wy0) * (bb ? 1.0f - wx0 : wx0);
+          const int pw = (ry + a) * WIN + rx + bb;
+          const float4 va = *reinterpret_cast<const float4*>(sa + pw * kFirCh + q * 4);
+          const float4 vr = *reinterpret_cast<const float4*>(sr + pw * kFirCh + q * 4);
+          acc.x += kw * va.x; acc.y += kw * va.y; acc.z += kw * va.z; acc.w += kw * va.w;
+          raw.x += kw * vr.x; raw.y += kw * vr.y; raw.z += kw * vr.z; raw.w += kw * vr.w;
+        }
+      }
+    }
+    const size_t o = ((static_cast<size_t>(b) * Hout + oy) * Wout + ox) * C + c0 + q * 4;
+    auto put = [&](T* dst, const float4& v4) {
+      if constexpr (DT<T>::kIsBf16) {
+        __nv_bfloat162 lo = __floats2bfloat162_rn(v4.x, v4.y), hi = __floats2bfloat162_rn(v4.z, v4.w);
+        *reinterpret_cast<uint2*>(dst + o) = make_uint2(*reinterpret_cast<uint32_t*>(&lo), *reinterpret_cast<uint32_t*>(&hi));
+      } else {
+        *reinterpret_cast<float4*>(dst + o) = as_operand ? make_float4(round_tf32(v4.x), round_tf32(v4.y), round_tf32(v4.z), round_tf32(v4.w)) : v4;
+      }
+    };
+    put(out_act, acc);
+    if (out_raw != nullptr) put(out_raw, raw);
+  }
+}
+
 void launch_gn_apply(int dt, GnSrc s0, GnSrc s1, const float* gamma, const float* beta, float eps, int fir, bool do_silu,
                      bool as_operand, void* out_act, void* out_raw, int B, int Hin, int Win, cudaStream_t st) {
   const int Ct = s0.C + s1.C;
   const int Hout = fir == 1 ? Hin / 2 : (fir == 2 ? Hin * 2 : Hin);
   const int Wout = fir == 1 ? Win / 2 : (fir == 2 ? Win * 2 : Win);
+  if (fir != 0 && s1.C == 0 && s0.C % kFirCh == 0) {
+    DISPATCH_DT(dt, {
+      GnSrcT<T> a{(const T*)s0.x, s0.stats, s0.C};
+      if (fir == 1) {
+        dim3 grid(((Hout + 7) / 8) * ((Wout + 7) / 8), s0.C / kFirCh, B);
+        const size_t sm = (2 * 18 * 18 * kFirCh + 2 * kFirCh) * sizeof(float);
+        auto kern = gn_apply_fir_tiled_kernel<T, 1>;
+        cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(sm));
+        kern<<<grid, 256, sm, st>>>(a, gamma, beta, eps, do_silu, as_operand, (T*)out_act, (T*)out_raw, Hin, Win);
+      } else {
+        dim3 grid(((Hout + 15) / 16) * ((Wout + 15) / 16), s0.C / kFirCh, B);
+        const size_t sm = (2 * 10 * 10 * kFirCh + 2 * kFirCh) * sizeof(float);
+        gn_apply_fir_tiled_kernel<T, 2><<<grid, 256, sm, st>>>(a, gamma, beta, eps, do_silu, as_operand, (T*)out_act,
+                                                              (T*)out_raw, Hin, Win);
+      }
+    });
+    return;
+  }
   DISPATCH_DT(dt, {
     constexpr int V = Vec<T>::N;
     const int vpp = Ct / V;
