@@ -115,10 +115,12 @@ def test_conv_tc_fused_groupnorm_stats(dt, shape):
     got, stats = run_conv_tc(dt, segs, B, H, W, N, bias, None, 1.0, want_stats=True)
     got2, stats2 = run_conv_tc(dt, segs, B, H, W, N, bias, None, 1.0, want_stats=True)
     assert torch.equal(stats, stats2) and torch.equal(got, got2)
-    ref_sum = got.double().sum(dim=(2, 3))
-    ref_sq = (got.double() ** 2).sum(dim=(2, 3))
-    assert torch.allclose(stats[..., 0], ref_sum, rtol=2e-5, atol=2e-3), describe_mismatch(stats[..., 0], ref_sum)
-    assert torch.allclose(stats[..., 1], ref_sq, rtol=2e-5, atol=2e-3), describe_mismatch(stats[..., 1], ref_sq)
+    # the statistics describe the fp32 epilogue values (before the bf16 rounding of the store): compare with the fp64
+    # reference convolution; bf16 rounding noise of `got` would be sqrt(n) * 2^-9 here
+    ref = ref_conv(dt, segs, bias, None, 1.0).double()
+    ref_sum, ref_sq = ref.sum(dim=(2, 3)), (ref ** 2).sum(dim=(2, 3))
+    assert torch.allclose(stats[..., 0], ref_sum, rtol=1e-4, atol=2e-2), describe_mismatch(stats[..., 0], ref_sum)
+    assert torch.allclose(stats[..., 1], ref_sq, rtol=1e-4, atol=2e-2), describe_mismatch(stats[..., 1], ref_sq)
 
 
 @pytest.mark.parametrize("dt", [F32, BF16], ids=["tf32", "bf16"])

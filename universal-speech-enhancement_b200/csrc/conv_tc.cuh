@@ -63,7 +63,8 @@ struct ConvCfg {
   static constexpr int THREADS = 64 + 32 * EPI_WARPS;
   static constexpr int NBARS = 2 * A_SLOTS + 2 * B_SLOTS + 4;
   static constexpr int STAT_BYTES = EPI_WARPS * N * 2 * 4;  // per-warp column statistics of the current tile
-  static constexpr int SMEM_BYTES = 1024 + A_SLOTS * A_SLOT + B_SLOTS * B_TILE + STAT_BYTES + NBARS * 8 + 16;
+  static constexpr int XPOSE_BYTES = 0;
+  static constexpr int SMEM_BYTES = 1024 + A_SLOTS * A_SLOT + B_SLOTS * B_TILE + STAT_BYTES + XPOSE_BYTES + NBARS * 8 + 16;
   static_assert(TMEM_COLS <= 512 && (TMEM_COLS & (TMEM_COLS - 1)) == 0, "TMEM columns must be a power of two <= 512");
   static_assert(SMEM_BYTES <= 232448, "shared memory budget");
   static_assert(N % 32 == 0 && N <= 256, "N");
@@ -92,7 +93,8 @@ __global__ void __launch_bounds__(ConvCfg<T, N, NSUB>::THREADS, 1) conv_tc_kerne
   uint8_t* sA = smem;
   uint8_t* sB = sA + C::A_SLOTS * C::A_SLOT;
   float* stat_s = reinterpret_cast<float*>(sB + C::B_SLOTS * C::B_TILE);
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sB + C::B_SLOTS * C::B_TILE + C::STAT_BYTES);
+  float* xpose_s = reinterpret_cast<float*>(sB + C::B_SLOTS * C::B_TILE + C::STAT_BYTES);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sB + C::B_SLOTS * C::B_TILE + C::STAT_BYTES + C::XPOSE_BYTES);
   uint64_t* a_full = bars;
   uint64_t* a_empty = a_full + C::A_SLOTS;
   uint64_t* b_full = a_empty + C::A_SLOTS;
@@ -300,7 +302,8 @@ __global__ void __launch_bounds__(ConvCfg<T, N, NSUB>::THREADS, 1) conv_tc_kerne
           float v[32];
 #pragma unroll
           for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]) + bias_c;
-          // 8x8 transposes across the 8 lanes of a group: afterwards v[8i+m8] = (channel cb+m8, pixel 8i + l8)
+          // 8x8 transposes across the 8 lanes of a group (register shuffles: measured faster than staging through
+          // shared memory, whose bandwidth the MMAs need): afterwards v[8i+m8] = (channel cb+m8, pixel 8i + l8)
 #pragma unroll
           for (int i = 0; i < 4; ++i) {
 #pragma unroll
@@ -337,10 +340,7 @@ __global__ void __launch_bounds__(ConvCfg<T, N, NSUB>::THREADS, 1) conv_tc_kerne
               }
             }
 #pragma unroll
-            for (int m8 = 0; m8 < 8; ++m8) {
-              o[m8] *= p.scale;
-              if constexpr (kBf16) o[m8] = __bfloat162float(__float2bfloat16_rn(o[m8]));
-            }
+            for (int m8 = 0; m8 < 8; ++m8) o[m8] *= p.scale;
             if (ok) {
 #pragma unroll
               for (int j = 0; j < 8; j += V) {
@@ -434,10 +434,7 @@ __global__ void __launch_bounds__(ConvCfg<T, N, NSUB>::THREADS, 1) conv_tc_kerne
           }
         }
 #pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          f[j] *= p.scale;
-          if constexpr (kBf16) f[j] = __bfloat162float(__float2bfloat16_rn(f[j]));  // the value that is stored
-        }
+        for (int j = 0; j < 32; ++j) f[j] *= p.scale;  // statistics below use these fp32 values (pre-rounding)
         if (valid) {
 #pragma unroll
           for (int j = 0; j < 32; j += V) {
