@@ -189,26 +189,36 @@ __global__ void __launch_bounds__(256) gn_apply_kernel(GnSrcT<T> s0, GnSrcT<T> s
 
   if constexpr (FIR == 0) {
     constexpr int U = 4;  // independent 16-byte loads in flight per thread
-    for (int p = p0 + prow; p < p1; p += rows * U) {
+    const int n = (p1 - p0 - prow + rows - 1) / rows;  // pixels of this thread: p0 + prow + k * rows, k < n
+    const T* src = sb + static_cast<size_t>(p0 + prow) * Cs;
+    T* dst = oa + static_cast<size_t>(p0 + prow) * Ct;
+    const size_t sstep = static_cast<size_t>(rows) * Cs, dstep = static_cast<size_t>(rows) * Ct;
+    int k = 0;
+    for (; k + U <= n; k += U) {
       float f[U][V];
 #pragma unroll
-      for (int u = 0; u < U; ++u) {
-        const int pp = p + u * rows;
-        if (pp < p1) Vec<T>::load(sb + static_cast<size_t>(pp) * Cs, f[u]);
-      }
+      for (int u = 0; u < U; ++u) Vec<T>::load(src + (k + u) * sstep, f[u]);
 #pragma unroll
       for (int u = 0; u < U; ++u) {
-        const int pp = p + u * rows;
-        if (pp < p1) {
 #pragma unroll
-          for (int j = 0; j < V; ++j) {
-            const float n = fmaf(f[u][j], sc[j], sh[j]);
-            f[u][j] = do_silu ? silu_act<T>(n) : n;
-          }
-          if (as_operand) Vec<T>::store_operand(oa + static_cast<size_t>(pp) * Ct, f[u]);
-          else Vec<T>::store(oa + static_cast<size_t>(pp) * Ct, f[u]);
+        for (int j = 0; j < V; ++j) {
+          const float nn = fmaf(f[u][j], sc[j], sh[j]);
+          f[u][j] = do_silu ? silu_act<T>(nn) : nn;
         }
+        if (as_operand) Vec<T>::store_operand(dst + (k + u) * dstep, f[u]);
+        else Vec<T>::store(dst + (k + u) * dstep, f[u]);
       }
+    }
+    for (; k < n; ++k) {
+      float f[V];
+      Vec<T>::load(src + k * sstep, f);
+#pragma unroll
+      for (int j = 0; j < V; ++j) {
+        const float nn = fmaf(f[j], sc[j], sh[j]);
+        f[j] = do_silu ? silu_act<T>(nn) : nn;
+      }
+      if (as_operand) Vec<T>::store_operand(dst + k * dstep, f);
+      else Vec<T>::store(dst + k * dstep, f);
     }
   } else if constexpr (FIR == 2) {
     // x2 upsample: each thread produces the 2x2 output block of input pixel (m, n) from its 3x3 neighbourhood
@@ -375,20 +385,30 @@ __global__ void __launch_bounds__(256) gn_apply_fir_tiled_kernel(GnSrcT<T> s0, c
   // ---- load + activate the input window (zero outside the image: the FIR pads the ACTIVATED tensor with zeros) ----
   const int iy0 = FIR == 1 ? 2 * oy0 - 1 : oy0 / 2 - 1, ix0 = FIR == 1 ? 2 * ox0 - 1 : ox0 / 2 - 1;
   const T* src = s0.x + static_cast<size_t>(b) * Hin * Win * C + c0;
-  for (int it = threadIdx.x; it < WIN * WIN * VPC; it += blockDim.x) {
+  constexpr int NIT = (WIN * WIN * VPC + 255) / 256;
+  uint4 raw4[NIT];
+#pragma unroll
+  for (int k = 0; k < NIT; ++k) {
+    const int it = threadIdx.x + k * 256;
     const int v = it % VPC, pw = it / VPC;
     const int iy = iy0 + pw / WIN, ix = ix0 + pw % WIN;
+    const bool in = it < WIN * WIN * VPC && iy >= 0 && iy < Hin && ix >= 0 && ix < Win;
+    raw4[k] = in ? __ldg(reinterpret_cast<const uint4*>(src + (static_cast<size_t>(iy) * Win + ix) * C + v * V))
+                 : make_uint4(0, 0, 0, 0);
+  }
+#pragma unroll
+  for (int k = 0; k < NIT; ++k) {
+    const int it = threadIdx.x + k * 256;
+    if (it >= WIN * WIN * VPC) break;
+    const int v = it % VPC, pw = it / VPC;
+    const int iy = iy0 + pw / WIN, ix = ix0 + pw % WIN;
+    const bool in = iy >= 0 && iy < Hin && ix >= 0 && ix < Win;
     float f[V], a[V];
-    if (iy >= 0 && iy < Hin && ix >= 0 && ix < Win) {
-      Vec<T>::load(src + (static_cast<size_t>(iy) * Win + ix) * C + v * V, f);
+    Vec<T>::unpack(raw4[k], f);
 #pragma unroll
-      for (int j = 0; j < V; ++j) {
-        const float n = fmaf(f[j], saff[v * V + j], saff[kFirCh + v * V + j]);
-        a[j] = do_silu ? silu_act<T>(n) : n;
-      }
-    } else {
-#pragma unroll
-      for (int j = 0; j < V; ++j) f[j] = a[j] = 0.f;
+    for (int j = 0; j < V; ++j) {
+      const float n = fmaf(f[j], saff[v * V + j], saff[kFirCh + v * V + j]);
+      a[j] = in ? (do_silu ? silu_act<T>(n) : n) : 0.f;  // zero padding applies to the ACTIVATED tensor
     }
 #pragma unroll
     for (int j = 0; j < V; j += 4) {
