@@ -269,109 +269,118 @@ __global__ void __launch_bounds__(ConvCfg<T, N, NSUB>::THREADS, 1) conv_tc_kerne
       tc_fence_after();
       if constexpr (SWAP) {
         // channel-major accumulator: this thread = output channel quad*32 + lane; warp half `sub` owns pixel columns
-        // [128*sub, 128*sub + 128) of the 256-pixel tile
+        // [128*sub, 128*sub + 128) of the 256-pixel tile = tile rows [16*sub, 16*sub + 16).  Every pixel is written
+        // by one warp-wide store of 32 consecutive channels (64 B bf16 / 128 B fp32): no transposition needed, and the
+        // GroupNorm statistics of a channel are a plain in-register sum over the thread's pixels.
         const int tw0 = (rem - th * p.tiles_w) * C::TILE_W;
         const int th0 = th * C::TILE_H;
-        const int grp = lane >> 3, l8 = lane & 7;
-        const int cb = quad * 32 + grp * 8;  // first of the 8 channels this thread stores after the transposition
-        const float bias_c = __ldg(bias + quad * 32 + lane);
+        const int c = quad * 32 + lane;
+        const float bias_c = __ldg(bias + c);
         const uint32_t tcol = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + acs * C::ACC_COLS + sub * 128;
-        float s8[8], q8[8];
+        const size_t rowstride = static_cast<size_t>(p.W) * N;
+        const size_t tile_off = (static_cast<size_t>(b) * p.H + th0) * rowstride + static_cast<size_t>(tw0) * N + c;
+        T* obase = out + tile_off;
+        const T* rbase = res + tile_off;
+        uint32_t wmask = 0;
 #pragma unroll
-        for (int m8 = 0; m8 < 8; ++m8) s8[m8] = q8[m8] = 0.f;
-        constexpr int RV = 8 / DT<T>::kVec;  // 16-byte vectors per 8 channels
+        for (int j = 0; j < 8; ++j) wmask |= (tw0 + j < p.W) ? (1u << j) : 0u;
+        if (ghost) wmask = 0;
+        if constexpr (kBf16) {
+          // bf16: lanes (2k, 2k+1) = channels (c, c+1) trade every other pixel so that each lane stores packed
+          // bf16x2 words (128 B per warp-wide store instead of 64 B; measured: 2-byte stores cost 17 % of conv time)
+          const bool odd = (lane & 1) != 0;
+          const int ce = c & ~1;  // even channel of the pair
+          __nv_bfloat16* ob2 = reinterpret_cast<__nv_bfloat16*>(out) + (tile_off - c + ce);
+          const __nv_bfloat16* rb2 = reinterpret_cast<const __nv_bfloat16*>(res) + (tile_off - c + ce);
+          float s2[2] = {0.f, 0.f}, q2[2] = {0.f, 0.f};  // partial sums for channels ce, ce+1 over this lane's pixels
+#pragma unroll 1
+          for (int ch = 0; ch < 4; ++ch) {
+            const int row0 = sub * 16 + ch * 4;
+            uint32_t rres[16];
+            if (res != nullptr) {
+#pragma unroll
+              for (int k = 0; k < 16; ++k) {
+                const int idx = 2 * k + (odd ? 1 : 0), i = idx >> 3, j = idx & 7;
+                const bool ok = (th0 + row0 + i < p.H) && ((wmask >> j) & 1u);
+                rres[k] = ok ? __ldg(reinterpret_cast<const uint32_t*>(rb2 + (row0 + i) * rowstride + static_cast<size_t>(j) * N))
+                             : 0u;
+              }
+            }
+            uint32_t r[32];
+            tmem_ld32(tcol + ch * 32, r);
+            tmem_ld_wait();
+#pragma unroll
+            for (int k = 0; k < 16; ++k) {
+              const float mine_e = __uint_as_float(r[2 * k]) + bias_c, mine_o = __uint_as_float(r[2 * k + 1]) + bias_c;
+              const float recv = __shfl_xor_sync(0xffffffffu, odd ? mine_e : mine_o, 1);
+              // this lane's pixel: 2k (even lane) / 2k+1 (odd lane); lo = channel ce, hi = channel ce+1
+              float lo = odd ? recv : mine_e, hi = odd ? mine_o : recv;
+              if (res != nullptr) {
+                lo += __uint_as_float(rres[k] << 16);
+                hi += __uint_as_float(rres[k] & 0xffff0000u);
+              }
+              lo *= p.scale;
+              hi *= p.scale;
+              const int idx = 2 * k + (odd ? 1 : 0), i = idx >> 3, j = idx & 7;
+              if ((th0 + row0 + i < p.H) && ((wmask >> j) & 1u)) {
+                const __nv_bfloat162 pk = __floats2bfloat162_rn(lo, hi);
+                *reinterpret_cast<__nv_bfloat162*>(ob2 + (row0 + i) * rowstride + static_cast<size_t>(j) * N) = pk;
+                s2[0] += lo; q2[0] = fmaf(lo, lo, q2[0]);
+                s2[1] += hi; q2[1] = fmaf(hi, hi, q2[1]);
+              }
+            }
+          }
+          if (p.stats_partial != nullptr) {
+            // even lane finishes channel ce (its own pixels + the partner's), odd lane channel ce+1; fixed order
+            const float os = __shfl_xor_sync(0xffffffffu, odd ? s2[0] : s2[1], 1);
+            const float oq = __shfl_xor_sync(0xffffffffu, odd ? q2[0] : q2[1], 1);
+            const float ts = odd ? (os + s2[1]) : (s2[0] + os);  // (even-lane pixels) + (odd-lane pixels)
+            const float tq = odd ? (oq + q2[1]) : (q2[0] + oq);
+            stat_s[(sub * N + c) * 2] = ts;
+            stat_s[(sub * N + c) * 2 + 1] = tq;
+          }
+        } else {
+        float s_sum = 0.f, s_sq = 0.f;
 #pragma unroll 1
         for (int ch = 0; ch < 4; ++ch) {
-          // residual vectors of this chunk: issued before the TMEM load and the transposition so their latency overlaps
-          uint4 rq[4][RV];
+          const int row0 = sub * 16 + ch * 4;  // first tile row of this 32-pixel chunk (4 rows x 8 columns)
+          float rv[32];
           if (res != nullptr) {
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
-              const int n = sub * 128 + ch * 32 + 8 * i + l8;
-              const int hh = th0 + (n >> 3), ww = tw0 + l8;
-              const bool ok = !ghost && (hh < p.H) && (ww < p.W);
-              const size_t px = (static_cast<size_t>(b) * p.H + hh) * p.W + ww;
+              const bool rok = th0 + row0 + i < p.H;
 #pragma unroll
-              for (int j = 0; j < RV; ++j)
-                rq[i][j] = ok ? __ldg(reinterpret_cast<const uint4*>(res + px * N + cb) + j) : make_uint4(0, 0, 0, 0);
+              for (int j = 0; j < 8; ++j)
+                rv[i * 8 + j] = (rok && ((wmask >> j) & 1u))
+                                    ? static_cast<float>(rbase[(row0 + i) * rowstride + static_cast<size_t>(j) * N])
+                                    : 0.f;
             }
           }
           uint32_t r[32];
           tmem_ld32(tcol + ch * 32, r);
           tmem_ld_wait();
-          float v[32];
-#pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]) + bias_c;
-          // 8x8 transposes across the 8 lanes of a group (register shuffles: measured faster than staging through
-          // shared memory, whose bandwidth the MMAs need): afterwards v[8i+m8] = (channel cb+m8, pixel 8i + l8)
 #pragma unroll
           for (int i = 0; i < 4; ++i) {
+            const bool rok = th0 + row0 + i < p.H;
 #pragma unroll
-            for (int st = 4; st >= 1; st >>= 1) {
-              const bool up = (l8 & st) != 0;
-#pragma unroll
-              for (int k = 0; k < 8; ++k) {
-                if ((k & st) == 0) {
-                  const float lo = v[8 * i + k], hi = v[8 * i + (k | st)];
-                  const float recv = __shfl_xor_sync(0xffffffffu, up ? lo : hi, st);
-                  v[8 * i + k] = up ? recv : lo;
-                  v[8 * i + (k | st)] = up ? hi : recv;
-                }
+            for (int j = 0; j < 8; ++j) {
+              float v = __uint_as_float(r[i * 8 + j]) + bias_c;
+              if (res != nullptr) v += rv[i * 8 + j];
+              v *= p.scale;
+              if (rok && ((wmask >> j) & 1u)) {
+                obase[(row0 + i) * rowstride + static_cast<size_t>(j) * N] = static_cast<T>(v);
+                s_sum += v;
+                s_sq = fmaf(v, v, s_sq);
               }
-            }
-          }
-#pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            const int n = sub * 128 + ch * 32 + 8 * i + l8;  // pixel column: row n >> 3 of the tile, w = l8
-            const int hh = th0 + (n >> 3), ww = tw0 + l8;
-            const bool ok = !ghost && (hh < p.H) && (ww < p.W);
-            const size_t px = (static_cast<size_t>(b) * p.H + hh) * p.W + ww;
-            float o[8];
-#pragma unroll
-            for (int m8 = 0; m8 < 8; ++m8) o[m8] = v[8 * i + m8];
-            constexpr int V = DT<T>::kVec;
-            if (res != nullptr) {
-#pragma unroll
-              for (int j = 0; j < RV; ++j) {
-                float rr[V];
-                Vec<T>::unpack(rq[i][j], rr);
-#pragma unroll
-                for (int q = 0; q < V; ++q) o[j * V + q] += rr[q];
-              }
-            }
-#pragma unroll
-            for (int m8 = 0; m8 < 8; ++m8) o[m8] *= p.scale;
-            if (ok) {
-#pragma unroll
-              for (int j = 0; j < 8; j += V) {
-                float vv[V];
-#pragma unroll
-                for (int q = 0; q < V; ++q) vv[q] = o[j + q];
-                Vec<T>::store(out + px * N + cb + j, vv);
-              }
-#pragma unroll
-              for (int m8 = 0; m8 < 8; ++m8) { s8[m8] += o[m8]; q8[m8] += o[m8] * o[m8]; }
             }
           }
         }
         if (p.stats_partial != nullptr) {
-          // the 8 lanes of a group hold the same 8 channels for different pixels: recursive halving, lane l8 keeps
-          // channel cb + l8
-#pragma unroll
-          for (int st = 4; st >= 1; st >>= 1) {
-            const bool up = (l8 & st) != 0;
-#pragma unroll
-            for (int k = 0; k < st; ++k) {
-              const float ks = up ? s8[k + st] : s8[k], ss = up ? s8[k] : s8[k + st];
-              s8[k] = ks + __shfl_xor_sync(0xffffffffu, ss, st);
-              const float kq = up ? q8[k + st] : q8[k], sq = up ? q8[k] : q8[k + st];
-              q8[k] = kq + __shfl_xor_sync(0xffffffffu, sq, st);
-            }
-          }
           // stat_s layout in this mode: [half = sub][N][2]
-          stat_s[(sub * N + cb + l8) * 2] = s8[0];
-          stat_s[(sub * N + cb + l8) * 2 + 1] = q8[0];
+          stat_s[(sub * N + c) * 2] = s_sum;
+          stat_s[(sub * N + c) * 2 + 1] = s_sq;
         }
+        }  // fp32 direct stores
       } else {
       const uint32_t trow = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + acs * C::ACC_COLS + sub * N;
       if (p.out4 != nullptr) {

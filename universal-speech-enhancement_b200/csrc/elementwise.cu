@@ -339,11 +339,31 @@ __global__ void __launch_bounds__(256) gn_apply_kernel(GnSrcT<T> s0, GnSrcT<T> s
 
 // ------------------------------------------------------------------------------------------------
 // Shared-memory tiled normalise + SiLU + FIR x2 (single source): every input element is loaded and activated ONCE
-// per block (halo overlap 1.27x down / 1.56x up instead of 9x / 2.25x SiLU evaluations per output in the direct form),
-// then the 16-tap (down) or 4-tap (up) filter runs out of shared memory for both the activated and the raw tensor.
-// Block = one output tile x 32 channels x one sample.  Down: 8x8 outputs from an 18x18 window; up: 16x16 from 10x10.
+// per block, then the 16-tap (down) or 4-tap (up) filter runs out of shared memory for both the activated and the
+// raw tensor.  Each thread produces a 2x2 output block for 4 channels, separably, so a filter tap costs 9 (down) /
+// 2.25 (up) shared-memory reads per output instead of 16 / 4.  The window is staged in the act dtype (bf16 mode: the
+// same rounding the activated tensor would get if it were materialised, and half the shared-memory bytes).
+// Block = one output tile x CH channels x one sample.  Down: 8x8 outputs from an 18x18 window; up: 16x16 from 10x10.
 // ------------------------------------------------------------------------------------------------
-constexpr int kFirCh = 32;
+template <typename T> struct FirCh { static constexpr int value = DT<T>::kIsBf16 ? 64 : 32; };
+
+template <typename T> __device__ __forceinline__ float4 lds4(const T* p);
+template <> __device__ __forceinline__ float4 lds4<float>(const float* p) { return *reinterpret_cast<const float4*>(p); }
+template <> __device__ __forceinline__ float4 lds4<__nv_bfloat16>(const __nv_bfloat16* p) {
+  const uint2 t = *reinterpret_cast<const uint2*>(p);
+  return make_float4(__uint_as_float(t.x << 16), __uint_as_float(t.x & 0xffff0000u), __uint_as_float(t.y << 16),
+                     __uint_as_float(t.y & 0xffff0000u));
+}
+template <typename T> __device__ __forceinline__ void sts_vec(T* p, const float (&v)[Vec<T>::N]);
+template <> __device__ __forceinline__ void sts_vec<float>(float* p, const float (&v)[4]) {
+  *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
+}
+template <> __device__ __forceinline__ void sts_vec<__nv_bfloat16>(__nv_bfloat16* p, const float (&v)[8]) {
+  Vec<__nv_bfloat16>::store(p, v);
+}
+__device__ __forceinline__ void fma4(float4& acc, float w, const float4& v) {
+  acc.x = fmaf(w, v.x, acc.x); acc.y = fmaf(w, v.y, acc.y); acc.z = fmaf(w, v.z, acc.z); acc.w = fmaf(w, v.w, acc.w);
+}
 
 template <typename T, int FIR>
 __global__ void __launch_bounds__(256) gn_apply_fir_tiled_kernel(GnSrcT<T> s0, const float* __restrict__ gamma,
@@ -351,20 +371,21 @@ __global__ void __launch_bounds__(256) gn_apply_fir_tiled_kernel(GnSrcT<T> s0, c
                                                                   int as_operand, T* __restrict__ out_act,
                                                                   T* __restrict__ out_raw, int Hin, int Win) {
   constexpr int V = Vec<T>::N;
+  constexpr int CH = FirCh<T>::value;
   constexpr int TO = FIR == 1 ? 8 : 16;        // output tile edge
   constexpr int WIN = FIR == 1 ? 18 : 10;      // input window edge
-  constexpr int VPC = kFirCh / V;              // 16-byte vectors per pixel of the channel chunk
-  extern __shared__ float sm[];
-  float* sa = sm;                              // activated  [WIN*WIN][32]
-  float* sr = sm + WIN * WIN * kFirCh;         // raw        [WIN*WIN][32]
-  float* saff = sr + WIN * WIN * kFirCh;       // scale[32], shift[32]
+  constexpr int VPC = CH / V;                  // 16-byte vectors per pixel of the channel chunk
+  extern __shared__ __align__(16) unsigned char smraw[];
+  T* sa = reinterpret_cast<T*>(smraw);         // activated  [WIN*WIN][CH]
+  T* sr = sa + WIN * WIN * CH;                 // raw        [WIN*WIN][CH]
+  float* saff = reinterpret_cast<float*>(sr + WIN * WIN * CH);  // scale[CH], shift[CH]
   const int C = s0.C;
   const int G = min(C / 4, 32), cpg = C / G;
-  const int b = blockIdx.z, c0 = blockIdx.y * kFirCh;
+  const int b = blockIdx.z, c0 = blockIdx.y * CH;
   const int Hout = FIR == 1 ? Hin / 2 : Hin * 2, Wout = FIR == 1 ? Win / 2 : Win * 2;
   const int tiles_x = (Wout + TO - 1) / TO;
   const int oy0 = (blockIdx.x / tiles_x) * TO, ox0 = (blockIdx.x % tiles_x) * TO;
-  if (threadIdx.x < kFirCh) {
+  if (threadIdx.x < CH) {
     const int c = c0 + threadIdx.x, g = c / cpg;
     const double inv_cnt = 1.0 / (static_cast<double>(Hin) * Win * cpg);
     double sum = 0.0, sq = 0.0;
@@ -379,10 +400,11 @@ __global__ void __launch_bounds__(256) gn_apply_fir_tiled_kernel(GnSrcT<T> s0, c
     const float rstd = rsqrtf(static_cast<float>(var) + eps);
     const float sc = gamma[c] * rstd;
     saff[threadIdx.x] = sc;
-    saff[kFirCh + threadIdx.x] = beta[c] - static_cast<float>(mean) * sc;
+    saff[CH + threadIdx.x] = beta[c] - static_cast<float>(mean) * sc;
   }
   __syncthreads();
-  // ---- load + activate the input window (zero outside the image: the FIR pads the ACTIVATED tensor with zeros) ----
+  // ---- load (all requests in flight first) + activate the input window; zero outside the image: the FIR pads the
+  //      ACTIVATED tensor with zeros ----
   const int iy0 = FIR == 1 ? 2 * oy0 - 1 : oy0 / 2 - 1, ix0 = FIR == 1 ? 2 * ox0 - 1 : ox0 / 2 - 1;
   const T* src = s0.x + static_cast<size_t>(b) * Hin * Win * C + c0;
   constexpr int NIT = (WIN * WIN * VPC + 255) / 256;
@@ -407,65 +429,84 @@ __global__ void __launch_bounds__(256) gn_apply_fir_tiled_kernel(GnSrcT<T> s0, c
     Vec<T>::unpack(raw4[k], f);
 #pragma unroll
     for (int j = 0; j < V; ++j) {
-      const float n = fmaf(f[j], saff[v * V + j], saff[kFirCh + v * V + j]);
-      a[j] = in ? (do_silu ? silu_act<T>(n) : n) : 0.f;  // zero padding applies to the ACTIVATED tensor
+      const float n = fmaf(f[j], saff[v * V + j], saff[CH + v * V + j]);
+      a[j] = in ? (do_silu ? silu_act<T>(n) : n) : 0.f;
     }
-#pragma unroll
-    for (int j = 0; j < V; j += 4) {
-      *reinterpret_cast<float4*>(sa + pw * kFirCh + v * V + j) = make_float4(a[j], a[j + 1], a[j + 2], a[j + 3]);
-      *reinterpret_cast<float4*>(sr + pw * kFirCh + v * V + j) = make_float4(f[j], f[j + 1], f[j + 2], f[j + 3]);
-    }
+    sts_vec<T>(sa + pw * CH + v * V, a);
+    sts_vec<T>(sr + pw * CH + v * V, f);
   }
   __syncthreads();
-  // ---- FIR out of shared memory: one item = (output pixel, 4-channel quad) ----
-  const float k1[4] = {0.125f, 0.375f, 0.375f, 0.125f};
-  for (int it = threadIdx.x; it < TO * TO * (kFirCh / 4); it += blockDim.x) {
-    const int q = it % (kFirCh / 4), pl = it / (kFirCh / 4);
-    const int ty = pl / TO, tx = pl % TO;
-    const int oy = oy0 + ty, ox = ox0 + tx;
-    if (oy >= Hout || ox >= Wout) continue;
-    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f), raw = acc;
+  // ---- FIR out of shared memory: one item = (2x2 output block, 4-channel quad) ----
+  constexpr int NB = TO / 2;  // 2x2 blocks per tile edge
+  for (int it = threadIdx.x; it < NB * NB * (CH / 4); it += blockDim.x) {
+    const int q = it % (CH / 4), bl = it / (CH / 4);
+    const int by = bl / NB, bx = bl % NB;
+    float4 acc[2][2], raw[2][2];
+#pragma unroll
+    for (int dy = 0; dy < 2; ++dy)
+#pragma unroll
+      for (int dx = 0; dx < 2; ++dx) acc[dy][dx] = raw[dy][dx] = make_float4(0.f, 0.f, 0.f, 0.f);
     if constexpr (FIR == 1) {
+      // outputs (2by+dy, 2bx+dx) read window rows 4by + 2dy + a, a < 4: a 6x6 window, filtered separably
+      const float k1[4] = {0.125f, 0.375f, 0.375f, 0.125f};
 #pragma unroll
-      for (int a = 0; a < 4; ++a) {
+      for (int cc = 0; cc < 6; ++cc) {
+        float4 va[2], vr[2];
+        va[0] = va[1] = vr[0] = vr[1] = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
-        for (int bb = 0; bb < 4; ++bb) {
-          const float kw = k1[a] * k1[bb];
-          const int pw = (2 * ty + a) * WIN + 2 * tx + bb;
-          const float4 va = *reinterpret_cast<const float4*>(sa + pw * kFirCh + q * 4);
-          const float4 vr = *reinterpret_cast<const float4*>(sr + pw * kFirCh + q * 4);
-          acc.x += kw * va.x; acc.y += kw * va.y; acc.z += kw * va.z; acc.w += kw * va.w;
-          raw.x += kw * vr.x; raw.y += kw * vr.y; raw.z += kw * vr.z; raw.w += kw * vr.w;
+        for (int rr = 0; rr < 6; ++rr) {
+          const int pw = (4 * by + rr) * WIN + 4 * bx + cc;
+          const float4 xa = lds4<T>(sa + pw * CH + q * 4), xr = lds4<T>(sr + pw * CH + q * 4);
+          if (rr < 4) { fma4(va[0], k1[rr], xa); fma4(vr[0], k1[rr], xr); }
+          if (rr >= 2) { fma4(va[1], k1[rr - 2], xa); fma4(vr[1], k1[rr - 2], xr); }
+        }
+#pragma unroll
+        for (int dy = 0; dy < 2; ++dy) {
+          if (cc < 4) { fma4(acc[dy][0], k1[cc], va[dy]); fma4(raw[dy][0], k1[cc], vr[dy]); }
+          if (cc >= 2) { fma4(acc[dy][1], k1[cc - 2], va[dy]); fma4(raw[dy][1], k1[cc - 2], vr[dy]); }
         }
       }
     } else {
-      // per axis: out[2m] = (in[m-1] + 3 in[m]) / 4 ; out[2m+1] = (3 in[m] + in[m+1]) / 4 ; window row 0 = m0 - 1
-      const int ry = (ty >> 1) + (ty & 1), rx = (tx >> 1) + (tx & 1);  // first of the two window rows / cols used
-      const float wy0 = (ty & 1) ? 0.75f : 0.25f, wx0 = (tx & 1) ? 0.75f : 0.25f;
+      // input pixel (by, bx) of the tile = window (by+1, bx+1); out[2m] = (in[m-1] + 3 in[m])/4, out[2m+1] = (3 in[m] + in[m+1])/4
+      const float we[3] = {0.25f, 0.75f, 0.f}, wo[3] = {0.f, 0.75f, 0.25f};
 #pragma unroll
-      for (int a = 0; a < 2; ++a) {
+      for (int cc = 0; cc < 3; ++cc) {
+        float4 va[2], vr[2];
+        va[0] = va[1] = vr[0] = vr[1] = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
-        for (int bb = 0; bb < 2; ++bb) {
-          const float kw = (a ? 1.0f - wy0 : wy0) * (bb ? 1.0f - wx0 : wx0);
-          const int pw = (ry + a) * WIN + rx + bb;
-          const float4 va = *reinterpret_cast<const float4*>(sa + pw * kFirCh + q * 4);
-          const float4 vr = *reinterpret_cast<const float4*>(sr + pw * kFirCh + q * 4);
-          acc.x += kw * va.x; acc.y += kw * va.y; acc.z += kw * va.z; acc.w += kw * va.w;
-          raw.x += kw * vr.x; raw.y += kw * vr.y; raw.z += kw * vr.z; raw.w += kw * vr.w;
+        for (int rr = 0; rr < 3; ++rr) {
+          const int pw = (by + rr) * WIN + bx + cc;
+          const float4 xa = lds4<T>(sa + pw * CH + q * 4), xr = lds4<T>(sr + pw * CH + q * 4);
+          if (rr < 2) { fma4(va[0], we[rr], xa); fma4(vr[0], we[rr], xr); }
+          if (rr >= 1) { fma4(va[1], wo[rr], xa); fma4(vr[1], wo[rr], xr); }
+        }
+#pragma unroll
+        for (int dy = 0; dy < 2; ++dy) {
+          if (cc < 2) { fma4(acc[dy][0], we[cc], va[dy]); fma4(raw[dy][0], we[cc], vr[dy]); }
+          if (cc >= 1) { fma4(acc[dy][1], wo[cc], va[dy]); fma4(raw[dy][1], wo[cc], vr[dy]); }
         }
       }
     }
-    const size_t o = ((static_cast<size_t>(b) * Hout + oy) * Wout + ox) * C + c0 + q * 4;
-    auto put = [&](T* dst, const float4& v4) {
-      if constexpr (DT<T>::kIsBf16) {
-        __nv_bfloat162 lo = __floats2bfloat162_rn(v4.x, v4.y), hi = __floats2bfloat162_rn(v4.z, v4.w);
-        *reinterpret_cast<uint2*>(dst + o) = make_uint2(*reinterpret_cast<uint32_t*>(&lo), *reinterpret_cast<uint32_t*>(&hi));
-      } else {
-        *reinterpret_cast<float4*>(dst + o) = as_operand ? make_float4(round_tf32(v4.x), round_tf32(v4.y), round_tf32(v4.z), round_tf32(v4.w)) : v4;
+#pragma unroll
+    for (int dy = 0; dy < 2; ++dy) {
+#pragma unroll
+      for (int dx = 0; dx < 2; ++dx) {
+        const int oy = oy0 + 2 * by + dy, ox = ox0 + 2 * bx + dx;
+        if (oy >= Hout || ox >= Wout) continue;
+        const size_t o = ((static_cast<size_t>(b) * Hout + oy) * Wout + ox) * C + c0 + q * 4;
+        auto put = [&](T* dst, const float4& v4) {
+          if constexpr (DT<T>::kIsBf16) {
+            __nv_bfloat162 lo = __floats2bfloat162_rn(v4.x, v4.y), hi = __floats2bfloat162_rn(v4.z, v4.w);
+            *reinterpret_cast<uint2*>(dst + o) = make_uint2(*reinterpret_cast<uint32_t*>(&lo), *reinterpret_cast<uint32_t*>(&hi));
+          } else {
+            *reinterpret_cast<float4*>(dst + o) =
+                as_operand ? make_float4(round_tf32(v4.x), round_tf32(v4.y), round_tf32(v4.z), round_tf32(v4.w)) : v4;
+          }
+        };
+        put(out_act, acc[dy][dx]);
+        if (out_raw != nullptr) put(out_raw, raw[dy][dx]);
       }
-    };
-    put(out_act, acc);
-    if (out_raw != nullptr) put(out_raw, raw);
+    }
   }
 }
 
@@ -474,18 +515,19 @@ void launch_gn_apply(int dt, GnSrc s0, GnSrc s1, const float* gamma, const float
   const int Ct = s0.C + s1.C;
   const int Hout = fir == 1 ? Hin / 2 : (fir == 2 ? Hin * 2 : Hin);
   const int Wout = fir == 1 ? Win / 2 : (fir == 2 ? Win * 2 : Win);
-  if (fir != 0 && s1.C == 0 && s0.C % kFirCh == 0) {
+  if (fir != 0 && s1.C == 0 && s0.C % (dt == kBF16 ? 64 : 32) == 0) {
     DISPATCH_DT(dt, {
+      constexpr int CH = FirCh<T>::value;
       GnSrcT<T> a{(const T*)s0.x, s0.stats, s0.C};
       if (fir == 1) {
-        dim3 grid(((Hout + 7) / 8) * ((Wout + 7) / 8), s0.C / kFirCh, B);
-        const size_t sm = (2 * 18 * 18 * kFirCh + 2 * kFirCh) * sizeof(float);
+        dim3 grid(((Hout + 7) / 8) * ((Wout + 7) / 8), s0.C / CH, B);
+        const size_t sm = 2 * 18 * 18 * CH * sizeof(T) + 2 * CH * sizeof(float);
         auto kern = gn_apply_fir_tiled_kernel<T, 1>;
         cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(sm));
         kern<<<grid, 256, sm, st>>>(a, gamma, beta, eps, do_silu, as_operand, (T*)out_act, (T*)out_raw, Hin, Win);
       } else {
-        dim3 grid(((Hout + 15) / 16) * ((Wout + 15) / 16), s0.C / kFirCh, B);
-        const size_t sm = (2 * 10 * 10 * kFirCh + 2 * kFirCh) * sizeof(float);
+        dim3 grid(((Hout + 15) / 16) * ((Wout + 15) / 16), s0.C / CH, B);
+        const size_t sm = 2 * 10 * 10 * CH * sizeof(T) + 2 * CH * sizeof(float);
         gn_apply_fir_tiled_kernel<T, 2><<<grid, 256, sm, st>>>(a, gamma, beta, eps, do_silu, as_operand, (T*)out_act,
                                                               (T*)out_raw, Hin, Win);
       }
