@@ -255,11 +255,25 @@ def main():
     conv = prof["conv_tc"]
     achieved = conv["flops"] / (conv["ms"] * 1e-3) / 1e12 if conv["ms"] > 0 else 0.0
     net_ms = sum(v["ms"] for k, v in prof.items() if k != "top_conv")
+    # DRAM traffic of the conv launches from the committed ncu capture (taken at a small batch; scales with the batch)
+    traffic, traffic_note = None, "no ncu summary committed for this dtype"
+    try:
+        summ = json.load(open(os.path.join(ROOT, "profiles", f"r01_kernel_summary_{args.dtype}.json")))
+        tot_b = sum(v["dram_bytes_total"] for k, v in summ["kernels"].items() if "conv_tc_kernel" in k)
+        tot_n = sum(v["launches"] for k, v in summ["kernels"].items() if "conv_tc_kernel" in k)
+        cap_b = summ.get("batch", 2)
+        if tot_n:
+            traffic = tot_b / tot_n / cap_b * B
+            traffic_note = (f"dram__bytes_read+write per conv_tc launch from profiles/r01_kernel_summary_{args.dtype}.json "
+                            f"(ncu, batch {cap_b}, {tot_n} launches of one evaluation), scaled linearly to batch {B}")
+    except Exception:
+        pass
     roofline = {
         "bound": "tensor", "kernel": "conv_tc_kernel (tcgen05 implicit-GEMM 3x3/1x1 convolutions, all launches of one "
                                      "network evaluation)",
         "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak if peak else None,
-        "traffic": None, "peak_source": peak_note,
+        "traffic": traffic, "traffic_note": traffic_note,
+        "algorithmic_bytes_per_launch": conv["bytes"] / max(1, conv["launches"]), "peak_source": peak_note,
         "conv_share_of_network_time": conv["ms"] / net_ms if net_ms else None,
         "launches_per_eval": conv["launches"],
         "per_class_ms_per_eval": {k: round(v["ms"], 3) for k, v in prof.items() if k != "top_conv"},
