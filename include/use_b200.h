@@ -111,24 +111,22 @@ int use_upfirdn2d_f32(const float* in, float* out, int major, int in_h, int in_w
                       int pad_y1, void* stream);
 
 /* ---- single kernels (parity tests) ----------------------------------------------------------------- */
-/* per-channel sum / sum of squares, double [B][C][2]; bitwise deterministic.  scratch: use_op_gn_stats_scratch_bytes
- * device bytes; tickets: device uint32 [B], zero on entry (left zero). */
-size_t use_op_gn_stats_scratch_bytes(int B, int HW, int C);
-int use_op_gn_stats(int dtype, const void* x, double* stats, void* scratch, void* tickets, int B, int HW, int C,
-                    void* stream);
-int use_op_gn_apply(int dtype, const void* x0, const double* stats0, int C0, const void* x1, const double* stats1, int C1,
+/* GroupNorm statistics: int64 FIXED POINT [B][C][2] = (sum * 2^28, sum of squares * 2^24) per channel, ACCUMULATED with
+ * integer atomics into `stats` (zero it first): bit-reproducible, independent of launch geometry and batch size. */
+#define USE_STAT_SUM_SCALE 268435456.0
+#define USE_STAT_SQ_SCALE 16777216.0
+int use_op_gn_stats(int dtype, const void* x, long long* stats, int B, int HW, int C, void* stream);
+int use_op_gn_apply(int dtype, const void* x0, const long long* stats0, int C0, const void* x1, const long long* stats1, int C1,
                     const float* gamma, const float* beta, float eps, int fir, int do_silu, int as_operand, void* out_act,
                     void* out_raw, int B, int Hin, int Win, void* stream);
 /* tcgen05 implicit-GEMM convolution; up to 3 segments summed into one accumulator.
  * seg_act[i]: act tensor [B][H][W][seg_ctensor[i]], channel window [seg_c0, seg_c0+seg_c);
  * seg_w[i]: packed weights [taps][N][seg_cw[i]] in act dtype, window starting at seg_wc0[i].
- * stats (optional): double [B][N][2] GroupNorm statistics of `out`, produced by the epilogue (deterministic);
- * needs stats_scratch of use_op_conv_tc_stats_scratch_bytes() device bytes. */
+ * stats (optional): fixed-point [B][N][2] GroupNorm statistics of `out` accumulated by the epilogue (zero it first). */
 int use_op_conv_tc(int dtype, int nseg, const void* const* seg_act, const int* seg_ctensor, const int* seg_c0,
                    const int* seg_c, const void* const* seg_w, const int* seg_cw, const int* seg_wc0, const int* seg_taps,
                    int B, int H, int W, int N, const float* bias, int bias_bstride, const void* res, float scale, void* out,
-                   double* stats, void* stats_scratch, void* stream);
-size_t use_op_conv_tc_stats_scratch_bytes(int dtype, int B, int H, int W, int N);
+                   long long* stats, void* stream);
 int use_op_conv_ref(int dtype, const void* x, const float* w, const float* bias, int bias_bstride, const void* res,
                     float scale, void* out, int B, int H, int W, int Cin, int Cout, int ksize, void* stream);
 int use_op_conv_in4(int dtype, const float* x, const float* w, const float* bias, void* out, int B, int H, int W, int N,

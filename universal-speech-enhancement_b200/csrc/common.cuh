@@ -77,6 +77,22 @@ template <> struct Vec<__nv_bfloat16> {
 
 __device__ __forceinline__ float silu(float x) { return x / (1.0f + __expf(-x)); }
 
+// GroupNorm statistics are accumulated as 64-bit FIXED-POINT integers with atomicAdd: integer addition is associative,
+// so the result is bit-reproducible and independent of tile order, batch size and launch geometry without any
+// finalize pass.  Per-channel sum uses 2^-28 resolution (|sum| < 3.4e10), sum of squares 2^-24 (< 5.5e11).
+constexpr float kStatSumScale = 268435456.0f;   // 2^28
+constexpr float kStatSqScale = 16777216.0f;     // 2^24
+__device__ __forceinline__ void stat_atomic_add(long long* dst, float sum, float sq) {
+  atomicAdd(reinterpret_cast<unsigned long long*>(dst), static_cast<unsigned long long>(__float2ll_rn(sum * kStatSumScale)));
+  atomicAdd(reinterpret_cast<unsigned long long*>(dst + 1), static_cast<unsigned long long>(__float2ll_rn(sq * kStatSqScale)));
+}
+__device__ __forceinline__ void stat_atomic_add(long long* dst, double sum, double sq) {
+  atomicAdd(reinterpret_cast<unsigned long long*>(dst),
+            static_cast<unsigned long long>(__double2ll_rn(sum * static_cast<double>(kStatSumScale))));
+  atomicAdd(reinterpret_cast<unsigned long long*>(dst + 1),
+            static_cast<unsigned long long>(__double2ll_rn(sq * static_cast<double>(kStatSqScale))));
+}
+
 // ------------------------------------------------------------------------------------------
 // PTX: mbarrier
 // ------------------------------------------------------------------------------------------

@@ -169,7 +169,7 @@ TcConvPlan* tc_conv_plan_create(int dt, const TcConvDesc& d, int num_sms, char* 
   P.tiles_h = (d.H + tile_h - 1) / tile_h;
   P.ntiles = P.tiles_w * P.tiles_h * d.B;
   P.out = d.out; P.bias = d.bias; P.bias_bstride = d.bias_bstride; P.res = d.res; P.scale = d.scale;
-  P.stats_partial = d.stats_partial;
+  P.stats_acc = d.stats_acc;
   P.out4 = d.out4; P.prev4 = d.prev4;
   const int units = (P.ntiles + p->mc - 1) / p->mc;           // tile groups
   const int max_groups = num_sms / p->mc;
@@ -182,42 +182,6 @@ void tc_conv_plan_destroy(TcConvPlan* p) { delete p; }
 int tc_conv_tiles_per_image(int dt, int N, int H, int W) {
   const int tile_h = (N == 256) ? 16 : 32;  // NSUB = 1 for N = 256, 2 otherwise (see tc_conv_plan_create)
   return ((W + 7) / 8) * ((H + tile_h - 1) / tile_h);
-}
-
-// grid (kFinalizeSlices, B), block 256
-__global__ void __launch_bounds__(256) gn_finalize_kernel(const float* __restrict__ partial, double* __restrict__ stats,
-                                                           double* __restrict__ slices, unsigned int* __restrict__ tickets,
-                                                           int tiles, int N) {
-  __shared__ unsigned int s_ticket;
-  const int b = blockIdx.y, sl = blockIdx.x, ns = gridDim.x;
-  const int per = (tiles + ns - 1) / ns;
-  const int t0 = sl * per, t1 = min(tiles, t0 + per);
-  const float* pb = partial + static_cast<size_t>(b) * tiles * N * 2;
-  double* mine = slices + (static_cast<size_t>(b) * ns + sl) * N * 2;
-  for (int i = threadIdx.x; i < N * 2; i += blockDim.x) {
-    double acc = 0.0;
-    for (int t = t0; t < t1; ++t) acc += static_cast<double>(__ldcg(pb + static_cast<size_t>(t) * N * 2 + i));
-    mine[i] = acc;
-  }
-  __threadfence();
-  __syncthreads();
-  if (threadIdx.x == 0) s_ticket = atomicAdd(&tickets[b], 1u);
-  __syncthreads();
-  if (s_ticket == static_cast<unsigned>(ns - 1)) {
-    __threadfence();
-    const double* sb = slices + static_cast<size_t>(b) * ns * N * 2;
-    for (int i = threadIdx.x; i < N * 2; i += blockDim.x) {
-      double acc = 0.0;
-      for (int k = 0; k < ns; ++k) acc += __ldcg(sb + static_cast<size_t>(k) * N * 2 + i);
-      stats[static_cast<size_t>(b) * N * 2 + i] = acc;
-    }
-    if (threadIdx.x == 0) tickets[b] = 0;
-  }
-}
-
-void launch_gn_finalize(const float* partial, double* stats, double* slices, unsigned int* tickets, int B,
-                        int tiles_per_img, int N, cudaStream_t st) {
-  gn_finalize_kernel<<<dim3(kFinalizeSlices, B), 256, 0, st>>>(partial, stats, slices, tickets, tiles_per_img, N);
 }
 
 void tc_conv_launch(const TcConvPlan* p, cudaStream_t st) {

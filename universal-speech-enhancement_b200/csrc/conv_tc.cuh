@@ -41,7 +41,7 @@ struct alignas(64) ConvParams {
   int bias_bstride;   // N (per-sample bias incl. the time-embedding term) or 0
   const void* res;    // optional residual, T [B][H][W][N]
   float scale;        // out = (acc + bias [+ res]) * scale
-  float* stats_partial;  // optional [B][tiles_per_img][N][2]: per-tile column sums / sums of squares of `out`
+  long long* stats_acc;  // optional [B][N][2] fixed-point accumulators (zero on entry): sum / sum of squares of `out`
   // "pyramid head" mode (N = 32, only output channels 0..3 are real): fp32 [B][H][W][4] = acc + bias (+ FIR-up(prev4))
   float* out4;
   const float* prev4;    // optional fp32 [B][H/2][W/2][4]
@@ -330,7 +330,7 @@ __global__ void __launch_bounds__(ConvCfg<T, N, NSUB>::THREADS, 1) conv_tc_kerne
               }
             }
           }
-          if (p.stats_partial != nullptr) {
+          if (p.stats_acc != nullptr) {
             // even lane finishes channel ce (its own pixels + the partner's), odd lane channel ce+1; fixed order
             const float os = __shfl_xor_sync(0xffffffffu, odd ? s2[0] : s2[1], 1);
             const float oq = __shfl_xor_sync(0xffffffffu, odd ? q2[0] : q2[1], 1);
@@ -375,7 +375,7 @@ __global__ void __launch_bounds__(ConvCfg<T, N, NSUB>::THREADS, 1) conv_tc_kerne
             }
           }
         }
-        if (p.stats_partial != nullptr) {
+        if (p.stats_acc != nullptr) {
           // stat_s layout in this mode: [half = sub][N][2]
           stat_s[(sub * N + c) * 2] = s_sum;
           stat_s[(sub * N + c) * 2 + 1] = s_sq;
@@ -453,7 +453,7 @@ __global__ void __launch_bounds__(ConvCfg<T, N, NSUB>::THREADS, 1) conv_tc_kerne
             Vec<T>::store(out + pix * N + c0 + j, v);
           }
         }
-        if (p.stats_partial != nullptr) {
+        if (p.stats_acc != nullptr) {
           // column sums over this warp's 32 rows by recursive halving (31 shuffles): lane j ends with column c0 + j
           float a[32];
 #pragma unroll
@@ -489,20 +489,21 @@ __global__ void __launch_bounds__(ConvCfg<T, N, NSUB>::THREADS, 1) conv_tc_kerne
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&t_empty[acs]);
-      if (p.stats_partial != nullptr) {
+      if (p.stats_acc != nullptr) {
         // combine the epilogue warps of this tile in a fixed order (deterministic) and publish the tile partial
         constexpr int ET = 32 * C::EPI_WARPS;
         asm volatile("bar.sync 1, %0;" ::"r"(ET) : "memory");
-        float* dst = p.stats_partial + static_cast<size_t>(tile) * N * 2;  // tile = b * tiles_per_img + rem
-        for (int i = threadIdx.x - 64; i < N * 2 && !ghost; i += ET) {
-          float acc = 0.f;
+        long long* dst = p.stats_acc + static_cast<size_t>(b) * N * 2;
+        for (int i = threadIdx.x - 64; i < N && !ghost; i += ET) {
+          float sm_ = 0.f, sq_ = 0.f;
           if constexpr (SWAP) {
-            acc = stat_s[i] + stat_s[N * 2 + i];  // the two pixel halves
+            sm_ = stat_s[i * 2] + stat_s[(N + i) * 2];  // the two pixel halves, fixed order
+            sq_ = stat_s[i * 2 + 1] + stat_s[(N + i) * 2 + 1];
           } else {
 #pragma unroll
-            for (int w = 0; w < C::EPI_WARPS; ++w) acc += stat_s[w * N * 2 + i];
+            for (int w = 0; w < C::EPI_WARPS; ++w) { sm_ += stat_s[(w * N + i) * 2]; sq_ += stat_s[(w * N + i) * 2 + 1]; }
           }
-          dst[i] = acc;
+          stat_atomic_add(dst + i * 2, sm_, sq_);  // integer atomics: order-independent, hence deterministic
         }
         asm volatile("bar.sync 1, %0;" ::"r"(ET) : "memory");
       }

@@ -22,35 +22,31 @@ namespace use {
   } while (0)
 
 // ------------------------------------------------------------------------------------------------
-// GroupNorm statistics: per sample and per CHANNEL sum and sum of squares.
-// Channels (not groups) so that a GroupNorm over a channel concat whose group boundary straddles the
-// two sources (384 = 256 + 128 channels, 12 per group) can be assembled from per-tensor partials.
-// BITWISE DETERMINISTIC and independent of the batch size: no floating-point atomics anywhere.  Every
-// block reduces a fixed pixel range in a fixed order and publishes a double partial; the block that
-// takes the last ticket of its sample sums the partials in block order.  (Any run-to-run ulp difference
-// would be amplified to the bf16 / TF32 rounding-noise floor within a few layers, which would break
-// "clips sampled alone == clips sampled in a batch".)
+// GroupNorm statistics of a tensor that no conv epilogue produced (Combine outputs): per sample and per CHANNEL
+// sum and sum of squares.  Channels (not groups) so that a GroupNorm over a channel concat whose group boundary
+// straddles the two sources (384 = 256 + 128 channels, 12 per group) can be assembled from per-tensor partials.
+// Every block reduces a fixed pixel range in a fixed order and adds its partial with 64-bit fixed-point integer
+// atomics (common.cuh): bit-reproducible and independent of the batch size.  (Any run-to-run ulp difference would be
+// amplified to the bf16 / TF32 rounding-noise floor within a few layers, which would break "a clip sampled alone ==
+// the same clip sampled in a batch".)
 // ------------------------------------------------------------------------------------------------
 constexpr int kGnPixPerBlock = 2048;
 
 template <typename T>
-__global__ void __launch_bounds__(256) gn_stats_kernel(const T* __restrict__ x, double* __restrict__ stats,
-                                                        double* __restrict__ partials, unsigned int* __restrict__ tickets,
-                                                        int HW, int C) {
+__global__ void __launch_bounds__(256) gn_stats_kernel(const T* __restrict__ x, long long* __restrict__ stats, int HW, int C) {
   constexpr int V = Vec<T>::N;
   extern __shared__ float sred[];  // [rows][C][2]
-  __shared__ unsigned int s_ticket;
-  const int b = blockIdx.y, nblk = gridDim.x;
+  const int b = blockIdx.y;
   const int vp = C / V;  // vectors per pixel
   const int p0 = blockIdx.x * kGnPixPerBlock;
   const int p1 = min(HW, p0 + kGnPixPerBlock);
   const T* base = x + (static_cast<size_t>(b) * HW) * C;
-  // thread -> fixed vector column v and pixel row r; rows = number of pixel rows processed concurrently
+  const int lanes = min(vp, static_cast<int>(blockDim.x));
   const int rows = max(1, static_cast<int>(blockDim.x) / vp);
-  const int nact = rows * min(vp, static_cast<int>(blockDim.x));
+  const int nact = rows * lanes;
   for (int v0 = 0; v0 < vp; v0 += blockDim.x) {  // vp > blockDim only for very wide tensors
-    const int v = v0 + (threadIdx.x % min(vp, static_cast<int>(blockDim.x)));
-    const int r = threadIdx.x / min(vp, static_cast<int>(blockDim.x));
+    const int v = v0 + (threadIdx.x % lanes);
+    const int r = threadIdx.x / lanes;
     float s[V], ss[V];
 #pragma unroll
     for (int i = 0; i < V; ++i) s[i] = ss[i] = 0.f;
@@ -69,42 +65,23 @@ __global__ void __launch_bounds__(256) gn_stats_kernel(const T* __restrict__ x, 
     }
   }
   __syncthreads();
-  double* mine = partials + (static_cast<size_t>(b) * nblk + blockIdx.x) * C * 2;
-  for (int i = threadIdx.x; i < C * 2; i += blockDim.x) {
-    double acc = 0.0;
-    for (int r = 0; r < rows; ++r) acc += static_cast<double>(sred[r * C * 2 + i]);
-    mine[i] = acc;
-  }
-  __threadfence();
-  __syncthreads();
-  if (threadIdx.x == 0) s_ticket = atomicAdd(&tickets[b], 1u);
-  __syncthreads();
-  if (s_ticket == static_cast<unsigned>(nblk - 1)) {
-    __threadfence();
-    const double* pb = partials + static_cast<size_t>(b) * nblk * C * 2;
-    for (int i = threadIdx.x; i < C * 2; i += blockDim.x) {
-      double acc = 0.0;
-      for (int k = 0; k < nblk; ++k) acc += __ldcg(pb + static_cast<size_t>(k) * C * 2 + i);
-      stats[static_cast<size_t>(b) * C * 2 + i] = acc;
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    double a = 0.0, q = 0.0;
+    for (int r = 0; r < rows; ++r) {
+      a += static_cast<double>(sred[(r * C + c) * 2]);
+      q += static_cast<double>(sred[(r * C + c) * 2 + 1]);
     }
-    if (threadIdx.x == 0) tickets[b] = 0;  // ready for the next launch that shares the scratch
+    stat_atomic_add(stats + (static_cast<size_t>(b) * C + c) * 2, a, q);
   }
 }
 
-size_t gn_stats_scratch_bytes(int B, int HW, int C) {
-  const size_t nblk = (HW + kGnPixPerBlock - 1) / kGnPixPerBlock;
-  return static_cast<size_t>(B) * nblk * C * 2 * sizeof(double);
-}
-
-void launch_gn_stats(int dt, const void* x, double* stats, double* partials, unsigned int* tickets, int B, int HW, int C,
-                     cudaStream_t st) {
+void launch_gn_stats(int dt, const void* x, long long* stats, int B, int HW, int C, cudaStream_t st) {
   dim3 grid((HW + kGnPixPerBlock - 1) / kGnPixPerBlock, B);
   DISPATCH_DT(dt, {
     constexpr int V = Vec<T>::N;
     const int vp = C / V;
     const int rows = vp >= 256 ? 1 : 256 / vp;
-    gn_stats_kernel<T><<<grid, 256, static_cast<size_t>(rows) * C * 2 * sizeof(float), st>>>((const T*)x, stats, partials,
-                                                                                            tickets, HW, C);
+    gn_stats_kernel<T><<<grid, 256, static_cast<size_t>(rows) * C * 2 * sizeof(float), st>>>((const T*)x, stats, HW, C);
   });
 }
 
@@ -114,7 +91,7 @@ void launch_gn_stats(int dt, const void* x, double* stats, double* partials, uns
 template <typename T>
 struct GnSrcT {
   const T* x;
-  const double* stats;
+  const long long* stats;
   int C;
 };
 
@@ -151,11 +128,11 @@ __global__ void __launch_bounds__(256) gn_apply_kernel(GnSrcT<T> s0, GnSrcT<T> s
     const int g = c / cpg;
     double sum = 0.0, sq = 0.0;
     for (int cc = g * cpg; cc < (g + 1) * cpg; ++cc) {  // channel index in the concatenation
-      const double2 st = __ldg(reinterpret_cast<const double2*>(
+      const longlong2 st = __ldg(reinterpret_cast<const longlong2*>(
           (cc < s0.C) ? s0.stats + (static_cast<size_t>(b) * s0.C + cc) * 2
                       : s1.stats + (static_cast<size_t>(b) * s1.C + (cc - s0.C)) * 2));
-      sum += st.x;
-      sq += st.y;
+      sum += static_cast<double>(st.x) * (1.0 / kStatSumScale);
+      sq += static_cast<double>(st.y) * (1.0 / kStatSqScale);
     }
     const double mean = sum * inv_cnt;
     double var = sq * inv_cnt - mean * mean;  // biased variance, like nn.GroupNorm
@@ -390,9 +367,9 @@ __global__ void __launch_bounds__(256) gn_apply_fir_tiled_kernel(GnSrcT<T> s0, c
     const double inv_cnt = 1.0 / (static_cast<double>(Hin) * Win * cpg);
     double sum = 0.0, sq = 0.0;
     for (int cc = g * cpg; cc < (g + 1) * cpg; ++cc) {
-      const double2 st = __ldg(reinterpret_cast<const double2*>(s0.stats + (static_cast<size_t>(b) * C + cc) * 2));
-      sum += st.x;
-      sq += st.y;
+      const longlong2 st = __ldg(reinterpret_cast<const longlong2*>(s0.stats + (static_cast<size_t>(b) * C + cc) * 2));
+      sum += static_cast<double>(st.x) * (1.0 / kStatSumScale);
+      sq += static_cast<double>(st.y) * (1.0 / kStatSqScale);
     }
     const double mean = sum * inv_cnt;
     double var = sq * inv_cnt - mean * mean;

@@ -191,7 +191,7 @@ struct use_engine {
   int num_sms = 148;
   std::map<std::string, std::unique_ptr<Program>> programs;  // keyed by "B,F,T,base"
   // fixed head of the workspace (byte offsets)
-  struct Head { size_t xr, xpad, t, gfp, temb, dense, stats, gn_scratch, tickets, conv_part, fin_slices, arena; } head;
+  struct Head { size_t xr, xpad, t, gfp, temb, dense, stats, arena; } head;
   // instrumentation
   long long launches = 0;
   bool profiling = false;
@@ -403,9 +403,6 @@ struct Builder {
   int B, F, T;
   Arena arena;
   size_t stats_top = 0;
-  size_t gn_scratch_max = 0;
-  size_t conv_part_max = 0;  // bytes of the largest per-tile statistics scratch any conv needs
-  int fin_nmax = 0;
   char* base;      // workspace base (nullptr on the dry run)
   bool dry;
   int err = 0;
@@ -415,7 +412,7 @@ struct Builder {
   char* ws(size_t off) const { return base + e->head.arena + off; }
   char* wt(size_t off) const { return e->dev_w + off; }
   const float* wf(const std::string& k) const { return (const float*)(e->dev_w + e->off.at(k)); }
-  double* stats_ptr(size_t off) const { return (double*)(base + e->head.stats + off); }
+  long long* stats_ptr(size_t off) const { return (long long*)(base + e->head.stats + off); }
 
   Act new_act(int C, int H, int W) {
     Act a;
@@ -435,15 +432,12 @@ struct Builder {
   void ensure_stats(Act& a) {
     if (a.stats_off != (size_t)-1) return;
     a.stats_off = stats_top;
-    stats_top += (size_t)B * a.C * 2 * sizeof(double);
-    gn_scratch_max = std::max(gn_scratch_max, gn_stats_scratch_bytes(B, a.H * a.W, a.C));
+    stats_top += (size_t)B * a.C * 2 * sizeof(long long);
     if (dry) return;
     const int dt = e->dt, Bn = B, HW = a.H * a.W, C = a.C;
     const void* x = ws(a.off);
-    double* st = stats_ptr(a.stats_off);
-    double* scratch = (double*)(base + e->head.gn_scratch);
-    unsigned int* tickets = (unsigned int*)(base + e->head.tickets);
-    emit([=](cudaStream_t s) { launch_gn_stats(dt, x, st, scratch, tickets, Bn, HW, C, s); }, TAG_GN_STATS, 1, 3.0 * Bn * HW * C,
+    long long* st = stats_ptr(a.stats_off);
+    emit([=](cudaStream_t s) { launch_gn_stats(dt, x, st, Bn, HW, C, s); }, TAG_GN_STATS, 1, 3.0 * Bn * HW * C,
          (double)Bn * HW * C * es());
   }
   void gn_apply(Act& s0, Act* s1, size_t gamma_off, size_t beta_off, int fir, bool silu, bool operand, Act& out, Act* raw) {
@@ -467,14 +461,10 @@ struct Builder {
   }
   // stat_target: the conv's output tensor when the epilogue should also produce its GroupNorm statistics
   void conv_tc(TcConvDesc d, Act* stat_target = nullptr) {
-    int tiles = 0;
     if (stat_target) {
-      tiles = tc_conv_tiles_per_image(e->dt, d.N, d.H, d.W);
-      conv_part_max = std::max(conv_part_max, (size_t)B * tiles * d.N * 2 * sizeof(float));
-      fin_nmax = std::max(fin_nmax, d.N);
       stat_target->stats_off = stats_top;
-      stats_top += (size_t)B * d.N * 2 * sizeof(double);
-      if (!dry) d.stats_partial = (float*)(base + e->head.conv_part);
+      stats_top += (size_t)B * d.N * 2 * sizeof(long long);
+      if (!dry) d.stats_acc = stats_ptr(stat_target->stats_off);
     }
     if (dry) return;
     char msg[512];
@@ -486,15 +476,6 @@ struct Builder {
     const double px = (double)d.B * d.H * d.W;
     emit([=](cudaStream_t s) { tc_conv_launch(p, s); }, TAG_CONV_TC, 1, 2.0 * px * d.N * k,
          (px * (cin + d.N * (d.res ? 2 : 1))) * es());
-    if (stat_target) {
-      const float* part = d.stats_partial;
-      double* st = stats_ptr(stat_target->stats_off);
-      double* slices = (double*)(base + e->head.fin_slices);
-      unsigned int* tickets = (unsigned int*)(base + e->head.tickets);
-      const int Bn = B, N = d.N;
-      emit([=](cudaStream_t s) { launch_gn_finalize(part, st, slices, tickets, Bn, tiles, N, s); }, TAG_GN_STATS, 1, 0,
-           (double)Bn * tiles * N * 8);
-    }
   }
 
   // ResnetBlockBigGANpp.forward (layerspp.py:282-314).  x1 != nullptr: input is cat[x0, x1].
@@ -747,10 +728,6 @@ static int plan_workspace(use_engine* e, int B, int F, int T, size_t* total, siz
   e->head.temb = off; off = align_up(off + (size_t)B * 4 * c.nf * 4, 1024);
   e->head.dense = off; off = align_up(off + (size_t)B * e->dense_rows * 4, 1024);
   e->head.stats = off; off = align_up(off + b.stats_top, 1024);
-  e->head.gn_scratch = off; off = align_up(off + b.gn_scratch_max, 1024);
-  e->head.tickets = off; off = align_up(off + (size_t)B * 4, 1024);
-  e->head.conv_part = off; off = align_up(off + b.conv_part_max, 1024);
-  e->head.fin_slices = off; off = align_up(off + (size_t)B * kFinalizeSlices * 2 * b.fin_nmax * sizeof(double), 1024);
   e->head.arena = off;
   *total = off + b.arena.peak;
   if (stats_bytes) *stats_bytes = b.stats_top;
@@ -786,7 +763,7 @@ static Program* get_program(use_engine* e, int B, int F, int T, void* workspace,
 static void run_network(use_engine* e, Program* p, cudaStream_t st) {
   char* base = p->base;
   const int nf = e->cfg.nf;
-  cudaMemsetAsync(base + e->head.tickets, 0, (size_t)p->B * 4, st);
+  cudaMemsetAsync(base + e->head.stats, 0, p->stats_bytes, st);  // fixed-point accumulators start at zero
   launch_temb_mlp((const float*)(base + e->head.gfp), (const float*)(e->dev_w + e->off.at("l1.w")),
                   (const float*)(e->dev_w + e->off.at("l1.b")), (const float*)(e->dev_w + e->off.at("l2.w")),
                   (const float*)(e->dev_w + e->off.at("l2.b")), (float*)(base + e->head.temb), p->B, nf, st);
@@ -1046,14 +1023,12 @@ int use_upfirdn2d_f32(const float* in, float* out, int major, int in_h, int in_w
 }
 
 // ---- single-kernel exports ----------------------------------------------------------------------
-size_t use_op_gn_stats_scratch_bytes(int B, int HW, int C) { return gn_stats_scratch_bytes(B, HW, C); }
-int use_op_gn_stats(int dtype, const void* x, double* stats, void* scratch, void* tickets, int B, int HW, int C,
-                    void* stream) {
-  if (!x || !stats || !scratch || !tickets) return fail("null argument");
-  launch_gn_stats(dtype, x, stats, (double*)scratch, (unsigned int*)tickets, B, HW, C, (cudaStream_t)stream);
+int use_op_gn_stats(int dtype, const void* x, long long* stats, int B, int HW, int C, void* stream) {
+  if (!x || !stats) return fail("null argument");
+  launch_gn_stats(dtype, x, stats, B, HW, C, (cudaStream_t)stream);
   return cuda_check("use_op_gn_stats");
 }
-int use_op_gn_apply(int dtype, const void* x0, const double* stats0, int C0, const void* x1, const double* stats1, int C1,
+int use_op_gn_apply(int dtype, const void* x0, const long long* stats0, int C0, const void* x1, const long long* stats1, int C1,
                     const float* gamma, const float* beta, float eps, int fir, int do_silu, int as_operand, void* out_act,
                     void* out_raw, int B, int Hin, int Win, void* stream) {
   launch_gn_apply(dtype, GnSrc{x0, stats0, C0}, GnSrc{x1, stats1, C1}, gamma, beta, eps, fir, do_silu != 0, as_operand != 0,
@@ -1063,24 +1038,15 @@ int use_op_gn_apply(int dtype, const void* x0, const double* stats0, int C0, con
 int use_op_conv_tc(int dtype, int nseg, const void* const* seg_act, const int* seg_ctensor, const int* seg_c0,
                    const int* seg_c, const void* const* seg_w, const int* seg_cw, const int* seg_wc0, const int* seg_taps,
                    int B, int H, int W, int N, const float* bias, int bias_bstride, const void* res, float scale, void* out,
-                   double* stats, void* stats_scratch, void* stream) {
+                   long long* stats, void* stream) {
   if (nseg < 1 || nseg > 3) return fail("nseg must be 1..3");
-  if (stats && !stats_scratch) return fail("stats requested without scratch");
   TcConvDesc d{};
   d.nseg = nseg;
   for (int i = 0; i < nseg; ++i)
     d.seg[i] = TcSegDesc{seg_act[i], seg_ctensor[i], seg_c0[i], seg_c[i], seg_w[i], seg_cw[i], seg_wc0[i], seg_taps[i]};
   d.B = B; d.H = H; d.W = W; d.N = N;
   d.out = out; d.bias = bias; d.bias_bstride = bias_bstride; d.res = res; d.scale = scale;
-  // scratch layout: tickets [B] u32 (zeroed here) | slices | per-tile partials
-  const int tiles = tc_conv_tiles_per_image(dtype, N, H, W);
-  char* sc = (char*)stats_scratch;
-  const size_t off_slices = ((size_t)B * 4 + 255) & ~size_t(255);
-  const size_t off_part = off_slices + (size_t)B * kFinalizeSlices * 2 * N * sizeof(double);
-  if (stats) {
-    cudaMemsetAsync(sc, 0, (size_t)B * 4, (cudaStream_t)stream);
-    d.stats_partial = (float*)(sc + off_part);
-  }
+  d.stats_acc = stats;  // fixed-point accumulators, zeroed by the caller
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
@@ -1088,16 +1054,9 @@ int use_op_conv_tc(int dtype, int nseg, const void* const* seg_act, const int* s
   TcConvPlan* p = tc_conv_plan_create(dtype, d, sms, msg, sizeof(msg));
   if (!p) return fail("%s", msg);
   tc_conv_launch(p, (cudaStream_t)stream);
-  if (stats)
-    launch_gn_finalize(d.stats_partial, stats, (double*)(sc + off_slices), (unsigned int*)sc, B, tiles, N, (cudaStream_t)stream);
   cudaStreamSynchronize((cudaStream_t)stream);  // the plan (tensor maps live in kernel params) can go now
   tc_conv_plan_destroy(p);
   return cuda_check("use_op_conv_tc");
-}
-size_t use_op_conv_tc_stats_scratch_bytes(int dtype, int B, int H, int W, int N) {
-  const int tiles = tc_conv_tiles_per_image(dtype, N, H, W);
-  return (((size_t)B * 4 + 255) & ~size_t(255)) + (size_t)B * kFinalizeSlices * 2 * N * sizeof(double) +
-         (size_t)B * tiles * N * 2 * sizeof(float);
 }
 int use_op_conv_ref(int dtype, const void* x, const float* w, const float* bias, int bias_bstride, const void* res,
                     float scale, void* out, int B, int H, int W, int Cin, int Cout, int ksize, void* stream) {

@@ -12,15 +12,13 @@ enum ActDtype { kF32 = 0, kBF16 = 1 };
 inline size_t act_size(int dt) { return dt == kBF16 ? 2 : 4; }
 
 // ---- GroupNorm ---------------------------------------------------------------------------------
-// stats: double [B][C][2] (sum, sum of squares per channel), overwritten.  Deterministic (no fp atomics):
-// `partials` is scratch of gn_stats_scratch_bytes(B, HW, C) bytes, `tickets` [B] uint32 zero on entry (left zero).
-size_t gn_stats_scratch_bytes(int B, int HW, int C);
-void launch_gn_stats(int dt, const void* x, double* stats, double* partials, unsigned int* tickets, int B, int HW, int C,
-                     cudaStream_t st);
+// stats: int64 fixed point [B][C][2] (sum * 2^28, sum of squares * 2^24 per channel), ACCUMULATED into (zero it first).
+// Integer atomics only: bit-reproducible, independent of launch geometry and batch size.
+void launch_gn_stats(int dt, const void* x, long long* stats, int B, int HW, int C, cudaStream_t st);
 
 struct GnSrc {
   const void* x;        // act [B][Hin][Win][C]
-  const double* stats;  // [B][C][2]
+  const long long* stats;  // fixed point [B][C][2]
   int C;
 };
 // out_act = FIR(silu?(groupnorm(cat[s0,s1])))  (fir: 0 none, 1 down x2, 2 up x2), written as an MMA operand
@@ -126,7 +124,7 @@ struct TcConvDesc {
   int bias_bstride;
   const void* res;
   float scale;
-  float* stats_partial;  // optional scratch [B][tiles_per_img][N][2] floats, see tc_conv_stats_scratch_bytes
+  long long* stats_acc;  // optional fixed-point GroupNorm statistics of `out`, [B][N][2], zero on entry
   float* out4;           // pyramid-head mode (N must be 32): fp32 [B][H][W][4] output instead of `out`
   const float* prev4;    // optional previous pyramid level, fp32 [B][H/2][W/2][4], FIR-upsampled and added
 };
@@ -137,10 +135,5 @@ void tc_conv_plan_destroy(TcConvPlan* p);
 void tc_conv_launch(const TcConvPlan* p, cudaStream_t st);
 bool tc_conv_supported(int dt, int N);
 int tc_conv_tiles_per_image(int dt, int N, int H, int W);
-// Sum the per-tile partials written by the conv epilogue in tile order (double accumulation) into stats [B][N][2].
-// slices: double scratch [B][kFinalizeSlices][2N]; tickets [B] zero on entry (left zero).  Deterministic.
-constexpr int kFinalizeSlices = 8;
-void launch_gn_finalize(const float* partial, double* stats, double* slices, unsigned int* tickets, int B,
-                        int tiles_per_img, int N, cudaStream_t st);
 
 }  // namespace use
