@@ -71,6 +71,9 @@ int use_engine_pack(use_engine* e, size_t* bytes);
 int use_engine_upload(use_engine* e, void* dev_weights, size_t bytes, void* stream);
 /* Workspace (device bytes) a forward / sample over B spectrograms of F x T (T % 2^(levels-1) == 0) needs. */
 int use_engine_workspace_bytes(use_engine* e, int B, int F, int T, size_t* bytes);
+/* Options: "overlap_groups" = 1 | 2 (default 2): use_pc_sample splits an even batch >= 4 into two halves that run
+ * on their own streams so the HBM-bound kernels of one half overlap the tensor-bound convolutions of the other. */
+int use_engine_set_option(use_engine* e, const char* key, int value);
 
 /* Instrumentation: kernels launched so far by this engine; per-op-class CUDA-event timing of network evaluations
  * (events on the launch stream, one pair per op; enable only outside timed regions). */

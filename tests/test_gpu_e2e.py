@@ -179,6 +179,12 @@ def test_full_size_properties_bf16():
     assert torch.equal(a, a2)  # same seed, same result
     c = m.sample({"perturbed": y}, N=2, seed=6)["enhanced"]
     assert rel_l2(c.cpu(), a.cpu()) > 1e-3  # a different seed gives a different sample
+    # batch of 4 = two half-batches on two streams inside use_pc_sample: still bit-identical per clip
+    y4 = O.synthetic_clips(4, 96000).cuda()
+    a4 = m.sample({"perturbed": y4}, N=2, seed=5)["enhanced"]
+    assert torch.equal(a4[:2], a) and bool(torch.isfinite(a4).all())
+    b3 = m.sample({"perturbed": y4[3:4]}, N=2, seed=5, clip0=3)["enhanced"]
+    assert torch.equal(b3, a4[3:4])
 
 
 def test_generic_sampler_route_matches_fused():

@@ -21,7 +21,7 @@ DTYPE_BF16 = 1
 # every symbol include/use_b200.h declares (tests check the header against this list and the .so)
 SYMBOLS = [
     "use_abi_version", "use_last_error", "use_engine_create", "use_engine_destroy", "use_engine_set_weight",
-    "use_engine_pack", "use_engine_upload", "use_engine_workspace_bytes", "use_engine_launch_count", "use_engine_set_profiling",
+    "use_engine_pack", "use_engine_upload", "use_engine_workspace_bytes", "use_engine_set_option", "use_engine_launch_count", "use_engine_set_profiling",
     "use_engine_get_profile", "use_engine_get_profile_ops", "use_score_forward", "use_pc_sample",
     "use_stft", "use_istft", "use_upfirdn2d_f32", "use_op_gn_stats", "use_op_gn_apply", "use_op_conv_tc",
     "use_op_conv_ref", "use_op_conv_in4", "use_op_conv_out4", "use_op_combine", "use_op_fir4_down", "use_op_philox",
@@ -75,6 +75,7 @@ def lib() -> C.CDLL:
         L.use_engine_pack.argtypes = [vp, C.POINTER(sz)]
         L.use_engine_upload.argtypes = [vp, vp, sz, vp]
         L.use_engine_workspace_bytes.argtypes = [vp, i32, i32, i32, C.POINTER(sz)]
+        L.use_engine_set_option.argtypes = [vp, C.c_char_p, i32]
         L.use_engine_launch_count.restype = C.c_longlong
         L.use_engine_launch_count.argtypes = [vp]
         L.use_engine_set_profiling.argtypes = [vp, i32]

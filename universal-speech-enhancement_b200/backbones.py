@@ -14,6 +14,7 @@ from __future__ import annotations
 
 import ctypes as C
 import math
+import os
 from typing import Dict, List, Tuple
 
 import numpy as np
@@ -234,6 +235,9 @@ class _Engine:
             self.h = self.L.use_engine_create(C.byref(cfg))
             if not self.h:
                 raise RuntimeError("use_engine_create failed: " + self.L.use_last_error().decode())
+            # two half-batches on two streams (HBM-bound kernels of one overlap the convolutions of the other)
+            _lib.check(self.L.use_engine_set_option(self.h, b"overlap_groups", int(os.environ.get("USE_B200_OVERLAP", "2"))),
+                       "use_engine_set_option")
             for name, p in net.state_dict().items():
                 w = p.detach().to("cpu", torch.float32).contiguous()
                 shape = (C.c_int64 * max(w.dim(), 1))(*w.shape)

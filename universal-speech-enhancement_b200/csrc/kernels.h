@@ -54,7 +54,8 @@ void launch_pack_input(int dt, const float2* x, const float2* Y, float* xr, void
 
 struct StepArgs {
   const float* pyramid;  // fp32 [B][F][T][4]
-  const float* t;        // [B] time value of each sample (divides the pyramid: scale_by_sigma)
+  const float* t;        // time value of sample b at t[b * t_bstride] (divides the pyramid: scale_by_sigma)
+  int t_bstride;         // 1 = per-sample times, 0 = one batch-uniform time
   const float* ow;       // output_layer weight [2][4]
   const float* ob;       // output_layer bias [2]
   float2* score;         // optional out: -net(x)   (ScoreModel.forward)
@@ -80,8 +81,8 @@ void launch_philox_fill(float2* z, unsigned long long seed, unsigned int step, u
                         size_t per_clip, cudaStream_t st);
 
 // ---- time embedding ---------------------------------------------------------------------------------
-// gfp [B][2*nf] (host-computed Fourier features) -> silu(Linear(silu(Linear(gfp)))) [B][4*nf]
-void launch_temb_mlp(const float* gfp, const float* w1, const float* b1, const float* w2, const float* b2, float* out,
+// gfp (Fourier features, sample b at gfp + b * gfp_bstride) -> silu(Linear(silu(Linear(gfp)))) [B][4*nf]
+void launch_temb_mlp(const float* gfp, int gfp_bstride, const float* w1, const float* b1, const float* w2, const float* b2, float* out,
                      int B, int nf, cudaStream_t st);
 // out[b][n] = base[n] + sum_k W[n][k] * temb[b][k]  for all rows of all ResBlocks at once
 void launch_dense_all(const float* temb, const float* W, const float* base, float* out, int B, int rows, int K,

@@ -76,7 +76,7 @@ __global__ void __launch_bounds__(256) final_step_kernel(StepArgs a) {
   for (size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n;
        i += static_cast<size_t>(gridDim.x) * blockDim.x) {
     const int b = static_cast<int>(i / a.per_clip);
-    const float t = a.t[b];
+    const float t = a.t[static_cast<size_t>(b) * a.t_bstride];
     float4 p = __ldg(reinterpret_cast<const float4*>(a.pyramid) + i);
     p.x /= t; p.y /= t; p.z /= t; p.w /= t;
     const float ore = b0 + w00 * p.x + w01 * p.y + w02 * p.z + w03 * p.w;

@@ -15,7 +15,8 @@ __device__ __forceinline__ float warp_sum(float v) {
 }
 
 // one block per sample; warp-per-output-row GEMVs with coalesced weight reads
-__global__ void __launch_bounds__(512) temb_mlp_kernel(const float* __restrict__ gfp, const float* __restrict__ w1,
+__global__ void __launch_bounds__(512) temb_mlp_kernel(const float* __restrict__ gfp, int gfp_bstride,
+                                                        const float* __restrict__ w1,
                                                         const float* __restrict__ b1, const float* __restrict__ w2,
                                                         const float* __restrict__ b2, float* __restrict__ out, int nf) {
   extern __shared__ float sm[];  // in[2nf], h1[4nf]
@@ -23,7 +24,7 @@ __global__ void __launch_bounds__(512) temb_mlp_kernel(const float* __restrict__
   float* h1 = sm + 2 * nf;
   const int b = blockIdx.x, K1 = 2 * nf, D = 4 * nf;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
-  for (int i = threadIdx.x; i < K1; i += blockDim.x) sin_[i] = gfp[b * K1 + i];
+  for (int i = threadIdx.x; i < K1; i += blockDim.x) sin_[i] = gfp[static_cast<size_t>(b) * gfp_bstride + i];
   __syncthreads();
   for (int n = warp; n < D; n += nw) {
     float acc = 0.f;
@@ -40,9 +41,9 @@ __global__ void __launch_bounds__(512) temb_mlp_kernel(const float* __restrict__
   }
 }
 
-void launch_temb_mlp(const float* gfp, const float* w1, const float* b1, const float* w2, const float* b2, float* out,
-                     int B, int nf, cudaStream_t st) {
-  temb_mlp_kernel<<<B, 512, 6 * nf * sizeof(float), st>>>(gfp, w1, b1, w2, b2, out, nf);
+void launch_temb_mlp(const float* gfp, int gfp_bstride, const float* w1, const float* b1, const float* w2, const float* b2,
+                     float* out, int B, int nf, cudaStream_t st) {
+  temb_mlp_kernel<<<B, 512, 6 * nf * sizeof(float), st>>>(gfp, gfp_bstride, w1, b1, w2, b2, out, nf);
 }
 
 // out[b][n] = base[n] + W[n][:] . temb[b][:]   (all Dense_0 of all ResBlocks stacked along n)
