@@ -36,7 +36,7 @@ extern "C" {
 #pragma GCC visibility push(default)
 #endif
 
-#define USE_B200_ABI_VERSION 1
+#define USE_B200_ABI_VERSION 2
 
 #define USE_DTYPE_F32 0  /* fp32 storage, TF32 tensor-core math (PyTorch's own GPU default for conv) */
 #define USE_DTYPE_BF16 1 /* bf16 storage + bf16 tensor-core math, fp32 accumulate / statistics / SDE state */
@@ -48,12 +48,14 @@ typedef struct use_config {
   int num_levels;       /* len(ch_mult) (7) */
   int ch_mult[8];       /* (1,1,2,2,2,2,2) */
   int num_res_blocks;   /* 2 */
-  int input_channels;   /* 4 = [Re x, Im x, Re Y, Im Y] */
+  int input_channels;   /* 4 = [Re x, Im x, Re Y, Im Y] (score network); 2 = [Re x, Im x] (discriminative network) */
   int act_dtype;        /* USE_DTYPE_* */
   int n_fft, hop;       /* 1022, 160 */
   float spec_factor;    /* 0.15 */
   float spec_abs_exponent; /* 0.5 */
   float theta;          /* OUVE stiffness 1.5 */
+  int conditional;      /* 1: time embedding -> per-ResBlock bias (score network); 0: NCSNpp(discriminative=True) */
+  int scale_by_sigma;   /* 1: the output pyramid is divided by the time value (ncsnpp.py:492-494) */
 } use_config;
 
 int use_abi_version(void);
@@ -88,6 +90,12 @@ int use_engine_get_profile_ops(use_engine* e, char* csv, size_t cap);
  * evaluated by the host layer with torch so the embedding is bit-identical to the reference's). */
 int use_score_forward(use_engine* e, int B, int F, int T, const void* x, const void* Y, const float* t_host,
                       const float* gfp_host, void* score, void* workspace, size_t workspace_bytes, void* stream);
+
+/* out = +net(...): NCSNpp.forward itself (ncsnpp.py:324-501).  For the discriminative generator of the LSGAN stage
+ * (GAN/generator/ncsnpp/model_wrapper.py:54,114-121: input_channels = 2, conditional = 0, scale_by_sigma = 0) pass
+ * Y = t_host = gfp_host = NULL. */
+int use_net_forward(use_engine* e, int B, int F, int T, const void* x, const void* Y, const float* t_host,
+                    const float* gfp_host, void* out, void* workspace, size_t workspace_bytes, void* stream);
 
 /* N reverse-diffusion predictor steps.  Y: device complex64 [B][F][T]; x_mean (out) same shape: the
  * noise-free mean of the last step (denoise=True).  x_state: device scratch of the same shape.
@@ -137,8 +145,8 @@ int use_op_conv_in4(int dtype, const float* x, const float* w, const float* bias
 int use_op_conv_out4(int dtype, const void* a, const float* w, const float* bias, const float* prev, float* out, int B,
                      int H, int W, int C, void* stream);
 int use_op_combine(int dtype, const void* h, const float* pyr, const float* w, const float* bias, void* out, int B, int HW,
-                   int C, void* stream);
-int use_op_fir4_down(const float* x, float* out, int B, int Hin, int Win, void* stream);
+                   int C, int pc, void* stream);
+int use_op_fir4_down(const float* x, float* out, int B, int Hin, int Win, int pc, void* stream);
 int use_op_philox(void* z, uint64_t seed, uint32_t step, uint32_t clip0, int B, size_t per_clip, void* stream);
 /* pack fp32 OIHW conv weights into the tcgen05 layout [taps][O][I] of the act dtype (host -> host). */
 int use_pack_conv_weight(int dtype, const float* w_oihw, int O, int I, int ksize, void* out);

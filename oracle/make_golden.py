@@ -33,12 +33,14 @@ def import_reference():
     from src.models.components.sgmse.backbones.ncsnpp import NCSNpp  # type: ignore
     from src.models.components.sgmse.backbones.ncsnpp_utils import up_or_down_sampling as UD  # type: ignore
 
-    return ScoreModel, NCSNpp, UD
+    from src.models.components.GAN.generator.ncsnpp.model_wrapper import NCSNPP_Wrapper  # type: ignore
+
+    return ScoreModel, NCSNpp, UD, NCSNPP_Wrapper
 
 
 def main():
     torch.set_num_threads(os.cpu_count())
-    ScoreModel, NCSNpp, UD = import_reference()
+    ScoreModel, NCSNpp, UD, NCSNPP_Wrapper = import_reference()
     out_dir = os.path.join(ROOT, "tests", "golden")
     os.makedirs(out_dir, exist_ok=True)
 
@@ -95,7 +97,21 @@ def main():
     np.savez_compressed(os.path.join(out_dir, "sample_large_T64_N3.npz"), y=y.numpy(), enhanced=ref.numpy(),
                         xmean_re=xm.real[:, 0, ::16, ::4].numpy(), xmean_im=xm.imag[:, 0, ::16, ::4].numpy(),
                         B=B, L=L, N=N, seed=seed, weight_seed=7)
-    print("sample ok; goldens written to", out_dir)
+    print("sample ok")
+
+    # ---- 5. LSGAN generator: NCSNPP_Wrapper inference branch, B=2, 0.4 s clips ------
+    sdG = O.make_state_dict(O.GAN_G, seed=13)
+    G = NCSNPP_Wrapper(n_fft=1022, hop_length=160, num_frames=480, window="hann", spec_factor=0.15,
+                       spec_abs_exponent=0.5).eval()
+    G.net.load_state_dict(sdG, strict=True)
+    with torch.no_grad():
+        refG = G({"perturbed": y.clone()})["fake"]
+    mineG = O.gan_denoise(sdG, y)
+    dG = float((refG - mineG).abs().max())
+    print("gan generator max|ref-oracle| =", dG)
+    assert dG == 0.0
+    np.savez_compressed(os.path.join(out_dir, "gan_generator_T64.npz"), y=y.numpy(), fake=refG.numpy(), weight_seed=13)
+    print("goldens written to", out_dir)
 
 
 if __name__ == "__main__":

@@ -52,6 +52,9 @@ class NetCfg:
     input_channels: int = 4
     fourier_scale: float = 16.0
     fir_kernel: Tuple[int, ...] = (1, 3, 3, 1)
+    # discriminative=True (the GAN generator, ncsnpp.py:88-94) switches both off and uses input_channels=2
+    conditional: bool = True
+    scale_by_sigma: bool = True
 
     @property
     def num_resolutions(self) -> int:
@@ -86,6 +89,9 @@ class SdeCfg:
 
 LARGE = NetCfg()
 TINY = NetCfg(nf=64, ch_mult=(1, 2), num_res_blocks=1)
+# NCSNpp(discriminative=True) with the class defaults: the LSGAN generator (GAN/generator/ncsnpp/model_wrapper.py:54)
+GAN_G = NetCfg(nf=128, ch_mult=(1, 2, 2, 2), num_res_blocks=1, input_channels=2, conditional=False, scale_by_sigma=False)
+GAN_TINY = NetCfg(nf=64, ch_mult=(1, 2), num_res_blocks=1, input_channels=2, conditional=False, scale_by_sigma=False)
 
 
 # --------------------------------------------------------------------------------------------
@@ -94,12 +100,10 @@ TINY = NetCfg(nf=64, ch_mult=(1, 2), num_res_blocks=1)
 def module_plan(cfg: NetCfg) -> List[dict]:
     """The ``all_modules`` list in construction order: kind + channel info per entry."""
     nf, nres = cfg.nf, cfg.num_resolutions
-    plan: List[dict] = [
-        {"kind": "gfp"},
-        {"kind": "linear", "cin": 2 * nf, "cout": 4 * nf},
-        {"kind": "linear", "cin": 4 * nf, "cout": 4 * nf},
-        {"kind": "conv3", "cin": cfg.input_channels, "cout": nf},
-    ]
+    plan: List[dict] = [{"kind": "gfp"}]
+    if cfg.conditional:
+        plan += [{"kind": "linear", "cin": 2 * nf, "cout": 4 * nf}, {"kind": "linear", "cin": 4 * nf, "cout": 4 * nf}]
+    plan.append({"kind": "conv3", "cin": cfg.input_channels, "cout": nf})
     hs_c = [nf]
     in_ch = nf
     for lvl in range(nres):
@@ -264,7 +268,8 @@ def resblock(sd, p: str, m: dict, x: Tensor, temb: Tensor, fir_k) -> Tensor:
         h = fir_downsample_2d(h, fir_k)
         x = fir_downsample_2d(x, fir_k)
     h = _conv(sd, p + ".Conv_0", h, 1)
-    h = h + F.linear(F.silu(temb), sd[p + ".Dense_0.weight"], sd[p + ".Dense_0.bias"])[:, :, None, None]
+    if temb is not None:
+        h = h + F.linear(F.silu(temb), sd[p + ".Dense_0.weight"], sd[p + ".Dense_0.bias"])[:, :, None, None]
     h = F.silu(_gn(sd, p + ".GroupNorm_1", h))
     h = _conv(sd, p + ".Conv_1", h, 1)
     if m["cin"] != m["cout"] or m["up"] or m["down"]:
@@ -298,8 +303,9 @@ def time_embedding(sd, t: Tensor) -> Tensor:
     return temb
 
 
-def ncsnpp_forward(sd: Dict[str, Tensor], cfg: NetCfg, x: Tensor, t: Tensor, taps: Optional[dict] = None) -> Tensor:
+def ncsnpp_forward(sd: Dict[str, Tensor], cfg: NetCfg, x: Tensor, t: Optional[Tensor], taps: Optional[dict] = None) -> Tensor:
     """x: complex [B, 2, F, T] (= cat[x_t, Y]);  t: [B].  Returns complex [B, 1, F, T].
+    Discriminative configs (cfg.conditional False): x complex [B, 1, F, T], t None.
 
     ``taps`` (optional dict) receives intermediate real tensors for per-layer debugging of the CUDA path.
     """
@@ -307,10 +313,10 @@ def ncsnpp_forward(sd: Dict[str, Tensor], cfg: NetCfg, x: Tensor, t: Tensor, tap
     fir_k = cfg.fir_kernel
     # complex -> [Re x, Im x, Re Y, Im Y]  (ncsnpp.py:333-347)
     xr = torch.cat([torch.cat([x[:, [c]].real, x[:, [c]].imag], dim=1) for c in range(cfg.input_channels // 2)], dim=1)
-    temb = time_embedding(sd, t)
+    temb = time_embedding(sd, t) if cfg.conditional else None
     xr = 2 * xr - 1.0
     input_pyramid = xr
-    i = 3
+    i = 3 if cfg.conditional else 1
     hs = [_conv(sd, f"all_modules.{i}", xr, 1)]
     i += 1
     nres = cfg.num_resolutions
@@ -357,7 +363,9 @@ def ncsnpp_forward(sd: Dict[str, Tensor], cfg: NetCfg, x: Tensor, t: Tensor, tap
     assert not hs and i == len(plan)
     if taps is not None:
         taps["pyramid"] = pyramid
-    h = pyramid / t.reshape(-1, 1, 1, 1)  # scale_by_sigma divides by the TIME value (ncsnpp.py:492-494)
+    h = pyramid
+    if cfg.scale_by_sigma:
+        h = pyramid / t.reshape(-1, 1, 1, 1)  # scale_by_sigma divides by the TIME value (ncsnpp.py:492-494)
     h = _conv(sd, "output_layer", h, 0)
     h = torch.reshape(h, (h.size(0), 2, 1, h.size(2), h.size(3)))
     h = torch.permute(h, (0, 2, 3, 4, 1)).contiguous()
@@ -489,6 +497,16 @@ def sample(sd: Dict[str, Tensor], y: Tensor, N: int, noise: Optional[Tensor] = N
         xm = pc_sample_spec(score_fn, Y, N, noise, sde)
         out = istft(spec_back(xm.squeeze(1), spec), spec, T_orig)
     return (out, xm, Y) if return_spec else out
+
+
+def gan_denoise(sd: Dict[str, Tensor], y: Tensor, net: NetCfg = GAN_G, spec: SpecCfg = SpecCfg()) -> Tensor:
+    """NCSNPP_Wrapper.forward, inference branch (GAN/generator/ncsnpp/model_wrapper.py:114-121): one forward of the
+    discriminative NCSN++ on the compressed spectrogram: y float [B, L] -> batch["fake"] float [B, L]."""
+    with torch.no_grad():
+        T_orig = y.size(1)
+        Y = pad_spec(spec_fwd(stft(y, spec), spec).unsqueeze(1))
+        out = ncsnpp_forward(sd, net, Y, None)
+        return istft(spec_back(out.squeeze(1), spec), spec, T_orig)
 
 
 def synthetic_clips(B: int, L: int = 96000, seed: int = 1234) -> Tensor:

@@ -30,7 +30,7 @@ def test_library_exports_every_declared_symbol():
     assert exported == set(header_symbols())
     for name in header_symbols():
         assert hasattr(L, name)
-    assert L.use_abi_version() == 1
+    assert L.use_abi_version() == 2
 
 
 def _engine(L, net, dt):
@@ -39,6 +39,8 @@ def _engine(L, net, dt):
     for i, m in enumerate(net.ch_mult):
         cfg.ch_mult[i] = m
     cfg.n_fft, cfg.hop, cfg.spec_factor, cfg.spec_abs_exponent, cfg.theta = 1022, 160, 0.15, 0.5, 1.5
+    cfg.conditional, cfg.scale_by_sigma = int(net.conditional), int(net.scale_by_sigma)
+    cfg.input_channels = net.input_channels
     return L.use_engine_create(C.byref(cfg))
 
 
@@ -70,6 +72,18 @@ def test_engine_host_logic_tiny(dt):
     L.use_engine_destroy(h)
 
 
+def test_engine_host_logic_discriminative_generator():
+    """The LSGAN generator configuration (2 input channels, no time embedding) plans and packs on CPU."""
+    L = _lib.lib()
+    h = _engine(L, O.GAN_TINY, 1)
+    assert h, L.use_last_error()
+    _feed(L, h, O.make_state_dict(O.GAN_TINY, seed=3))
+    n, w = C.c_size_t(), C.c_size_t()
+    assert L.use_engine_pack(h, C.byref(n)) == 0, L.use_last_error()
+    assert L.use_engine_workspace_bytes(h, 2, 16, 24, C.byref(w)) == 0 and w.value > 0, L.use_last_error()
+    L.use_engine_destroy(h)
+
+
 def test_engine_rejects_missing_and_misshaped_weights():
     L = _lib.lib()
     h = _engine(L, O.TINY, 0)
@@ -91,6 +105,7 @@ def test_unsupported_architecture_fails_loudly():
     cfg = _lib.UseConfig()
     cfg.nf, cfg.num_levels, cfg.num_res_blocks, cfg.input_channels, cfg.act_dtype = 96, 2, 1, 4, 1  # ncsnpp12M-like width
     cfg.ch_mult[0], cfg.ch_mult[1] = 1, 2
+    cfg.conditional, cfg.scale_by_sigma = 1, 1
     assert not L.use_engine_create(C.byref(cfg))
     assert b"not supported" in L.use_last_error()
 

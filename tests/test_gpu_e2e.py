@@ -161,6 +161,26 @@ def test_large_score_forward(dtype):
     assert e <= TOL_SCORE[dtype], e
 
 
+@pytest.mark.parametrize("dtype", ["fp32", "bf16"])
+def test_large_score_forward_full_size(dtype):
+    """One score evaluation at the BASELINE shape (512 x 640 = a 4 s clip) against the CPU oracle (one evaluation
+    costs the oracle ~10-25 s on the GPU box's host cores; the full 30-step chain would take minutes)."""
+    m, sd = large_model(dtype)
+    y = O.synthetic_clips(1, 96000, seed=77)
+    spec = O.SpecCfg()
+    Y = O.pad_spec(O.spec_fwd(O.stft(y, spec), spec).unsqueeze(1))
+    g = torch.Generator().manual_seed(14)
+    x = Y + 0.3 * torch.randn(Y.shape, dtype=torch.complex64, generator=g)
+    t = torch.tensor([0.41])
+    with torch.no_grad():
+        ref = -O.ncsnpp_forward(sd, O.LARGE, torch.cat([x, Y], 1), t)
+    got = m(x.cuda(), t.cuda(), score_conditioning=[Y.cuda()], sde_input=Y.cuda()).cpu()
+    assert got.shape == (1, 1, 512, 640)
+    e = rel_l2(torch.view_as_real(got), torch.view_as_real(ref))
+    record(f"large_full_size_score_rel_l2_{dtype}", e)
+    assert e <= TOL_SCORE[dtype], e
+
+
 def test_full_size_properties_bf16():
     """BASELINE shape (4 s @ 24 kHz -> 512 x 640) where the oracle is too slow: size-independent properties.
     (1) shard invariance: clips sampled together == clips sampled alone with their global clip index (Philox streams
@@ -203,3 +223,20 @@ def test_generic_sampler_route_matches_fused():
     torch.manual_seed(0)
     _, xm = pred.update_fn(Y, torch.ones(B, device="cuda"), Y, conditioning=[Y])
     assert rel_l2(torch.view_as_real(fused.cpu()), torch.view_as_real(xm.cpu())) < 1e-5
+
+
+@pytest.mark.parametrize("dtype", ["fp32", "bf16"])
+def test_gan_generator_matches_reference_golden(dtype):
+    """LSGAN generator (NCSNPP_Wrapper inference branch): B=2, 0.4 s clips, against the
+    committed output of the UNMODIFIED reference."""
+    g = np.load(os.path.join(GOLDEN, "gan_generator_T64.npz"))
+    G = use_b200.NCSNPP_Wrapper(n_fft=1022, hop_length=160, num_frames=480, dtype=dtype)
+    G.net.load_state_dict(O.make_state_dict(O.GAN_G, seed=int(g["weight_seed"])), strict=True)
+    got = G({"perturbed": torch.from_numpy(g["y"]).cuda()})["fake"].cpu()
+    ref = torch.from_numpy(g["fake"])
+    e = rel_l2(got, ref)
+    record(f"gan_generator_wave_rel_l2_{dtype}", e)
+    assert e <= {"fp32": 5e-3, "bf16": 5e-2}[dtype], e
+    mod = use_b200.GANModule(G=G)
+    out = mod.predict_step({"perturbed": torch.from_numpy(g["y"]).cuda()}, 0, write=False)["fake"]
+    assert torch.equal(out.cpu(), got)

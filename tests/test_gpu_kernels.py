@@ -320,7 +320,7 @@ def test_combine_and_fir4(dt):
     pyr = torch.randn(B, 4, H, W, generator=g)
     pd = pyr.permute(0, 2, 3, 1).contiguous().cuda()
     pdown = torch.empty(B, H // 2, W // 2, 4, device="cuda")
-    assert L.use_op_fir4_down(pd.data_ptr(), pdown.data_ptr(), B, H, W, stream()) == 0
+    assert L.use_op_fir4_down(pd.data_ptr(), pdown.data_ptr(), B, H, W, 4, stream()) == 0
     _sync()
     ref_down = O.fir_downsample_2d(pyr)
     assert float((pdown.permute(0, 3, 1, 2).cpu() - ref_down).abs().max()) < 1e-5
@@ -330,7 +330,7 @@ def test_combine_and_fir4(dt):
     hd = act_tensor(h, dt)
     wd, bd = w.cuda(), bias.cuda()
     assert L.use_op_combine(dt, hd.data_ptr(), pdown.data_ptr(), wd.data_ptr(), bd.data_ptr(), hd.data_ptr(), B,
-                            (H // 2) * (W // 2), Cc, stream()) == 0
+                            (H // 2) * (W // 2), Cc, 4, stream()) == 0
     _sync()
     ref = Fnn.conv2d(ref_down.double(), w.double(), bias.double()).float() + h
     got = from_act(hd)

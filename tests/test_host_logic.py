@@ -104,3 +104,22 @@ def test_generic_sampler_loop_shapes_with_fake_score_fn():
         x, n = s()
         assert x.shape == y.shape and bool(torch.isfinite(torch.view_as_real(x)).all())
         assert n == sde.N * ((0 if corr == "none" else 1) + 1)
+
+
+def test_gan_generator_host_structure():
+    """NCSNPP_Wrapper / GANModule (LSGAN stage): discriminative NCSN++ parameter layout and config surface."""
+    G = use_b200.NCSNPP_Wrapper(n_fft=1022, hop_length=160, num_frames=480)
+    sd_ref = O.make_state_dict(O.GAN_G, seed=13)  # names / shapes validated against the reference by make_golden.py
+    sd = G.net.state_dict()
+    assert set(sd.keys()) == set(sd_ref.keys())
+    assert all(tuple(sd[k].shape) == tuple(sd_ref[k].shape) for k in sd)
+    G.net.load_state_dict(sd_ref, strict=True)
+    cfg = compose(os.path.join(ROOT, "configs"), "predict.yaml", ["model=LSGAN"])
+    m = instantiate(cfg["model"])
+    assert isinstance(m, use_b200.GANModule) and isinstance(m.G, use_b200.NCSNPP_Wrapper) and m.G.n_fft == 1022
+    m.load_state_dict({"G.net." + k: v for k, v in sd_ref.items()})
+    assert torch.equal(m.G.net.all_modules[1].weight, sd_ref["all_modules.1.weight"])
+    with pytest.raises(NotImplementedError):
+        G({"clean": torch.zeros(1, 8), "perturbed": torch.zeros(1, 8)})
+    with pytest.raises(RuntimeError, match="CUDA"):
+        G({"perturbed": torch.zeros(1, 9600)})

@@ -10,6 +10,7 @@ from .registry import Registry  # noqa: F401
 from .sampling import CorrectorRegistry, PredictorRegistry, get_pc_sampler  # noqa: F401
 from .sdes import OUVESDE, SDERegistry  # noqa: F401
 from .sgmse_module import SGMSEModule  # noqa: F401
+from .gan import GANModule, NCSNPP_Wrapper  # noqa: F401
 
 __all__ = ["ScoreModel", "SGMSEModule", "NCSNpp", "NCSNppLarge", "BackboneRegistry", "SDERegistry", "PredictorRegistry",
-           "CorrectorRegistry", "OUVESDE", "Registry", "get_pc_sampler", "pad_spec"]
+           "CorrectorRegistry", "OUVESDE", "Registry", "get_pc_sampler", "pad_spec", "GANModule", "NCSNPP_Wrapper"]

@@ -22,7 +22,7 @@ DTYPE_BF16 = 1
 SYMBOLS = [
     "use_abi_version", "use_last_error", "use_engine_create", "use_engine_destroy", "use_engine_set_weight",
     "use_engine_pack", "use_engine_upload", "use_engine_workspace_bytes", "use_engine_set_option", "use_engine_launch_count", "use_engine_set_profiling",
-    "use_engine_get_profile", "use_engine_get_profile_ops", "use_score_forward", "use_pc_sample",
+    "use_engine_get_profile", "use_engine_get_profile_ops", "use_score_forward", "use_net_forward", "use_pc_sample",
     "use_stft", "use_istft", "use_upfirdn2d_f32", "use_op_gn_stats", "use_op_gn_apply", "use_op_conv_tc",
     "use_op_conv_ref", "use_op_conv_in4", "use_op_conv_out4", "use_op_combine", "use_op_fir4_down", "use_op_philox",
     "use_pack_conv_weight",
@@ -34,6 +34,7 @@ class UseConfig(C.Structure):
         ("nf", C.c_int), ("num_levels", C.c_int), ("ch_mult", C.c_int * 8), ("num_res_blocks", C.c_int),
         ("input_channels", C.c_int), ("act_dtype", C.c_int), ("n_fft", C.c_int), ("hop", C.c_int),
         ("spec_factor", C.c_float), ("spec_abs_exponent", C.c_float), ("theta", C.c_float),
+        ("conditional", C.c_int), ("scale_by_sigma", C.c_int),
     ]
 
 
@@ -82,6 +83,7 @@ def lib() -> C.CDLL:
         L.use_engine_get_profile.argtypes = [vp, C.c_char_p, sz]
         L.use_engine_get_profile_ops.argtypes = [vp, C.c_char_p, sz]
         L.use_score_forward.argtypes = [vp, i32, i32, i32, vp, vp, vp, vp, vp, vp, sz, vp]
+        L.use_net_forward.argtypes = [vp, i32, i32, i32, vp, vp, vp, vp, vp, vp, sz, vp]
         L.use_pc_sample.argtypes = [vp, i32, i32, i32, vp, vp, vp, i32, vp, vp, vp, f32, vp, u64, u32, vp, sz, vp]
         L.use_stft.argtypes = [vp, i32, i32, i32, vp, vp, vp, vp, vp]
         L.use_istft.argtypes = [vp, i32, i32, i32, vp, vp, vp, vp, vp, vp, vp]
@@ -94,15 +96,15 @@ def lib() -> C.CDLL:
         L.use_op_conv_ref.argtypes = [i32, vp, vp, vp, i32, vp, f32, vp, i32, i32, i32, i32, i32, i32, vp]
         L.use_op_conv_in4.argtypes = [i32, vp, vp, vp, vp, i32, i32, i32, i32, vp]
         L.use_op_conv_out4.argtypes = [i32, vp, vp, vp, vp, vp, i32, i32, i32, i32, vp]
-        L.use_op_combine.argtypes = [i32, vp, vp, vp, vp, vp, i32, i32, i32, vp]
-        L.use_op_fir4_down.argtypes = [vp, vp, i32, i32, i32, vp]
+        L.use_op_combine.argtypes = [i32, vp, vp, vp, vp, vp, i32, i32, i32, i32, vp]
+        L.use_op_fir4_down.argtypes = [vp, vp, i32, i32, i32, i32, vp]
         L.use_op_philox.argtypes = [vp, u64, u32, u32, i32, sz, vp]
         L.use_pack_conv_weight.argtypes = [i32, vp, i32, i32, i32, vp]
         for name in SYMBOLS:
             fn = getattr(L, name)  # AttributeError here = header / library mismatch
             if fn.restype is C.c_int and name not in ("use_abi_version",):
                 fn.restype = C.c_int
-        if L.use_abi_version() != 1:
+        if L.use_abi_version() != 2:
             raise RuntimeError("use_b200: ABI version mismatch between the Python layer and libuse_b200.so")
         _lib = L
         return L

@@ -68,12 +68,16 @@ def _nin_bag(c, init_scale=0.1):
     return b
 
 
-def module_plan(nf: int, ch_mult: Tuple[int, ...], num_res_blocks: int, input_channels: int) -> List[dict]:
+def module_plan(nf: int, ch_mult: Tuple[int, ...], num_res_blocks: int, input_channels: int,
+                conditional: bool = True) -> List[dict]:
     """Construction order of ``all_modules`` (ncsnpp.py:186-316) for the 'biggan' / 'output_skip' /
-    'input_skip' / 'sum' / fir configuration, the only one the shipped configs use."""
+    'input_skip' / 'sum' / fir configuration, the only one the shipped configs use.  Without the noise
+    conditioning (discriminative=True) the two time-embedding Linear layers are absent (ncsnpp.py:196-202)."""
     nres = len(ch_mult)
-    plan = [dict(kind="gfp"), dict(kind="linear", cin=2 * nf, cout=4 * nf), dict(kind="linear", cin=4 * nf, cout=4 * nf),
-            dict(kind="conv3", cin=input_channels, cout=nf)]
+    plan = [dict(kind="gfp")]
+    if conditional:
+        plan += [dict(kind="linear", cin=2 * nf, cout=4 * nf), dict(kind="linear", cin=4 * nf, cout=4 * nf)]
+    plan.append(dict(kind="conv3", cin=input_channels, cout=nf))
     hs_c, in_ch = [nf], nf
     for lvl in range(nres):
         for _ in range(num_res_blocks):
@@ -108,11 +112,17 @@ class NCSNpp(nn.Module):
     _SUPPORTED = dict(scale_by_sigma=True, nonlinearity="swish", resamp_with_conv=True, conditional=True, fir=True,
                       fir_kernel=[1, 3, 3, 1], skip_rescale=True, resblock_type="biggan", progressive="output_skip",
                       progressive_input="input_skip", progressive_combine="sum", embedding_type="fourier",
-                      spatial_channels=1, dropout=0.0, centered=False, discriminative=False)
+                      spatial_channels=1, dropout=0.0, centered=False)
 
     def __init__(self, nf=128, ch_mult=(1, 2, 2, 2), num_res_blocks=1, attn_resolutions=(0,), init_scale=0.0,
-                 fourier_scale=16, image_size=256, input_channels=4, compute_dtype="fp32", **kwargs):
+                 fourier_scale=16, image_size=256, input_channels=4, discriminative=False, compute_dtype="fp32", **kwargs):
         super().__init__()
+        self.discriminative = bool(discriminative)
+        if self.discriminative:
+            # ncsnpp.py:88-94: no noise conditioning, no 1/t scaling, input = [Re y, Im y]
+            kwargs.pop("conditional", None)
+            kwargs.pop("scale_by_sigma", None)
+            input_channels = 2
         for k, v in kwargs.items():
             if k not in self._SUPPORTED:
                 raise TypeError(f"NCSNpp: unknown argument {k!r}")
@@ -121,13 +131,16 @@ class NCSNpp(nn.Module):
                 raise NotImplementedError(f"NCSNpp(B200): {k}={v!r} is not supported on this path (only {want!r})")
         if tuple(attn_resolutions) != (0,):
             raise NotImplementedError("NCSNpp(B200): only attn_resolutions=(0,) (bottleneck attention) is supported")
-        if input_channels != 4:
-            raise NotImplementedError("NCSNpp(B200): only condition='noisy' (4 input channels) is supported")
+        if input_channels != (2 if self.discriminative else 4):
+            raise NotImplementedError("NCSNpp(B200): only condition='noisy' (4 input channels) or the discriminative "
+                                      "2-channel generator are supported")
+        self.conditional = not self.discriminative
+        self.scale_by_sigma = not self.discriminative
         self.nf, self.ch_mult, self.num_res_blocks = nf, tuple(ch_mult), num_res_blocks
         self.input_channels = input_channels
         self.num_resolutions = len(self.ch_mult)
         self.compute_dtype = compute_dtype
-        self.plan = module_plan(nf, self.ch_mult, num_res_blocks, input_channels)
+        self.plan = module_plan(nf, self.ch_mult, num_res_blocks, input_channels, self.conditional)
 
         self.output_layer = nn.Conv2d(input_channels, 2, 1)  # parameters only; never called
         mods = []
@@ -196,13 +209,15 @@ class NCSNpp(nn.Module):
         x_proj = torch.log(t)[:, None] * W[None, :] * 2 * np.pi
         return torch.cat([torch.sin(x_proj), torch.cos(x_proj)], dim=-1).contiguous()
 
-    def forward(self, x: torch.Tensor, time_cond: torch.Tensor) -> torch.Tensor:
-        """x: complex64 [B, 2, F, T] = cat[x_t, Y] on a CUDA device; returns complex64 [B, 1, F, T]."""
+    def forward(self, x: torch.Tensor, time_cond: torch.Tensor = None) -> torch.Tensor:
+        """x: complex64 [B, 2, F, T] = cat[x_t, Y] on a CUDA device (discriminative: [B, 1, F, T], no time);
+        returns complex64 [B, 1, F, T]."""
         if not x.is_cuda:
             raise RuntimeError("NCSNpp(B200) runs on CUDA tensors only; there is no CPU path")
+        if self.discriminative:
+            return self.engine(x.device).net(x[:, 0].contiguous(), None, None).unsqueeze(1)
         xt, Y = x[:, 0].contiguous(), x[:, 1].contiguous()
-        score = self.engine(x.device).score(xt, Y, time_cond)  # = -net(x)
-        return torch.neg(score).unsqueeze(1)
+        return self.engine(x.device).net(xt, Y, time_cond).unsqueeze(1)
 
 
 @BackboneRegistry.register("ncsnpplarge")
@@ -218,7 +233,7 @@ class _Engine:
 
     def __init__(self, net: NCSNpp, device: torch.device, dtype_code: int, spec=None, theta: float = 1.5):
         self.L = _lib.lib()
-        self.net = net
+        self.net_module = net
         self.device = device
         self.dtype_code = dtype_code
         cfg = _lib.UseConfig()
@@ -230,6 +245,7 @@ class _Engine:
         cfg.n_fft, cfg.hop = sp.get("n_fft", 1022), sp.get("hop_length", 160)
         cfg.spec_factor, cfg.spec_abs_exponent = sp.get("spec_factor", 0.15), sp.get("spec_abs_exponent", 0.5)
         cfg.theta = theta
+        cfg.conditional, cfg.scale_by_sigma = int(net.conditional), int(net.scale_by_sigma)
         self.cfg = cfg
         with torch.cuda.device(device):
             self.h = self.L.use_engine_create(C.byref(cfg))
@@ -274,7 +290,7 @@ class _Engine:
         B, F, T = x.shape
         x, Y = x.contiguous(), Y.contiguous()
         t_host = t.detach().to("cpu", torch.float32).contiguous()
-        gfp = self.net.gfp_features(t_host)
+        gfp = self.net_module.gfp_features(t_host)
         out = torch.empty_like(x)
         with torch.cuda.device(self.device):
             ws = self.workspace(B, F, T)
@@ -282,6 +298,31 @@ class _Engine:
                                                 gfp.data_ptr(), out.data_ptr(), ws.data_ptr(), ws.numel(),
                                                 _lib.stream_ptr()), "use_score_forward")
         return out
+
+    def net(self, x: torch.Tensor, Y, t) -> torch.Tensor:
+        """+net(...) = NCSNpp.forward: complex64 [B, F, T] in and out.  Discriminative networks take Y = t = None."""
+        assert x.dtype == torch.complex64 and x.dim() == 3
+        B, F, T = x.shape
+        x = x.contiguous()
+        yp = tp = gp = None
+        keep = []
+        if Y is not None:
+            Y = Y.contiguous()
+            yp = Y.data_ptr()
+        if t is not None:
+            t_host = t.detach().to("cpu", torch.float32).contiguous()
+            gfp = self.net_gfp(t_host)
+            keep += [t_host, gfp]
+            tp, gp = t_host.data_ptr(), gfp.data_ptr()
+        out = torch.empty_like(x)
+        with torch.cuda.device(self.device):
+            ws = self.workspace(B, F, T)
+            _lib.check(self.L.use_net_forward(self.h, B, F, T, x.data_ptr(), yp, tp, gp, out.data_ptr(), ws.data_ptr(),
+                                              ws.numel(), _lib.stream_ptr()), "use_net_forward")
+        return out
+
+    def net_gfp(self, t_host):
+        return self.net_module.gfp_features(t_host)
 
     def pc_sample(self, Y: torch.Tensor, ts: torch.Tensor, G: torch.Tensor, prior_std: float, noise=None, seed: int = 0,
                   clip0: int = 0) -> torch.Tensor:
@@ -292,7 +333,7 @@ class _Engine:
         N = int(ts.numel())
         ts = ts.detach().to("cpu", torch.float32).contiguous()
         G = G.detach().to("cpu", torch.float32).contiguous()
-        gfp = self.net.gfp_features(ts)
+        gfp = self.net_module.gfp_features(ts)
         x_state, x_mean = torch.empty_like(Y), torch.empty_like(Y)
         nptr = None
         if noise is not None:

@@ -21,6 +21,8 @@ TARGET_ALIASES = {
     "src.models.SGMSE_module.SGMSEModule": "use_b200.sgmse_module.SGMSEModule",
     "src.models.components.sgmse.model_wrapper.ScoreModel": "use_b200.model_wrapper.ScoreModel",
     "src.data.loadwav_datamodule.LoadWavDataModule": "use_b200.predict.LoadWavDataModule",
+    "src.models.LSGAN_module.GANModule": "use_b200.gan.GANModule",
+    "src.models.components.GAN.generator.ncsnpp.model_wrapper.NCSNPP_Wrapper": "use_b200.gan.NCSNPP_Wrapper",
 }
 
 

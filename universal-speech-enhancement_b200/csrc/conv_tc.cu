@@ -170,7 +170,7 @@ TcConvPlan* tc_conv_plan_create(int dt, const TcConvDesc& d, int num_sms, char* 
   P.ntiles = P.tiles_w * P.tiles_h * d.B;
   P.out = d.out; P.bias = d.bias; P.bias_bstride = d.bias_bstride; P.res = d.res; P.scale = d.scale;
   P.stats_acc = d.stats_acc;
-  P.out4 = d.out4; P.prev4 = d.prev4;
+  P.out4 = d.out4; P.prev4 = d.prev4; P.out_pc = d.out_pc ? d.out_pc : 4;
   const int units = (P.ntiles + p->mc - 1) / p->mc;           // tile groups
   const int max_groups = num_sms / p->mc;
   p->grid = (units < max_groups ? units : max_groups) * p->mc;  // a multiple of the cluster width

@@ -44,7 +44,8 @@ struct alignas(64) ConvParams {
   long long* stats_acc;  // optional [B][N][2] fixed-point accumulators (zero on entry): sum / sum of squares of `out`
   // "pyramid head" mode (N = 32, only output channels 0..3 are real): fp32 [B][H][W][4] = acc + bias (+ FIR-up(prev4))
   float* out4;
-  const float* prev4;    // optional fp32 [B][H/2][W/2][4]
+  const float* prev4;    // optional fp32 [B][H/2][W/2][out_pc]
+  int out_pc;            // real output channels of the head (4 or 2)
 };
 
 template <typename T, int N, int NSUB>
@@ -389,8 +390,9 @@ __global__ void __launch_bounds__(ConvCfg<T, N, NSUB>::THREADS, 1) conv_tc_kerne
         tmem_ld32(trow, r);
         tmem_ld_wait();
         if (valid) {
-          float4 o = make_float4(__uint_as_float(r[0]) + bias[0], __uint_as_float(r[1]) + bias[1],
-                                 __uint_as_float(r[2]) + bias[2], __uint_as_float(r[3]) + bias[3]);
+          float o[4] = {__uint_as_float(r[0]) + bias[0], __uint_as_float(r[1]) + bias[1], __uint_as_float(r[2]) + bias[2],
+                        __uint_as_float(r[3]) + bias[3]};
+          const int pc = p.out_pc;
           if (p.prev4 != nullptr) {
             const int Hp = p.H >> 1, Wp = p.W >> 1;
             const int my = h >> 1, mx = w >> 1;
@@ -405,12 +407,19 @@ __global__ void __launch_bounds__(ConvCfg<T, N, NSUB>::THREADS, 1) conv_tc_kerne
                 const int xx = xa + dx;
                 if (xx < 0 || xx >= Wp) continue;
                 const float kw = (dy ? 1.f - wya : wya) * (dx ? 1.f - wxa : wxa);
-                const float4 pv = __ldg(reinterpret_cast<const float4*>(p.prev4) + (static_cast<size_t>(b) * Hp + yy) * Wp + xx);
-                o.x += kw * pv.x; o.y += kw * pv.y; o.z += kw * pv.z; o.w += kw * pv.w;
+                const float* pv = p.prev4 + ((static_cast<size_t>(b) * Hp + yy) * Wp + xx) * pc;
+                if (pc == 4) {
+                  const float4 q = __ldg(reinterpret_cast<const float4*>(pv));
+                  o[0] += kw * q.x; o[1] += kw * q.y; o[2] += kw * q.z; o[3] += kw * q.w;
+                } else {
+                  const float2 q = __ldg(reinterpret_cast<const float2*>(pv));
+                  o[0] += kw * q.x; o[1] += kw * q.y;
+                }
               }
             }
           }
-          reinterpret_cast<float4*>(p.out4)[pix] = o;
+          if (pc == 4) reinterpret_cast<float4*>(p.out4)[pix] = make_float4(o[0], o[1], o[2], o[3]);
+          else reinterpret_cast<float2*>(p.out4)[pix] = make_float2(o[0], o[1]);
         }
       } else
 #pragma unroll 1

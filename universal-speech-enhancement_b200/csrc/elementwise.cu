@@ -697,7 +697,7 @@ void launch_conv_out4(int dt, const void* a, const float* w, const float* bias, 
 // ------------------------------------------------------------------------------------------------
 // Combine(sum): out = h + bias + W[C][4] . pyr
 // ------------------------------------------------------------------------------------------------
-template <typename T>
+template <typename T, int PC>
 __global__ void __launch_bounds__(256) combine_kernel(const T* __restrict__ h, const float* __restrict__ pyr,
                                                        const float* __restrict__ w, const float* __restrict__ bias,
                                                        T* __restrict__ out, int C, long long total) {
@@ -707,42 +707,58 @@ __global__ void __launch_bounds__(256) combine_kernel(const T* __restrict__ h, c
        i += static_cast<long long>(gridDim.x) * blockDim.x) {
     const int cv = static_cast<int>(i % vpp);
     const long long pix = i / vpp;
-    const float4 pv = __ldg(reinterpret_cast<const float4*>(pyr) + pix);
+    float pv[PC];
+    if constexpr (PC == 4) {
+      const float4 q = __ldg(reinterpret_cast<const float4*>(pyr) + pix);
+      pv[0] = q.x; pv[1] = q.y; pv[2] = q.z; pv[3] = q.w;
+    } else {
+      const float2 q = __ldg(reinterpret_cast<const float2*>(pyr) + pix);
+      pv[0] = q.x; pv[1] = q.y;
+    }
     float f[V];
     Vec<T>::load(h + pix * C + cv * V, f);
 #pragma unroll
     for (int j = 0; j < V; ++j) {
       const int c = cv * V + j;
-      const float4 ww = __ldg(reinterpret_cast<const float4*>(w) + c);
-      // same association as conv2d then "+ h": (bias + w.p) + h
-      f[j] = (bias[c] + ww.x * pv.x + ww.y * pv.y + ww.z * pv.z + ww.w * pv.w) + f[j];
+      float acc = bias[c];
+      if constexpr (PC == 4) {
+        const float4 ww = __ldg(reinterpret_cast<const float4*>(w) + c);
+        acc += ww.x * pv[0] + ww.y * pv[1] + ww.z * pv[2] + ww.w * pv[3];
+      } else {
+        const float2 ww = __ldg(reinterpret_cast<const float2*>(w) + c);
+        acc += ww.x * pv[0] + ww.y * pv[1];
+      }
+      f[j] = acc + f[j];  // same association as conv2d then "+ h": (bias + w.p) + h
     }
     Vec<T>::store(out + pix * C + cv * V, f);
   }
 }
 
 void launch_combine(int dt, const void* h, const float* pyr, const float* w, const float* bias, void* out, int B, int HW,
-                    int C, cudaStream_t st) {
+                    int C, int pc, cudaStream_t st) {
   DISPATCH_DT(dt, {
     constexpr int V = Vec<T>::N;
     const long long total = static_cast<long long>(B) * HW * (C / V);
     const int blocks = static_cast<int>(std::min<long long>((total + 255) / 256, 148LL * 32));
-    combine_kernel<T><<<blocks, 256, 0, st>>>((const T*)h, pyr, w, bias, (T*)out, C, total);
+    if (pc == 4) combine_kernel<T, 4><<<blocks, 256, 0, st>>>((const T*)h, pyr, w, bias, (T*)out, C, total);
+    else combine_kernel<T, 2><<<blocks, 256, 0, st>>>((const T*)h, pyr, w, bias, (T*)out, C, total);
   });
 }
 
 // ------------------------------------------------------------------------------------------------
-// FIR downsample of the 4-channel fp32 input pyramid
+// FIR downsample of the pc-channel fp32 input pyramid (one thread = one output pixel channel)
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) fir4_down_kernel(const float4* __restrict__ x, float4* __restrict__ out, int Hin,
-                                                         int Win, long long total) {
+__global__ void __launch_bounds__(256) fir4_down_kernel(const float* __restrict__ x, float* __restrict__ out, int Hin,
+                                                         int Win, int pc, long long total) {
   const int Ho = Hin / 2, Wo = Win / 2;
   const float k1[4] = {0.125f, 0.375f, 0.375f, 0.125f};
   for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
        i += static_cast<long long>(gridDim.x) * blockDim.x) {
-    const int ox = static_cast<int>(i % Wo), oy = static_cast<int>((i / Wo) % Ho);
-    const long long b = i / (static_cast<long long>(Wo) * Ho);
-    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    const int c = static_cast<int>(i % pc);
+    const long long pix = i / pc;
+    const int ox = static_cast<int>(pix % Wo), oy = static_cast<int>((pix / Wo) % Ho);
+    const long long b = pix / (static_cast<long long>(Wo) * Ho);
+    float acc = 0.f;
 #pragma unroll
     for (int a = 0; a < 4; ++a) {
       const int iy = 2 * oy + a - 1;
@@ -751,19 +767,17 @@ __global__ void __launch_bounds__(256) fir4_down_kernel(const float4* __restrict
       for (int bb = 0; bb < 4; ++bb) {
         const int ix = 2 * ox + bb - 1;
         if (ix < 0 || ix >= Win) continue;
-        const float kw = k1[a] * k1[bb];
-        const float4 v = __ldg(x + (b * Hin + iy) * Win + ix);
-        acc.x += kw * v.x; acc.y += kw * v.y; acc.z += kw * v.z; acc.w += kw * v.w;
+        acc += (k1[a] * k1[bb]) * __ldg(x + ((b * Hin + iy) * Win + ix) * pc + c);
       }
     }
     out[i] = acc;
   }
 }
 
-void launch_fir4_down(const float* x, float* out, int B, int Hin, int Win, cudaStream_t st) {
-  const long long total = static_cast<long long>(B) * (Hin / 2) * (Win / 2);
+void launch_fir4_down(const float* x, float* out, int B, int Hin, int Win, int pc, cudaStream_t st) {
+  const long long total = static_cast<long long>(B) * (Hin / 2) * (Win / 2) * pc;
   const int blocks = static_cast<int>(std::min<long long>((total + 255) / 256, 148LL * 32));
-  fir4_down_kernel<<<blocks, 256, 0, st>>>((const float4*)x, (float4*)out, Hin, Win, total);
+  fir4_down_kernel<<<blocks, 256, 0, st>>>(x, out, Hin, Win, pc, total);
 }
 
 // ------------------------------------------------------------------------------------------------

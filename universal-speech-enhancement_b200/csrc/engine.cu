@@ -187,6 +187,7 @@ struct use_engine {
   std::map<int, RbW> rbw;                         // module index -> ResBlock weight offsets
   std::map<std::string, size_t> off;              // misc named offsets
   int dense_rows = 0;
+  int in_conv_idx = 3;  // index of the input convolution in all_modules (3 with the time-embedding MLP, 1 without)
   char* dev_w = nullptr;
   int num_sms = 148;
   std::map<std::string, std::unique_ptr<Program>> programs;  // keyed by "B,F,T,base"
@@ -214,8 +215,11 @@ static void build_mods(use_engine* e) {
   m.clear();
   const int nf = c.nf, L = c.num_levels;
   m.push_back({K_GFP});
-  m.push_back({K_LINEAR, 2 * nf, 4 * nf});
-  m.push_back({K_LINEAR, 4 * nf, 4 * nf});
+  if (c.conditional) {
+    m.push_back({K_LINEAR, 2 * nf, 4 * nf});
+    m.push_back({K_LINEAR, 4 * nf, 4 * nf});
+  }
+  e->in_conv_idx = (int)m.size();
   m.push_back({K_CONV3, c.input_channels, nf});
   std::vector<int> hs{nf};
   int in_ch = nf;
@@ -305,14 +309,16 @@ static int pack_all(use_engine* e) {
     return 0;
   };
   if (putf("gfp.W", P(0) + ".W", {nf})) return 1;
-  if (putf("l1.w", P(1) + ".weight", {D, 2 * nf}) || putf("l1.b", P(1) + ".bias", {D})) return 1;
-  if (putf("l2.w", P(2) + ".weight", {D, D}) || putf("l2.b", P(2) + ".bias", {D})) return 1;
+  if (c.conditional) {
+    if (putf("l1.w", P(1) + ".weight", {D, 2 * nf}) || putf("l1.b", P(1) + ".bias", {D})) return 1;
+    if (putf("l2.w", P(2) + ".weight", {D, D}) || putf("l2.b", P(2) + ".bias", {D})) return 1;
+  }
   if (putf("out.w", "output_layer.weight", {2, c.input_channels, 1, 1}) || putf("out.b", "output_layer.bias", {2})) return 1;
   // stacked Dense_0 matrix + base bias (conv0 bias + dense bias)
   int rows = 0;
   for (auto& m : e->mods) if (m.kind == K_RB) rows += m.cout;
   e->dense_rows = rows;
-  std::vector<float> dW((size_t)rows * D), dbase(rows);
+  std::vector<float> dW(c.conditional ? (size_t)rows * D : 0), dbase(rows);
   int row = 0;
   for (size_t i = 0; i < e->mods.size(); ++i) {
     const Mod& m = e->mods[i];
@@ -369,8 +375,10 @@ static int pack_all(use_engine* e) {
         const HostTensor *g0 = getw(e, p + ".GroupNorm_0.weight", {m.cin}), *b0 = getw(e, p + ".GroupNorm_0.bias", {m.cin});
         const HostTensor *g1 = getw(e, p + ".GroupNorm_1.weight", {m.cout}), *b1 = getw(e, p + ".GroupNorm_1.bias", {m.cout});
         const HostTensor *c0b = getw(e, p + ".Conv_0.bias", {m.cout}), *c1b = getw(e, p + ".Conv_1.bias", {m.cout});
-        const HostTensor *dw = getw(e, p + ".Dense_0.weight", {m.cout, D}), *db = getw(e, p + ".Dense_0.bias", {m.cout});
-        if (!g0 || !b0 || !g1 || !b1 || !c0b || !c1b || !dw || !db) return 1;
+        // Dense_0 exists in the state dict either way (temb_dim is always passed) but is dead without a time embedding
+        const HostTensor *dw = c.conditional ? getw(e, p + ".Dense_0.weight", {m.cout, D}) : nullptr;
+        const HostTensor *db = c.conditional ? getw(e, p + ".Dense_0.bias", {m.cout}) : nullptr;
+        if (!g0 || !b0 || !g1 || !b1 || !c0b || !c1b || (c.conditional && (!dw || !db))) return 1;
         r.gn0_g = bw.put(g0->data.data(), m.cin * 4);
         r.gn0_b = bw.put(b0->data.data(), m.cin * 4);
         r.gn1_g = bw.put(g1->data.data(), m.cout * 4);
@@ -386,15 +394,15 @@ static int pack_all(use_engine* e) {
         }
         r.bias1 = bw.put(bias1.data(), m.cout * 4);
         r.dense_off = row;
-        memcpy(&dW[(size_t)row * D], dw->data.data(), (size_t)m.cout * D * 4);
-        for (int k = 0; k < m.cout; ++k) dbase[row + k] = c0b->data[k] + db->data[k];
+        if (c.conditional) memcpy(&dW[(size_t)row * D], dw->data.data(), (size_t)m.cout * D * 4);
+        for (int k = 0; k < m.cout; ++k) dbase[row + k] = c0b->data[k] + (c.conditional ? db->data[k] : 0.f);
         row += m.cout;
         e->rbw[(int)i] = r;
         break;
       }
     }
   }
-  e->off["dense.W"] = bw.put(dW.data(), dW.size() * 4);
+  if (c.conditional) e->off["dense.W"] = bw.put(dW.data(), dW.size() * 4);
   e->off["dense.base"] = bw.put(dbase.data(), dbase.size() * 4);
   return 0;
 }
@@ -502,8 +510,13 @@ struct Builder {
       d.seg[0] = TcSegDesc{dry ? nullptr : ws(a0.off), Cin, 0, Cin, dry ? nullptr : wt(w.w0), Cin, 0, 9};
       d.B = B; d.H = Ho; d.W = Wo; d.N = Cout;
       d.out = dry ? nullptr : ws(h1.off);
-      d.bias = dry ? nullptr : (const float*)(base + e->head.dense) + w.dense_off;
-      d.bias_bstride = e->dense_rows;
+      if (e->cfg.conditional) {  // conv bias + Dense_0(act(temb)), per sample
+        d.bias = dry ? nullptr : (const float*)(base + e->head.dense) + w.dense_off;
+        d.bias_bstride = e->dense_rows;
+      } else {
+        d.bias = dry ? nullptr : wf("dense.base") + w.dense_off;
+        d.bias_bstride = 0;
+      }
       d.res = nullptr;
       d.scale = 1.0f;
       conv_tc(d, &h1);
@@ -583,32 +596,34 @@ struct Builder {
     const use_config& c = e->cfg;
     const int L = c.num_levels;
     const int dt = e->dt, Bn = B;
-    int idx = 3;
+    const int npc = c.input_channels;  // channels of the input / output pyramids
+    int idx = e->in_conv_idx;
     // input conv (ncsnpp.py:381); the input pyramid level 0 is the packed network input itself
     std::vector<Act> hs;
     const float* xr = dry ? nullptr : (const float*)(base + e->head.xr);
     {
       Act h0 = new_act(c.nf, F, T);
-      if (e->off.count("all_modules.3.wtc")) {
+      const std::string inp = "all_modules." + std::to_string(e->in_conv_idx);
+      if (e->off.count(inp + ".wtc")) {
         const int ck = 128 / (int)es();
         TcConvDesc d{};
         d.nseg = 1;
-        d.seg[0] = TcSegDesc{dry ? nullptr : base + e->head.xpad, ck, 0, ck, dry ? nullptr : wt(e->off.at("all_modules.3.wtc")), ck, 0, 9};
+        d.seg[0] = TcSegDesc{dry ? nullptr : base + e->head.xpad, ck, 0, ck, dry ? nullptr : wt(e->off.at(inp + ".wtc")), ck, 0, 9};
         d.B = B; d.H = F; d.W = T; d.N = c.nf;
         d.out = dry ? nullptr : ws(h0.off);
-        d.bias = dry ? nullptr : wf("all_modules.3.b");
+        d.bias = dry ? nullptr : wf(inp + ".b");
         d.bias_bstride = 0;
         d.scale = 1.0f;
         conv_tc(d, &h0);
       } else if (!dry) {
-        const float *w = wf("all_modules.3.w"), *b = wf("all_modules.3.b");
+        const float *w = wf(inp + ".w"), *b = wf(inp + ".b");
         void* o = ws(h0.off);
         const int H = F, W = T, N = c.nf;
         emit([=](cudaStream_t s) { launch_conv_in4(dt, xr, w, b, o, Bn, H, W, N, s); }, TAG_SMALL_CONV, 1,
              2.0 * Bn * H * W * N * 36, (double)Bn * H * W * (16 + N * es()));
       }
       hs.push_back(h0);
-      idx = 4;
+      idx = e->in_conv_idx + 1;
     }
     size_t pyr_off = (size_t)-1;  // fp32 input pyramid of the current level (arena), level 0 = xr
     int pH = F, pW = T;
@@ -620,7 +635,7 @@ struct Builder {
       if (l != L - 1) {
         Act h = resblock(idx++, hs.back(), nullptr);
         // input_pyramid = FIR-down(input_pyramid); h = Conv1x1(input_pyramid) + h  (ncsnpp.py:404-406)
-        size_t np = new_f32((size_t)B * (pH / 2) * (pW / 2) * 4);
+        size_t np = new_f32((size_t)B * (pH / 2) * (pW / 2) * npc);
         if (!dry) {
           const float* src = (pyr_off == (size_t)-1) ? xr : (const float*)ws(pyr_off);
           float* dst = (float*)ws(np);
@@ -630,8 +645,8 @@ struct Builder {
           void* hp = ws(h.off);
           const int HW = h.H * h.W, C = h.C;
           emit([=](cudaStream_t s) {
-            launch_fir4_down(src, dst, Bn, H, W, s);
-            launch_combine(dt, hp, dst, cw, cb, hp, Bn, HW, C, s);
+            launch_fir4_down(src, dst, Bn, H, W, npc, s);
+            launch_combine(dt, hp, dst, cw, cb, hp, Bn, HW, C, npc, s);
           }, TAG_SMALL_CONV, 2, 2.0 * Bn * HW * C * 4, 2.0 * Bn * HW * C * es());
         }
         if (pyr_off != (size_t)-1) arena.release(pyr_off);
@@ -671,7 +686,7 @@ struct Builder {
         Act a = new_act(h.C, h.H, h.W);
         const bool head_tc = e->off.count(pc + ".wtc") != 0;
         gn_apply(h, nullptr, e->off.at(pg + ".g"), e->off.at(pg + ".b"), 0, true, head_tc, a, nullptr);
-        size_t np = new_f32((size_t)B * h.H * h.W * 4);
+        size_t np = new_f32((size_t)B * h.H * h.W * npc);
         if (head_tc) {
           TcConvDesc d{};
           d.nseg = 1;
@@ -682,8 +697,11 @@ struct Builder {
           d.bias_bstride = 0;
           d.scale = 1.0f;
           d.out4 = dry ? (float*)1 : (float*)ws(np);
+          d.out_pc = npc;
           d.prev4 = (dry || opyr == (size_t)-1) ? nullptr : (const float*)ws(opyr);
           conv_tc(d);
+        } else if (npc != 4) {
+          err = fail("pyramid head with %d channels needs C %% %d == 0", npc, 128 / (int)es());
         } else if (!dry) {
           const void* ap = ws(a.off);
           const float *w = wf(pc + ".w"), *b = wf(pc + ".b");
@@ -727,7 +745,7 @@ static int plan_workspace(use_engine* e, int B, int F, int T, size_t* total, siz
   b.build();
   if (b.err) return 1;
   size_t off = 0;
-  e->head.xr = off; off = align_up(off + (size_t)B * F * T * 4 * 4, 1024);
+  e->head.xr = off; off = align_up(off + (size_t)B * F * T * c.input_channels * 4, 1024);
   e->head.xpad = off; off = align_up(off + (size_t)B * F * T * 128, 1024);
   e->head.t = off; off = align_up(off + (size_t)B * 4, 1024);
   e->head.gfp = off; off = align_up(off + (size_t)B * 2 * c.nf * 4, 1024);
@@ -771,13 +789,15 @@ static void run_network(use_engine* e, Program* p, cudaStream_t st, const float*
   char* base = p->base;
   const int nf = e->cfg.nf;
   cudaMemsetAsync(base + e->head.stats, 0, p->stats_bytes, st);  // fixed-point accumulators start at zero
-  launch_temb_mlp(gfp, gfp_bstride, (const float*)(e->dev_w + e->off.at("l1.w")),
-                  (const float*)(e->dev_w + e->off.at("l1.b")), (const float*)(e->dev_w + e->off.at("l2.w")),
-                  (const float*)(e->dev_w + e->off.at("l2.b")), (float*)(base + e->head.temb), p->B, nf, st);
-  launch_dense_all((const float*)(base + e->head.temb), (const float*)(e->dev_w + e->off.at("dense.W")),
-                   (const float*)(e->dev_w + e->off.at("dense.base")), (float*)(base + e->head.dense), p->B,
-                   e->dense_rows, 4 * nf, st);
-  e->launches += 2;
+  if (e->cfg.conditional) {
+    launch_temb_mlp(gfp, gfp_bstride, (const float*)(e->dev_w + e->off.at("l1.w")),
+                    (const float*)(e->dev_w + e->off.at("l1.b")), (const float*)(e->dev_w + e->off.at("l2.w")),
+                    (const float*)(e->dev_w + e->off.at("l2.b")), (float*)(base + e->head.temb), p->B, nf, st);
+    launch_dense_all((const float*)(base + e->head.temb), (const float*)(e->dev_w + e->off.at("dense.W")),
+                     (const float*)(e->dev_w + e->off.at("dense.base")), (float*)(base + e->head.dense), p->B,
+                     e->dense_rows, 4 * nf, st);
+    e->launches += 2;
+  }
   if (!e->profiling) {
     for (auto& op : p->ops) { op.fn(st); e->launches += op.launches; }
     return;
@@ -818,7 +838,7 @@ const char* use_last_error(void) { return g_err; }
 
 use_engine* use_engine_create(const use_config* cfg) {
   if (!cfg) { fail("null config"); return nullptr; }
-  if (cfg->num_levels < 1 || cfg->num_levels > 8 || cfg->nf <= 0 || cfg->input_channels != 4 ||
+  if (cfg->num_levels < 1 || cfg->num_levels > 8 || cfg->nf <= 0 || (cfg->input_channels != 4 && cfg->input_channels != 2) ||
       (cfg->act_dtype != USE_DTYPE_F32 && cfg->act_dtype != USE_DTYPE_BF16)) {
     fail("unsupported config (levels=%d nf=%d input_channels=%d dtype=%d)", cfg->num_levels, cfg->nf,
          cfg->input_channels, cfg->act_dtype);
@@ -904,36 +924,47 @@ int use_engine_set_option(use_engine* e, const char* key, int value) {
   return fail("unknown option '%s'", key);
 }
 
-static int stage_head(use_engine* e, Program* p, const float* t_host, const float* gfp_host, cudaStream_t st) {
-  char* base = p->base;
-  cudaMemcpyAsync(base + e->head.t, t_host, (size_t)p->B * 4, cudaMemcpyHostToDevice, st);
-  cudaMemcpyAsync(base + e->head.gfp, gfp_host, (size_t)p->B * 2 * e->cfg.nf * 4, cudaMemcpyHostToDevice, st);
-  return 0;
-}
-
-int use_score_forward(use_engine* e, int B, int F, int T, const void* x, const void* Y, const float* t_host,
-                      const float* gfp_host, void* score, void* workspace, size_t workspace_bytes, void* stream) {
-  if (!e || !x || !Y || !t_host || !gfp_host || !score || !workspace) return fail("null argument");
+// one evaluation of the network; sign = -1 gives the score (-net), +1 the raw network output
+static int net_forward(use_engine* e, int B, int F, int T, const void* x, const void* Y, const float* t_host,
+                       const float* gfp_host, void* out, float sign, void* workspace, size_t workspace_bytes, void* stream) {
+  if (!e || !x || !out || !workspace) return fail("null argument");
+  const bool cond = e->cfg.conditional != 0;
+  if (e->cfg.input_channels == 4 && !Y) return fail("the conditioning spectrogram Y is required (input_channels = 4)");
+  if ((cond || e->cfg.scale_by_sigma) && (!t_host || (cond && !gfp_host))) return fail("time inputs are required");
   Program* p = get_program(e, B, F, T, workspace, workspace_bytes);
   if (!p) return 1;
   cudaStream_t st = (cudaStream_t)stream;
-  stage_head(e, p, t_host, gfp_host, st);
+  if (t_host) cudaMemcpyAsync(p->base + e->head.t, t_host, (size_t)B * 4, cudaMemcpyHostToDevice, st);
+  if (cond) cudaMemcpyAsync(p->base + e->head.gfp, gfp_host, (size_t)B * 2 * e->cfg.nf * 4, cudaMemcpyHostToDevice, st);
   const size_t per = (size_t)F * T;
-  launch_pack_input(e->dt, (const float2*)x, (const float2*)Y, (float*)(p->base + e->head.xr), p->base + e->head.xpad, per * B, st);
+  launch_pack_input(e->dt, e->cfg.input_channels, (const float2*)x, (const float2*)Y, (float*)(p->base + e->head.xr),
+                    p->base + e->head.xpad, per * B, st);
   run_network(e, p, st, (const float*)(p->base + e->head.gfp), 2 * e->cfg.nf);
   StepArgs a{};
   a.pyramid = (const float*)(p->base + p->pyramid_off);
-  a.t = (const float*)(p->base + e->head.t);
+  a.pc = e->cfg.input_channels;
+  a.out_sign = sign;
+  a.t = e->cfg.scale_by_sigma ? (const float*)(p->base + e->head.t) : nullptr;
   a.t_bstride = 1;
   a.ow = (const float*)(e->dev_w + e->off.at("out.w"));
   a.ob = (const float*)(e->dev_w + e->off.at("out.b"));
-  a.score = (float2*)score;
+  a.score = (float2*)out;
   a.x = nullptr;
   a.B = B;
   a.per_clip = per;
   launch_final_step(a, st);
   e->launches += 2;
-  return cuda_check("use_score_forward");
+  return cuda_check("net_forward");
+}
+
+int use_score_forward(use_engine* e, int B, int F, int T, const void* x, const void* Y, const float* t_host,
+                      const float* gfp_host, void* score, void* workspace, size_t workspace_bytes, void* stream) {
+  return net_forward(e, B, F, T, x, Y, t_host, gfp_host, score, -1.0f, workspace, workspace_bytes, stream);
+}
+
+int use_net_forward(use_engine* e, int B, int F, int T, const void* x, const void* Y, const float* t_host,
+                    const float* gfp_host, void* out, void* workspace, size_t workspace_bytes, void* stream) {
+  return net_forward(e, B, F, T, x, Y, t_host, gfp_host, out, 1.0f, workspace, workspace_bytes, stream);
 }
 
 int use_pc_sample(use_engine* e, int B, int F, int T, const void* Y, void* x_state, void* x_mean, int N,
@@ -941,6 +972,8 @@ int use_pc_sample(use_engine* e, int B, int F, int T, const void* Y, void* x_sta
                   uint64_t seed, uint32_t clip0, void* workspace, size_t workspace_bytes, void* stream) {
   if (!e || !Y || !x_state || !x_mean || !t_host || !G_host || !gfp_host || !workspace) return fail("null argument");
   if (N < 1 || N > kMaxSteps) return fail("N must be in [1, %d]", kMaxSteps);
+  if (e->cfg.input_channels != 4 || !e->cfg.conditional || !e->cfg.scale_by_sigma)
+    return fail("use_pc_sample needs the noise-conditional score network (input_channels=4, conditional, scale_by_sigma)");
   cudaStream_t st = (cudaStream_t)stream;
   const int G = group_count(e, B), Bg = B / G;
   const size_t per = (size_t)F * T;
@@ -986,11 +1019,13 @@ int use_pc_sample(use_engine* e, int B, int F, int T, const void* Y, void* x_sta
       const size_t o = (size_t)g * Bg * per, n = per * Bg;
       const float* t_dev = (const float*)(base + e->head.sched) + i;
       const float* gfp_dev = (const float*)(base + e->head.sched) + N + (size_t)i * nf2;
-      launch_pack_input(e->dt, (const float2*)x_state + o, (const float2*)Y + o, (float*)(base + e->head.xr),
+      launch_pack_input(e->dt, 4, (const float2*)x_state + o, (const float2*)Y + o, (float*)(base + e->head.xr),
                         base + e->head.xpad, n, gs[g]);
       run_network(e, p, gs[g], gfp_dev, 0);
       StepArgs a{};
       a.pyramid = (const float*)(base + p->pyramid_off);
+      a.pc = 4;
+      a.out_sign = -1.0f;
       a.t = t_dev;
       a.t_bstride = 0;
       a.ow = (const float*)(e->dev_w + e->off.at("out.w"));
@@ -1139,12 +1174,13 @@ int use_op_conv_out4(int dtype, const void* a, const float* w, const float* bias
   return cuda_check("use_op_conv_out4");
 }
 int use_op_combine(int dtype, const void* h, const float* pyr, const float* w, const float* bias, void* out, int B, int HW,
-                   int C, void* stream) {
-  launch_combine(dtype, h, pyr, w, bias, out, B, HW, C, (cudaStream_t)stream);
+                   int C, int pc, void* stream) {
+  if (pc != 2 && pc != 4) return fail("pc must be 2 or 4");
+  launch_combine(dtype, h, pyr, w, bias, out, B, HW, C, pc, (cudaStream_t)stream);
   return cuda_check("use_op_combine");
 }
-int use_op_fir4_down(const float* x, float* out, int B, int Hin, int Win, void* stream) {
-  launch_fir4_down(x, out, B, Hin, Win, (cudaStream_t)stream);
+int use_op_fir4_down(const float* x, float* out, int B, int Hin, int Win, int pc, void* stream) {
+  launch_fir4_down(x, out, B, Hin, Win, pc, (cudaStream_t)stream);
   return cuda_check("use_op_fir4_down");
 }
 int use_op_philox(void* z, uint64_t seed, uint32_t step, uint32_t clip0, int B, size_t per_clip, void* stream) {

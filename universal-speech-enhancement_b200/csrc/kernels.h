@@ -35,11 +35,11 @@ void launch_conv_in4(int dt, const float* x, const float* w, const float* bias, 
 // If prev != nullptr adds FIR-upsample-x2(prev) where prev is fp32 [B][H/2][W/2][4].
 void launch_conv_out4(int dt, const void* a, const float* w, const float* bias, const float* prev, float* out, int B,
                       int H, int W, int C, cudaStream_t st);
-// out = h + bias + conv1x1_{4->C}(pyr): Combine(method="sum").  w: [C][4] fp32.  In place allowed.
+// out = h + bias + conv1x1_{pc->C}(pyr): Combine(method="sum").  w: [C][pc] fp32, pyr fp32 [.][pc].  In place allowed.
 void launch_combine(int dt, const void* h, const float* pyr, const float* w, const float* bias, void* out, int B, int HW,
-                    int C, cudaStream_t st);
-// FIR [1,3,3,1] downsample x2 of an fp32 4-channel map.
-void launch_fir4_down(const float* x, float* out, int B, int Hin, int Win, cudaStream_t st);
+                    int C, int pc, cudaStream_t st);
+// FIR [1,3,3,1] downsample x2 of an fp32 pc-channel map (pc = 2 or 4).
+void launch_fir4_down(const float* x, float* out, int B, int Hin, int Win, int pc, cudaStream_t st);
 void launch_upfirdn2d(const float* in, float* out, int major, int in_h, int in_w, int minor, const float* kernel, int kh,
                       int kw, int up_x, int up_y, int down_x, int down_y, int pad_x0, int pad_x1, int pad_y0, int pad_y1,
                       cudaStream_t st);
@@ -50,13 +50,15 @@ void launch_conv_ref(int dt, const void* x, const float* w, const float* bias, i
 // ---- network input / output, SDE arithmetic -------------------------------------------------------
 // xr[b][f][t][:] = 2*[Re x, Im x, Re Y, Im Y] - 1 (fp32 x4); xpad (optional): the same 4 values as act-dtype MMA
 // operands zero-padded to one 128-byte channel chunk per pixel (input of the tcgen05 input convolution)
-void launch_pack_input(int dt, const float2* x, const float2* Y, float* xr, void* xpad, size_t n, cudaStream_t st);
+void launch_pack_input(int dt, int pc, const float2* x, const float2* Y, float* xr, void* xpad, size_t n, cudaStream_t st);
 
 struct StepArgs {
-  const float* pyramid;  // fp32 [B][F][T][4]
-  const float* t;        // time value of sample b at t[b * t_bstride] (divides the pyramid: scale_by_sigma)
+  const float* pyramid;  // fp32 [B][F][T][pc]
+  int pc;                // pyramid channels: 4 (score network) or 2 (discriminative network)
+  float out_sign;        // -1: score = -net(x) (ScoreModel.forward_score); +1: the raw network output
+  const float* t;        // time value of sample b at t[b * t_bstride] (divides the pyramid: scale_by_sigma) or nullptr
   int t_bstride;         // 1 = per-sample times, 0 = one batch-uniform time
-  const float* ow;       // output_layer weight [2][4]
+  const float* ow;       // output_layer weight [2][pc]
   const float* ob;       // output_layer bias [2]
   float2* score;         // optional out: -net(x)   (ScoreModel.forward)
   // fused ReverseDiffusionPredictor step (all optional as a group; enabled when x != nullptr)
@@ -126,8 +128,9 @@ struct TcConvDesc {
   const void* res;
   float scale;
   long long* stats_acc;  // optional fixed-point GroupNorm statistics of `out`, [B][N][2], zero on entry
-  float* out4;           // pyramid-head mode (N must be 32): fp32 [B][H][W][4] output instead of `out`
-  const float* prev4;    // optional previous pyramid level, fp32 [B][H/2][W/2][4], FIR-upsampled and added
+  float* out4;           // pyramid-head mode (N must be 32): fp32 [B][H][W][out_pc] output instead of `out`
+  const float* prev4;    // optional previous pyramid level, fp32 [B][H/2][W/2][out_pc], FIR-upsampled and added
+  int out_pc;            // real output channels of the head: 4 or 2
 };
 struct TcConvPlan;  // opaque: tensor maps + launch geometry
 // Build (host) the launch plan; returns nullptr and fills err on failure.

@@ -35,11 +35,12 @@ __device__ __forceinline__ float2 philox_cnormal(unsigned long long seed, uint32
   return make_float2(r * cs, r * sn);
 }
 
-// xr: fp32 [n][4] (input pyramid level 0).  xpad (optional): act dtype [n][128 B of channels], channels 0..3 = the
-// same values as MMA operands, the rest zero -- the tcgen05 input convolution reads it as one K chunk.
-template <typename T>
+// xr: fp32 [n][PC] (input pyramid level 0), PC = 4: [Re x, Im x, Re Y, Im Y], PC = 2: [Re x, Im x] (discriminative
+// network, no conditioning).  xpad (optional): act dtype [n][128 B of channels], channels 0..PC-1 = the same values as
+// MMA operands, the rest zero -- the tcgen05 input convolution reads it as one K chunk.
+template <typename T, int PC>
 __global__ void __launch_bounds__(256) pack_input_kernel(const float2* __restrict__ x, const float2* __restrict__ Y,
-                                                          float4* __restrict__ xr, T* __restrict__ xpad, size_t n) {
+                                                          float* __restrict__ xr, T* __restrict__ xpad, size_t n) {
   constexpr int V = Vec<T>::N;
   constexpr int VPP = 8;  // 16-byte vectors per padded pixel (128 B)
   for (size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n * VPP;
@@ -50,38 +51,56 @@ __global__ void __launch_bounds__(256) pack_input_kernel(const float2* __restric
 #pragma unroll
     for (int j = 0; j < V; ++j) f[j] = 0.f;
     if (v == 0) {
-      const float2 a = x[pix], b = Y[pix];
-      const float4 o = make_float4(2.f * a.x - 1.0f, 2.f * a.y - 1.0f, 2.f * b.x - 1.0f, 2.f * b.y - 1.0f);
-      xr[pix] = o;
-      f[0] = o.x; f[1] = o.y; f[2] = o.z; f[3] = o.w;
+      const float2 a = x[pix];
+      f[0] = 2.f * a.x - 1.0f;
+      f[1] = 2.f * a.y - 1.0f;
+      if constexpr (PC == 4) {
+        const float2 b = Y[pix];
+        f[2] = 2.f * b.x - 1.0f;
+        f[3] = 2.f * b.y - 1.0f;
+        reinterpret_cast<float4*>(xr)[pix] = make_float4(f[0], f[1], f[2], f[3]);
+      } else {
+        reinterpret_cast<float2*>(xr)[pix] = make_float2(f[0], f[1]);
+      }
     }
     if (xpad != nullptr) Vec<T>::store_operand(xpad + pix * (VPP * V) + v * V, f);
   }
 }
 
-void launch_pack_input(int dt, const float2* x, const float2* Y, float* xr, void* xpad, size_t n, cudaStream_t st) {
+void launch_pack_input(int dt, int pc, const float2* x, const float2* Y, float* xr, void* xpad, size_t n, cudaStream_t st) {
   const int blocks = static_cast<int>(std::min<size_t>((n * 8 + 255) / 256, 148 * 32));
-  if (dt == kBF16)
-    pack_input_kernel<__nv_bfloat16><<<blocks, 256, 0, st>>>(x, Y, reinterpret_cast<float4*>(xr), (__nv_bfloat16*)xpad, n);
-  else
-    pack_input_kernel<float><<<blocks, 256, 0, st>>>(x, Y, reinterpret_cast<float4*>(xr), (float*)xpad, n);
+  if (dt == kBF16) {
+    if (pc == 4) pack_input_kernel<__nv_bfloat16, 4><<<blocks, 256, 0, st>>>(x, Y, xr, (__nv_bfloat16*)xpad, n);
+    else pack_input_kernel<__nv_bfloat16, 2><<<blocks, 256, 0, st>>>(x, Y, xr, (__nv_bfloat16*)xpad, n);
+  } else {
+    if (pc == 4) pack_input_kernel<float, 4><<<blocks, 256, 0, st>>>(x, Y, xr, (float*)xpad, n);
+    else pack_input_kernel<float, 2><<<blocks, 256, 0, st>>>(x, Y, xr, (float*)xpad, n);
+  }
 }
 
 __global__ void __launch_bounds__(256) final_step_kernel(StepArgs a) {
   const size_t n = a.per_clip * a.B;
-  const float w00 = a.ow[0], w01 = a.ow[1], w02 = a.ow[2], w03 = a.ow[3];
-  const float w10 = a.ow[4], w11 = a.ow[5], w12 = a.ow[6], w13 = a.ow[7];
+  float w0[4] = {0.f, 0.f, 0.f, 0.f}, w1[4] = {0.f, 0.f, 0.f, 0.f};
+  for (int j = 0; j < a.pc; ++j) { w0[j] = a.ow[j]; w1[j] = a.ow[a.pc + j]; }
   const float b0 = a.ob[0], b1 = a.ob[1];
   const float G2 = a.G * a.G;
   for (size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n;
        i += static_cast<size_t>(gridDim.x) * blockDim.x) {
     const int b = static_cast<int>(i / a.per_clip);
-    const float t = a.t[static_cast<size_t>(b) * a.t_bstride];
-    float4 p = __ldg(reinterpret_cast<const float4*>(a.pyramid) + i);
-    p.x /= t; p.y /= t; p.z /= t; p.w /= t;
-    const float ore = b0 + w00 * p.x + w01 * p.y + w02 * p.z + w03 * p.w;
-    const float oim = b1 + w10 * p.x + w11 * p.y + w12 * p.z + w13 * p.w;
-    const float2 score = make_float2(-ore, -oim);
+    float4 p = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (a.pc == 4) {
+      p = __ldg(reinterpret_cast<const float4*>(a.pyramid) + i);
+    } else {
+      const float2 q = __ldg(reinterpret_cast<const float2*>(a.pyramid) + i);
+      p.x = q.x; p.y = q.y;
+    }
+    if (a.t != nullptr) {  // scale_by_sigma: divide by the TIME value (ncsnpp.py:492-494)
+      const float t = a.t[static_cast<size_t>(b) * a.t_bstride];
+      p.x /= t; p.y /= t; p.z /= t; p.w /= t;
+    }
+    const float ore = b0 + w0[0] * p.x + w0[1] * p.y + w0[2] * p.z + w0[3] * p.w;
+    const float oim = b1 + w1[0] * p.x + w1[1] * p.y + w1[2] * p.z + w1[3] * p.w;
+    const float2 score = make_float2(a.out_sign * ore, a.out_sign * oim);
     if (a.score != nullptr) a.score[i] = score;
     if (a.x != nullptr) {
       const float2 x = a.x[i], Y = a.Y[i];
