@@ -36,7 +36,7 @@ extern "C" {
 #pragma GCC visibility push(default)
 #endif
 
-#define USE_B200_ABI_VERSION 2
+#define USE_B200_ABI_VERSION 3
 
 #define USE_DTYPE_F32 0  /* fp32 storage, TF32 tensor-core math (PyTorch's own GPU default for conv) */
 #define USE_DTYPE_BF16 1 /* bf16 storage + bf16 tensor-core math, fp32 accumulate / statistics / SDE state */
@@ -138,6 +138,17 @@ int use_op_conv_tc(int dtype, int nseg, const void* const* seg_act, const int* s
                    const int* seg_c, const void* const* seg_w, const int* seg_cw, const int* seg_wc0, const int* seg_taps,
                    int B, int H, int W, int N, const float* bias, int bias_bstride, const void* res, float scale, void* out,
                    long long* stats, void* stream);
+/* Same convolution with FUSED GroupNorm + SiLU operands (layerspp.py:283-285,304-306 without materialising the
+ * normalised tensor): a 3x3 segment whose seg_aff[i] != NULL reads the RAW tensor seg_act[i] and applies
+ * silu(x * scale + shift) + operand rounding on the way into shared memory; seg_aff[i] = fp32 [B][2][seg_aff_c[i]]
+ * (scale row, shift row) from use_op_gn_affine, channel seg_c0[i] of the tensor <-> column seg_aff_c0[i]. */
+int use_op_gn_affine(const long long* stats0, int C0, const long long* stats1, int C1, const float* gamma,
+                     const float* beta, float eps, int HW, float* aff, int B, void* stream);
+int use_op_conv_tc_gn(int dtype, int nseg, const void* const* seg_act, const int* seg_ctensor, const int* seg_c0,
+                      const int* seg_c, const void* const* seg_w, const int* seg_cw, const int* seg_wc0, const int* seg_taps,
+                      const float* const* seg_aff, const int* seg_aff_c, const int* seg_aff_c0, int B, int H, int W, int N,
+                      const float* bias, int bias_bstride, const void* res, float scale, void* out, long long* stats,
+                      void* stream);
 int use_op_conv_ref(int dtype, const void* x, const float* w, const float* bias, int bias_bstride, const void* res,
                     float scale, void* out, int B, int H, int W, int Cin, int Cout, int ksize, void* stream);
 int use_op_conv_in4(int dtype, const float* x, const float* w, const float* bias, void* out, int B, int H, int W, int N,

@@ -254,6 +254,97 @@ def test_groupnorm_silu_fir(dt, C0, C1, fir):
             describe_mismatch(gr, ref_raw)
 
 
+FUSED_CASES = [
+    # name, B, H, W, N, sources (channels of the concatenated raw tensors), extra 1x1 segments (channels)
+    ("c128_n128", 2, 40, 20, 128, [128], []),
+    ("c256_n128_ragged", 2, 20, 10, 128, [256], []),
+    ("concat_256_128_n128", 1, 32, 24, 128, [256, 128], []),
+    ("c256_n256", 2, 16, 24, 256, [256], []),
+    ("concat_256_256_n256_small", 3, 8, 10, 256, [256, 256], []),
+    ("conv1_with_skip_segments", 2, 32, 16, 128, [128], [256, 128]),
+    ("many_tiles", 3, 96, 80, 128, [128], []),
+]
+
+
+@pytest.mark.parametrize("dt", [F32, BF16], ids=["tf32", "bf16"])
+@pytest.mark.parametrize("case", FUSED_CASES, ids=[c[0] for c in FUSED_CASES])
+def test_conv_tc_fused_groupnorm_operand(case, dt):
+    """GroupNorm + SiLU applied inside the convolution's operand path (transform warps) == the separate gn_apply kernel
+    followed by the same convolution, BIT FOR BIT (identical arithmetic, identical accumulation order), and both match
+    torch group_norm -> silu -> conv2d within the operand-rounding tolerance."""
+    name, B, H, W, N, srcC, extra = case
+    L = _lib.lib()
+    g = torch.Generator().manual_seed(len(name) * 31 + B)
+    srcs = [to_operand((1.0 + 0.5 * i) * torch.randn(B, c, H, W, generator=g) + 0.2 * i, dt) for i, c in enumerate(srcC)]
+    Ct = sum(srcC)
+    gamma, beta = 1 + 0.1 * torch.randn(Ct, generator=g), 0.1 * torch.randn(Ct, generator=g)
+    w3 = to_operand(torch.randn(N, Ct, 3, 3, generator=g) / np.sqrt(Ct * 9), dt)
+    xs = [to_operand(torch.randn(B, c, H, W, generator=g), dt) for c in extra]
+    w1 = to_operand(torch.randn(N, sum(extra), 1, 1, generator=g) / np.sqrt(max(1, sum(extra))), dt) if extra else None
+    bias = torch.randn(B, N, generator=g)
+    acts = [act_tensor(s, dt) for s in srcs]
+    stats = [gn_stats_raw(L, dt, a, B, H * W, c) for a, c in zip(acts, srcC)]
+    gd, bd = gamma.cuda(), beta.cuda()
+    C0, C1 = srcC[0], (srcC[1] if len(srcC) > 1 else 0)
+    # (1) unfused: gn_apply materialises the activated operand tensor, then a plain 3x3 segment over it
+    a_act = torch.empty(B, H, W, Ct, device="cuda", dtype=acts[0].dtype)
+    rc = L.use_op_gn_apply(dt, acts[0].data_ptr(), stats[0].data_ptr(), C0, acts[1].data_ptr() if C1 else None,
+                           stats[1].data_ptr() if C1 else None, C1, gd.data_ptr(), bd.data_ptr(), 1e-6, 0, 1, 1,
+                           a_act.data_ptr(), None, B, H, W, stream())
+    assert rc == 0, L.use_last_error()
+    pw3 = pack_weight(L, w3, dt)
+    pw1 = pack_weight(L, w1, dt) if extra else None
+    xacts = [act_tensor(x, dt) for x in xs]
+    bias_d = bias.cuda()
+
+    def run(fused):
+        seg_act, ct, c0, cc, ws, cw, wc0, taps, aff, affc, affc0 = [], [], [], [], [], [], [], [], [], [], []
+        afft = None
+        if fused:
+            afft = torch.empty(B, 2, Ct, device="cuda", dtype=torch.float32)
+            rc = L.use_op_gn_affine(stats[0].data_ptr(), C0, stats[1].data_ptr() if C1 else None, C1, gd.data_ptr(),
+                                    bd.data_ptr(), 1e-6, H * W, afft.data_ptr(), B, stream())
+            assert rc == 0, L.use_last_error()
+            off = 0
+            for a, c in zip(acts, srcC):
+                seg_act.append(a.data_ptr()); ct.append(c); c0.append(0); cc.append(c); ws.append(pw3.data_ptr()); cw.append(Ct)
+                wc0.append(off); taps.append(9); aff.append(afft.data_ptr()); affc.append(Ct); affc0.append(off)
+                off += c
+        else:
+            seg_act.append(a_act.data_ptr()); ct.append(Ct); c0.append(0); cc.append(Ct); ws.append(pw3.data_ptr()); cw.append(Ct)
+            wc0.append(0); taps.append(9); aff.append(None); affc.append(0); affc0.append(0)
+        if len(seg_act) + len(xacts) > 3:
+            pytest.skip("more than 3 segments")
+        off = 0
+        for xa, c in zip(xacts, extra):
+            seg_act.append(xa.data_ptr()); ct.append(c); c0.append(0); cc.append(c); ws.append(pw1.data_ptr()); cw.append(sum(extra))
+            wc0.append(off); taps.append(1); aff.append(None); affc.append(0); affc0.append(0)
+            off += c
+        out = torch.empty(B, H, W, N, device="cuda", dtype=acts[0].dtype)
+        st = torch.zeros(B, N, 2, dtype=torch.int64, device="cuda")
+        rc = L.use_op_conv_tc_gn(dt, len(seg_act), ptr_array(seg_act), int_array(ct), int_array(c0), int_array(cc),
+                                 ptr_array(ws), int_array(cw), int_array(wc0), int_array(taps), ptr_array(aff),
+                                 int_array(affc), int_array(affc0), B, H, W, N, bias_d.data_ptr(), N, None, 0.70710678,
+                                 out.data_ptr(), st.data_ptr(), stream())
+        assert rc == 0, L.use_last_error()
+        _sync()
+        return out, st, afft
+
+    out_u, st_u, _ = run(False)
+    out_f, st_f, _ = run(True)
+    assert torch.equal(out_u, out_f), describe_mismatch(from_act(out_f), from_act(out_u))
+    assert torch.equal(st_u, st_f)
+    ref_a = to_operand(_gn_ref(torch.cat(srcs, 1), gamma, beta, True), dt)
+    ref = Fnn.conv2d(ref_a.double(), w3.double(), padding=1)
+    if extra:
+        ref = ref + Fnn.conv2d(torch.cat(xs, 1).double(), w1.double())
+    ref = ((ref + bias.double()[:, :, None, None]) * 0.70710678).float()
+    got = from_act(out_f)
+    # the activated operand is re-rounded to bf16 / TF32: one operand ulp on a few inputs moves the sum slightly
+    tol = (2e-3 if dt == F32 else 1.5e-2) * float(ref.abs().max())
+    assert float((got - ref).abs().max()) <= tol, describe_mismatch(got, ref)
+
+
 def test_gn_apply_operand_rounding_fp32():
     """as_operand=1 in fp32 mode stores TF32-representable values (low 13 mantissa bits clear)."""
     L = _lib.lib()

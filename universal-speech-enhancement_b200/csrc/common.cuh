@@ -49,6 +49,10 @@ template <> struct Vec<float> {
   __device__ __forceinline__ static void store_operand(float* p, const float (&v)[4]) {
     *reinterpret_cast<float4*>(p) = make_float4(round_tf32(v[0]), round_tf32(v[1]), round_tf32(v[2]), round_tf32(v[3]));
   }
+  __device__ __forceinline__ static uint4 pack_operand(const float (&v)[4]) {
+    return make_uint4(__float_as_uint(round_tf32(v[0])), __float_as_uint(round_tf32(v[1])), __float_as_uint(round_tf32(v[2])),
+                      __float_as_uint(round_tf32(v[3])));
+  }
 };
 template <> struct Vec<__nv_bfloat16> {
   static constexpr int N = 8;
@@ -73,9 +77,30 @@ template <> struct Vec<__nv_bfloat16> {
     *reinterpret_cast<uint4*>(p) = make_uint4(w[0], w[1], w[2], w[3]);
   }
   __device__ __forceinline__ static void store_operand(__nv_bfloat16* p, const float (&v)[8]) { store(p, v); }
+  __device__ __forceinline__ static uint4 pack_operand(const float (&v)[8]) {
+    uint32_t w[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      __nv_bfloat162 h = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]);
+      w[i] = *reinterpret_cast<uint32_t*>(&h);
+    }
+    return make_uint4(w[0], w[1], w[2], w[3]);
+  }
 };
 
 __device__ __forceinline__ float silu(float x) { return x / (1.0f + __expf(-x)); }
+__device__ __forceinline__ float silu_fast(float x) { return __fdividef(x, 1.0f + __expf(-x)); }
+// x * sigmoid(x) = x * (0.5 + 0.5 tanh(x/2)): ONE MUFU op.  tanh.approx has ~2^-11 relative error, invisible after the
+// bf16 rounding of the result (2^-9) but not acceptable for the fp32 path, which keeps the exp + rcp form.
+__device__ __forceinline__ float silu_tanh(float x) {
+  float t;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(0.5f * x));
+  return x * fmaf(0.5f, t, 0.5f);
+}
+template <typename T> __device__ __forceinline__ float silu_act(float x) {
+  if constexpr (DT<T>::kIsBf16) return silu_tanh(x);
+  else return silu_fast(x);
+}
 
 // GroupNorm statistics are accumulated as 64-bit FIXED-POINT integers with atomicAdd: integer addition is associative,
 // so the result is bit-reproducible and independent of tile order, batch size and launch geometry without any
@@ -217,6 +242,21 @@ __device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr) {
   return d;
 }
 
+// Same, with an explicit stride between 8-row groups.  Measured on B200 (tools/swz_probe.cu): the 128-byte swizzle is a
+// function of the ABSOLUTE shared-memory address (bits [4,7) ^= bits [7,10)), with base_offset = 0, for any start
+// address that is a multiple of 128 B and any SBO -- so a descriptor may start at an arbitrary pixel row of a window
+// whose rows were written with the absolute-address swizzle (TMA does, and so do the transform warps), and the 8-pixel
+// groups of a 10-pixel-wide window are simply SBO = 1280 B apart.
+__device__ __forceinline__ uint64_t umma_desc_sw128_sbo(uint32_t smem_addr, uint32_t sbo) {
+  uint64_t d = 0;
+  d |= static_cast<uint64_t>((smem_addr & 0x3ffffu) >> 4);
+  d |= static_cast<uint64_t>(1) << 16;
+  d |= static_cast<uint64_t>(sbo >> 4) << 32;
+  d |= static_cast<uint64_t>(1) << 46;
+  d |= static_cast<uint64_t>(2) << 61;
+  return d;
+}
+
 // Instruction descriptor: D=f32 (bit 4), A/B format (1 = bf16, 2 = tf32) at bits 7 / 10, both K-major,
 // N>>3 at bit 17, M>>4 at bit 24.
 __host__ __device__ constexpr uint32_t umma_idesc(int fmt, int M, int N) {
@@ -254,6 +294,10 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
       : "memory");
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+__device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
 
 __device__ __forceinline__ bool elect_one() {
   uint32_t pred;

@@ -31,32 +31,20 @@ static EncodeTiledFn get_encode() {
 
 struct TcConvPlan {
   ConvParams params;
-  int dt, N, nsub, mc;
+  int dt, N, nsub;
   int grid, threads, smem;
   const void* kernel;
 };
 
-// CTA-pair weight multicast (cluster of 2) is OFF by default: measured on B200 it does not pay (bf16, batch 8:
-// 25.3 ms of convolutions per evaluation with it, 24.0 ms without) because the C_out = 128 layers are bound by the
-// shared-memory read bandwidth of single-CTA M128xN128 MMAs, not by L2 -> SM weight traffic.  USE_B200_CONV_MC=2
-// enables it for A/B measurements.
-static int multicast_width() {
-  static int mc = [] {
-    const char* v = getenv("USE_B200_CONV_MC");
-    return (v && v[0] == '2') ? 2 : 1;
-  }();
-  return mc;
-}
-
-static bool encode_act(CUtensorMap* m, int dt, const void* base, int B, int H, int W, int Ct, int rows, char* err,
-                       int errlen) {
+static bool encode_act(CUtensorMap* m, int dt, const void* base, int B, int H, int W, int Ct, int cols, int rows,
+                       char* err, int errlen) {
   EncodeTiledFn enc = get_encode();
   if (!enc) { snprintf(err, errlen, "cuTensorMapEncodeTiled unavailable"); return false; }
   const cuuint64_t es = act_size(dt);
   const cuuint32_t ck = 128 / es;
   cuuint64_t dims[4] = {(cuuint64_t)Ct, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
   cuuint64_t strides[3] = {Ct * es, (cuuint64_t)W * Ct * es, (cuuint64_t)H * W * Ct * es};
-  cuuint32_t box[4] = {ck, 8, (cuuint32_t)rows, 1};
+  cuuint32_t box[4] = {ck, (cuuint32_t)cols, (cuuint32_t)rows, 1};
   cuuint32_t estr[4] = {1, 1, 1, 1};
   CUresult r = enc(m, dt == kBF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4,
                    const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
@@ -97,24 +85,30 @@ static bool swap_ab_enabled() {
   return on;
 }
 
-template <typename T, int N, int NSUB>
-static void fill_kernel(TcConvPlan* p) {
-  using C = ConvCfg<T, N, NSUB>;
-  if (p->mc == 2) {
-    p->kernel = reinterpret_cast<const void*>(&conv_tc_kernel<T, N, NSUB, 2, false>);
-    cudaFuncSetAttribute(conv_tc_kernel<T, N, NSUB, 2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES);
-  } else if (N == 128 && NSUB == 2 && swap_ab_enabled()) {
-    if constexpr (N == 128 && NSUB == 2) {
-      p->kernel = reinterpret_cast<const void*>(&conv_tc_kernel<T, N, NSUB, 1, true>);
-      cudaFuncSetAttribute(conv_tc_kernel<T, N, NSUB, 1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES);
-    }
-  } else {
-    p->kernel = reinterpret_cast<const void*>(&conv_tc_kernel<T, N, NSUB, 1, false>);
-    cudaFuncSetAttribute(conv_tc_kernel<T, N, NSUB, 1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES);
-  }
+template <typename T, int N, int NSUB, bool SWAP, bool FUSE>
+static void set_kernel(TcConvPlan* p) {
+  using C = ConvCfg<T, N, NSUB, FUSE>;
+  auto k = &conv_tc_kernel<T, N, NSUB, SWAP, FUSE>;
+  p->kernel = reinterpret_cast<const void*>(k);
+  cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES);
   p->threads = C::THREADS;
   p->smem = C::SMEM_BYTES;
   p->nsub = NSUB;
+}
+
+template <typename T, int N, int NSUB>
+static void fill_kernel(TcConvPlan* p, bool fuse) {
+  if constexpr (N == 128 && NSUB == 2) {
+    if (swap_ab_enabled()) {
+      if (fuse) set_kernel<T, N, NSUB, true, true>(p);
+      else set_kernel<T, N, NSUB, true, false>(p);
+      return;
+    }
+  }
+  if constexpr (N >= 64) {
+    if (fuse) { set_kernel<T, N, NSUB, false, true>(p); return; }
+  }
+  set_kernel<T, N, NSUB, false, false>(p);
 }
 
 bool tc_conv_supported(int dt, int N) { return N == 32 || N == 64 || N == 128 || N == 256; }
@@ -128,17 +122,23 @@ TcConvPlan* tc_conv_plan_create(int dt, const TcConvDesc& d, int num_sms, char* 
   memset(&p->params, 0, sizeof(p->params));
   p->dt = dt;
   p->N = d.N;
-  p->mc = (d.N >= 64) ? multicast_width() : 1;  // the 32-wide pyramid head has 4 KB weight tiles: not worth pairing
+  bool fuse = false;
+  for (int i = 0; i < d.nseg; ++i) fuse = fuse || d.seg[i].aff != nullptr;
+  if (fuse && d.N < 64) {
+    snprintf(err, errlen, "tcgen05 conv: fused GroupNorm operands need C_out >= 64");
+    delete p;
+    return nullptr;
+  }
   if (dt == kBF16) {
-    if (d.N == 256) fill_kernel<__nv_bfloat16, 256, 1>(p);
-    else if (d.N == 128) fill_kernel<__nv_bfloat16, 128, 2>(p);
-    else if (d.N == 64) fill_kernel<__nv_bfloat16, 64, 2>(p);
-    else fill_kernel<__nv_bfloat16, 32, 2>(p);
+    if (d.N == 256) fill_kernel<__nv_bfloat16, 256, 1>(p, fuse);
+    else if (d.N == 128) fill_kernel<__nv_bfloat16, 128, 2>(p, fuse);
+    else if (d.N == 64) fill_kernel<__nv_bfloat16, 64, 2>(p, fuse);
+    else fill_kernel<__nv_bfloat16, 32, 2>(p, fuse);
   } else {
-    if (d.N == 256) fill_kernel<float, 256, 1>(p);
-    else if (d.N == 128) fill_kernel<float, 128, 2>(p);
-    else if (d.N == 64) fill_kernel<float, 64, 2>(p);
-    else fill_kernel<float, 32, 2>(p);
+    if (d.N == 256) fill_kernel<float, 256, 1>(p, fuse);
+    else if (d.N == 128) fill_kernel<float, 128, 2>(p, fuse);
+    else if (d.N == 64) fill_kernel<float, 64, 2>(p, fuse);
+    else fill_kernel<float, 32, 2>(p, fuse);
   }
   const int ck = 128 / (int)act_size(dt);
   const int tile_h = 16 * p->nsub;
@@ -152,13 +152,22 @@ TcConvPlan* tc_conv_plan_create(int dt, const TcConvDesc& d, int num_sms, char* 
       delete p;
       return nullptr;
     }
-    const int rows = s.taps == 9 ? tile_h + 2 : tile_h;
-    if (!encode_act(&P.seg[i].tmA, dt, s.act, d.B, d.H, d.W, s.C_tensor, rows, err, errlen) ||
-        !encode_w(&P.seg[i].tmW, dt, s.w, s.taps, d.N, s.Cw_total, d.N, err, errlen) ||
-        !encode_w(&P.seg[i].tmWh, dt, s.w, s.taps, d.N, s.Cw_total, d.N / 2, err, errlen)) {
+    if (s.aff != nullptr && s.taps != 9) {
+      snprintf(err, errlen, "tcgen05 conv: only 3x3 segments can take a fused GroupNorm operand");
       delete p;
       return nullptr;
     }
+    const int rows = s.taps == 9 ? tile_h + 2 : tile_h, cols = s.taps == 9 ? 10 : 8;
+    if (!encode_act(&P.seg[i].tmA, dt, s.act, d.B, d.H, d.W, s.C_tensor, cols, rows, err, errlen) ||
+        !encode_w(&P.seg[i].tmW, dt, s.w, s.taps, d.N, s.Cw_total, d.N, err, errlen)) {
+      delete p;
+      return nullptr;
+    }
+    P.seg[i].raw = s.aff != nullptr ? s.act : nullptr;
+    P.seg[i].aff = s.aff;
+    P.seg[i].Ct = s.C_tensor;
+    P.seg[i].aff_C = s.aff_C;
+    P.seg[i].aff_c0 = s.aff_c0;
     P.seg[i].nchunks = s.C / ck;
     P.seg[i].taps = s.taps;
     P.seg[i].wc0 = s.wc0;
@@ -171,9 +180,7 @@ TcConvPlan* tc_conv_plan_create(int dt, const TcConvDesc& d, int num_sms, char* 
   P.out = d.out; P.bias = d.bias; P.bias_bstride = d.bias_bstride; P.res = d.res; P.scale = d.scale;
   P.stats_acc = d.stats_acc;
   P.out4 = d.out4; P.prev4 = d.prev4; P.out_pc = d.out_pc ? d.out_pc : 4;
-  const int units = (P.ntiles + p->mc - 1) / p->mc;           // tile groups
-  const int max_groups = num_sms / p->mc;
-  p->grid = (units < max_groups ? units : max_groups) * p->mc;  // a multiple of the cluster width
+  p->grid = P.ntiles < num_sms ? P.ntiles : num_sms;  // persistent CTAs, one per SM
   return p;
 }
 
@@ -191,13 +198,8 @@ void tc_conv_launch(const TcConvPlan* p, cudaStream_t st) {
   cfg.blockDim = dim3(p->threads);
   cfg.dynamicSmemBytes = p->smem;
   cfg.stream = st;
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeClusterDimension;
-  attr[0].val.clusterDim.x = p->mc;
-  attr[0].val.clusterDim.y = 1;
-  attr[0].val.clusterDim.z = 1;
-  cfg.attrs = attr;
-  cfg.numAttrs = 1;
+  cfg.attrs = nullptr;
+  cfg.numAttrs = 0;
   cudaLaunchKernelExC(&cfg, p->kernel, args);
 }
 

@@ -7,28 +7,40 @@
 // so the skip projection and the residual add cost no extra pass over HBM.
 //
 // GEMM view: D[M = 128 pixels][N = C_out] += A[pixels][K = 128 B of channels] * W[C_out][K]^T per filter tap.
-// Tile = 8 (w) x 16*NSUB (h) output pixels.  Per channel chunk and horizontal tap s the TMA producer
-// loads ONE (16*NSUB+2) x 8 pixel box (zero-filled outside the image = the conv padding); each image row
-// of the box is exactly one 1024-byte SWIZZLE_128B atom, so the three vertical taps r are the same smem
-// tile at +r*1024 B: 3 activation loads per chunk instead of 9.  NSUB sub-tiles share every weight tile.
+// Tile = 8 (w) x 16*NSUB (h) output pixels.  Per channel chunk ONE (16*NSUB+2) x 10 pixel window is staged in shared
+// memory, 128 B per pixel, pixels 128 B apart, every 128-byte row swizzled by its absolute address (SWIZZLE_128B).
+// All nine filter taps read that one window: the operand descriptor of tap (r, s) simply starts at pixel
+// (r, s) of the window and steps SBO = 1280 B (one window row) between 8-pixel groups -- the hardware swizzle is a
+// function of the absolute shared-memory address (measured: tools/swz_probe.cu), so a descriptor may start at any
+// 128-byte row.  1 activation stage per chunk instead of 9 (or 3 horizontally shifted copies).
+//
+// The window is filled either by TMA (zero fill outside the image = the conv padding) or, for a FUSED segment, by six
+// "transform" warps that read the RAW producer output from global memory and apply GroupNorm (per-sample, per-channel
+// scale / shift table) + SiLU + operand rounding on the way into shared memory: the normalised activation tensor of
+// `GroupNorm -> SiLU -> Conv3x3` (layerspp.py:283-285,304-306) is never materialised in HBM.
 //
 // Warp roles: warp 0 = TMA producer (1 thread), warp 1 = TMEM owner + MMA issuer (1 thread),
-// warps 2.. = epilogue (TMEM -> registers -> bias / residual / scale -> global).  Accumulators are
-// double-buffered in TMEM (2 x NSUB x N columns) so the epilogue of tile i overlaps the MMAs of tile i+1.
-// Persistent CTAs, static round-robin over tiles (w fastest: neighbours share halos and weights in L2).
+// warps 2..2+4*NSUB = epilogue (TMEM -> registers -> bias / residual / scale -> global), then 6 transform warps.
+// Accumulators are double-buffered in TMEM (2 x NSUB x N columns) so the epilogue of tile i overlaps the MMAs of
+// tile i+1.  Persistent CTAs, static round-robin over tiles (w fastest: neighbours share halos and weights in L2).
 #pragma once
 #include "common.cuh"
 
 namespace use {
 
 struct alignas(64) ConvSeg {
-  CUtensorMap tmA;  // rank 4 {C, W, H, B}, box {CK, 8, rows, 1}; rows = 16*NSUB+2 (3x3) or 16*NSUB (1x1)
+  CUtensorMap tmA;  // rank 4 {C, W, H, B}; 3x3: box {CK, 10, 16*NSUB+2, 1}; 1x1: box {CK, 8, 16*NSUB, 1}
   CUtensorMap tmW;  // rank 3 {C_total, N, taps}, box {CK, N, 1}
-  CUtensorMap tmWh; // same tensor, box {CK, N/2, 1}: the half each CTA of a pair loads and multicasts
   int nchunks;      // channels of this segment / CK
   int taps;         // 9 or 1
   int wc0;          // first weight channel of this segment inside tmW (concatenated inputs)
-  int ac0;          // first channel inside tmA
+  int ac0;          // first channel inside the activation tensor
+  // fused GroupNorm + SiLU operand (3x3 only): raw != nullptr -> the transform warps fill the window
+  const void* raw;   // T [B][H][W][Ct]
+  const float* aff;  // fp32 [B][2][aff_C]: per-sample scale row, then shift row (launch_gn_affine)
+  int Ct;            // channel pitch of raw
+  int aff_C;         // row length of aff
+  int aff_c0;        // channel of aff that corresponds to channel ac0 of raw
 };
 
 struct alignas(64) ConvParams {
@@ -48,54 +60,50 @@ struct alignas(64) ConvParams {
   int out_pc;            // real output channels of the head (4 or 2)
 };
 
-template <typename T, int N, int NSUB>
+template <typename T, int N, int NSUB, bool FUSE>
 struct ConvCfg {
   static constexpr int CK = 128 / sizeof(T);
   static constexpr int TILE_W = 8;
   static constexpr int TILE_H = 16 * NSUB;
   static constexpr int A_ROWS = TILE_H + 2;
-  static constexpr int A_SLOT = A_ROWS * 1024;
+  static constexpr int WIN_W = 10;                       // window width in pixels (8 + halo)
+  static constexpr int WIN_PITCH = WIN_W * 128;          // bytes between window rows = SBO of a 3x3 operand
+  static constexpr int NPIX = A_ROWS * WIN_W;            // pixels of one window
+  static constexpr int A_SLOT = (NPIX * 128 + 1023) & ~1023;
   static constexpr int B_TILE = N * 128;
-  static constexpr int A_SLOTS = 3;
+  static constexpr int A_SLOTS = 2;
   static constexpr int B_SLOTS = (N == 256) ? 5 : (N == 128 ? 7 : 8);  // N <= 64: 8 slots
   static constexpr int ACC_COLS = NSUB * N;
   static constexpr int TMEM_COLS = (2 * ACC_COLS < 32) ? 32 : 2 * ACC_COLS;
   static constexpr int EPI_WARPS = 4 * NSUB;
-  static constexpr int THREADS = 64 + 32 * EPI_WARPS;
+  static constexpr int XF_THREADS = FUSE ? 192 : 0;      // transform warps (6)
+  static constexpr int XF_T0 = 64 + 32 * EPI_WARPS;      // first transform thread
+  static constexpr int THREADS = XF_T0 + XF_THREADS;
   static constexpr int NBARS = 2 * A_SLOTS + 2 * B_SLOTS + 4;
   static constexpr int STAT_BYTES = EPI_WARPS * N * 2 * 4;  // per-warp column statistics of the current tile
-  static constexpr int XPOSE_BYTES = 0;
-  static constexpr int SMEM_BYTES = 1024 + A_SLOTS * A_SLOT + B_SLOTS * B_TILE + STAT_BYTES + XPOSE_BYTES + NBARS * 8 + 16;
+  static constexpr int SMEM_BYTES = 1024 + A_SLOTS * A_SLOT + B_SLOTS * B_TILE + STAT_BYTES + NBARS * 8 + 16;
   static_assert(TMEM_COLS <= 512 && (TMEM_COLS & (TMEM_COLS - 1)) == 0, "TMEM columns must be a power of two <= 512");
   static_assert(SMEM_BYTES <= 232448, "shared memory budget");
   static_assert(N % 32 == 0 && N <= 256, "N");
 };
 
-// MC = 2: CTA pairs (cluster of 2).  Both CTAs of a pair walk their own tiles through the same weight-tile
-// sequence; each loads HALF of every weight tile and multicasts it into both CTAs' shared memory, which halves the
-// L2 -> SM weight traffic (the binding resource of the C_out = 128 layers: 295 KB of weights per 256-pixel tile).
-// A weight slot is recycled only when the MMAs of BOTH CTAs have released it (b_empty counts 2 arrivals, one of
-// them a multicast tcgen05.commit from the peer).
-//
 // SWAP (C_out = 128 only): "swap-AB".  A single-CTA M128 x N128 MMA reads 4 KB (A) + 4 KB (B) of shared memory per 64
 // cycles = the 128 B/clk shared-memory limit, which capped these layers (80 % of the FLOPs) near 70 % of the tensor
 // peak.  With the roles swapped -- weights [128 c_out x K] as the M operand, the 256 pixels of the tile as the N
 // operand -- one MMA reads 4 + 8 KB per 128 cycles (96 B/clk, the profile of the C_out = 256 layers).  The accumulator
-// is then channel-major (TMEM lane = output channel, column = pixel); the epilogue transposes 8x8 blocks across lanes
-// with shuffles so that every thread still stores 16-byte NHWC vectors, and per-channel GroupNorm statistics become
-// in-register sums.
-template <typename T, int N, int NSUB, int MC, bool SWAP>
-__global__ void __launch_bounds__(ConvCfg<T, N, NSUB>::THREADS, 1) conv_tc_kernel(const __grid_constant__ ConvParams p) {
-  using C = ConvCfg<T, N, NSUB>;
-  static_assert(!SWAP || (N == 128 && NSUB == 2 && MC == 1), "swap-AB is built for C_out = 128, 256-pixel tiles");
+// is then channel-major (TMEM lane = output channel, column = pixel); the epilogue stores 32 consecutive channels per
+// pixel per warp, and per-channel GroupNorm statistics become in-register sums.
+template <typename T, int N, int NSUB, bool SWAP, bool FUSE>
+__global__ void __launch_bounds__(ConvCfg<T, N, NSUB, FUSE>::THREADS, 1) conv_tc_kernel(const __grid_constant__ ConvParams p) {
+  using C = ConvCfg<T, N, NSUB, FUSE>;
+  static_assert(!SWAP || (N == 128 && NSUB == 2), "swap-AB is built for C_out = 128, 256-pixel tiles");
   constexpr bool kBf16 = DT<T>::kIsBf16;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* sA = smem;
   uint8_t* sB = sA + C::A_SLOTS * C::A_SLOT;
   float* stat_s = reinterpret_cast<float*>(sB + C::B_SLOTS * C::B_TILE);
-  float* xpose_s = reinterpret_cast<float*>(sB + C::B_SLOTS * C::B_TILE + C::STAT_BYTES);
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sB + C::B_SLOTS * C::B_TILE + C::STAT_BYTES + C::XPOSE_BYTES);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sB + C::B_SLOTS * C::B_TILE + C::STAT_BYTES);
   uint64_t* a_full = bars;
   uint64_t* a_empty = a_full + C::A_SLOTS;
   uint64_t* b_full = a_empty + C::A_SLOTS;
@@ -111,10 +119,9 @@ __global__ void __launch_bounds__(ConvCfg<T, N, NSUB>::THREADS, 1) conv_tc_kerne
     for (int i = 0; i < p.nseg; ++i) {
       prefetch_tmap(&p.seg[i].tmA);
       prefetch_tmap(&p.seg[i].tmW);
-      prefetch_tmap(&p.seg[i].tmWh);
     }
     for (int i = 0; i < C::A_SLOTS; ++i) { mbar_init(&a_full[i], 1); mbar_init(&a_empty[i], 1); }
-    for (int i = 0; i < C::B_SLOTS; ++i) { mbar_init(&b_full[i], 1); mbar_init(&b_empty[i], MC); }
+    for (int i = 0; i < C::B_SLOTS; ++i) { mbar_init(&b_full[i], 1); mbar_init(&b_empty[i], 1); }
     for (int i = 0; i < 2; ++i) { mbar_init(&t_full[i], 1); mbar_init(&t_empty[i], C::EPI_WARPS); }
     fence_barrier_init();
   }
@@ -124,23 +131,19 @@ __global__ void __launch_bounds__(ConvCfg<T, N, NSUB>::THREADS, 1) conv_tc_kerne
   }
   tc_fence_before();
   __syncthreads();
-  if constexpr (MC > 1) cluster_sync_all();  // the peer's barriers are initialised before anything targets them
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
   const int tiles_per_img = p.tiles_w * p.tiles_h;
-  const uint32_t crank = MC > 1 ? cluster_ctarank() : 0u;
-  const int g0 = blockIdx.x / MC, gstep = gridDim.x / MC;  // tile groups of MC consecutive tiles
-  // Both CTAs of a pair run the same number of iterations; a CTA whose tile index falls past the end processes a
-  // "ghost" tile (loads are zero-filled out of bounds, nothing is stored) to keep the weight pipeline in lockstep.
+  const int g0 = blockIdx.x, gstep = gridDim.x;
 
   if (warp == 0) {
     // ================================ TMA producer ================================
+    // weights of every segment; activation windows of the segments that are not fused
     if (lane == 0) {
-      uint32_t ai = 0, bi = 0;  // running slot counters
-      for (int g = g0; g * MC < p.ntiles; g += gstep) {
-        const int tile = g * MC + crank;
-        const int b = tile / tiles_per_img;  // == p.B for a ghost tile: every TMA box is out of bounds -> zeros
+      uint32_t ai = 0, bi = 0;  // running slot counters (ai counts every window, whoever fills it)
+      for (int tile = g0; tile < p.ntiles; tile += gstep) {
+        const int b = tile / tiles_per_img;
         const int rem = tile - b * tiles_per_img;
         const int th = rem / p.tiles_w;
         const int w0 = (rem - th * p.tiles_w) * C::TILE_W;
@@ -148,27 +151,24 @@ __global__ void __launch_bounds__(ConvCfg<T, N, NSUB>::THREADS, 1) conv_tc_kerne
         for (int sg = 0; sg < p.nseg; ++sg) {
           const ConvSeg& S = p.seg[sg];
           const bool k3 = S.taps == 9;
-          const int ns = k3 ? 3 : 1;
-          const uint32_t a_bytes = (k3 ? C::A_ROWS : C::TILE_H) * 1024;
+          const uint32_t a_bytes = (k3 ? C::NPIX : C::TILE_H * 8) * 128;
           for (int kc = 0; kc < S.nchunks; ++kc) {
-            for (int s = 0; s < ns; ++s) {
+            if constexpr (!FUSE) {  // (in a FUSE kernel the transform warps own the activation ring, see below)
               const uint32_t as = ai % C::A_SLOTS, aph = (ai / C::A_SLOTS) & 1;
               mbar_wait(&a_empty[as], aph ^ 1);
               mbar_arrive_expect_tx(&a_full[as], a_bytes);
-              tma_load_4d(sA + as * C::A_SLOT, &S.tmA, &a_full[as], S.ac0 + kc * C::CK, k3 ? (w0 + s - 1) : w0,
+              tma_load_4d(sA + as * C::A_SLOT, &S.tmA, &a_full[as], S.ac0 + kc * C::CK, k3 ? (w0 - 1) : w0,
                           k3 ? (h0 - 1) : h0, b);
-              ++ai;
-              for (int r = 0; r < ns; ++r) {
-                const uint32_t bs = bi % C::B_SLOTS, bph = (bi / C::B_SLOTS) & 1;
-                mbar_wait(&b_empty[bs], bph ^ 1);
-                mbar_arrive_expect_tx(&b_full[bs], C::B_TILE);
-                if constexpr (MC > 1)
-                  tma_load_3d_mc(sB + bs * C::B_TILE + crank * (C::B_TILE / 2), &S.tmWh, &b_full[bs], S.wc0 + kc * C::CK,
-                                 crank * (N / 2), k3 ? (r * 3 + s) : 0, uint16_t(3));
-                else
-                  tma_load_3d(sB + bs * C::B_TILE, &S.tmW, &b_full[bs], S.wc0 + kc * C::CK, 0, k3 ? (r * 3 + s) : 0);
-                ++bi;
-              }
+            }
+            ++ai;
+            for (int tap = 0; tap < S.taps; ++tap) {
+              const uint32_t bs = bi % C::B_SLOTS, bph = (bi / C::B_SLOTS) & 1;
+              mbar_wait(&b_empty[bs], bph ^ 1);
+              mbar_arrive_expect_tx(&b_full[bs], C::B_TILE);
+              // tap order s-major (s = tap / 3, r = tap % 3): the accumulation order of the previous 3-copy kernel
+              tma_load_3d(sB + bs * C::B_TILE, &S.tmW, &b_full[bs], S.wc0 + kc * C::CK, 0,
+                          k3 ? ((tap % 3) * 3 + tap / 3) : 0);
+              ++bi;
             }
           }
         }
@@ -180,54 +180,141 @@ __global__ void __launch_bounds__(ConvCfg<T, N, NSUB>::THREADS, 1) conv_tc_kerne
       constexpr uint32_t idesc = SWAP ? umma_idesc(kBf16 ? 1 : 2, 128, 128 * NSUB) : umma_idesc(kBf16 ? 1 : 2, 128, N);
       const uint32_t sA_addr = smem_u32(sA), sB_addr = smem_u32(sB);
       uint32_t ai = 0, bi = 0, ti = 0;
-      for (int g = g0; g * MC < p.ntiles; g += gstep, ++ti) {
+      for (int tile = g0; tile < p.ntiles; tile += gstep, ++ti) {
         const uint32_t acs = ti & 1, acph = (ti >> 1) & 1;
         mbar_wait(&t_empty[acs], acph ^ 1);
         tc_fence_after();
         bool first = true;
         for (int sg = 0; sg < p.nseg; ++sg) {
           const ConvSeg& S = p.seg[sg];
-          const int ns = S.taps == 9 ? 3 : 1;
+          const bool k3 = S.taps == 9;
+          const uint32_t sbo = k3 ? C::WIN_PITCH : 1024;
           for (int kc = 0; kc < S.nchunks; ++kc) {
-            for (int s = 0; s < ns; ++s) {
-              const uint32_t as = ai % C::A_SLOTS, aph = (ai / C::A_SLOTS) & 1;
-              mbar_wait(&a_full[as], aph);
-              for (int r = 0; r < ns; ++r) {
-                const uint32_t bs = bi % C::B_SLOTS, bph = (bi / C::B_SLOTS) & 1;
-                mbar_wait(&b_full[bs], bph);
-                tc_fence_after();
-                if constexpr (SWAP) {
-                  // D[c_out][pixel] += W[c_out][K] * X[pixel][K]^T : M operand = weight tile, N operand = 256 pixel rows
+            const uint32_t as = ai % C::A_SLOTS, aph = (ai / C::A_SLOTS) & 1;
+            mbar_wait(&a_full[as], aph);
+            for (int tap = 0; tap < S.taps; ++tap) {
+              const int s = tap / 3, r = tap - s * 3;  // (0, 0) for a 1x1 segment
+              const uint32_t bs = bi % C::B_SLOTS, bph = (bi / C::B_SLOTS) & 1;
+              mbar_wait(&b_full[bs], bph);
+              tc_fence_after();
+              const uint32_t win = sA_addr + as * C::A_SLOT + (k3 ? (r * C::WIN_W + s) * 128 : 0);
+              if constexpr (SWAP) {
+                // D[c_out][pixel] += W[c_out][K] * X[pixel][K]^T : M operand = weight tile, N operand = 256 pixel rows
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                  const uint64_t wd = umma_desc_sw128(sB_addr + bs * C::B_TILE + k * 32);
+                  const uint64_t xd = umma_desc_sw128_sbo(win + k * 32, sbo);
+                  umma_ss<kBf16>(tmem_base + acs * C::ACC_COLS, wd, xd, idesc, (first && k == 0) ? 0u : 1u);
+                }
+              } else {
+#pragma unroll
+                for (int sub = 0; sub < NSUB; ++sub) {
 #pragma unroll
                   for (int k = 0; k < 4; ++k) {
-                    const uint64_t wd = umma_desc_sw128(sB_addr + bs * C::B_TILE + k * 32);
-                    const uint64_t xd = umma_desc_sw128(sA_addr + as * C::A_SLOT + r * 1024 + k * 32);
-                    umma_ss<kBf16>(tmem_base + acs * C::ACC_COLS, wd, xd, idesc, (first && k == 0) ? 0u : 1u);
-                  }
-                } else {
-#pragma unroll
-                  for (int sub = 0; sub < NSUB; ++sub) {
-#pragma unroll
-                    for (int k = 0; k < 4; ++k) {
-                      const uint64_t ad = umma_desc_sw128(sA_addr + as * C::A_SLOT + (sub * 16 + r) * 1024 + k * 32);
-                      const uint64_t bd = umma_desc_sw128(sB_addr + bs * C::B_TILE + k * 32);
-                      umma_ss<kBf16>(tmem_base + acs * C::ACC_COLS + sub * N, ad, bd, idesc, (first && k == 0) ? 0u : 1u);
-                    }
+                    const uint64_t ad = umma_desc_sw128_sbo(win + sub * 16 * sbo + k * 32, sbo);
+                    const uint64_t bd = umma_desc_sw128(sB_addr + bs * C::B_TILE + k * 32);
+                    umma_ss<kBf16>(tmem_base + acs * C::ACC_COLS + sub * N, ad, bd, idesc, (first && k == 0) ? 0u : 1u);
                   }
                 }
-                first = false;
-                if constexpr (MC > 1) umma_commit_mc(&b_empty[bs], uint16_t(3));
-                else umma_commit(&b_empty[bs]);
-                ++bi;
               }
-              umma_commit(&a_empty[as]);
-              ++ai;
+              first = false;
+              umma_commit(&b_empty[bs]);
+              ++bi;
             }
+            umma_commit(&a_empty[as]);
+            ++ai;
           }
         }
         umma_commit(&t_full[acs]);
       }
     }
+  } else if (threadIdx.x >= C::XF_T0) {
+    if constexpr (FUSE) {
+    // ================================ transform warps ================================
+    // GroupNorm (scale / shift) + SiLU + operand rounding of the raw producer output, global -> registers -> the
+    // swizzled window in shared memory.  Thread = one 16-byte channel vector (v) of the pixels pb, pb + 24, ...
+    constexpr int V = DT<T>::kVec;
+    constexpr int XT = C::XF_THREADS;
+    constexpr int PSTEP = XT / 8;
+    constexpr int NIT = (C::NPIX + PSTEP - 1) / PSTEP;
+    const int tt = threadIdx.x - C::XF_T0;
+    const int v = tt & 7, pb = tt >> 3;
+    uint32_t ai = 0;
+    for (int tile = g0; tile < p.ntiles; tile += gstep) {
+      const int b = tile / tiles_per_img;
+      const int rem = tile - b * tiles_per_img;
+      const int th = rem / p.tiles_w;
+      const int w0 = (rem - th * p.tiles_w) * C::TILE_W;
+      const int h0 = th * C::TILE_H;
+      int poff[NIT];  // pixel index inside the image, -1 outside (zero padding of the ACTIVATED tensor) / past the window
+#pragma unroll
+      for (int i = 0; i < NIT; ++i) {
+        const int q = pb + PSTEP * i;
+        const int row = q / C::WIN_W, col = q - row * C::WIN_W;
+        const int hh = h0 - 1 + row, ww = w0 - 1 + col;
+        poff[i] = (q < C::NPIX && hh >= 0 && hh < p.H && ww >= 0 && ww < p.W) ? hh * p.W + ww : -1;
+      }
+      for (int sg = 0; sg < p.nseg; ++sg) {
+        const ConvSeg& S = p.seg[sg];
+        if (S.raw == nullptr) {
+          // TMA-fed segment of a fused launch (1x1 skip projections, pre-activated FIR operands): the transform warps
+          // own the whole activation ring -- a ring with two independent producers would let one of them run two
+          // phases ahead of (or behind) an mbarrier, which a 1-bit phase parity cannot tell apart -- so thread 0
+          // issues the TMA and everybody stays in lockstep through the named barrier.
+          const bool k3 = S.taps == 9;
+          for (int kc = 0; kc < S.nchunks; ++kc, ++ai) {
+            const uint32_t as = ai % C::A_SLOTS, aph = (ai / C::A_SLOTS) & 1;
+            mbar_wait(&a_empty[as], aph ^ 1);
+            if (tt == 0) {
+              mbar_arrive_expect_tx(&a_full[as], (k3 ? C::NPIX : C::TILE_H * 8) * 128);
+              tma_load_4d(sA + as * C::A_SLOT, &S.tmA, &a_full[as], S.ac0 + kc * C::CK, k3 ? (w0 - 1) : w0,
+                          k3 ? (h0 - 1) : h0, b);
+            }
+            named_bar_sync(2, XT);
+          }
+          continue;
+        }
+        const T* src = reinterpret_cast<const T*>(S.raw) + static_cast<size_t>(b) * p.H * p.W * S.Ct + S.ac0 + v * V;
+        const float* aff = S.aff + static_cast<size_t>(b) * 2 * S.aff_C + S.aff_c0 + v * V;
+        for (int kc = 0; kc < S.nchunks; ++kc, ++ai) {
+          uint4 d[NIT];
+#pragma unroll
+          for (int i = 0; i < NIT; ++i)
+            d[i] = poff[i] >= 0 ? __ldg(reinterpret_cast<const uint4*>(src + static_cast<size_t>(poff[i]) * S.Ct + kc * C::CK))
+                                : make_uint4(0u, 0u, 0u, 0u);
+          float sc[V], sh[V];
+#pragma unroll
+          for (int j = 0; j < V; j += 4) {
+            const float4 a = __ldg(reinterpret_cast<const float4*>(aff + kc * C::CK + j));
+            const float4 c = __ldg(reinterpret_cast<const float4*>(aff + S.aff_C + kc * C::CK + j));
+            sc[j] = a.x; sc[j + 1] = a.y; sc[j + 2] = a.z; sc[j + 3] = a.w;
+            sh[j] = c.x; sh[j + 1] = c.y; sh[j + 2] = c.z; sh[j + 3] = c.w;
+          }
+#pragma unroll
+          for (int i = 0; i < NIT; ++i) {
+            if (poff[i] >= 0) {
+              float f[V];
+              Vec<T>::unpack(d[i], f);
+#pragma unroll
+              for (int j = 0; j < V; ++j) f[j] = silu_act<T>(fmaf(f[j], sc[j], sh[j]));
+              d[i] = Vec<T>::pack_operand(f);
+            }
+          }
+          const uint32_t as = ai % C::A_SLOTS, aph = (ai / C::A_SLOTS) & 1;
+          mbar_wait(&a_empty[as], aph ^ 1);
+          uint8_t* slot = sA + as * C::A_SLOT;  // 1024-byte aligned: the swizzle phase of window pixel q is q & 7
+#pragma unroll
+          for (int i = 0; i < NIT; ++i) {
+            const int q = pb + PSTEP * i;
+            if (q < C::NPIX) *reinterpret_cast<uint4*>(slot + q * 128 + ((v ^ (q & 7)) << 4)) = d[i];
+          }
+          fence_proxy_async();  // generic-proxy writes -> visible to the tensor core's async-proxy reads
+          named_bar_sync(2, XT);
+          if (tt == 0) mbar_arrive(&a_full[as]);
+        }
+      }
+    }
+    }  // FUSE
   } else {
     // ================================ epilogue ================================
     const int ew = warp - 2;
@@ -238,10 +325,9 @@ __global__ void __launch_bounds__(ConvCfg<T, N, NSUB>::THREADS, 1) conv_tc_kerne
     T* out = reinterpret_cast<T*>(p.out);
     const T* res = reinterpret_cast<const T*>(p.res);
     uint32_t ti = 0;
-    for (int g = g0; g * MC < p.ntiles; g += gstep, ++ti) {
-      const int tile = g * MC + crank;
-      const bool ghost = tile >= p.ntiles;
-      const int b = ghost ? 0 : tile / tiles_per_img;
+    for (int tile = g0; tile < p.ntiles; tile += gstep, ++ti) {
+      constexpr bool ghost = false;
+      const int b = tile / tiles_per_img;
       const int rem = tile - (tile / tiles_per_img) * tiles_per_img;
       const int th = rem / p.tiles_w;
       const int w = (rem - th * p.tiles_w) * C::TILE_W + wl;
@@ -521,7 +607,6 @@ __global__ void __launch_bounds__(ConvCfg<T, N, NSUB>::THREADS, 1) conv_tc_kerne
 
   tc_fence_before();
   __syncthreads();
-  if constexpr (MC > 1) cluster_sync_all();  // no CTA leaves while its peer may still multicast into it
   if (warp == 1) tmem_dealloc(tmem_base, C::TMEM_COLS);
 }
 

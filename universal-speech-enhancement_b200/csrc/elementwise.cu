@@ -95,17 +95,39 @@ struct GnSrcT {
   int C;
 };
 
-__device__ __forceinline__ float silu_fast(float x) { return __fdividef(x, 1.0f + __expf(-x)); }
-// x * sigmoid(x) = x * (0.5 + 0.5 tanh(x/2)): ONE MUFU op.  tanh.approx has ~2^-11 relative error, invisible after the
-// bf16 rounding of the result (2^-9) but not acceptable for the fp32 path, which keeps the exp + rcp form.
-__device__ __forceinline__ float silu_tanh(float x) {
-  float t;
-  asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(0.5f * x));
-  return x * fmaf(0.5f, t, 0.5f);
+// Scale / shift table of a GroupNorm over cat[s0, s1] for the convolution kernel's fused operand path: one block per
+// sample, identical arithmetic to the prologue of gn_apply_kernel (the two paths give bit-identical operands).
+__global__ void __launch_bounds__(256) gn_affine_kernel(const long long* __restrict__ st0, int C0,
+                                                         const long long* __restrict__ st1, int C1,
+                                                         const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                         float eps, int HW, float* __restrict__ aff) {
+  const int Ct = C0 + C1;
+  const int G = min(Ct / 4, 32);
+  const int cpg = Ct / G;
+  const int b = blockIdx.x;
+  const double inv_cnt = 1.0 / (static_cast<double>(HW) * cpg);
+  for (int c = threadIdx.x; c < Ct; c += blockDim.x) {
+    const int g = c / cpg;
+    double sum = 0.0, sq = 0.0;
+    for (int cc = g * cpg; cc < (g + 1) * cpg; ++cc) {
+      const longlong2 st = __ldg(reinterpret_cast<const longlong2*>(
+          (cc < C0) ? st0 + (static_cast<size_t>(b) * C0 + cc) * 2 : st1 + (static_cast<size_t>(b) * C1 + (cc - C0)) * 2));
+      sum += static_cast<double>(st.x) * (1.0 / kStatSumScale);
+      sq += static_cast<double>(st.y) * (1.0 / kStatSqScale);
+    }
+    const double mean = sum * inv_cnt;
+    double var = sq * inv_cnt - mean * mean;
+    if (var < 0.0) var = 0.0;
+    const float rstd = rsqrtf(static_cast<float>(var) + eps);
+    const float sc = gamma[c] * rstd;
+    aff[(static_cast<size_t>(b) * 2) * Ct + c] = sc;
+    aff[(static_cast<size_t>(b) * 2 + 1) * Ct + c] = beta[c] - static_cast<float>(mean) * sc;
+  }
 }
-template <typename T> __device__ __forceinline__ float silu_act(float x) {
-  if constexpr (DT<T>::kIsBf16) return silu_tanh(x);
-  else return silu_fast(x);
+
+void launch_gn_affine(GnSrc s0, GnSrc s1, const float* gamma, const float* beta, float eps, int HW, float* aff, int B,
+                      cudaStream_t st) {
+  gn_affine_kernel<<<B, 256, 0, st>>>(s0.stats, s0.C, s1.stats, s1.C, gamma, beta, eps, HW, aff);
 }
 
 // One thread owns a fixed 16-byte channel vector (scale / shift live in registers) and walks over pixels;

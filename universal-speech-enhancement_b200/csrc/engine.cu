@@ -5,6 +5,7 @@
 #include <math.h>
 #include <stdarg.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
@@ -196,6 +197,9 @@ struct use_engine {
   // concurrency: a batch is split into `groups` halves that run on their own streams, so the HBM-bound GroupNorm
   // kernels of one half overlap the tensor-bound convolutions of the other (they fit beside the persistent conv CTA)
   int groups = 2;
+  // GroupNorm + SiLU applied inside the convolution kernel's operand path (no normalised tensor in HBM); off: the
+  // separate gn_apply kernel feeds the same convolutions (A/B testing: both give bit-identical results)
+  bool fuse_gn = true;
   cudaStream_t gstream[2] = {nullptr, nullptr};
   cudaEvent_t ev_fork = nullptr, ev_join[2] = {nullptr, nullptr};
   // instrumentation
@@ -472,6 +476,23 @@ struct Builder {
            TAG_GN_APPLY, 1, 8.0 * nout, (nin + nout * (raw ? 2 : 1)) * es());
     }
   }
+  // scale / shift table [B][2][C] of GroupNorm(cat[s0, s1]) for a fused conv operand; returns its arena offset
+  size_t gn_affine(Act& s0, Act* s1, size_t gamma_off, size_t beta_off) {
+    ensure_stats(s0);
+    if (s1) ensure_stats(*s1);
+    const int Ct = s0.C + (s1 ? s1->C : 0);
+    const size_t off = new_f32((size_t)B * 2 * Ct);
+    if (dry) return off;
+    GnSrc a{nullptr, stats_ptr(s0.stats_off), s0.C};
+    GnSrc b{nullptr, nullptr, 0};
+    if (s1) b = GnSrc{nullptr, stats_ptr(s1->stats_off), s1->C};
+    const float* g = (const float*)wt(gamma_off);
+    const float* bt = (const float*)wt(beta_off);
+    float* o = (float*)ws(off);
+    const int Bn = B, HW = s0.H * s0.W;
+    emit([=](cudaStream_t s) { launch_gn_affine(a, b, g, bt, 1e-6f, HW, o, Bn, s); }, TAG_GN_STATS, 1, 0, 0);
+    return off;
+  }
   // stat_target: the conv's output tensor when the epilogue should also produce its GroupNorm statistics
   void conv_tc(TcConvDesc d, Act* stat_target = nullptr) {
     if (stat_target) {
@@ -499,15 +520,32 @@ struct Builder {
     const int fir = m.down ? 1 : (m.up ? 2 : 0);
     const int Ho = m.down ? x0.H / 2 : (m.up ? x0.H * 2 : x0.H);
     const int Wo = m.down ? x0.W / 2 : (m.up ? x0.W * 2 : x0.W);
-    Act a0 = new_act(Cin, Ho, Wo);
-    Act raw;
-    if (fir) raw = new_act(Cin, Ho, Wo);
-    gn_apply(x0, x1, w.gn0_g, w.gn0_b, fir, true, true, a0, fir ? &raw : nullptr);
+    const bool fuse = e->fuse_gn;
+    const bool fuse0 = fuse && fir == 0;  // FIR blocks resample between GroupNorm/SiLU and Conv_0: separate kernel
+    Act a0, raw;
+    size_t aff0 = (size_t)-1;
+    if (fuse0) {
+      aff0 = gn_affine(x0, x1, w.gn0_g, w.gn0_b);
+    } else {
+      a0 = new_act(Cin, Ho, Wo);
+      if (fir) raw = new_act(Cin, Ho, Wo);
+      gn_apply(x0, x1, w.gn0_g, w.gn0_b, fir, true, true, a0, fir ? &raw : nullptr);
+    }
     Act h1 = new_act(Cout, Ho, Wo);
     {
       TcConvDesc d{};
-      d.nseg = 1;
-      d.seg[0] = TcSegDesc{dry ? nullptr : ws(a0.off), Cin, 0, Cin, dry ? nullptr : wt(w.w0), Cin, 0, 9};
+      if (fuse0) {
+        const float* ap = dry ? (const float*)1 : (const float*)ws(aff0);
+        d.seg[0] = TcSegDesc{dry ? nullptr : ws(x0.off), x0.C, 0, x0.C, dry ? nullptr : wt(w.w0), Cin, 0, 9, ap, Cin, 0};
+        d.nseg = 1;
+        if (x1) {
+          d.seg[1] = TcSegDesc{dry ? nullptr : ws(x1->off), x1->C, 0, x1->C, dry ? nullptr : wt(w.w0), Cin, x0.C, 9, ap, Cin, x0.C};
+          d.nseg = 2;
+        }
+      } else {
+        d.nseg = 1;
+        d.seg[0] = TcSegDesc{dry ? nullptr : ws(a0.off), Cin, 0, Cin, dry ? nullptr : wt(w.w0), Cin, 0, 9};
+      }
       d.B = B; d.H = Ho; d.W = Wo; d.N = Cout;
       d.out = dry ? nullptr : ws(h1.off);
       if (e->cfg.conditional) {  // conv bias + Dense_0(act(temb)), per sample
@@ -521,14 +559,25 @@ struct Builder {
       d.scale = 1.0f;
       conv_tc(d, &h1);
     }
-    free_act(a0);
-    Act a1 = new_act(Cout, Ho, Wo);
-    gn_apply(h1, nullptr, w.gn1_g, w.gn1_b, 0, true, true, a1, nullptr);
-    free_act(h1);
+    if (fuse0) arena.release(aff0);
+    else free_act(a0);
+    Act a1;
+    size_t aff1 = (size_t)-1;
+    if (fuse) {
+      aff1 = gn_affine(h1, nullptr, w.gn1_g, w.gn1_b);
+    } else {
+      a1 = new_act(Cout, Ho, Wo);
+      gn_apply(h1, nullptr, w.gn1_g, w.gn1_b, 0, true, true, a1, nullptr);
+      free_act(h1);
+    }
     Act out = new_act(Cout, Ho, Wo);
     {
       TcConvDesc d{};
-      d.seg[0] = TcSegDesc{dry ? nullptr : ws(a1.off), Cout, 0, Cout, dry ? nullptr : wt(w.w1), Cout, 0, 9};
+      if (fuse)
+        d.seg[0] = TcSegDesc{dry ? nullptr : ws(h1.off), Cout, 0, Cout, dry ? nullptr : wt(w.w1), Cout, 0, 9,
+                             dry ? (const float*)1 : (const float*)ws(aff1), Cout, 0};
+      else
+        d.seg[0] = TcSegDesc{dry ? nullptr : ws(a1.off), Cout, 0, Cout, dry ? nullptr : wt(w.w1), Cout, 0, 9};
       d.nseg = 1;
       d.res = nullptr;
       if (w.has_conv2) {
@@ -553,7 +602,8 @@ struct Builder {
       d.scale = kInvSqrt2;
       conv_tc(d, m.down ? nullptr : &out);  // a down block's output is modified by Combine before any GroupNorm
     }
-    free_act(a1);
+    if (fuse) { arena.release(aff1); free_act(h1); }
+    else free_act(a1);
     if (fir) free_act(raw);
     return out;
   }
@@ -864,6 +914,7 @@ use_engine* use_engine_create(const use_config* cfg) {
     if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && sms > 0) e->num_sms = sms;
   }
   cudaGetLastError();
+  if (const char* v = getenv("USE_B200_FUSE_GN")) e->fuse_gn = v[0] != '0';
   return e;
 }
 
@@ -919,6 +970,11 @@ int use_engine_set_option(use_engine* e, const char* key, int value) {
   if (!strcmp(key, "overlap_groups")) {
     if (value != 1 && value != 2) return fail("overlap_groups must be 1 or 2");
     e->groups = value;
+    return 0;
+  }
+  if (!strcmp(key, "fuse_gn")) {
+    e->fuse_gn = value != 0;
+    e->programs.clear();
     return 0;
   }
   return fail("unknown option '%s'", key);
@@ -1135,15 +1191,24 @@ int use_op_gn_apply(int dtype, const void* x0, const long long* stats0, int C0, 
                   out_act, out_raw, B, Hin, Win, (cudaStream_t)stream);
   return cuda_check("use_op_gn_apply");
 }
-int use_op_conv_tc(int dtype, int nseg, const void* const* seg_act, const int* seg_ctensor, const int* seg_c0,
-                   const int* seg_c, const void* const* seg_w, const int* seg_cw, const int* seg_wc0, const int* seg_taps,
-                   int B, int H, int W, int N, const float* bias, int bias_bstride, const void* res, float scale, void* out,
-                   long long* stats, void* stream) {
+int use_op_gn_affine(const long long* stats0, int C0, const long long* stats1, int C1, const float* gamma,
+                     const float* beta, float eps, int HW, float* aff, int B, void* stream) {
+  if (!stats0 || !gamma || !beta || !aff) return fail("null argument");
+  launch_gn_affine(GnSrc{nullptr, stats0, C0}, GnSrc{nullptr, stats1, stats1 ? C1 : 0}, gamma, beta, eps, HW, aff, B,
+                   (cudaStream_t)stream);
+  return cuda_check("use_op_gn_affine");
+}
+int use_op_conv_tc_gn(int dtype, int nseg, const void* const* seg_act, const int* seg_ctensor, const int* seg_c0,
+                      const int* seg_c, const void* const* seg_w, const int* seg_cw, const int* seg_wc0, const int* seg_taps,
+                      const float* const* seg_aff, const int* seg_aff_c, const int* seg_aff_c0, int B, int H, int W, int N,
+                      const float* bias, int bias_bstride, const void* res, float scale, void* out, long long* stats,
+                      void* stream) {
   if (nseg < 1 || nseg > 3) return fail("nseg must be 1..3");
   TcConvDesc d{};
   d.nseg = nseg;
   for (int i = 0; i < nseg; ++i)
-    d.seg[i] = TcSegDesc{seg_act[i], seg_ctensor[i], seg_c0[i], seg_c[i], seg_w[i], seg_cw[i], seg_wc0[i], seg_taps[i]};
+    d.seg[i] = TcSegDesc{seg_act[i], seg_ctensor[i], seg_c0[i], seg_c[i], seg_w[i], seg_cw[i], seg_wc0[i], seg_taps[i],
+                         seg_aff ? seg_aff[i] : nullptr, seg_aff ? seg_aff_c[i] : 0, seg_aff ? seg_aff_c0[i] : 0};
   d.B = B; d.H = H; d.W = W; d.N = N;
   d.out = out; d.bias = bias; d.bias_bstride = bias_bstride; d.res = res; d.scale = scale;
   d.stats_acc = stats;  // fixed-point accumulators, zeroed by the caller
@@ -1157,6 +1222,13 @@ int use_op_conv_tc(int dtype, int nseg, const void* const* seg_act, const int* s
   cudaStreamSynchronize((cudaStream_t)stream);  // the plan (tensor maps live in kernel params) can go now
   tc_conv_plan_destroy(p);
   return cuda_check("use_op_conv_tc");
+}
+int use_op_conv_tc(int dtype, int nseg, const void* const* seg_act, const int* seg_ctensor, const int* seg_c0,
+                   const int* seg_c, const void* const* seg_w, const int* seg_cw, const int* seg_wc0, const int* seg_taps,
+                   int B, int H, int W, int N, const float* bias, int bias_bstride, const void* res, float scale, void* out,
+                   long long* stats, void* stream) {
+  return use_op_conv_tc_gn(dtype, nseg, seg_act, seg_ctensor, seg_c0, seg_c, seg_w, seg_cw, seg_wc0, seg_taps, nullptr,
+                           nullptr, nullptr, B, H, W, N, bias, bias_bstride, res, scale, out, stats, stream);
 }
 int use_op_conv_ref(int dtype, const void* x, const float* w, const float* bias, int bias_bstride, const void* res,
                     float scale, void* out, int B, int H, int W, int Cin, int Cout, int ksize, void* stream) {

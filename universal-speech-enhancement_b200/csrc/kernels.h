@@ -27,6 +27,11 @@ struct GnSrc {
 void launch_gn_apply(int dt, GnSrc s0, GnSrc s1, const float* gamma, const float* beta, float eps, int fir, bool do_silu,
                      bool as_operand, void* out_act, void* out_raw, int B, int Hin, int Win, cudaStream_t st);
 
+// GroupNorm scale / shift table of cat[s0, s1] for the fused conv operand: aff[b][0][c] = gamma[c] * rstd,
+// aff[b][1][c] = beta[c] - mean * gamma[c] * rstd (same arithmetic as launch_gn_apply)
+void launch_gn_affine(GnSrc s0, GnSrc s1, const float* gamma, const float* beta, float eps, int HW, float* aff, int B,
+                      cudaStream_t st);
+
 // ---- small / bandwidth-bound convolutions ---------------------------------------------------------
 // 3x3 pad 1, C_in = 4 (fp32 NHWC input) -> N channels of act dtype.  w: [N][4][3][3] fp32, bias [N].
 void launch_conv_in4(int dt, const float* x, const float* w, const float* bias, void* out, int B, int H, int W, int N,
@@ -117,6 +122,11 @@ struct TcSegDesc {
   int Cw_total;      // total input channels of the weight tensor
   int wc0;           // first weight channel used by this segment
   int taps;          // 9 or 1
+  // fused GroupNorm + SiLU operand (3x3 only): `act` is the RAW tensor and the kernel normalises it on the way into
+  // shared memory with the per-sample table aff = fp32 [B][2][aff_C] (scale row, shift row; launch_gn_affine);
+  // channel c0 of `act` uses column aff_c0 of the table.  nullptr: `act` is consumed as is.
+  const float* aff;
+  int aff_C, aff_c0;
 };
 struct TcConvDesc {
   TcSegDesc seg[3];
