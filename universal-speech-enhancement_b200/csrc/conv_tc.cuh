@@ -58,6 +58,7 @@ struct alignas(64) ConvParams {
   float* out4;
   const float* prev4;    // optional fp32 [B][H/2][W/2][out_pc]
   int out_pc;            // real output channels of the head (4 or 2)
+  int dbg;               // experiment switches (USE_B200_CONV_DBG), unused by the shipping kernels
 };
 
 template <typename T, int N, int NSUB, bool FUSE>
@@ -71,15 +72,16 @@ struct ConvCfg {
   static constexpr int NPIX = A_ROWS * WIN_W;            // pixels of one window
   static constexpr int A_SLOT = (NPIX * 128 + 1023) & ~1023;
   static constexpr int B_TILE = N * 128;
-  static constexpr int A_SLOTS = 2;
-  static constexpr int B_SLOTS = (N == 256) ? 5 : (N == 128 ? 7 : 8);  // N <= 64: 8 slots
+  // plain: 2 windows (loading / consumed).  fused: 3 (TMA loading the raw window / being normalised in place / consumed)
+  static constexpr int A_SLOTS = FUSE ? 3 : 2;
+  static constexpr int B_SLOTS = (N == 256) ? (FUSE ? 4 : 5) : (N == 128 ? (FUSE ? 5 : 7) : 8);  // N <= 64: 8 slots
   static constexpr int ACC_COLS = NSUB * N;
   static constexpr int TMEM_COLS = (2 * ACC_COLS < 32) ? 32 : 2 * ACC_COLS;
   static constexpr int EPI_WARPS = 4 * NSUB;
   static constexpr int XF_THREADS = FUSE ? 192 : 0;      // transform warps (6)
   static constexpr int XF_T0 = 64 + 32 * EPI_WARPS;      // first transform thread
   static constexpr int THREADS = XF_T0 + XF_THREADS;
-  static constexpr int NBARS = 2 * A_SLOTS + 2 * B_SLOTS + 4;
+  static constexpr int NBARS = 3 * A_SLOTS + 2 * B_SLOTS + 4;
   static constexpr int STAT_BYTES = EPI_WARPS * N * 2 * 4;  // per-warp column statistics of the current tile
   static constexpr int SMEM_BYTES = 1024 + A_SLOTS * A_SLOT + B_SLOTS * B_TILE + STAT_BYTES + NBARS * 8 + 16;
   static_assert(TMEM_COLS <= 512 && (TMEM_COLS & (TMEM_COLS - 1)) == 0, "TMEM columns must be a power of two <= 512");
@@ -106,7 +108,8 @@ __global__ void __launch_bounds__(ConvCfg<T, N, NSUB, FUSE>::THREADS, 1) conv_tc
   uint64_t* bars = reinterpret_cast<uint64_t*>(sB + C::B_SLOTS * C::B_TILE + C::STAT_BYTES);
   uint64_t* a_full = bars;
   uint64_t* a_empty = a_full + C::A_SLOTS;
-  uint64_t* b_full = a_empty + C::A_SLOTS;
+  uint64_t* a_raw = a_empty + C::A_SLOTS;  // fused segments: raw window landed (TMA -> transform warps)
+  uint64_t* b_full = a_raw + C::A_SLOTS;
   uint64_t* b_empty = b_full + C::B_SLOTS;
   uint64_t* t_full = b_empty + C::B_SLOTS;
   uint64_t* t_empty = t_full + 2;
@@ -120,7 +123,7 @@ __global__ void __launch_bounds__(ConvCfg<T, N, NSUB, FUSE>::THREADS, 1) conv_tc
       prefetch_tmap(&p.seg[i].tmA);
       prefetch_tmap(&p.seg[i].tmW);
     }
-    for (int i = 0; i < C::A_SLOTS; ++i) { mbar_init(&a_full[i], 1); mbar_init(&a_empty[i], 1); }
+    for (int i = 0; i < C::A_SLOTS; ++i) { mbar_init(&a_full[i], 1); mbar_init(&a_empty[i], 1); mbar_init(&a_raw[i], 1); }
     for (int i = 0; i < C::B_SLOTS; ++i) { mbar_init(&b_full[i], 1); mbar_init(&b_empty[i], 1); }
     for (int i = 0; i < 2; ++i) { mbar_init(&t_full[i], 1); mbar_init(&t_empty[i], C::EPI_WARPS); }
     fence_barrier_init();
@@ -139,29 +142,43 @@ __global__ void __launch_bounds__(ConvCfg<T, N, NSUB, FUSE>::THREADS, 1) conv_tc
 
   if (warp == 0) {
     // ================================ TMA producer ================================
-    // weights of every segment; activation windows of the segments that are not fused
+    // Two streams issued by one thread: weight tiles (B ring) and activation windows (A ring).  The window stream runs
+    // ahead of the weight stream by up to A_SLOTS - 1 chunks (it is polled, non-blocking, before every weight tile), so a
+    // raw window of a fused segment lands -- and is normalised in place by the transform warps -- well before its MMAs.
     if (lane == 0) {
-      uint32_t ai = 0, bi = 0;  // running slot counters (ai counts every window, whoever fills it)
-      for (int tile = g0; tile < p.ntiles; tile += gstep) {
-        const int b = tile / tiles_per_img;
-        const int rem = tile - b * tiles_per_img;
+      // window-stream cursor
+      int a_tile = g0, a_sg = 0, a_kc = 0;
+      uint32_t ai = 0;
+      auto a_pending = [&]() { return a_tile < p.ntiles; };
+      auto a_issue = [&](bool blocking) -> bool {
+        const uint32_t as = ai % C::A_SLOTS, aph = (ai / C::A_SLOTS) & 1;
+        if (blocking) mbar_wait(&a_empty[as], aph ^ 1);
+        else if (!mbar_try_wait(&a_empty[as], aph ^ 1)) return false;
+        const ConvSeg& S = p.seg[a_sg];
+        const int b = a_tile / tiles_per_img;
+        const int rem = a_tile - b * tiles_per_img;
         const int th = rem / p.tiles_w;
-        const int w0 = (rem - th * p.tiles_w) * C::TILE_W;
-        const int h0 = th * C::TILE_H;
+        const int w0 = (rem - th * p.tiles_w) * C::TILE_W, h0 = th * C::TILE_H;
+        const bool k3 = S.taps == 9;
+        uint64_t* bar = (FUSE && S.raw != nullptr) ? &a_raw[as] : &a_full[as];
+        mbar_arrive_expect_tx(bar, (k3 ? C::NPIX : C::TILE_H * 8) * 128);
+        tma_load_4d(sA + as * C::A_SLOT, &S.tmA, bar, S.ac0 + a_kc * C::CK, k3 ? (w0 - 1) : w0, k3 ? (h0 - 1) : h0, b);
+        ++ai;
+        if (++a_kc == S.nchunks) {
+          a_kc = 0;
+          if (++a_sg == p.nseg) { a_sg = 0; a_tile += gstep; }
+        }
+        return true;
+      };
+      uint32_t bi = 0, bj = 0;  // weight tiles issued, chunks whose weights have been issued
+      for (int tile = g0; tile < p.ntiles; tile += gstep) {
         for (int sg = 0; sg < p.nseg; ++sg) {
           const ConvSeg& S = p.seg[sg];
           const bool k3 = S.taps == 9;
-          const uint32_t a_bytes = (k3 ? C::NPIX : C::TILE_H * 8) * 128;
-          for (int kc = 0; kc < S.nchunks; ++kc) {
-            if constexpr (!FUSE) {  // (in a FUSE kernel the transform warps own the activation ring, see below)
-              const uint32_t as = ai % C::A_SLOTS, aph = (ai / C::A_SLOTS) & 1;
-              mbar_wait(&a_empty[as], aph ^ 1);
-              mbar_arrive_expect_tx(&a_full[as], a_bytes);
-              tma_load_4d(sA + as * C::A_SLOT, &S.tmA, &a_full[as], S.ac0 + kc * C::CK, k3 ? (w0 - 1) : w0,
-                          k3 ? (h0 - 1) : h0, b);
-            }
-            ++ai;
+          for (int kc = 0; kc < S.nchunks; ++kc, ++bj) {
+            while (ai <= bj) a_issue(true);  // the window of this chunk is always issued before its weights
             for (int tap = 0; tap < S.taps; ++tap) {
+              if (a_pending() && ai < bj + C::A_SLOTS) a_issue(false);
               const uint32_t bs = bi % C::B_SLOTS, bph = (bi / C::B_SLOTS) & 1;
               mbar_wait(&b_empty[bs], bph ^ 1);
               mbar_arrive_expect_tx(&b_full[bs], C::B_TILE);
@@ -231,57 +248,35 @@ __global__ void __launch_bounds__(ConvCfg<T, N, NSUB, FUSE>::THREADS, 1) conv_tc
   } else if (threadIdx.x >= C::XF_T0) {
     if constexpr (FUSE) {
     // ================================ transform warps ================================
-    // GroupNorm (scale / shift) + SiLU + operand rounding of the raw producer output, global -> registers -> the
-    // swizzled window in shared memory.  Thread = one 16-byte channel vector (v) of the pixels pb, pb + 24, ...
+    // GroupNorm (scale / shift) + SiLU + operand rounding of the raw window the TMA just landed, IN PLACE in shared
+    // memory (the transform never waits on global memory).  Thread = one 16-byte channel vector (v) of the window
+    // pixels pb, pb + PSTEP, ...; pixels outside the image keep the TMA's zero fill: the conv pads the ACTIVATED tensor.
     constexpr int V = DT<T>::kVec;
     constexpr int XT = C::XF_THREADS;
     constexpr int PSTEP = XT / 8;
     constexpr int NIT = (C::NPIX + PSTEP - 1) / PSTEP;
     const int tt = threadIdx.x - C::XF_T0;
     const int v = tt & 7, pb = tt >> 3;
-    uint32_t ai = 0;
+    uint32_t ai = 0, rawph = 0;  // rawph: phase parity of a_raw per slot (it only advances on fused fills)
     for (int tile = g0; tile < p.ntiles; tile += gstep) {
       const int b = tile / tiles_per_img;
       const int rem = tile - b * tiles_per_img;
       const int th = rem / p.tiles_w;
       const int w0 = (rem - th * p.tiles_w) * C::TILE_W;
       const int h0 = th * C::TILE_H;
-      int poff[NIT];  // pixel index inside the image, -1 outside (zero padding of the ACTIVATED tensor) / past the window
+      uint32_t inside = 0;  // bit i: window pixel pb + PSTEP * i lies inside the image
 #pragma unroll
       for (int i = 0; i < NIT; ++i) {
         const int q = pb + PSTEP * i;
         const int row = q / C::WIN_W, col = q - row * C::WIN_W;
         const int hh = h0 - 1 + row, ww = w0 - 1 + col;
-        poff[i] = (q < C::NPIX && hh >= 0 && hh < p.H && ww >= 0 && ww < p.W) ? hh * p.W + ww : -1;
+        if (q < C::NPIX && hh >= 0 && hh < p.H && ww >= 0 && ww < p.W) inside |= 1u << i;
       }
       for (int sg = 0; sg < p.nseg; ++sg) {
         const ConvSeg& S = p.seg[sg];
-        if (S.raw == nullptr) {
-          // TMA-fed segment of a fused launch (1x1 skip projections, pre-activated FIR operands): the transform warps
-          // own the whole activation ring -- a ring with two independent producers would let one of them run two
-          // phases ahead of (or behind) an mbarrier, which a 1-bit phase parity cannot tell apart -- so thread 0
-          // issues the TMA and everybody stays in lockstep through the named barrier.
-          const bool k3 = S.taps == 9;
-          for (int kc = 0; kc < S.nchunks; ++kc, ++ai) {
-            const uint32_t as = ai % C::A_SLOTS, aph = (ai / C::A_SLOTS) & 1;
-            mbar_wait(&a_empty[as], aph ^ 1);
-            if (tt == 0) {
-              mbar_arrive_expect_tx(&a_full[as], (k3 ? C::NPIX : C::TILE_H * 8) * 128);
-              tma_load_4d(sA + as * C::A_SLOT, &S.tmA, &a_full[as], S.ac0 + kc * C::CK, k3 ? (w0 - 1) : w0,
-                          k3 ? (h0 - 1) : h0, b);
-            }
-            named_bar_sync(2, XT);
-          }
-          continue;
-        }
-        const T* src = reinterpret_cast<const T*>(S.raw) + static_cast<size_t>(b) * p.H * p.W * S.Ct + S.ac0 + v * V;
+        if (S.raw == nullptr) { ai += S.nchunks; continue; }
         const float* aff = S.aff + static_cast<size_t>(b) * 2 * S.aff_C + S.aff_c0 + v * V;
         for (int kc = 0; kc < S.nchunks; ++kc, ++ai) {
-          uint4 d[NIT];
-#pragma unroll
-          for (int i = 0; i < NIT; ++i)
-            d[i] = poff[i] >= 0 ? __ldg(reinterpret_cast<const uint4*>(src + static_cast<size_t>(poff[i]) * S.Ct + kc * C::CK))
-                                : make_uint4(0u, 0u, 0u, 0u);
           float sc[V], sh[V];
 #pragma unroll
           for (int j = 0; j < V; j += 4) {
@@ -290,23 +285,21 @@ __global__ void __launch_bounds__(ConvCfg<T, N, NSUB, FUSE>::THREADS, 1) conv_tc
             sc[j] = a.x; sc[j + 1] = a.y; sc[j + 2] = a.z; sc[j + 3] = a.w;
             sh[j] = c.x; sh[j + 1] = c.y; sh[j + 2] = c.z; sh[j + 3] = c.w;
           }
-#pragma unroll
-          for (int i = 0; i < NIT; ++i) {
-            if (poff[i] >= 0) {
-              float f[V];
-              Vec<T>::unpack(d[i], f);
-#pragma unroll
-              for (int j = 0; j < V; ++j) f[j] = silu_act<T>(fmaf(f[j], sc[j], sh[j]));
-              d[i] = Vec<T>::pack_operand(f);
-            }
-          }
-          const uint32_t as = ai % C::A_SLOTS, aph = (ai / C::A_SLOTS) & 1;
-          mbar_wait(&a_empty[as], aph ^ 1);
+          const uint32_t as = ai % C::A_SLOTS;
+          mbar_wait(&a_raw[as], (rawph >> as) & 1u);
+          rawph ^= 1u << as;
           uint8_t* slot = sA + as * C::A_SLOT;  // 1024-byte aligned: the swizzle phase of window pixel q is q & 7
 #pragma unroll
           for (int i = 0; i < NIT; ++i) {
-            const int q = pb + PSTEP * i;
-            if (q < C::NPIX) *reinterpret_cast<uint4*>(slot + q * 128 + ((v ^ (q & 7)) << 4)) = d[i];
+            if ((inside >> i) & 1u) {
+              const int q = pb + PSTEP * i;
+              uint4* ptr = reinterpret_cast<uint4*>(slot + q * 128 + ((v ^ (q & 7)) << 4));
+              float f[V];
+              Vec<T>::unpack(*ptr, f);
+#pragma unroll
+              for (int j = 0; j < V; ++j) f[j] = silu_act<T>(fmaf(f[j], sc[j], sh[j]));
+              *ptr = Vec<T>::pack_operand(f);
+            }
           }
           fence_proxy_async();  // generic-proxy writes -> visible to the tensor core's async-proxy reads
           named_bar_sync(2, XT);

@@ -1219,6 +1219,21 @@ int use_op_conv_tc_gn(int dtype, int nseg, const void* const* seg_act, const int
   TcConvPlan* p = tc_conv_plan_create(dtype, d, sms, msg, sizeof(msg));
   if (!p) return fail("%s", msg);
   tc_conv_launch(p, (cudaStream_t)stream);
+  if (const char* reps_s = getenv("USE_B200_CONV_TIME")) {  // kernel-tuning hook (tools/conv_bench.py): time `reps` launches
+    const int reps = atoi(reps_s) > 0 ? atoi(reps_s) : 1;
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0);
+    cudaEventCreate(&e1);
+    cudaEventRecord(e0, (cudaStream_t)stream);
+    for (int i = 0; i < reps; ++i) tc_conv_launch(p, (cudaStream_t)stream);
+    cudaEventRecord(e1, (cudaStream_t)stream);
+    cudaEventSynchronize(e1);
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, e0, e1);
+    fprintf(stderr, "USE_B200_CONV_TIME ms_per_launch=%.5f reps=%d\n", ms / reps, reps);
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+  }
   cudaStreamSynchronize((cudaStream_t)stream);  // the plan (tensor maps live in kernel params) can go now
   tc_conv_plan_destroy(p);
   return cuda_check("use_op_conv_tc");
