@@ -155,6 +155,11 @@ int use_op_conv_in4(int dtype, const float* x, const float* w, const float* bias
                     void* stream);
 int use_op_conv_out4(int dtype, const void* a, const float* w, const float* bias, const float* prev, float* out, int B,
                      int H, int W, int C, void* stream);
+/* Pyramid head (ncsnpp.py:440-461): 3x3 pad 1, C -> pc (4 or 2) fp32 channels of the activated tensor a (+ FIR-upsample
+ * x2 of prev, fp32 [B][H/2][W/2][pc]) on the tensor cores with the nine taps folded into the MMA's N dimension.
+ * w_oihw_host: fp32 [pc][C][3][3] on the HOST; w_packed_dev: device scratch of 48 * C * sizeof(act) bytes. */
+int use_op_head_tc(int dtype, const void* a, const float* w_oihw_host, const float* bias, const float* prev, float* out,
+                   int B, int H, int W, int C, int pc, void* w_packed_dev, void* stream);
 int use_op_combine(int dtype, const void* h, const float* pyr, const float* w, const float* bias, void* out, int B, int HW,
                    int C, int pc, void* stream);
 int use_op_fir4_down(const float* x, float* out, int B, int Hin, int Win, int pc, void* stream);

@@ -403,6 +403,45 @@ def test_conv_out4(dt, with_prev):
     assert float((got - ref).abs().max()) <= 2e-5 * float(ref.abs().max()), describe_mismatch(got, ref)
 
 
+HEAD_CASES = [
+    # B, H, W, C, pc, with_prev
+    (2, 16, 20, 128, 4, False),
+    (2, 16, 20, 128, 4, True),
+    (1, 8, 1, 256, 4, True),       # bottom of a short-clip pyramid: a single column
+    (3, 28, 42, 256, 4, True),     # exact multiples of the 14 x 14 tile
+    (2, 64, 80, 128, 4, True),     # many tiles, persistent loop + accumulator double buffering
+    (2, 30, 18, 128, 2, True),     # 2-channel head (discriminative generator)
+]
+
+
+@pytest.mark.parametrize("dt", [F32, BF16], ids=["tf32", "bf16"])
+@pytest.mark.parametrize("case", HEAD_CASES, ids=[f"B{c[0]}_{c[1]}x{c[2]}_C{c[3]}_pc{c[4]}_{'prev' if c[5] else 'noprev'}" for c in HEAD_CASES])
+def test_head_tc(case, dt):
+    """pyramid head on the tensor cores with the nine taps folded into N (head_tc.cuh) vs torch conv2d (+ FIR-up)."""
+    B, H, W, Cc, pc, with_prev = case
+    L = _lib.lib()
+    g = torch.Generator().manual_seed(B * 1000 + H + W + Cc)
+    a = to_operand(torch.randn(B, Cc, H, W, generator=g), dt)
+    w = torch.randn(pc, Cc, 3, 3, generator=g) / np.sqrt(9 * Cc)
+    bias = torch.randn(pc, generator=g)
+    prev = torch.randn(B, pc, H // 2, W // 2, generator=g) if with_prev and H % 2 == 0 and W % 2 == 0 else None
+    ad = act_tensor(a, dt)
+    wh = w.contiguous()
+    bd = bias.cuda()
+    pd = prev.permute(0, 2, 3, 1).contiguous().cuda() if prev is not None else None
+    out = torch.full((B, H, W, pc), float("nan"), device="cuda")
+    scratch = torch.empty(48 * Cc * 4, dtype=torch.uint8, device="cuda")
+    rc = L.use_op_head_tc(dt, ad.data_ptr(), wh.data_ptr(), bd.data_ptr(), pd.data_ptr() if pd is not None else None,
+                          out.data_ptr(), B, H, W, Cc, pc, scratch.data_ptr(), stream())
+    assert rc == 0, L.use_last_error()
+    _sync()
+    ref = Fnn.conv2d(a.double(), to_operand(w, dt).double(), bias.double(), padding=1).float()
+    if prev is not None:
+        ref = ref + O.fir_upsample_2d(prev)
+    got = out.permute(0, 3, 1, 2).cpu()
+    assert float((got - ref).abs().max()) <= 2e-5 * float(ref.abs().max()), describe_mismatch(got, ref)
+
+
 @pytest.mark.parametrize("dt", [F32, BF16], ids=["fp32", "bf16"])
 def test_combine_and_fir4(dt):
     L = _lib.lib()

@@ -99,10 +99,29 @@ def main():
         assert rc == 0, L.use_last_error()
         torch.cuda.synchronize()
 
-    for dtn in (["fp32", "bf16"] if args.dtype == "both" else [args.dtype]):
+    def run_head(dtn, H, W, Cc):
+        dt = BF16 if dtn == "bf16" else F32
+        B = args.batch
+        tdt = torch.bfloat16 if dt == BF16 else torch.float32
+        a = torch.randn(B, H, W, Cc, device="cuda").to(tdt)
+        w = torch.randn(4, Cc, 3, 3)
+        bias = torch.zeros(4, device="cuda")
+        prev = torch.randn(B, H // 2, W // 2, 4, device="cuda")
+        out = torch.empty(B, H, W, 4, device="cuda")
+        scratch = torch.empty(48 * Cc * 4, dtype=torch.uint8, device="cuda")
+        rc = L.use_op_head_tc(dt, a.data_ptr(), w.data_ptr(), bias.data_ptr(), prev.data_ptr(), out.data_ptr(), B, H, W, Cc, 4,
+                              scratch.data_ptr(), stream())
+        assert rc == 0, L.use_last_error()
+        torch.cuda.synchronize()
+
+    dts = ["fp32", "bf16"] if args.dtype == "both" else [args.dtype]
+    for dtn in dts:
         for ci in range(len(CASES)):
             for fused in (0, 1):
                 run_case(dtn, ci, fused)
+    for dtn in dts:
+        run_head(dtn, 512, 640, 128)
+        run_head(dtn, 256, 320, 128)
     report(args)
 
 
@@ -120,6 +139,12 @@ def report(args):
                     line += f" | {'fused' if fused else 'plain'} {ms[k]:7.3f} ms {flops / ms[k] / 1e9:7.1f} TF/s"
                 k += 1
             print(line, flush=True)
+    for dtn in (["fp32", "bf16"] if args.dtype == "both" else [args.dtype]):
+        for (H, W, Cc) in ((512, 640, 128), (256, 320, 128)):
+            if k < len(ms):
+                gb = args.batch * H * W * Cc * (2 if dtn == "bf16" else 4) / 1e9
+                print(f"{dtn} head {H}x{W} C{Cc}: {ms[k]:7.3f} ms  {gb / ms[k] * 1e3:7.1f} GB/s (operand read)", flush=True)
+            k += 1
 
 
 if __name__ == "__main__":

@@ -6,6 +6,7 @@
 #include <mutex>
 
 #include "conv_tc.cuh"
+#include "head_tc.cuh"
 #include "kernels.h"
 
 namespace use {
@@ -186,6 +187,70 @@ TcConvPlan* tc_conv_plan_create(int dt, const TcConvDesc& d, int num_sms, char* 
 }
 
 void tc_conv_plan_destroy(TcConvPlan* p) { delete p; }
+
+// ---- pyramid head (head_tc.cuh) ---------------------------------------------------------------------------
+struct HeadPlan {
+  HeadParams params;
+  int dt, grid;
+};
+
+bool head_tc_supported(int dt, int C, int pc) {
+  const int ck = 128 / (int)act_size(dt);
+  return (pc == 4 || pc == 2) && C % ck == 0 && C / ck <= kHeadMaxChunks;
+}
+
+HeadPlan* head_tc_plan_create(int dt, const void* act, const void* w_packed, const float* bias, const float* prev4,
+                              float* out4, int B, int H, int W, int C, int pc, int num_sms, char* err, int errlen) {
+  if (!head_tc_supported(dt, C, pc)) {
+    snprintf(err, errlen, "pyramid head: unsupported C=%d pc=%d", C, pc);
+    return nullptr;
+  }
+  EncodeTiledFn enc = get_encode();
+  if (!enc) { snprintf(err, errlen, "cuTensorMapEncodeTiled unavailable"); return nullptr; }
+  HeadPlan* p = new HeadPlan();
+  memset(&p->params, 0, sizeof(p->params));
+  p->dt = dt;
+  const cuuint64_t es = act_size(dt);
+  const cuuint32_t ck = 128 / es;
+  const CUtensorMapDataType tdt = dt == kBF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32;
+  {
+    cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
+    cuuint64_t strides[3] = {C * es, (cuuint64_t)W * C * es, (cuuint64_t)H * W * C * es};
+    cuuint32_t box[4] = {ck, kHeadWin, kHeadWin, 1};
+    cuuint32_t estr[4] = {1, 1, 1, 1};
+    CUresult r = enc(&p->params.tmA, tdt, 4, const_cast<void*>(act), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                     CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { snprintf(err, errlen, "pyramid head: act tensor map failed: %d", (int)r); delete p; return nullptr; }
+  }
+  {
+    cuuint64_t dims[2] = {(cuuint64_t)C, (cuuint64_t)kHeadN};
+    cuuint64_t strides[1] = {C * es};
+    cuuint32_t box[2] = {ck, kHeadN};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = enc(&p->params.tmW, tdt, 2, const_cast<void*>(w_packed), dims, strides, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { snprintf(err, errlen, "pyramid head: weight tensor map failed: %d", (int)r); delete p; return nullptr; }
+  }
+  HeadParams& P = p->params;
+  P.nchunks = C / ck;
+  P.B = B; P.H = H; P.W = W;
+  P.tiles_w = (W + kHeadTile - 1) / kHeadTile;
+  P.tiles_h = (H + kHeadTile - 1) / kHeadTile;
+  P.ntiles = P.tiles_w * P.tiles_h * B;
+  P.bias = bias; P.out4 = out4; P.prev4 = prev4; P.pc = pc;
+  p->grid = P.ntiles < num_sms ? P.ntiles : num_sms;
+  if (dt == kBF16) cudaFuncSetAttribute(head_tc_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, kHeadSmem);
+  else cudaFuncSetAttribute(head_tc_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, kHeadSmem);
+  return p;
+}
+
+void head_tc_plan_destroy(HeadPlan* p) { delete p; }
+
+void head_tc_launch(const HeadPlan* p, cudaStream_t st) {
+  if (p->dt == kBF16) head_tc_kernel<__nv_bfloat16><<<p->grid, kHeadThreads, kHeadSmem, st>>>(p->params);
+  else head_tc_kernel<float><<<p->grid, kHeadThreads, kHeadSmem, st>>>(p->params);
+}
 
 int tc_conv_tiles_per_image(int dt, int N, int H, int W) {
   const int tile_h = (N == 256) ? 16 : 32;  // NSUB = 1 for N = 256, 2 otherwise (see tc_conv_plan_create)

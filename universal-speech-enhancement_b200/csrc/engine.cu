@@ -68,6 +68,19 @@ static void pack_conv_weight(int dt, const float* w, int O, int I, int ks, void*
       }
 }
 
+// pyramid-head weights [pc][C][3][3] fp32 -> act dtype [48][C], row tap * pc + co (rows >= 9 * pc are zero)
+static void pack_head_weight(int dt, const float* w, int pc, int C, void* out) {
+  memset(out, 0, (size_t)48 * C * act_size(dt));
+  for (int tap = 0; tap < 9; ++tap)
+    for (int co = 0; co < pc; ++co)
+      for (int c = 0; c < C; ++c) {
+        const float v = w[((size_t)co * C + c) * 9 + tap];
+        const size_t idx = (size_t)(tap * pc + co) * C + c;
+        if (dt == kBF16) ((uint16_t*)out)[idx] = f32_to_bf16(v);
+        else ((float*)out)[idx] = f32_to_tf32(v);
+      }
+}
+
 // ---------------------------------------------------------------------------------------------
 // architecture plan (same order as the reference's all_modules list)
 // ---------------------------------------------------------------------------------------------
@@ -166,11 +179,13 @@ struct Program {
   int B = 0, F = 0, T = 0;
   std::vector<Op> ops;
   std::vector<TcConvPlan*> plans;
+  std::vector<HeadPlan*> heads;
   size_t stats_bytes = 0;
   size_t pyramid_off = 0;  // final fp32 [B][F][T][4]
   char* base = nullptr;
   ~Program() {
     for (auto* p : plans) tc_conv_plan_destroy(p);
+    for (auto* p : heads) head_tc_plan_destroy(p);
   }
 };
 
@@ -343,17 +358,12 @@ static int pack_all(use_engine* e) {
           pack_conv_weight(dt, wp.data(), m.cout, ck, 3, e->blob.data() + off);
           e->off[p + ".wtc"] = off;
         }
-        if (m.cout == c.input_channels && m.cin % (128 / (int)es) == 0) {
-          // pyramid head C -> 4: tcgen05 layout with the output channels zero-padded to 32
+        if (m.cout == c.input_channels && head_tc_supported(dt, m.cin, m.cout)) {
+          // pyramid head C -> pc: the nine taps folded into the MMA's N dimension (head_tc.cuh), rows tap * pc + co
           const HostTensor* t = getw(e, p + ".weight", {m.cout, m.cin, 3, 3});
-          const HostTensor* tb = getw(e, p + ".bias", {m.cout});
-          std::vector<float> wp((size_t)32 * m.cin * 9, 0.f), bp(32, 0.f);
-          memcpy(wp.data(), t->data.data(), t->data.size() * 4);
-          memcpy(bp.data(), tb->data.data(), tb->data.size() * 4);
-          size_t off = bw.reserve((size_t)9 * 32 * m.cin * es);
-          pack_conv_weight(dt, wp.data(), 32, m.cin, 3, e->blob.data() + off);
-          e->off[p + ".wtc"] = off;
-          e->off[p + ".btc"] = bw.put(bp.data(), 32 * 4);
+          size_t off = bw.reserve((size_t)48 * m.cin * es);
+          pack_head_weight(dt, t->data.data(), m.cout, m.cin, e->blob.data() + off);
+          e->off[p + ".whd"] = off;
         }
         break;
       }
@@ -734,22 +744,21 @@ struct Builder {
       {
         const std::string pg = "all_modules." + std::to_string(idx), pc = "all_modules." + std::to_string(idx + 1);
         Act a = new_act(h.C, h.H, h.W);
-        const bool head_tc = e->off.count(pc + ".wtc") != 0;
+        const bool head_tc = e->off.count(pc + ".whd") != 0;
         gn_apply(h, nullptr, e->off.at(pg + ".g"), e->off.at(pg + ".b"), 0, true, head_tc, a, nullptr);
         size_t np = new_f32((size_t)B * h.H * h.W * npc);
         if (head_tc) {
-          TcConvDesc d{};
-          d.nseg = 1;
-          d.seg[0] = TcSegDesc{dry ? nullptr : ws(a.off), h.C, 0, h.C, dry ? nullptr : wt(e->off.at(pc + ".wtc")), h.C, 0, 9};
-          d.B = B; d.H = h.H; d.W = h.W; d.N = 32;
-          d.out = nullptr;
-          d.bias = dry ? nullptr : (const float*)wt(e->off.at(pc + ".btc"));
-          d.bias_bstride = 0;
-          d.scale = 1.0f;
-          d.out4 = dry ? (float*)1 : (float*)ws(np);
-          d.out_pc = npc;
-          d.prev4 = (dry || opyr == (size_t)-1) ? nullptr : (const float*)ws(opyr);
-          conv_tc(d);
+          if (!dry) {
+            char msg[512];
+            HeadPlan* hp = head_tc_plan_create(e->dt, ws(a.off), wt(e->off.at(pc + ".whd")), wf(pc + ".b"),
+                                               opyr == (size_t)-1 ? nullptr : (const float*)ws(opyr), (float*)ws(np), B, h.H,
+                                               h.W, h.C, npc, e->num_sms, msg, sizeof(msg));
+            if (!hp) { err = fail("%s", msg); return; }
+            prog->heads.push_back(hp);
+            const double px = (double)B * h.H * h.W;
+            emit([=](cudaStream_t s) { head_tc_launch(hp, s); }, TAG_SMALL_CONV, 1, 2.0 * px * h.C * 9 * npc,
+                 px * (h.C * es() + 4.0 * npc));
+          }
         } else if (npc != 4) {
           err = fail("pyramid head with %d channels needs C %% %d == 0", npc, 128 / (int)es());
         } else if (!dry) {
@@ -1259,6 +1268,40 @@ int use_op_conv_out4(int dtype, const void* a, const float* w, const float* bias
                      int H, int W, int C, void* stream) {
   launch_conv_out4(dtype, a, w, bias, prev, out, B, H, W, C, (cudaStream_t)stream);
   return cuda_check("use_op_conv_out4");
+}
+int use_op_head_tc(int dtype, const void* a, const float* w_oihw_host, const float* bias, const float* prev, float* out,
+                   int B, int H, int W, int C, int pc, void* w_packed_dev, void* stream) {
+  if (!a || !w_oihw_host || !bias || !out || !w_packed_dev) return fail("null argument");
+  if (!head_tc_supported(dtype, C, pc)) return fail("pyramid head: unsupported C=%d pc=%d", C, pc);
+  std::vector<uint8_t> packed((size_t)48 * C * act_size(dtype));
+  pack_head_weight(dtype, w_oihw_host, pc, C, packed.data());
+  cudaMemcpyAsync(w_packed_dev, packed.data(), packed.size(), cudaMemcpyHostToDevice, (cudaStream_t)stream);
+  cudaStreamSynchronize((cudaStream_t)stream);
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  char msg[512];
+  HeadPlan* p = head_tc_plan_create(dtype, a, w_packed_dev, bias, prev, out, B, H, W, C, pc, sms, msg, sizeof(msg));
+  if (!p) return fail("%s", msg);
+  head_tc_launch(p, (cudaStream_t)stream);
+  if (const char* reps_s = getenv("USE_B200_CONV_TIME")) {
+    const int reps = atoi(reps_s) > 0 ? atoi(reps_s) : 1;
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0);
+    cudaEventCreate(&e1);
+    cudaEventRecord(e0, (cudaStream_t)stream);
+    for (int i = 0; i < reps; ++i) head_tc_launch(p, (cudaStream_t)stream);
+    cudaEventRecord(e1, (cudaStream_t)stream);
+    cudaEventSynchronize(e1);
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, e0, e1);
+    fprintf(stderr, "USE_B200_CONV_TIME ms_per_launch=%.5f reps=%d\n", ms / reps, reps);
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+  }
+  cudaStreamSynchronize((cudaStream_t)stream);
+  head_tc_plan_destroy(p);
+  return cuda_check("use_op_head_tc");
 }
 int use_op_combine(int dtype, const void* h, const float* pyr, const float* w, const float* bias, void* out, int B, int HW,
                    int C, int pc, void* stream) {

@@ -148,6 +148,15 @@ TcConvPlan* tc_conv_plan_create(int dt, const TcConvDesc& d, int num_sms, char* 
 void tc_conv_plan_destroy(TcConvPlan* p);
 void tc_conv_launch(const TcConvPlan* p, cudaStream_t st);
 bool tc_conv_supported(int dt, int N);
+
+// ---- pyramid head: 3x3 pad 1, C -> pc (4 or 2) fp32 channels (+ FIR-upsampled previous pyramid), nine taps folded into
+// the MMA's N dimension (head_tc.cuh).  w_packed: act dtype [48][C], row tap * pc + co (use_pack_head_weight).
+struct HeadPlan;
+bool head_tc_supported(int dt, int C, int pc);
+HeadPlan* head_tc_plan_create(int dt, const void* act, const void* w_packed, const float* bias, const float* prev4,
+                              float* out4, int B, int H, int W, int C, int pc, int num_sms, char* err, int errlen);
+void head_tc_plan_destroy(HeadPlan* p);
+void head_tc_launch(const HeadPlan* p, cudaStream_t st);
 int tc_conv_tiles_per_image(int dt, int N, int H, int W);
 
 }  // namespace use
