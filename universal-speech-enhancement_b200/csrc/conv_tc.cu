@@ -180,7 +180,6 @@ TcConvPlan* tc_conv_plan_create(int dt, const TcConvDesc& d, int num_sms, char* 
   P.ntiles = P.tiles_w * P.tiles_h * d.B;
   P.out = d.out; P.bias = d.bias; P.bias_bstride = d.bias_bstride; P.res = d.res; P.scale = d.scale;
   P.stats_acc = d.stats_acc;
-  if (const char* v = getenv("USE_B200_CONV_DBG")) P.dbg = atoi(v);
   P.out4 = d.out4; P.prev4 = d.prev4; P.out_pc = d.out_pc ? d.out_pc : 4;
   p->grid = P.ntiles < num_sms ? P.ntiles : num_sms;  // persistent CTAs, one per SM
   return p;

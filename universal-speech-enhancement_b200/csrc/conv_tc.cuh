@@ -14,10 +14,12 @@
 // function of the absolute shared-memory address (measured: tools/swz_probe.cu), so a descriptor may start at any
 // 128-byte row.  1 activation stage per chunk instead of 9 (or 3 horizontally shifted copies).
 //
-// The window is filled either by TMA (zero fill outside the image = the conv padding) or, for a FUSED segment, by six
-// "transform" warps that read the RAW producer output from global memory and apply GroupNorm (per-sample, per-channel
-// scale / shift table) + SiLU + operand rounding on the way into shared memory: the normalised activation tensor of
-// `GroupNorm -> SiLU -> Conv3x3` (layerspp.py:283-285,304-306) is never materialised in HBM.
+// The window is always landed by TMA (zero fill outside the image = the conv padding).  For a FUSED segment the TMA
+// brings the RAW producer output and six "transform" warps apply GroupNorm (per-sample, per-channel scale / shift
+// table) + SiLU + operand rounding IN PLACE in shared memory before the MMAs read it: the normalised activation tensor
+// of `GroupNorm -> SiLU -> Conv3x3` (layerspp.py:283-285,304-306) is never materialised in HBM.  (Measured
+// alternatives: global -> registers -> smem in the transform warps exposes the load latency, 70 % of the plain conv
+// speed; in place behind a 3-deep TMA ring: 92-94 %.  L2 prefetch hints made both variants slower.)
 //
 // Warp roles: warp 0 = TMA producer (1 thread), warp 1 = TMEM owner + MMA issuer (1 thread),
 // warps 2..2+4*NSUB = epilogue (TMEM -> registers -> bias / residual / scale -> global), then 6 transform warps.
@@ -58,7 +60,6 @@ struct alignas(64) ConvParams {
   float* out4;
   const float* prev4;    // optional fp32 [B][H/2][W/2][out_pc]
   int out_pc;            // real output channels of the head (4 or 2)
-  int dbg;               // experiment switches (USE_B200_CONV_DBG), unused by the shipping kernels
 };
 
 template <typename T, int N, int NSUB, bool FUSE>
