@@ -162,6 +162,9 @@ int use_op_head_tc(int dtype, const void* a, const float* w_oihw_host, const flo
                    int B, int H, int W, int C, int pc, void* w_packed_dev, void* stream);
 int use_op_combine(int dtype, const void* h, const float* pyr, const float* w, const float* bias, void* out, int B, int HW,
                    int C, int pc, void* stream);
+/* Combine that also accumulates the fixed-point GroupNorm statistics [B][C][2] of its output (zero `stats` first). */
+int use_op_combine_stats(int dtype, const void* h, const float* pyr, const float* w, const float* bias, void* out,
+                         long long* stats, int B, int HW, int C, int pc, void* stream);
 int use_op_fir4_down(const float* x, float* out, int B, int Hin, int Win, int pc, void* stream);
 int use_op_philox(void* z, uint64_t seed, uint32_t step, uint32_t clip0, int B, size_t per_clip, void* stream);
 /* pack fp32 OIHW conv weights into the tcgen05 layout [taps][O][I] of the act dtype (host -> host). */

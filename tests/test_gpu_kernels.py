@@ -467,6 +467,44 @@ def test_combine_and_fir4(dt):
     assert float((got - ref).abs().max()) <= OUT_TOL[dt] * float(ref.abs().max()), describe_mismatch(got, ref)
 
 
+@pytest.mark.parametrize("dt", [F32, BF16], ids=["fp32", "bf16"])
+@pytest.mark.parametrize("Cc,pc,HW", [(128, 4, (48, 40)), (256, 4, (30, 36)), (256, 2, (64, 20))])
+def test_combine_with_statistics(dt, Cc, pc, HW):
+    """Combine + fused GroupNorm statistics of its output: values vs torch, statistics vs the fp64 sums, bit-reproducible
+    and batch-invariant (fixed block partition, integer atomics)."""
+    L = _lib.lib()
+    g = torch.Generator().manual_seed(Cc + pc)
+    B, (H, W) = 3, HW
+    pyr = torch.randn(B, pc, H, W, generator=g)
+    h = to_operand(torch.randn(B, Cc, H, W, generator=g), dt)
+    w = torch.randn(Cc, pc, 1, 1, generator=g) / 2
+    bias = torch.randn(Cc, generator=g)
+    pd = pyr.permute(0, 2, 3, 1).contiguous().cuda()
+    hd = act_tensor(h, dt)
+    wd, bd = w.cuda(), bias.cuda()
+
+    def run(hh, pp, nb):
+        out = torch.empty_like(hh)
+        st = torch.zeros(nb, Cc, 2, dtype=torch.int64, device="cuda")
+        rc = L.use_op_combine_stats(dt, hh.data_ptr(), pp.data_ptr(), wd.data_ptr(), bd.data_ptr(), out.data_ptr(),
+                                    st.data_ptr(), nb, H * W, Cc, pc, stream())
+        assert rc == 0, L.use_last_error()
+        _sync()
+        return out, st
+
+    out, st = run(hd, pd, B)
+    out2, st2 = run(hd, pd, B)
+    assert torch.equal(out, out2) and torch.equal(st, st2)
+    out1, st1 = run(hd[1:2].contiguous(), pd[1:2].contiguous(), 1)
+    assert torch.equal(out[1:2], out1) and torch.equal(st[1:2], st1)
+    ref = Fnn.conv2d(pyr.double(), w.double(), bias.double()).float() + h
+    got = from_act(out)
+    assert float((got - ref).abs().max()) <= OUT_TOL[dt] * float(ref.abs().max()), describe_mismatch(got, ref)
+    stf = stats_to_float(st)
+    assert torch.allclose(stf[..., 0], ref.double().sum(dim=(2, 3)), rtol=1e-4, atol=2e-2)
+    assert torch.allclose(stf[..., 1], (ref.double() ** 2).sum(dim=(2, 3)), rtol=1e-4, atol=2e-2)
+
+
 @pytest.mark.parametrize("up,down,pad", [(2, 1, (2, 1)), (1, 2, (1, 1)), (1, 1, (0, 0)), (2, 2, (1, 0))])
 def test_upfirdn2d_abi(up, down, pad):
     """The reference's native op seam (op/upfirdn2d.cpp:12-23) against its CPU semantics."""

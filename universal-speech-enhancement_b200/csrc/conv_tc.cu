@@ -32,7 +32,7 @@ static EncodeTiledFn get_encode() {
 
 struct TcConvPlan {
   ConvParams params;
-  int dt, N, nsub;
+  int dt, N, nsub, mc;
   int grid, threads, smem;
   const void* kernel;
 };
@@ -86,37 +86,54 @@ static bool swap_ab_enabled() {
   return on;
 }
 
-template <typename T, int N, int NSUB, bool SWAP, bool FUSE>
+// CTA-pair weight multicast (cluster of 2) is OFF by default: measured on B200 it changes nothing (bf16 128 -> 128 at
+// 512 x 640 x 16: 1442 TFLOP/s with it, 1462 without).  The L2 -> SM path is the limiter of these layers (the PROF build
+// gains 18 % with the weight stream removed), but a multicast to fewer than ~8 CTAs is not deduplicated in L2 on this
+// part, so a pair saves no L2 bandwidth.  USE_B200_CONV_MC=2 enables it for A/B measurements.
+static int multicast_width() {
+  static int mc = [] {
+    const char* v = getenv("USE_B200_CONV_MC");
+    return (v && v[0] == '2') ? 2 : 1;
+  }();
+  return mc;
+}
+
+template <typename T, int N, int NSUB, bool SWAP, bool FUSE, int MC, bool PROF>
 static void set_kernel(TcConvPlan* p) {
   using C = ConvCfg<T, N, NSUB, FUSE>;
-  auto k = &conv_tc_kernel<T, N, NSUB, SWAP, FUSE>;
+  auto k = &conv_tc_kernel<T, N, NSUB, SWAP, FUSE, MC, PROF>;
   p->kernel = reinterpret_cast<const void*>(k);
   cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES);
   p->threads = C::THREADS;
   p->smem = C::SMEM_BYTES;
   p->nsub = NSUB;
+  p->mc = MC;
 }
 
 template <typename T, int N, int NSUB>
 static void fill_kernel(TcConvPlan* p, bool fuse) {
-  if constexpr (N == 128 && NSUB == 2) {
-    if (swap_ab_enabled()) {
-      if (fuse) set_kernel<T, N, NSUB, true, true>(p);
-      else set_kernel<T, N, NSUB, true, false>(p);
+  constexpr bool SWAP = (N == 128 && NSUB == 2);  // swap-AB for C_out = 128 (conv_tc.cuh)
+  const bool mc2 = multicast_width() == 2;
+  if constexpr (SWAP) {
+    if (getenv("USE_B200_CONV_PROF")) {
+      // instrumented build of the C_out = 128 kernel (tools/conv_bench.py): per-role mbarrier stall cycles
+      if (fuse) { if (mc2) set_kernel<T, N, NSUB, SWAP, true, 2, true>(p); else set_kernel<T, N, NSUB, SWAP, true, 1, true>(p); }
+      else { if (mc2) set_kernel<T, N, NSUB, SWAP, false, 2, true>(p); else set_kernel<T, N, NSUB, SWAP, false, 1, true>(p); }
+      if (const char* v = getenv("USE_B200_CONV_DBG")) p->params.dbg = atoi(v);
+      cudaMalloc(&p->params.prof, 16 * sizeof(unsigned long long));
+      cudaMemset(p->params.prof, 0, 16 * sizeof(unsigned long long));
       return;
     }
   }
-  if constexpr (N >= 64) {
-    if (fuse) { set_kernel<T, N, NSUB, false, true>(p); return; }
-  }
-  set_kernel<T, N, NSUB, false, false>(p);
+  if (fuse) { if (mc2) set_kernel<T, N, NSUB, SWAP, true, 2, false>(p); else set_kernel<T, N, NSUB, SWAP, true, 1, false>(p); }
+  else { if (mc2) set_kernel<T, N, NSUB, SWAP, false, 2, false>(p); else set_kernel<T, N, NSUB, SWAP, false, 1, false>(p); }
 }
 
-bool tc_conv_supported(int dt, int N) { return N == 32 || N == 64 || N == 128 || N == 256; }
+bool tc_conv_supported(int dt, int N) { return N == 64 || N == 128 || N == 256; }
 
 TcConvPlan* tc_conv_plan_create(int dt, const TcConvDesc& d, int num_sms, char* err, int errlen) {
-  if (!tc_conv_supported(dt, d.N) || ((d.N == 32) != (d.out4 != nullptr))) {
-    snprintf(err, errlen, "tcgen05 conv: unsupported C_out=%d (out4 %s)", d.N, d.out4 ? "set" : "unset");
+  if (!tc_conv_supported(dt, d.N)) {
+    snprintf(err, errlen, "tcgen05 conv: unsupported C_out=%d", d.N);
     return nullptr;
   }
   TcConvPlan* p = new TcConvPlan();
@@ -125,21 +142,14 @@ TcConvPlan* tc_conv_plan_create(int dt, const TcConvDesc& d, int num_sms, char* 
   p->N = d.N;
   bool fuse = false;
   for (int i = 0; i < d.nseg; ++i) fuse = fuse || d.seg[i].aff != nullptr;
-  if (fuse && d.N < 64) {
-    snprintf(err, errlen, "tcgen05 conv: fused GroupNorm operands need C_out >= 64");
-    delete p;
-    return nullptr;
-  }
   if (dt == kBF16) {
     if (d.N == 256) fill_kernel<__nv_bfloat16, 256, 1>(p, fuse);
     else if (d.N == 128) fill_kernel<__nv_bfloat16, 128, 2>(p, fuse);
-    else if (d.N == 64) fill_kernel<__nv_bfloat16, 64, 2>(p, fuse);
-    else fill_kernel<__nv_bfloat16, 32, 2>(p, fuse);
+    else fill_kernel<__nv_bfloat16, 64, 2>(p, fuse);
   } else {
     if (d.N == 256) fill_kernel<float, 256, 1>(p, fuse);
     else if (d.N == 128) fill_kernel<float, 128, 2>(p, fuse);
-    else if (d.N == 64) fill_kernel<float, 64, 2>(p, fuse);
-    else fill_kernel<float, 32, 2>(p, fuse);
+    else fill_kernel<float, 64, 2>(p, fuse);
   }
   const int ck = 128 / (int)act_size(dt);
   const int tile_h = 16 * p->nsub;
@@ -160,7 +170,8 @@ TcConvPlan* tc_conv_plan_create(int dt, const TcConvDesc& d, int num_sms, char* 
     }
     const int rows = s.taps == 9 ? tile_h + 2 : tile_h, cols = s.taps == 9 ? 10 : 8;
     if (!encode_act(&P.seg[i].tmA, dt, s.act, d.B, d.H, d.W, s.C_tensor, cols, rows, err, errlen) ||
-        !encode_w(&P.seg[i].tmW, dt, s.w, s.taps, d.N, s.Cw_total, d.N, err, errlen)) {
+        !encode_w(&P.seg[i].tmW, dt, s.w, s.taps, d.N, s.Cw_total, d.N, err, errlen) ||
+        !encode_w(&P.seg[i].tmWh, dt, s.w, s.taps, d.N, s.Cw_total, d.N / 2, err, errlen)) {
       delete p;
       return nullptr;
     }
@@ -180,12 +191,25 @@ TcConvPlan* tc_conv_plan_create(int dt, const TcConvDesc& d, int num_sms, char* 
   P.ntiles = P.tiles_w * P.tiles_h * d.B;
   P.out = d.out; P.bias = d.bias; P.bias_bstride = d.bias_bstride; P.res = d.res; P.scale = d.scale;
   P.stats_acc = d.stats_acc;
-  P.out4 = d.out4; P.prev4 = d.prev4; P.out_pc = d.out_pc ? d.out_pc : 4;
-  p->grid = P.ntiles < num_sms ? P.ntiles : num_sms;  // persistent CTAs, one per SM
+  const int units = (P.ntiles + p->mc - 1) / p->mc;  // tile groups
+  const int max_groups = num_sms / p->mc;
+  p->grid = (units < max_groups ? units : max_groups) * p->mc;  // persistent CTAs, one per SM, a multiple of the cluster
   return p;
 }
 
-void tc_conv_plan_destroy(TcConvPlan* p) { delete p; }
+void tc_conv_plan_destroy(TcConvPlan* p) {
+  if (p && p->params.prof) {
+    unsigned long long h[16];
+    cudaMemcpy(h, p->params.prof, sizeof(h), cudaMemcpyDeviceToHost);
+    const double g = p->grid;
+    fprintf(stderr,
+            "USE_B200_CONV_PROF per-CTA mean cycles: mma total %.0f wait[t_empty %.0f a_full %.0f b_full %.0f] | tma total %.0f "
+            "wait[a_empty %.0f b_empty %.0f] | epi total %.0f wait[t_full %.0f] | xf total %.0f wait[a_raw %.0f]\n",
+            h[3] / g, h[0] / g, h[1] / g, h[2] / g, h[6] / g, h[4] / g, h[5] / g, h[8] / g, h[7] / g, h[10] / g, h[9] / g);
+    cudaFree(p->params.prof);
+  }
+  delete p;
+}
 
 // ---- pyramid head (head_tc.cuh) ---------------------------------------------------------------------------
 struct HeadPlan {
@@ -263,8 +287,13 @@ void tc_conv_launch(const TcConvPlan* p, cudaStream_t st) {
   cfg.blockDim = dim3(p->threads);
   cfg.dynamicSmemBytes = p->smem;
   cfg.stream = st;
-  cfg.attrs = nullptr;
-  cfg.numAttrs = 0;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = p->mc;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
   cudaLaunchKernelExC(&cfg, p->kernel, args);
 }
 

@@ -33,6 +33,7 @@ namespace use {
 struct alignas(64) ConvSeg {
   CUtensorMap tmA;  // rank 4 {C, W, H, B}; 3x3: box {CK, 10, 16*NSUB+2, 1}; 1x1: box {CK, 8, 16*NSUB, 1}
   CUtensorMap tmW;  // rank 3 {C_total, N, taps}, box {CK, N, 1}
+  CUtensorMap tmWh; // same tensor, box {CK, N/2, 1}: the half each CTA of a pair loads and multicasts
   int nchunks;      // channels of this segment / CK
   int taps;         // 9 or 1
   int wc0;          // first weight channel of this segment inside tmW (concatenated inputs)
@@ -56,11 +57,22 @@ struct alignas(64) ConvParams {
   const void* res;    // optional residual, T [B][H][W][N]
   float scale;        // out = (acc + bias [+ res]) * scale
   long long* stats_acc;  // optional [B][N][2] fixed-point accumulators (zero on entry): sum / sum of squares of `out`
-  // "pyramid head" mode (N = 32, only output channels 0..3 are real): fp32 [B][H][W][4] = acc + bias (+ FIR-up(prev4))
-  float* out4;
-  const float* prev4;    // optional fp32 [B][H/2][W/2][out_pc]
-  int out_pc;            // real output channels of the head (4 or 2)
+  unsigned long long* prof;  // PROF kernels only: per-role stall counters (tools/conv_bench.py --prof)
+  int dbg;                   // PROF kernels only (USE_B200_CONV_DBG): 1 = epilogue skips TMEM loads and stores, 2 = epilogue
+                             // loads TMEM but stores nothing, 4 = transform skips its in-place pass
 };
+
+// PROF instrumentation: cycles a role's elected thread spends inside an mbarrier wait
+template <bool PROF>
+__device__ __forceinline__ void mbar_wait_p(uint64_t* bar, uint32_t parity, long long& acc) {
+  if constexpr (PROF) {
+    const long long t0 = clock64();
+    mbar_wait(bar, parity);
+    acc += clock64() - t0;
+  } else {
+    mbar_wait(bar, parity);
+  }
+}
 
 template <typename T, int N, int NSUB, bool FUSE>
 struct ConvCfg {
@@ -75,7 +87,7 @@ struct ConvCfg {
   static constexpr int B_TILE = N * 128;
   // plain: 2 windows (loading / consumed).  fused: 3 (TMA loading the raw window / being normalised in place / consumed)
   static constexpr int A_SLOTS = FUSE ? 3 : 2;
-  static constexpr int B_SLOTS = (N == 256) ? (FUSE ? 4 : 5) : (N == 128 ? (FUSE ? 5 : 7) : 8);  // N <= 64: 8 slots
+  static constexpr int B_SLOTS = (N == 256) ? (FUSE ? 4 : 5) : (N == 128 ? (FUSE ? 5 : 8) : 8);  // N <= 64: 8 slots
   static constexpr int ACC_COLS = NSUB * N;
   static constexpr int TMEM_COLS = (2 * ACC_COLS < 32) ? 32 : 2 * ACC_COLS;
   static constexpr int EPI_WARPS = 4 * NSUB;
@@ -96,7 +108,15 @@ struct ConvCfg {
 // operand -- one MMA reads 4 + 8 KB per 128 cycles (96 B/clk, the profile of the C_out = 256 layers).  The accumulator
 // is then channel-major (TMEM lane = output channel, column = pixel); the epilogue stores 32 consecutive channels per
 // pixel per warp, and per-channel GroupNorm statistics become in-register sums.
-template <typename T, int N, int NSUB, bool SWAP, bool FUSE>
+//
+// MC = 2: CTA pairs (cluster of 2).  Every tile re-reads the layer's whole weight tensor (295 KB for 128 -> 128 in bf16)
+// from L2, and with 148 CTAs doing so the L2 -> SM weight stream is what the MMA issuer waits for (measured with the
+// PROF build: 25 % of its time in b_full waits, 1 % in a_full).  Both CTAs of a pair walk their own tiles through the
+// same weight-tile sequence; each loads HALF of every weight tile and multicasts it into both CTAs' shared memory,
+// which halves that stream.  A weight slot is recycled only when the MMAs of BOTH CTAs have released it (b_empty
+// counts 2 arrivals, one of them a multicast tcgen05.commit from the peer).  A CTA whose tile index falls past the end
+// processes a "ghost" tile (loads are zero-filled out of bounds, nothing is stored) to keep the pair in lockstep.
+template <typename T, int N, int NSUB, bool SWAP, bool FUSE, int MC = 1, bool PROF = false>
 __global__ void __launch_bounds__(ConvCfg<T, N, NSUB, FUSE>::THREADS, 1) conv_tc_kernel(const __grid_constant__ ConvParams p) {
   using C = ConvCfg<T, N, NSUB, FUSE>;
   static_assert(!SWAP || (N == 128 && NSUB == 2), "swap-AB is built for C_out = 128, 256-pixel tiles");
@@ -123,9 +143,10 @@ __global__ void __launch_bounds__(ConvCfg<T, N, NSUB, FUSE>::THREADS, 1) conv_tc
     for (int i = 0; i < p.nseg; ++i) {
       prefetch_tmap(&p.seg[i].tmA);
       prefetch_tmap(&p.seg[i].tmW);
+      prefetch_tmap(&p.seg[i].tmWh);
     }
     for (int i = 0; i < C::A_SLOTS; ++i) { mbar_init(&a_full[i], 1); mbar_init(&a_empty[i], 1); mbar_init(&a_raw[i], 1); }
-    for (int i = 0; i < C::B_SLOTS; ++i) { mbar_init(&b_full[i], 1); mbar_init(&b_empty[i], 1); }
+    for (int i = 0; i < C::B_SLOTS; ++i) { mbar_init(&b_full[i], 1); mbar_init(&b_empty[i], MC); }
     for (int i = 0; i < 2; ++i) { mbar_init(&t_full[i], 1); mbar_init(&t_empty[i], C::EPI_WARPS); }
     fence_barrier_init();
   }
@@ -135,11 +156,16 @@ __global__ void __launch_bounds__(ConvCfg<T, N, NSUB, FUSE>::THREADS, 1) conv_tc
   }
   tc_fence_before();
   __syncthreads();
+  if constexpr (MC > 1) cluster_sync_all();  // the peer's barriers are initialised before anything targets them
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
   const int tiles_per_img = p.tiles_w * p.tiles_h;
-  const int g0 = blockIdx.x, gstep = gridDim.x;
+  // tile groups of MC consecutive tiles: CTA `crank` of a pair takes tile group * MC + crank.  T0 / TSTEP / TEND walk the
+  // tile index of THIS CTA; TEND is rounded up so both CTAs of a pair run the same number of iterations.
+  const int crank = MC > 1 ? static_cast<int>(cluster_ctarank()) : 0;
+  const int T0 = (blockIdx.x / MC) * MC + crank, TSTEP = (gridDim.x / MC) * MC;
+  const int TEND = (p.ntiles + MC - 1) / MC * MC;
 
   if (warp == 0) {
     // ================================ TMA producer ================================
@@ -148,12 +174,14 @@ __global__ void __launch_bounds__(ConvCfg<T, N, NSUB, FUSE>::THREADS, 1) conv_tc
     // raw window of a fused segment lands -- and is normalised in place by the transform warps -- well before its MMAs.
     if (lane == 0) {
       // window-stream cursor
-      int a_tile = g0, a_sg = 0, a_kc = 0;
+      int a_tile = T0, a_sg = 0, a_kc = 0;
       uint32_t ai = 0;
-      auto a_pending = [&]() { return a_tile < p.ntiles; };
+      long long w_a = 0, w_b = 0;
+      const long long t_begin = PROF ? clock64() : 0;
+      auto a_pending = [&]() { return a_tile < TEND; };
       auto a_issue = [&](bool blocking) -> bool {
         const uint32_t as = ai % C::A_SLOTS, aph = (ai / C::A_SLOTS) & 1;
-        if (blocking) mbar_wait(&a_empty[as], aph ^ 1);
+        if (blocking) mbar_wait_p<PROF>(&a_empty[as], aph ^ 1, w_a);
         else if (!mbar_try_wait(&a_empty[as], aph ^ 1)) return false;
         const ConvSeg& S = p.seg[a_sg];
         const int b = a_tile / tiles_per_img;
@@ -167,12 +195,12 @@ __global__ void __launch_bounds__(ConvCfg<T, N, NSUB, FUSE>::THREADS, 1) conv_tc
         ++ai;
         if (++a_kc == S.nchunks) {
           a_kc = 0;
-          if (++a_sg == p.nseg) { a_sg = 0; a_tile += gstep; }
+          if (++a_sg == p.nseg) { a_sg = 0; a_tile += TSTEP; }
         }
         return true;
       };
       uint32_t bi = 0, bj = 0;  // weight tiles issued, chunks whose weights have been issued
-      for (int tile = g0; tile < p.ntiles; tile += gstep) {
+      for (int tile = T0; tile < TEND; tile += TSTEP) {
         for (int sg = 0; sg < p.nseg; ++sg) {
           const ConvSeg& S = p.seg[sg];
           const bool k3 = S.taps == 9;
@@ -180,16 +208,26 @@ __global__ void __launch_bounds__(ConvCfg<T, N, NSUB, FUSE>::THREADS, 1) conv_tc
             while (ai <= bj) a_issue(true);  // the window of this chunk is always issued before its weights
             for (int tap = 0; tap < S.taps; ++tap) {
               if (a_pending() && ai < bj + C::A_SLOTS) a_issue(false);
+              if constexpr (PROF) { if (p.dbg & 8) continue; }
               const uint32_t bs = bi % C::B_SLOTS, bph = (bi / C::B_SLOTS) & 1;
-              mbar_wait(&b_empty[bs], bph ^ 1);
+              mbar_wait_p<PROF>(&b_empty[bs], bph ^ 1, w_b);
               mbar_arrive_expect_tx(&b_full[bs], C::B_TILE);
               // tap order s-major (s = tap / 3, r = tap % 3): the accumulation order of the previous 3-copy kernel
-              tma_load_3d(sB + bs * C::B_TILE, &S.tmW, &b_full[bs], S.wc0 + kc * C::CK, 0,
-                          k3 ? ((tap % 3) * 3 + tap / 3) : 0);
+              const int wtap = k3 ? ((tap % 3) * 3 + tap / 3) : 0;
+              if constexpr (MC > 1)
+                tma_load_3d_mc(sB + bs * C::B_TILE + crank * (C::B_TILE / 2), &S.tmWh, &b_full[bs], S.wc0 + kc * C::CK,
+                               crank * (N / 2), wtap, uint16_t(3));
+              else
+                tma_load_3d(sB + bs * C::B_TILE, &S.tmW, &b_full[bs], S.wc0 + kc * C::CK, 0, wtap);
               ++bi;
             }
           }
         }
+      }
+      if constexpr (PROF) {
+        atomicAdd(p.prof + 4, static_cast<unsigned long long>(w_a));
+        atomicAdd(p.prof + 5, static_cast<unsigned long long>(w_b));
+        atomicAdd(p.prof + 6, static_cast<unsigned long long>(clock64() - t_begin));
       }
     }
   } else if (warp == 1) {
@@ -198,9 +236,11 @@ __global__ void __launch_bounds__(ConvCfg<T, N, NSUB, FUSE>::THREADS, 1) conv_tc
       constexpr uint32_t idesc = SWAP ? umma_idesc(kBf16 ? 1 : 2, 128, 128 * NSUB) : umma_idesc(kBf16 ? 1 : 2, 128, N);
       const uint32_t sA_addr = smem_u32(sA), sB_addr = smem_u32(sB);
       uint32_t ai = 0, bi = 0, ti = 0;
-      for (int tile = g0; tile < p.ntiles; tile += gstep, ++ti) {
+      long long w_t = 0, w_a = 0, w_b = 0;
+      const long long t_begin = PROF ? clock64() : 0;
+      for (int tile = T0; tile < TEND; tile += TSTEP, ++ti) {
         const uint32_t acs = ti & 1, acph = (ti >> 1) & 1;
-        mbar_wait(&t_empty[acs], acph ^ 1);
+        mbar_wait_p<PROF>(&t_empty[acs], acph ^ 1, w_t);
         tc_fence_after();
         bool first = true;
         for (int sg = 0; sg < p.nseg; ++sg) {
@@ -209,11 +249,13 @@ __global__ void __launch_bounds__(ConvCfg<T, N, NSUB, FUSE>::THREADS, 1) conv_tc
           const uint32_t sbo = k3 ? C::WIN_PITCH : 1024;
           for (int kc = 0; kc < S.nchunks; ++kc) {
             const uint32_t as = ai % C::A_SLOTS, aph = (ai / C::A_SLOTS) & 1;
-            mbar_wait(&a_full[as], aph);
+            mbar_wait_p<PROF>(&a_full[as], aph, w_a);
             for (int tap = 0; tap < S.taps; ++tap) {
               const int s = tap / 3, r = tap - s * 3;  // (0, 0) for a 1x1 segment
               const uint32_t bs = bi % C::B_SLOTS, bph = (bi / C::B_SLOTS) & 1;
-              mbar_wait(&b_full[bs], bph);
+              bool dbg_nob = false;
+              if constexpr (PROF) dbg_nob = (p.dbg & 8) != 0;
+              if (!dbg_nob) mbar_wait_p<PROF>(&b_full[bs], bph, w_b);
               tc_fence_after();
               const uint32_t win = sA_addr + as * C::A_SLOT + (k3 ? (r * C::WIN_W + s) * 128 : 0);
               if constexpr (SWAP) {
@@ -236,7 +278,9 @@ __global__ void __launch_bounds__(ConvCfg<T, N, NSUB, FUSE>::THREADS, 1) conv_tc
                 }
               }
               first = false;
-              umma_commit(&b_empty[bs]);
+              if (dbg_nob) {
+              } else if constexpr (MC > 1) umma_commit_mc(&b_empty[bs], uint16_t(3));
+              else umma_commit(&b_empty[bs]);
               ++bi;
             }
             umma_commit(&a_empty[as]);
@@ -244,6 +288,12 @@ __global__ void __launch_bounds__(ConvCfg<T, N, NSUB, FUSE>::THREADS, 1) conv_tc
           }
         }
         umma_commit(&t_full[acs]);
+      }
+      if constexpr (PROF) {
+        atomicAdd(p.prof + 0, static_cast<unsigned long long>(w_t));
+        atomicAdd(p.prof + 1, static_cast<unsigned long long>(w_a));
+        atomicAdd(p.prof + 2, static_cast<unsigned long long>(w_b));
+        atomicAdd(p.prof + 3, static_cast<unsigned long long>(clock64() - t_begin));
       }
     }
   } else if (threadIdx.x >= C::XF_T0) {
@@ -259,7 +309,9 @@ __global__ void __launch_bounds__(ConvCfg<T, N, NSUB, FUSE>::THREADS, 1) conv_tc
     const int tt = threadIdx.x - C::XF_T0;
     const int v = tt & 7, pb = tt >> 3;
     uint32_t ai = 0, rawph = 0;  // rawph: phase parity of a_raw per slot (it only advances on fused fills)
-    for (int tile = g0; tile < p.ntiles; tile += gstep) {
+    long long w_r = 0;
+    const long long t_begin = PROF ? clock64() : 0;
+    for (int tile = T0; tile < TEND; tile += TSTEP) {
       const int b = tile / tiles_per_img;
       const int rem = tile - b * tiles_per_img;
       const int th = rem / p.tiles_w;
@@ -271,7 +323,7 @@ __global__ void __launch_bounds__(ConvCfg<T, N, NSUB, FUSE>::THREADS, 1) conv_tc
         const int q = pb + PSTEP * i;
         const int row = q / C::WIN_W, col = q - row * C::WIN_W;
         const int hh = h0 - 1 + row, ww = w0 - 1 + col;
-        if (q < C::NPIX && hh >= 0 && hh < p.H && ww >= 0 && ww < p.W) inside |= 1u << i;
+        if (tile < p.ntiles && q < C::NPIX && hh >= 0 && hh < p.H && ww >= 0 && ww < p.W) inside |= 1u << i;
       }
       for (int sg = 0; sg < p.nseg; ++sg) {
         const ConvSeg& S = p.seg[sg];
@@ -280,6 +332,9 @@ __global__ void __launch_bounds__(ConvCfg<T, N, NSUB, FUSE>::THREADS, 1) conv_tc
         for (int kc = 0; kc < S.nchunks; ++kc, ++ai) {
           float sc[V], sh[V];
 #pragma unroll
+          for (int j = 0; j < V; ++j) sc[j] = sh[j] = 0.f;
+          if (inside != 0)  // (a ghost tile has no pixel inside the image and no sample to take the table from)
+#pragma unroll
           for (int j = 0; j < V; j += 4) {
             const float4 a = __ldg(reinterpret_cast<const float4*>(aff + kc * C::CK + j));
             const float4 c = __ldg(reinterpret_cast<const float4*>(aff + S.aff_C + kc * C::CK + j));
@@ -287,12 +342,14 @@ __global__ void __launch_bounds__(ConvCfg<T, N, NSUB, FUSE>::THREADS, 1) conv_tc
             sh[j] = c.x; sh[j + 1] = c.y; sh[j + 2] = c.z; sh[j + 3] = c.w;
           }
           const uint32_t as = ai % C::A_SLOTS;
-          mbar_wait(&a_raw[as], (rawph >> as) & 1u);
+          mbar_wait_p<PROF>(&a_raw[as], (rawph >> as) & 1u, w_r);
           rawph ^= 1u << as;
           uint8_t* slot = sA + as * C::A_SLOT;  // 1024-byte aligned: the swizzle phase of window pixel q is q & 7
+          bool dbg_noxf = false;
+          if constexpr (PROF) dbg_noxf = (p.dbg & 4) != 0;
 #pragma unroll
           for (int i = 0; i < NIT; ++i) {
-            if ((inside >> i) & 1u) {
+            if (((inside >> i) & 1u) && !dbg_noxf) {
               const int q = pb + PSTEP * i;
               uint4* ptr = reinterpret_cast<uint4*>(slot + q * 128 + ((v ^ (q & 7)) << 4));
               float f[V];
@@ -308,6 +365,12 @@ __global__ void __launch_bounds__(ConvCfg<T, N, NSUB, FUSE>::THREADS, 1) conv_tc
         }
       }
     }
+    if constexpr (PROF) {
+      if (tt == 0) {
+        atomicAdd(p.prof + 9, static_cast<unsigned long long>(w_r));
+        atomicAdd(p.prof + 10, static_cast<unsigned long long>(clock64() - t_begin));
+      }
+    }
     }  // FUSE
   } else {
     // ================================ epilogue ================================
@@ -319,9 +382,11 @@ __global__ void __launch_bounds__(ConvCfg<T, N, NSUB, FUSE>::THREADS, 1) conv_tc
     T* out = reinterpret_cast<T*>(p.out);
     const T* res = reinterpret_cast<const T*>(p.res);
     uint32_t ti = 0;
-    for (int tile = g0; tile < p.ntiles; tile += gstep, ++ti) {
-      constexpr bool ghost = false;
-      const int b = tile / tiles_per_img;
+    long long w_f = 0;
+    const long long t_begin = PROF ? clock64() : 0;
+    for (int tile = T0; tile < TEND; tile += TSTEP, ++ti) {
+      const bool ghost = tile >= p.ntiles;
+      const int b = ghost ? 0 : tile / tiles_per_img;
       const int rem = tile - (tile / tiles_per_img) * tiles_per_img;
       const int th = rem / p.tiles_w;
       const int w = (rem - th * p.tiles_w) * C::TILE_W + wl;
@@ -346,9 +411,12 @@ __global__ void __launch_bounds__(ConvCfg<T, N, NSUB, FUSE>::THREADS, 1) conv_tc
           }
         }
       }
-      mbar_wait(&t_full[acs], acph);
+      mbar_wait_p<PROF>(&t_full[acs], acph, w_f);
       tc_fence_after();
-      if constexpr (SWAP) {
+      bool dbg_skip = false, dbg_nostore = false;
+      if constexpr (PROF) { dbg_skip = (p.dbg & 1) != 0; dbg_nostore = (p.dbg & 2) != 0; }
+      if (dbg_skip) {
+      } else if constexpr (SWAP) {
         // channel-major accumulator: this thread = output channel quad*32 + lane; warp half `sub` owns pixel columns
         // [128*sub, 128*sub + 128) of the 256-pixel tile = tile rows [16*sub, 16*sub + 16).  Every pixel is written
         // by one warp-wide store of 32 consecutive channels (64 B bf16 / 128 B fp32): no transposition needed, and the
@@ -405,7 +473,7 @@ __global__ void __launch_bounds__(ConvCfg<T, N, NSUB, FUSE>::THREADS, 1) conv_tc
               const int idx = 2 * k + (odd ? 1 : 0), i = idx >> 3, j = idx & 7;
               if ((th0 + row0 + i < p.H) && ((wmask >> j) & 1u)) {
                 const __nv_bfloat162 pk = __floats2bfloat162_rn(lo, hi);
-                *reinterpret_cast<__nv_bfloat162*>(ob2 + (row0 + i) * rowstride + static_cast<size_t>(j) * N) = pk;
+                if (!dbg_nostore) *reinterpret_cast<__nv_bfloat162*>(ob2 + (row0 + i) * rowstride + static_cast<size_t>(j) * N) = pk;
                 s2[0] += lo; q2[0] = fmaf(lo, lo, q2[0]);
                 s2[1] += hi; q2[1] = fmaf(hi, hi, q2[1]);
               }
@@ -464,44 +532,6 @@ __global__ void __launch_bounds__(ConvCfg<T, N, NSUB, FUSE>::THREADS, 1) conv_tc
         }  // fp32 direct stores
       } else {
       const uint32_t trow = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + acs * C::ACC_COLS + sub * N;
-      if (p.out4 != nullptr) {
-        // pyramid head: 4 real output channels, fp32, + FIR-upsampled previous pyramid (ncsnpp.py:440-461)
-        uint32_t r[32];
-        tmem_ld32(trow, r);
-        tmem_ld_wait();
-        if (valid) {
-          float o[4] = {__uint_as_float(r[0]) + bias[0], __uint_as_float(r[1]) + bias[1], __uint_as_float(r[2]) + bias[2],
-                        __uint_as_float(r[3]) + bias[3]};
-          const int pc = p.out_pc;
-          if (p.prev4 != nullptr) {
-            const int Hp = p.H >> 1, Wp = p.W >> 1;
-            const int my = h >> 1, mx = w >> 1;
-            const int ya = (h & 1) ? my : my - 1, xa = (w & 1) ? mx : mx - 1;
-            const float wya = (h & 1) ? 0.75f : 0.25f, wxa = (w & 1) ? 0.75f : 0.25f;
-#pragma unroll
-            for (int dy = 0; dy < 2; ++dy) {
-              const int yy = ya + dy;
-              if (yy < 0 || yy >= Hp) continue;
-#pragma unroll
-              for (int dx = 0; dx < 2; ++dx) {
-                const int xx = xa + dx;
-                if (xx < 0 || xx >= Wp) continue;
-                const float kw = (dy ? 1.f - wya : wya) * (dx ? 1.f - wxa : wxa);
-                const float* pv = p.prev4 + ((static_cast<size_t>(b) * Hp + yy) * Wp + xx) * pc;
-                if (pc == 4) {
-                  const float4 q = __ldg(reinterpret_cast<const float4*>(pv));
-                  o[0] += kw * q.x; o[1] += kw * q.y; o[2] += kw * q.z; o[3] += kw * q.w;
-                } else {
-                  const float2 q = __ldg(reinterpret_cast<const float2*>(pv));
-                  o[0] += kw * q.x; o[1] += kw * q.y;
-                }
-              }
-            }
-          }
-          if (pc == 4) reinterpret_cast<float4*>(p.out4)[pix] = make_float4(o[0], o[1], o[2], o[3]);
-          else reinterpret_cast<float2*>(p.out4)[pix] = make_float2(o[0], o[1]);
-        }
-      } else
 #pragma unroll 1
       for (int c0 = 0; c0 < N; c0 += 32) {
         constexpr int V = DT<T>::kVec;
@@ -597,10 +627,17 @@ __global__ void __launch_bounds__(ConvCfg<T, N, NSUB, FUSE>::THREADS, 1) conv_tc
         asm volatile("bar.sync 1, %0;" ::"r"(ET) : "memory");
       }
     }
+    if constexpr (PROF) {
+      if (threadIdx.x == 64) {
+        atomicAdd(p.prof + 7, static_cast<unsigned long long>(w_f));
+        atomicAdd(p.prof + 8, static_cast<unsigned long long>(clock64() - t_begin));
+      }
+    }
   }
 
   tc_fence_before();
   __syncthreads();
+  if constexpr (MC > 1) cluster_sync_all();  // no CTA leaves while its peer may still multicast into it
   if (warp == 1) tmem_dealloc(tmem_base, C::TMEM_COLS);
 }
 

@@ -717,53 +717,89 @@ void launch_conv_out4(int dt, const void* a, const float* w, const float* bias, 
 }
 
 // ------------------------------------------------------------------------------------------------
-// Combine(sum): out = h + bias + W[C][4] . pyr
+// Combine(sum): out = h + bias + W[C][pc] . pyr  (layerspp.py:50-55), optionally with the per-channel GroupNorm
+// statistics of `out` (fixed point, like the conv epilogue) so the next ResBlock needs no separate statistics pass.
+// One thread owns a 16-byte channel vector (its weights and bias live in registers) and walks over the pixels of the
+// block's fixed range: the block partition does not depend on the batch, so the statistics are batch-invariant.
 // ------------------------------------------------------------------------------------------------
+constexpr int kCombinePixPerBlock = 1024;
+
 template <typename T, int PC>
 __global__ void __launch_bounds__(256) combine_kernel(const T* __restrict__ h, const float* __restrict__ pyr,
                                                        const float* __restrict__ w, const float* __restrict__ bias,
-                                                       T* __restrict__ out, int C, long long total) {
+                                                       T* __restrict__ out, long long* __restrict__ stats, int HW, int C) {
   constexpr int V = Vec<T>::N;
+  extern __shared__ float sred[];  // [rows][C][2]
   const int vpp = C / V;
-  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
-       i += static_cast<long long>(gridDim.x) * blockDim.x) {
-    const int cv = static_cast<int>(i % vpp);
-    const long long pix = i / vpp;
-    float pv[PC];
-    if constexpr (PC == 4) {
-      const float4 q = __ldg(reinterpret_cast<const float4*>(pyr) + pix);
-      pv[0] = q.x; pv[1] = q.y; pv[2] = q.z; pv[3] = q.w;
-    } else {
-      const float2 q = __ldg(reinterpret_cast<const float2*>(pyr) + pix);
-      pv[0] = q.x; pv[1] = q.y;
+  const int rows = blockDim.x / vpp;
+  const int cv = threadIdx.x % vpp, prow = threadIdx.x / vpp;
+  const int b = blockIdx.y;
+  const int p0 = blockIdx.x * kCombinePixPerBlock, p1 = min(HW, p0 + kCombinePixPerBlock);
+  float wv[V][PC], bv[V];
+#pragma unroll
+  for (int j = 0; j < V; ++j) {
+    bv[j] = bias[cv * V + j];
+#pragma unroll
+    for (int k = 0; k < PC; ++k) wv[j][k] = w[(cv * V + j) * PC + k];
+  }
+  float s[V], q[V];
+#pragma unroll
+  for (int j = 0; j < V; ++j) s[j] = q[j] = 0.f;
+  const size_t base = static_cast<size_t>(b) * HW;
+  if (prow < rows) {
+    for (int p = p0 + prow; p < p1; p += rows) {
+      float pv[PC];
+      if constexpr (PC == 4) {
+        const float4 t = __ldg(reinterpret_cast<const float4*>(pyr) + base + p);
+        pv[0] = t.x; pv[1] = t.y; pv[2] = t.z; pv[3] = t.w;
+      } else {
+        const float2 t = __ldg(reinterpret_cast<const float2*>(pyr) + base + p);
+        pv[0] = t.x; pv[1] = t.y;
+      }
+      float f[V];
+      Vec<T>::load(h + (base + p) * C + cv * V, f);
+#pragma unroll
+      for (int j = 0; j < V; ++j) {
+        float acc = bv[j];
+        if constexpr (PC == 4) acc += wv[j][0] * pv[0] + wv[j][1] * pv[1] + wv[j][2] * pv[2] + wv[j][3] * pv[3];
+        else acc += wv[j][0] * pv[0] + wv[j][1] * pv[1];
+        f[j] = acc + f[j];  // same association as conv2d then "+ h": (bias + w.p) + h
+        s[j] += f[j];
+        q[j] = fmaf(f[j], f[j], q[j]);
+      }
+      Vec<T>::store(out + (base + p) * C + cv * V, f);
     }
-    float f[V];
-    Vec<T>::load(h + pix * C + cv * V, f);
+  }
+  if (stats == nullptr) return;
+  if (prow < rows) {
 #pragma unroll
     for (int j = 0; j < V; ++j) {
-      const int c = cv * V + j;
-      float acc = bias[c];
-      if constexpr (PC == 4) {
-        const float4 ww = __ldg(reinterpret_cast<const float4*>(w) + c);
-        acc += ww.x * pv[0] + ww.y * pv[1] + ww.z * pv[2] + ww.w * pv[3];
-      } else {
-        const float2 ww = __ldg(reinterpret_cast<const float2*>(w) + c);
-        acc += ww.x * pv[0] + ww.y * pv[1];
-      }
-      f[j] = acc + f[j];  // same association as conv2d then "+ h": (bias + w.p) + h
+      sred[(prow * C + cv * V + j) * 2] = s[j];
+      sred[(prow * C + cv * V + j) * 2 + 1] = q[j];
     }
-    Vec<T>::store(out + pix * C + cv * V, f);
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    double a = 0.0, qq = 0.0;
+    for (int r = 0; r < rows; ++r) {  // fixed order: deterministic
+      a += static_cast<double>(sred[(r * C + c) * 2]);
+      qq += static_cast<double>(sred[(r * C + c) * 2 + 1]);
+    }
+    stat_atomic_add(stats + (static_cast<size_t>(b) * C + c) * 2, a, qq);
   }
 }
 
-void launch_combine(int dt, const void* h, const float* pyr, const float* w, const float* bias, void* out, int B, int HW,
-                    int C, int pc, cudaStream_t st) {
+void launch_combine(int dt, const void* h, const float* pyr, const float* w, const float* bias, void* out, long long* stats,
+                    int B, int HW, int C, int pc, cudaStream_t st) {
   DISPATCH_DT(dt, {
     constexpr int V = Vec<T>::N;
-    const long long total = static_cast<long long>(B) * HW * (C / V);
-    const int blocks = static_cast<int>(std::min<long long>((total + 255) / 256, 148LL * 32));
-    if (pc == 4) combine_kernel<T, 4><<<blocks, 256, 0, st>>>((const T*)h, pyr, w, bias, (T*)out, C, total);
-    else combine_kernel<T, 2><<<blocks, 256, 0, st>>>((const T*)h, pyr, w, bias, (T*)out, C, total);
+    const int vpp = C / V;
+    const int threads = vpp >= 256 ? vpp : (256 / vpp) * vpp;
+    const int rows = threads / vpp;
+    dim3 grid((HW + kCombinePixPerBlock - 1) / kCombinePixPerBlock, B);
+    const size_t sm = static_cast<size_t>(rows) * C * 2 * sizeof(float);
+    if (pc == 4) combine_kernel<T, 4><<<grid, threads, sm, st>>>((const T*)h, pyr, w, bias, (T*)out, stats, HW, C);
+    else combine_kernel<T, 2><<<grid, threads, sm, st>>>((const T*)h, pyr, w, bias, (T*)out, stats, HW, C);
   });
 }
 

@@ -704,11 +704,17 @@ struct Builder {
           const float *cw = wf(p + ".w"), *cb = wf(p + ".b");
           void* hp = ws(h.off);
           const int HW = h.H * h.W, C = h.C;
+          // the Combine kernel also produces the GroupNorm statistics of its output (the next ResBlock's GroupNorm_0)
+          h.stats_off = stats_top;
+          long long* hst = stats_ptr(h.stats_off);
           emit([=](cudaStream_t s) {
             launch_fir4_down(src, dst, Bn, H, W, npc, s);
-            launch_combine(dt, hp, dst, cw, cb, hp, Bn, HW, C, npc, s);
+            launch_combine(dt, hp, dst, cw, cb, hp, hst, Bn, HW, C, npc, s);
           }, TAG_SMALL_CONV, 2, 2.0 * Bn * HW * C * 4, 2.0 * Bn * HW * C * es());
+        } else {
+          h.stats_off = stats_top;
         }
+        stats_top += (size_t)B * h.C * 2 * sizeof(long long);
         if (pyr_off != (size_t)-1) arena.release(pyr_off);
         pyr_off = np;
         pH /= 2; pW /= 2;
@@ -1306,8 +1312,14 @@ int use_op_head_tc(int dtype, const void* a, const float* w_oihw_host, const flo
 int use_op_combine(int dtype, const void* h, const float* pyr, const float* w, const float* bias, void* out, int B, int HW,
                    int C, int pc, void* stream) {
   if (pc != 2 && pc != 4) return fail("pc must be 2 or 4");
-  launch_combine(dtype, h, pyr, w, bias, out, B, HW, C, pc, (cudaStream_t)stream);
+  launch_combine(dtype, h, pyr, w, bias, out, nullptr, B, HW, C, pc, (cudaStream_t)stream);
   return cuda_check("use_op_combine");
+}
+int use_op_combine_stats(int dtype, const void* h, const float* pyr, const float* w, const float* bias, void* out,
+                         long long* stats, int B, int HW, int C, int pc, void* stream) {
+  if (pc != 2 && pc != 4) return fail("pc must be 2 or 4");
+  launch_combine(dtype, h, pyr, w, bias, out, stats, B, HW, C, pc, (cudaStream_t)stream);
+  return cuda_check("use_op_combine_stats");
 }
 int use_op_fir4_down(const float* x, float* out, int B, int Hin, int Win, int pc, void* stream) {
   launch_fir4_down(x, out, B, Hin, Win, pc, (cudaStream_t)stream);

@@ -41,8 +41,9 @@ void launch_conv_in4(int dt, const float* x, const float* w, const float* bias, 
 void launch_conv_out4(int dt, const void* a, const float* w, const float* bias, const float* prev, float* out, int B,
                       int H, int W, int C, cudaStream_t st);
 // out = h + bias + conv1x1_{pc->C}(pyr): Combine(method="sum").  w: [C][pc] fp32, pyr fp32 [.][pc].  In place allowed.
-void launch_combine(int dt, const void* h, const float* pyr, const float* w, const float* bias, void* out, int B, int HW,
-                    int C, int pc, cudaStream_t st);
+// stats (optional): fixed-point GroupNorm statistics [B][C][2] of `out`, accumulated (zero it first).
+void launch_combine(int dt, const void* h, const float* pyr, const float* w, const float* bias, void* out, long long* stats,
+                    int B, int HW, int C, int pc, cudaStream_t st);
 // FIR [1,3,3,1] downsample x2 of an fp32 pc-channel map (pc = 2 or 4).
 void launch_fir4_down(const float* x, float* out, int B, int Hin, int Win, int pc, cudaStream_t st);
 void launch_upfirdn2d(const float* in, float* out, int major, int in_h, int in_w, int minor, const float* kernel, int kh,
@@ -138,9 +139,6 @@ struct TcConvDesc {
   const void* res;
   float scale;
   long long* stats_acc;  // optional fixed-point GroupNorm statistics of `out`, [B][N][2], zero on entry
-  float* out4;           // pyramid-head mode (N must be 32): fp32 [B][H][W][out_pc] output instead of `out`
-  const float* prev4;    // optional previous pyramid level, fp32 [B][H/2][W/2][out_pc], FIR-upsampled and added
-  int out_pc;            // real output channels of the head: 4 or 2
 };
 struct TcConvPlan;  // opaque: tensor maps + launch geometry
 // Build (host) the launch plan; returns nullptr and fills err on failure.
