@@ -130,6 +130,11 @@ int use_op_gn_stats(int dtype, const void* x, long long* stats, int B, int HW, i
 int use_op_gn_apply(int dtype, const void* x0, const long long* stats0, int C0, const void* x1, const long long* stats1, int C1,
                     const float* gamma, const float* beta, float eps, int fir, int do_silu, int as_operand, void* out_act,
                     void* out_raw, int B, int Hin, int Win, void* stream);
+/* Same with the scale / shift table of use_op_gn_affine (fp32 [B][2][C0]) for the resampling forms (fir != 0, C1 == 0):
+ * the tiles read the table instead of re-deriving their channels' scale / shift from the statistics. */
+int use_op_gn_apply_aff(int dtype, const void* x0, const long long* stats0, int C0, const void* x1, const long long* stats1,
+                        int C1, const float* gamma, const float* beta, float eps, int fir, int do_silu, int as_operand,
+                        void* out_act, void* out_raw, int B, int Hin, int Win, const float* aff, void* stream);
 /* tcgen05 implicit-GEMM convolution; up to 3 segments summed into one accumulator.
  * seg_act[i]: act tensor [B][H][W][seg_ctensor[i]], channel window [seg_c0, seg_c0+seg_c);
  * seg_w[i]: packed weights [taps][N][seg_cw[i]] in act dtype, window starting at seg_wc0[i].

@@ -238,6 +238,17 @@ def test_groupnorm_silu_fir(dt, C0, C1, fir):
                            out.data_ptr(), raw.data_ptr() if fir else None, B, H, W, stream())
     assert rc == 0, L.use_last_error()
     _sync()
+    if fir and not C1:
+        # the engine's form: scale / shift table precomputed once (use_op_gn_affine) -> bit-identical outputs
+        afft = torch.empty(B, 2, C0, device="cuda", dtype=torch.float32)
+        assert L.use_op_gn_affine(stats[0].data_ptr(), C0, None, 0, gd.data_ptr(), bd.data_ptr(), 1e-6, H * W, afft.data_ptr(), B,
+                                  stream()) == 0
+        out2, raw2 = torch.empty_like(out), torch.empty_like(out)
+        rc = L.use_op_gn_apply_aff(dt, acts[0].data_ptr(), stats[0].data_ptr(), C0, None, None, 0, gd.data_ptr(), bd.data_ptr(),
+                                   1e-6, fir, 1, 0, out2.data_ptr(), raw2.data_ptr(), B, H, W, afft.data_ptr(), stream())
+        assert rc == 0, L.use_last_error()
+        _sync()
+        assert torch.equal(out, out2) and torch.equal(raw, raw2)
     xcat = torch.cat(srcs, 1)
     ref = _gn_ref(xcat, gamma, beta, True)
     ref_raw = xcat

@@ -114,7 +114,47 @@ def main():
         assert rc == 0, L.use_last_error()
         torch.cuda.synchronize()
 
+    def run_fir(dtn, H, W, Cc, fir):
+        dt = BF16 if dtn == "bf16" else F32
+        B = args.batch
+        tdt = torch.bfloat16 if dt == BF16 else torch.float32
+        x = torch.randn(B, H, W, Cc, device="cuda").to(tdt)
+        st = torch.zeros(B, Cc, 2, dtype=torch.int64, device="cuda")
+        assert L.use_op_gn_stats(dt, x.data_ptr(), st.data_ptr(), B, H * W, Cc, stream()) == 0
+        Ho, Wo = (H // 2, W // 2) if fir == 1 else ((H * 2, W * 2) if fir == 2 else (H, W))
+        out = torch.empty(B, Ho, Wo, Cc, device="cuda", dtype=tdt)
+        raw = torch.empty_like(out) if fir else None
+        g, bt = torch.ones(Cc, device="cuda"), torch.zeros(Cc, device="cuda")
+
+        afft = torch.empty(B, 2, Cc, device="cuda", dtype=torch.float32)
+        assert L.use_op_gn_affine(st.data_ptr(), Cc, None, 0, g.data_ptr(), bt.data_ptr(), 1e-6, H * W, afft.data_ptr(), B, stream()) == 0
+
+        def call():
+            rc = L.use_op_gn_apply_aff(dt, x.data_ptr(), st.data_ptr(), Cc, None, None, 0, g.data_ptr(), bt.data_ptr(), 1e-6, fir, 1, 1,
+                                       out.data_ptr(), raw.data_ptr() if fir else None, B, H, W, afft.data_ptr() if fir else None,
+                                       stream())
+            assert rc == 0, L.use_last_error()
+
+        call()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(args.reps):
+            call()
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / args.reps
+        es = 2 if dt == BF16 else 4
+        nbytes = B * H * W * Cc * es + (2 if fir else 1) * B * Ho * Wo * Cc * es
+        print(f"{dtn} gn_apply fir={fir} {H}x{W} C{Cc}: {ms:7.3f} ms  {nbytes / ms / 1e6:7.1f} GB/s (algorithmic)", flush=True)
+
     dts = ["fp32", "bf16"] if args.dtype == "both" else [args.dtype]
+    if os.environ.get("CONV_BENCH_ONLY_FIR"):
+        for dtn in dts:
+            for (H, W, Cc, fir) in ((512, 640, 128, 1), (256, 320, 128, 1), (128, 160, 256, 1), (256, 320, 128, 2), (128, 160, 128, 2),
+                                    (512, 640, 128, 0)):
+                run_fir(dtn, H, W, Cc, fir)
+        return
     for dtn in dts:
         for ci in range(len(CASES)):
             for fused in (0, 1):

@@ -368,7 +368,8 @@ template <typename T, int FIR>
 __global__ void __launch_bounds__(256) gn_apply_fir_tiled_kernel(GnSrcT<T> s0, const float* __restrict__ gamma,
                                                                   const float* __restrict__ beta, float eps, int do_silu,
                                                                   int as_operand, T* __restrict__ out_act,
-                                                                  T* __restrict__ out_raw, int Hin, int Win) {
+                                                                  T* __restrict__ out_raw, int Hin, int Win,
+                                                                  const float* __restrict__ aff) {
   constexpr int V = Vec<T>::N;
   constexpr int CH = FirCh<T>::value;
   constexpr int TO = FIR == 1 ? 8 : 16;        // output tile edge
@@ -384,7 +385,11 @@ __global__ void __launch_bounds__(256) gn_apply_fir_tiled_kernel(GnSrcT<T> s0, c
   const int Hout = FIR == 1 ? Hin / 2 : Hin * 2, Wout = FIR == 1 ? Win / 2 : Win * 2;
   const int tiles_x = (Wout + TO - 1) / TO;
   const int oy0 = (blockIdx.x / tiles_x) * TO, ox0 = (blockIdx.x % tiles_x) * TO;
-  if (threadIdx.x < CH) {
+  if (threadIdx.x < CH && aff != nullptr) {
+    const int c = c0 + threadIdx.x;
+    saff[threadIdx.x] = __ldg(aff + (static_cast<size_t>(b) * 2) * C + c);
+    saff[CH + threadIdx.x] = __ldg(aff + (static_cast<size_t>(b) * 2 + 1) * C + c);
+  } else if (threadIdx.x < CH) {
     const int c = c0 + threadIdx.x, g = c / cpg;
     const double inv_cnt = 1.0 / (static_cast<double>(Hin) * Win * cpg);
     double sum = 0.0, sq = 0.0;
@@ -509,8 +514,162 @@ __global__ void __launch_bounds__(256) gn_apply_fir_tiled_kernel(GnSrcT<T> s0, c
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// normalise + SiLU + FIR x2 DOWN (single source), second generation.  The first tiled kernel spent 41 instructions per
+// input element (ncu: 35 % of them useful math, half of the threads idle in the filter phase in fp32, 2 blocks per SM).
+// Here: 8 x 8 outputs from an 18 x 18 window for a 64-byte channel slice (16 fp32 / 32 bf16 channels): 41.5 KB of
+// shared memory per block (4-5 blocks per SM); every input element is loaded and activated once; the filter phase gives
+// every thread one output pixel x 4 channels with all sixteen taps at compile-time offsets from one base pointer.
+// ------------------------------------------------------------------------------------------------
+template <typename T> struct FirDownCh { static constexpr int value = 64 / sizeof(T); };
+
+template <typename T>
+__global__ void __launch_bounds__(256, 4) gn_fir_down_kernel(GnSrcT<T> s0, const float* __restrict__ gamma,
+                                                              const float* __restrict__ beta, float eps, int do_silu,
+                                                              int as_operand, T* __restrict__ out_act, T* __restrict__ out_raw,
+                                                              int Hin, int Win, int B, const float* __restrict__ aff) {
+  constexpr int V = Vec<T>::N;
+  constexpr int CH = FirDownCh<T>::value;
+  constexpr int VPC = CH / V;  // 4
+  constexpr int TO = 8, WIN = 18, NPX = WIN * WIN;
+  extern __shared__ __align__(16) unsigned char smraw[];
+  T* sa = reinterpret_cast<T*>(smraw);  // activated [NPX][CH]
+  T* sr = sa + NPX * CH;                // raw       [NPX][CH]
+  float* saff = reinterpret_cast<float*>(sr + NPX * CH);
+  const int C = s0.C;
+  const int Hout = Hin / 2, Wout = Win / 2;
+  const int tiles_x = (Wout + TO - 1) / TO, tiles_y = (Hout + TO - 1) / TO;
+  const int nchunk = C / CH;
+  const int ntiles = nchunk * tiles_x * tiles_y * B;  // channel slice fastest: concurrent blocks read whole DRAM rows
+  const int v = threadIdx.x & (VPC - 1), ps = threadIdx.x / VPC;
+  constexpr int PSTEP = 256 / VPC;                 // 64
+  constexpr int NIT = (NPX + PSTEP - 1) / PSTEP;   // 6
+
+  // One tile per block, channel slice fastest.  (Measured alternatives at 512 x 640 x 128 x 16 clips: persistent blocks
+  // with a register-level prefetch of the next window 1.7 TB/s, 128-byte slices with 2x2 outputs per thread 1.8 TB/s,
+  // this form 2.0 TB/s: the kernel is bound by issue slots lost at the two barriers, not by bytes in flight.)
+  auto decode = [&](int t, int& b, int& c0, int& oy0, int& ox0) {
+    c0 = (t % nchunk) * CH; t /= nchunk;
+    ox0 = (t % tiles_x) * TO; t /= tiles_x;
+    oy0 = (t % tiles_y) * TO; b = t / tiles_y;
+  };
+  auto load_window = [&](int t, uint4 (&r)[NIT], uint32_t& inb) {
+    int b, c0, oy0, ox0;
+    decode(t, b, c0, oy0, ox0);
+    const int iy0 = 2 * oy0 - 1, ix0 = 2 * ox0 - 1;
+    const T* src = s0.x + static_cast<size_t>(b) * Hin * Win * C + c0 + v * V;
+    inb = 0;
+#pragma unroll
+    for (int k = 0; k < NIT; ++k) {
+      const int pw = ps + k * PSTEP;
+      const int wr = pw / WIN, wc = pw - wr * WIN;
+      const int iy = iy0 + wr, ix = ix0 + wc;
+      const bool in = pw < NPX && iy >= 0 && iy < Hin && ix >= 0 && ix < Win;
+      inb |= in ? (1u << k) : 0u;
+      r[k] = in ? __ldg(reinterpret_cast<const uint4*>(src + (static_cast<size_t>(iy) * Win + ix) * C)) : make_uint4(0, 0, 0, 0);
+    }
+  };
+
+  uint4 cur[NIT];
+  uint32_t inb_cur = 0;
+  for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    int b, c0, oy0, ox0;
+    decode(tile, b, c0, oy0, ox0);
+    load_window(tile, cur, inb_cur);
+    if (threadIdx.x < CH) {
+      const int c = c0 + threadIdx.x;
+      if (aff != nullptr) {
+        // scale / shift precomputed once per launch (launch_gn_affine): the fp64 statistics arithmetic below costs
+        // ~2.5k cycles of one warp while the other seven wait at the barrier -- per TILE, it dominated the old kernel
+        saff[threadIdx.x] = __ldg(aff + (static_cast<size_t>(b) * 2) * C + c);
+        saff[CH + threadIdx.x] = __ldg(aff + (static_cast<size_t>(b) * 2 + 1) * C + c);
+      } else {
+        const int G = min(C / 4, 32), cpg = C / G;
+        const int g = c / cpg;
+        const double inv_cnt = 1.0 / (static_cast<double>(Hin) * Win * cpg);
+        double sum = 0.0, sq = 0.0;
+        for (int cc = g * cpg; cc < (g + 1) * cpg; ++cc) {
+          const longlong2 st = __ldg(reinterpret_cast<const longlong2*>(s0.stats + (static_cast<size_t>(b) * C + cc) * 2));
+          sum += static_cast<double>(st.x) * (1.0 / kStatSumScale);
+          sq += static_cast<double>(st.y) * (1.0 / kStatSqScale);
+        }
+        const double mean = sum * inv_cnt;
+        double var = sq * inv_cnt - mean * mean;
+        if (var < 0.0) var = 0.0;
+        const float rstd = rsqrtf(static_cast<float>(var) + eps);
+        const float sc = gamma[c] * rstd;
+        saff[threadIdx.x] = sc;
+        saff[CH + threadIdx.x] = beta[c] - static_cast<float>(mean) * sc;
+      }
+    }
+    __syncthreads();  // saff ready; the previous tile's filter phase is done with sa / sr
+    // ---- phase 1: activate the window (each input element once) ----
+    {
+      float sc[V], sh[V];
+#pragma unroll
+      for (int j = 0; j < V; ++j) { sc[j] = saff[v * V + j]; sh[j] = saff[CH + v * V + j]; }
+#pragma unroll
+      for (int k = 0; k < NIT; ++k) {
+        const int pw = ps + k * PSTEP;
+        if (pw < NPX) {
+          float f[V], a[V];
+          Vec<T>::unpack(cur[k], f);
+          const bool in = (inb_cur >> k) & 1u;
+#pragma unroll
+          for (int j = 0; j < V; ++j) {
+            const float n = fmaf(f[j], sc[j], sh[j]);
+            a[j] = in ? (do_silu ? silu_act<T>(n) : n) : 0.f;  // the FIR pads the ACTIVATED tensor with zeros
+          }
+          sts_vec<T>(sa + pw * CH + v * V, a);
+          *reinterpret_cast<uint4*>(sr + pw * CH + v * V) = cur[k];
+        }
+      }
+    }
+    __syncthreads();
+    // ---- phase 2: item = (output pixel, 4-channel quad); out[i][j] = sum_{a,b<4} k[a] k[b] win[2i+a][2j+b] ----
+    constexpr int NQ = CH / 4;
+    for (int it = threadIdx.x; it < TO * TO * NQ; it += 256) {
+      const int q = it % NQ, px = it / NQ;
+      const int oy = px / TO, ox = px - oy * TO;
+      const T* pa = sa + ((2 * oy) * WIN + 2 * ox) * CH + q * 4;
+      const T* pr = sr + ((2 * oy) * WIN + 2 * ox) * CH + q * 4;
+      float4 acc = make_float4(0.f, 0.f, 0.f, 0.f), raw = acc;
+      const float k1[4] = {0.125f, 0.375f, 0.375f, 0.125f};
+#pragma unroll
+      for (int a = 0; a < 4; ++a) {
+        float4 ha = make_float4(0.f, 0.f, 0.f, 0.f), hr = ha;
+#pragma unroll
+        for (int bb = 0; bb < 4; ++bb) {
+          fma4(ha, k1[bb], lds4<T>(pa + (a * WIN + bb) * CH));
+          fma4(hr, k1[bb], lds4<T>(pr + (a * WIN + bb) * CH));
+        }
+        fma4(acc, k1[a], ha);
+        fma4(raw, k1[a], hr);
+      }
+      const int gy = oy0 + oy, gx = ox0 + ox;
+      if (gy < Hout && gx < Wout) {
+        const size_t o = ((static_cast<size_t>(b) * Hout + gy) * Wout + gx) * C + c0 + q * 4;
+        auto put = [&](T* dst, const float4& v4) {
+          if constexpr (DT<T>::kIsBf16) {
+            __nv_bfloat162 lo = __floats2bfloat162_rn(v4.x, v4.y), hi = __floats2bfloat162_rn(v4.z, v4.w);
+            *reinterpret_cast<uint2*>(dst + o) = make_uint2(*reinterpret_cast<uint32_t*>(&lo), *reinterpret_cast<uint32_t*>(&hi));
+          } else {
+            *reinterpret_cast<float4*>(dst + o) =
+                as_operand ? make_float4(round_tf32(v4.x), round_tf32(v4.y), round_tf32(v4.z), round_tf32(v4.w)) : v4;
+          }
+        };
+        put(out_act, acc);
+        if (out_raw != nullptr) put(out_raw, raw);
+      }
+    }
+    // (a block that loops: the __syncthreads at the top of the next iteration orders this filter phase before the next
+    // window's stores)
+  }
+}
+
 void launch_gn_apply(int dt, GnSrc s0, GnSrc s1, const float* gamma, const float* beta, float eps, int fir, bool do_silu,
-                     bool as_operand, void* out_act, void* out_raw, int B, int Hin, int Win, cudaStream_t st) {
+                     bool as_operand, void* out_act, void* out_raw, int B, int Hin, int Win, cudaStream_t st,
+                     const float* aff) {
   const int Ct = s0.C + s1.C;
   const int Hout = fir == 1 ? Hin / 2 : (fir == 2 ? Hin * 2 : Hin);
   const int Wout = fir == 1 ? Win / 2 : (fir == 2 ? Win * 2 : Win);
@@ -519,16 +678,16 @@ void launch_gn_apply(int dt, GnSrc s0, GnSrc s1, const float* gamma, const float
       constexpr int CH = FirCh<T>::value;
       GnSrcT<T> a{(const T*)s0.x, s0.stats, s0.C};
       if (fir == 1) {
-        dim3 grid(((Hout + 7) / 8) * ((Wout + 7) / 8), s0.C / CH, B);
-        const size_t sm = 2 * 18 * 18 * CH * sizeof(T) + 2 * CH * sizeof(float);
-        auto kern = gn_apply_fir_tiled_kernel<T, 1>;
-        cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(sm));
-        kern<<<grid, 256, sm, st>>>(a, gamma, beta, eps, do_silu, as_operand, (T*)out_act, (T*)out_raw, Hin, Win);
+        constexpr int CHD = FirDownCh<T>::value;
+        const long long ntiles = static_cast<long long>(s0.C / CHD) * ((Hout + 7) / 8) * ((Wout + 7) / 8) * B;
+        const int grid = static_cast<int>(std::min<long long>(ntiles, 1LL << 30));
+        const size_t sm = 2 * 18 * 18 * CHD * sizeof(T) + 2 * CHD * sizeof(float);
+        gn_fir_down_kernel<T><<<grid, 256, sm, st>>>(a, gamma, beta, eps, do_silu, as_operand, (T*)out_act, (T*)out_raw, Hin, Win, B, aff);
       } else {
         dim3 grid(((Hout + 15) / 16) * ((Wout + 15) / 16), s0.C / CH, B);
         const size_t sm = 2 * 10 * 10 * CH * sizeof(T) + 2 * CH * sizeof(float);
         gn_apply_fir_tiled_kernel<T, 2><<<grid, 256, sm, st>>>(a, gamma, beta, eps, do_silu, as_operand, (T*)out_act,
-                                                              (T*)out_raw, Hin, Win);
+                                                              (T*)out_raw, Hin, Win, aff);
       }
     });
     return;

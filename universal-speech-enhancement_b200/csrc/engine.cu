@@ -468,9 +468,16 @@ struct Builder {
          (double)Bn * HW * C * es());
   }
   void gn_apply(Act& s0, Act* s1, size_t gamma_off, size_t beta_off, int fir, bool silu, bool operand, Act& out, Act* raw) {
+    // the resampling kernels work tile by tile: give them the scale / shift table instead of the statistics
+    size_t aff_off = (size_t)-1;
+    if (fir != 0 && !s1) aff_off = gn_affine(s0, nullptr, gamma_off, beta_off);
     ensure_stats(s0);
     if (s1) ensure_stats(*s1);
-    if (dry) return;
+    if (dry) {
+      if (aff_off != (size_t)-1) arena.release(aff_off);
+      return;
+    }
+    const float* affp = aff_off != (size_t)-1 ? (const float*)ws(aff_off) : nullptr;
     GnSrc a{ws(s0.off), stats_ptr(s0.stats_off), s0.C};
     GnSrc b{nullptr, nullptr, 0};
     if (s1) b = GnSrc{ws(s1->off), stats_ptr(s1->stats_off), s1->C};
@@ -482,9 +489,10 @@ struct Builder {
     {
       const double nin = (double)Bn * H * W * (s0.C + (s1 ? s1->C : 0));
       const double nout = fir == 1 ? nin / 4 : (fir == 2 ? nin * 4 : nin);
-      emit([=](cudaStream_t s) { launch_gn_apply(dt, a, b, g, bt, 1e-6f, fir, silu, operand, o, r, Bn, H, W, s); },
+      emit([=](cudaStream_t s) { launch_gn_apply(dt, a, b, g, bt, 1e-6f, fir, silu, operand, o, r, Bn, H, W, s, affp); },
            TAG_GN_APPLY, 1, 8.0 * nout, (nin + nout * (raw ? 2 : 1)) * es());
     }
+    if (aff_off != (size_t)-1) arena.release(aff_off);
   }
   // scale / shift table [B][2][C] of GroupNorm(cat[s0, s1]) for a fused conv operand; returns its arena offset
   size_t gn_affine(Act& s0, Act* s1, size_t gamma_off, size_t beta_off) {
@@ -1199,12 +1207,19 @@ int use_op_gn_stats(int dtype, const void* x, long long* stats, int B, int HW, i
   launch_gn_stats(dtype, x, stats, B, HW, C, (cudaStream_t)stream);
   return cuda_check("use_op_gn_stats");
 }
+int use_op_gn_apply_aff(int dtype, const void* x0, const long long* stats0, int C0, const void* x1, const long long* stats1,
+                        int C1, const float* gamma, const float* beta, float eps, int fir, int do_silu, int as_operand,
+                        void* out_act, void* out_raw, int B, int Hin, int Win, const float* aff, void* stream) {
+  if (aff != nullptr && (fir == 0 || C1 != 0)) return fail("aff is only used by the single-source resampling forms");
+  launch_gn_apply(dtype, GnSrc{x0, stats0, C0}, GnSrc{x1, stats1, C1}, gamma, beta, eps, fir, do_silu != 0, as_operand != 0,
+                  out_act, out_raw, B, Hin, Win, (cudaStream_t)stream, aff);
+  return cuda_check("use_op_gn_apply");
+}
 int use_op_gn_apply(int dtype, const void* x0, const long long* stats0, int C0, const void* x1, const long long* stats1, int C1,
                     const float* gamma, const float* beta, float eps, int fir, int do_silu, int as_operand, void* out_act,
                     void* out_raw, int B, int Hin, int Win, void* stream) {
-  launch_gn_apply(dtype, GnSrc{x0, stats0, C0}, GnSrc{x1, stats1, C1}, gamma, beta, eps, fir, do_silu != 0, as_operand != 0,
-                  out_act, out_raw, B, Hin, Win, (cudaStream_t)stream);
-  return cuda_check("use_op_gn_apply");
+  return use_op_gn_apply_aff(dtype, x0, stats0, C0, x1, stats1, C1, gamma, beta, eps, fir, do_silu, as_operand, out_act,
+                             out_raw, B, Hin, Win, nullptr, stream);
 }
 int use_op_gn_affine(const long long* stats0, int C0, const long long* stats1, int C1, const float* gamma,
                      const float* beta, float eps, int HW, float* aff, int B, void* stream) {

@@ -24,8 +24,11 @@ struct GnSrc {
 // out_act = FIR(silu?(groupnorm(cat[s0,s1])))  (fir: 0 none, 1 down x2, 2 up x2), written as an MMA operand
 // (TF32-rounded in fp32 mode) when as_operand
 // out_raw (optional, fir != 0 only) = FIR(cat[s0,s1]) un-normalised.
+// aff (optional, FIR forms with a single source): the scale / shift table of launch_gn_affine; without it every tile
+// recomputes its channels' scale / shift from the statistics
 void launch_gn_apply(int dt, GnSrc s0, GnSrc s1, const float* gamma, const float* beta, float eps, int fir, bool do_silu,
-                     bool as_operand, void* out_act, void* out_raw, int B, int Hin, int Win, cudaStream_t st);
+                     bool as_operand, void* out_act, void* out_raw, int B, int Hin, int Win, cudaStream_t st,
+                     const float* aff = nullptr);
 
 // GroupNorm scale / shift table of cat[s0, s1] for the fused conv operand: aff[b][0][c] = gamma[c] * rstd,
 // aff[b][1][c] = beta[c] - mean * gamma[c] * rstd (same arithmetic as launch_gn_apply)
