@@ -98,10 +98,10 @@ static int multicast_width() {
   return mc;
 }
 
-template <typename T, int N, int NSUB, bool SWAP, bool FUSE, int MC, bool PROF>
+template <typename T, int N, int NSUB, bool SWAP, bool FUSE, int MC, bool PROF, bool CG2 = false>
 static void set_kernel(TcConvPlan* p) {
-  using C = ConvCfg<T, N, NSUB, FUSE>;
-  auto k = &conv_tc_kernel<T, N, NSUB, SWAP, FUSE, MC, PROF>;
+  using C = ConvCfg<T, N, NSUB, FUSE, CG2>;
+  auto k = &conv_tc_kernel<T, N, NSUB, SWAP, FUSE, MC, PROF, CG2>;
   p->kernel = reinterpret_cast<const void*>(k);
   cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES);
   p->threads = C::THREADS;
@@ -110,10 +110,34 @@ static void set_kernel(TcConvPlan* p) {
   p->mc = MC;
 }
 
+// CTA-pair MMAs (tcgen05 cta_group::2) for the C_out = 128 layers: USE_B200_CONV_CG2=1 / 0
+static bool cg2_enabled() {
+  static bool on = [] {
+    const char* v = getenv("USE_B200_CONV_CG2");
+    return v && v[0] == '1';
+  }();
+  return on;
+}
+
 template <typename T, int N, int NSUB>
 static void fill_kernel(TcConvPlan* p, bool fuse) {
   constexpr bool SWAP = (N == 128 && NSUB == 2);  // swap-AB for C_out = 128 (conv_tc.cuh)
   const bool mc2 = multicast_width() == 2;
+  if constexpr (N == 128 && NSUB == 2) {
+    if (cg2_enabled()) {
+      if (getenv("USE_B200_CONV_PROF")) {
+        if (fuse) set_kernel<T, N, NSUB, false, true, 2, true, true>(p);
+        else set_kernel<T, N, NSUB, false, false, 2, true, true>(p);
+        if (const char* v = getenv("USE_B200_CONV_DBG")) p->params.dbg = atoi(v);
+        cudaMalloc(&p->params.prof, 16 * sizeof(unsigned long long));
+        cudaMemset(p->params.prof, 0, 16 * sizeof(unsigned long long));
+        return;
+      }
+      if (fuse) set_kernel<T, N, NSUB, false, true, 2, false, true>(p);
+      else set_kernel<T, N, NSUB, false, false, 2, false, true>(p);
+      return;
+    }
+  }
   if constexpr (SWAP) {
     if (getenv("USE_B200_CONV_PROF")) {
       // instrumented build of the C_out = 128 kernel (tools/conv_bench.py): per-role mbarrier stall cycles

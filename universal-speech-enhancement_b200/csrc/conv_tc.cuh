@@ -74,7 +74,7 @@ __device__ __forceinline__ void mbar_wait_p(uint64_t* bar, uint32_t parity, long
   }
 }
 
-template <typename T, int N, int NSUB, bool FUSE>
+template <typename T, int N, int NSUB, bool FUSE, bool CG2 = false>
 struct ConvCfg {
   static constexpr int CK = 128 / sizeof(T);
   static constexpr int TILE_W = 8;
@@ -84,10 +84,11 @@ struct ConvCfg {
   static constexpr int WIN_PITCH = WIN_W * 128;          // bytes between window rows = SBO of a 3x3 operand
   static constexpr int NPIX = A_ROWS * WIN_W;            // pixels of one window
   static constexpr int A_SLOT = (NPIX * 128 + 1023) & ~1023;
-  static constexpr int B_TILE = N * 128;
+  static constexpr int B_TILE = CG2 ? N * 64 : N * 128;  // CTA pair: each CTA stages half of the C_out rows
   // plain: 2 windows (loading / consumed).  fused: 3 (TMA loading the raw window / being normalised in place / consumed)
   static constexpr int A_SLOTS = FUSE ? 3 : 2;
-  static constexpr int B_SLOTS = (N == 256) ? (FUSE ? 4 : 5) : (N == 128 ? (FUSE ? 5 : 8) : 8);  // N <= 64: 8 slots
+  static constexpr int B_SLOTS = CG2 ? (FUSE ? 10 : 16)
+                                     : (N == 256) ? (FUSE ? 4 : 5) : (N == 128 ? (FUSE ? 5 : 8) : 8);  // N <= 64: 8 slots
   static constexpr int ACC_COLS = NSUB * N;
   static constexpr int TMEM_COLS = (2 * ACC_COLS < 32) ? 32 : 2 * ACC_COLS;
   static constexpr int EPI_WARPS = 4 * NSUB;
@@ -116,10 +117,19 @@ struct ConvCfg {
 // which halves that stream.  A weight slot is recycled only when the MMAs of BOTH CTAs have released it (b_empty
 // counts 2 arrivals, one of them a multicast tcgen05.commit from the peer).  A CTA whose tile index falls past the end
 // processes a "ghost" tile (loads are zero-filled out of bounds, nothing is stored) to keep the pair in lockstep.
-template <typename T, int N, int NSUB, bool SWAP, bool FUSE, int MC = 1, bool PROF = false>
-__global__ void __launch_bounds__(ConvCfg<T, N, NSUB, FUSE>::THREADS, 1) conv_tc_kernel(const __grid_constant__ ConvParams p) {
-  using C = ConvCfg<T, N, NSUB, FUSE>;
+//
+// CG2 (C_out = 128, pixel-major, MC = 2): the CTA pair issues ONE tcgen05.mma.cta_group::2 per step (M = 256 = the 128
+// pixels of a sub-tile of each CTA, N = 128): each CTA stages only HALF of every weight tile (its 64 C_out rows; the
+// tensor cores exchange the halves), which halves the L2 -> SM weight stream per SM -- the measured limiter of these
+// layers -- and doubles the time the weight ring covers.  Only the leader (cluster rank 0) issues MMAs; every barrier
+// that collects both CTAs' arrivals (a_full, b_full, t_empty) lives in the leader and is signalled remotely by the
+// peer's TMA loads (cp.async.bulk.tensor.cta_group::2), transform warps and epilogue warps; the leader's
+// tcgen05.commit releases slots / publishes accumulators in both CTAs by multicast.
+template <typename T, int N, int NSUB, bool SWAP, bool FUSE, int MC = 1, bool PROF = false, bool CG2 = false>
+__global__ void __launch_bounds__(ConvCfg<T, N, NSUB, FUSE, CG2>::THREADS, 1) conv_tc_kernel(const __grid_constant__ ConvParams p) {
+  using C = ConvCfg<T, N, NSUB, FUSE, CG2>;
   static_assert(!SWAP || (N == 128 && NSUB == 2), "swap-AB is built for C_out = 128, 256-pixel tiles");
+  static_assert(!CG2 || (!SWAP && MC == 2 && N == 128 && NSUB == 2), "the CTA-pair MMA form is built for C_out = 128");
   constexpr bool kBf16 = DT<T>::kIsBf16;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -145,14 +155,16 @@ __global__ void __launch_bounds__(ConvCfg<T, N, NSUB, FUSE>::THREADS, 1) conv_tc
       prefetch_tmap(&p.seg[i].tmW);
       prefetch_tmap(&p.seg[i].tmWh);
     }
-    for (int i = 0; i < C::A_SLOTS; ++i) { mbar_init(&a_full[i], 1); mbar_init(&a_empty[i], 1); mbar_init(&a_raw[i], 1); }
-    for (int i = 0; i < C::B_SLOTS; ++i) { mbar_init(&b_full[i], 1); mbar_init(&b_empty[i], MC); }
-    for (int i = 0; i < 2; ++i) { mbar_init(&t_full[i], 1); mbar_init(&t_empty[i], C::EPI_WARPS); }
+    // CG2: the "full" barriers and t_empty of the LEADER collect one arrival (or one group of arrivals) from each CTA
+    constexpr int kPair = CG2 ? 2 : 1;
+    for (int i = 0; i < C::A_SLOTS; ++i) { mbar_init(&a_full[i], kPair); mbar_init(&a_empty[i], 1); mbar_init(&a_raw[i], 1); }
+    for (int i = 0; i < C::B_SLOTS; ++i) { mbar_init(&b_full[i], 1); mbar_init(&b_empty[i], CG2 ? 1 : MC); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&t_full[i], 1); mbar_init(&t_empty[i], kPair * C::EPI_WARPS); }
     fence_barrier_init();
   }
   if (warp == 1) {
-    tmem_alloc(tmem_slot, C::TMEM_COLS);
-    tmem_relinquish();
+    if constexpr (CG2) { tmem_alloc_cg2(tmem_slot, C::TMEM_COLS); tmem_relinquish_cg2(); }
+    else { tmem_alloc(tmem_slot, C::TMEM_COLS); tmem_relinquish(); }
   }
   tc_fence_before();
   __syncthreads();
@@ -189,9 +201,24 @@ __global__ void __launch_bounds__(ConvCfg<T, N, NSUB, FUSE>::THREADS, 1) conv_tc
         const int th = rem / p.tiles_w;
         const int w0 = (rem - th * p.tiles_w) * C::TILE_W, h0 = th * C::TILE_H;
         const bool k3 = S.taps == 9;
-        uint64_t* bar = (FUSE && S.raw != nullptr) ? &a_raw[as] : &a_full[as];
-        mbar_arrive_expect_tx(bar, (k3 ? C::NPIX : C::TILE_H * 8) * 128);
-        tma_load_4d(sA + as * C::A_SLOT, &S.tmA, bar, S.ac0 + a_kc * C::CK, k3 ? (w0 - 1) : w0, k3 ? (h0 - 1) : h0, b);
+        const uint32_t a_bytes = (k3 ? C::NPIX : C::TILE_H * 8) * 128;
+        if (FUSE && S.raw != nullptr) {
+          mbar_arrive_expect_tx(&a_raw[as], a_bytes);
+          tma_load_4d(sA + as * C::A_SLOT, &S.tmA, &a_raw[as], S.ac0 + a_kc * C::CK, k3 ? (w0 - 1) : w0, k3 ? (h0 - 1) : h0, b);
+        } else if constexpr (CG2) {
+          // the leader's barrier takes the bytes of BOTH CTAs' windows.  No remote arrive here: a cluster-scope arrive
+          // costs this thread ~1 us, and it also has to keep the weight stream going (measured: 2.5x slower with it).
+          // a_full counts 2 (a fused window is published by one transform thread per CTA): the leader arrives twice.
+          const uint32_t lbar = mapa_u32(smem_u32(&a_full[as]), 0);
+          if (crank == 0) {
+            mbar_arrive_expect_tx(&a_full[as], 2 * a_bytes);
+            mbar_arrive(&a_full[as]);
+          }
+          tma_load_4d_cg2(sA + as * C::A_SLOT, &S.tmA, lbar, S.ac0 + a_kc * C::CK, k3 ? (w0 - 1) : w0, k3 ? (h0 - 1) : h0, b);
+        } else {
+          mbar_arrive_expect_tx(&a_full[as], a_bytes);
+          tma_load_4d(sA + as * C::A_SLOT, &S.tmA, &a_full[as], S.ac0 + a_kc * C::CK, k3 ? (w0 - 1) : w0, k3 ? (h0 - 1) : h0, b);
+        }
         ++ai;
         if (++a_kc == S.nchunks) {
           a_kc = 0;
@@ -211,9 +238,16 @@ __global__ void __launch_bounds__(ConvCfg<T, N, NSUB, FUSE>::THREADS, 1) conv_tc
               if constexpr (PROF) { if (p.dbg & 8) continue; }
               const uint32_t bs = bi % C::B_SLOTS, bph = (bi / C::B_SLOTS) & 1;
               mbar_wait_p<PROF>(&b_empty[bs], bph ^ 1, w_b);
-              mbar_arrive_expect_tx(&b_full[bs], C::B_TILE);
               // tap order s-major (s = tap / 3, r = tap % 3): the accumulation order of the previous 3-copy kernel
               const int wtap = k3 ? ((tap % 3) * 3 + tap / 3) : 0;
+              if constexpr (CG2) {
+                const uint32_t lbar = mapa_u32(smem_u32(&b_full[bs]), 0);
+                if (crank == 0) mbar_arrive_expect_tx(&b_full[bs], 2 * C::B_TILE);  // both halves land on the leader's barrier
+                tma_load_3d_cg2(sB + bs * C::B_TILE, &S.tmWh, lbar, S.wc0 + kc * C::CK, crank * (N / 2), wtap);
+                ++bi;
+                continue;
+              }
+              mbar_arrive_expect_tx(&b_full[bs], C::B_TILE);
               if constexpr (MC > 1)
                 tma_load_3d_mc(sB + bs * C::B_TILE + crank * (C::B_TILE / 2), &S.tmWh, &b_full[bs], S.wc0 + kc * C::CK,
                                crank * (N / 2), wtap, uint16_t(3));
@@ -232,8 +266,13 @@ __global__ void __launch_bounds__(ConvCfg<T, N, NSUB, FUSE>::THREADS, 1) conv_tc
     }
   } else if (warp == 1) {
     // ================================ MMA issuer ================================
-    if (lane == 0) {
-      constexpr uint32_t idesc = SWAP ? umma_idesc(kBf16 ? 1 : 2, 128, 128 * NSUB) : umma_idesc(kBf16 ? 1 : 2, 128, N);
+    // The whole warp runs this loop in lockstep and one ELECTED lane issues the tcgen05 instructions: with uniform control
+    // flow the descriptors stay in uniform registers.  (Issued from inside an `if (lane == 0)` the compiler wraps every
+    // tcgen05.mma in a register-broadcast loop, ~100 cycles per instruction -- enough to starve the CTA-pair form, whose
+    // leader issues for two SMs.)
+    if (!CG2 || crank == 0) {  // CTA pair: only the leader issues (for both CTAs)
+      constexpr uint32_t idesc = SWAP ? umma_idesc(kBf16 ? 1 : 2, 128, 128 * NSUB)
+                                      : umma_idesc(kBf16 ? 1 : 2, CG2 ? 256 : 128, N);
       const uint32_t sA_addr = smem_u32(sA), sB_addr = smem_u32(sB);
       uint32_t ai = 0, bi = 0, ti = 0;
       long long w_t = 0, w_a = 0, w_b = 0;
@@ -258,6 +297,7 @@ __global__ void __launch_bounds__(ConvCfg<T, N, NSUB, FUSE>::THREADS, 1) conv_tc
               if (!dbg_nob) mbar_wait_p<PROF>(&b_full[bs], bph, w_b);
               tc_fence_after();
               const uint32_t win = sA_addr + as * C::A_SLOT + (k3 ? (r * C::WIN_W + s) * 128 : 0);
+              if (elect_one()) {
               if constexpr (SWAP) {
                 // D[c_out][pixel] += W[c_out][K] * X[pixel][K]^T : M operand = weight tile, N operand = 256 pixel rows
 #pragma unroll
@@ -273,23 +313,37 @@ __global__ void __launch_bounds__(ConvCfg<T, N, NSUB, FUSE>::THREADS, 1) conv_tc
                   for (int k = 0; k < 4; ++k) {
                     const uint64_t ad = umma_desc_sw128_sbo(win + sub * 16 * sbo + k * 32, sbo);
                     const uint64_t bd = umma_desc_sw128(sB_addr + bs * C::B_TILE + k * 32);
-                    umma_ss<kBf16>(tmem_base + acs * C::ACC_COLS + sub * N, ad, bd, idesc, (first && k == 0) ? 0u : 1u);
+                    if constexpr (CG2)
+                      umma_ss_cg2<kBf16>(tmem_base + acs * C::ACC_COLS + sub * N, ad, bd, idesc, (first && k == 0) ? 0u : 1u);
+                    else
+                      umma_ss<kBf16>(tmem_base + acs * C::ACC_COLS + sub * N, ad, bd, idesc, (first && k == 0) ? 0u : 1u);
                   }
                 }
               }
-              first = false;
-              if (dbg_nob) {
+              if constexpr (CG2) umma_commit_cg2(&b_empty[bs], uint16_t(3));
+              else if (dbg_nob) {
               } else if constexpr (MC > 1) umma_commit_mc(&b_empty[bs], uint16_t(3));
               else umma_commit(&b_empty[bs]);
+              }  // elected lane
+              __syncwarp();
+              first = false;
               ++bi;
             }
-            umma_commit(&a_empty[as]);
+            if (elect_one()) {
+              if constexpr (CG2) umma_commit_cg2(&a_empty[as], uint16_t(3));
+              else umma_commit(&a_empty[as]);
+            }
+            __syncwarp();
             ++ai;
           }
         }
-        umma_commit(&t_full[acs]);
+        if (elect_one()) {
+          if constexpr (CG2) umma_commit_cg2(&t_full[acs], uint16_t(3));
+          else umma_commit(&t_full[acs]);
+        }
+        __syncwarp();
       }
-      if constexpr (PROF) {
+      if constexpr (PROF) if (lane == 0) {
         atomicAdd(p.prof + 0, static_cast<unsigned long long>(w_t));
         atomicAdd(p.prof + 1, static_cast<unsigned long long>(w_a));
         atomicAdd(p.prof + 2, static_cast<unsigned long long>(w_b));
@@ -361,7 +415,10 @@ __global__ void __launch_bounds__(ConvCfg<T, N, NSUB, FUSE>::THREADS, 1) conv_tc
           }
           fence_proxy_async();  // generic-proxy writes -> visible to the tensor core's async-proxy reads
           named_bar_sync(2, XT);
-          if (tt == 0) mbar_arrive(&a_full[as]);
+          if (tt == 0) {
+            if constexpr (CG2) mbar_arrive_cluster(mapa_u32(smem_u32(&a_full[as]), 0));
+            else mbar_arrive(&a_full[as]);
+          }
         }
       }
     }
@@ -607,7 +664,10 @@ __global__ void __launch_bounds__(ConvCfg<T, N, NSUB, FUSE>::THREADS, 1) conv_tc
       }  // !SWAP
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&t_empty[acs]);
+      if (lane == 0) {
+        if constexpr (CG2) mbar_arrive_cluster(mapa_u32(smem_u32(&t_empty[acs]), 0));
+        else mbar_arrive(&t_empty[acs]);
+      }
       if (p.stats_acc != nullptr) {
         // combine the epilogue warps of this tile in a fixed order (deterministic) and publish the tile partial
         constexpr int ET = 32 * C::EPI_WARPS;
@@ -638,7 +698,10 @@ __global__ void __launch_bounds__(ConvCfg<T, N, NSUB, FUSE>::THREADS, 1) conv_tc
   tc_fence_before();
   __syncthreads();
   if constexpr (MC > 1) cluster_sync_all();  // no CTA leaves while its peer may still multicast into it
-  if (warp == 1) tmem_dealloc(tmem_base, C::TMEM_COLS);
+  if (warp == 1) {
+    if constexpr (CG2) tmem_dealloc_cg2(tmem_base, C::TMEM_COLS);
+    else tmem_dealloc(tmem_base, C::TMEM_COLS);
+  }
 }
 
 }  // namespace use
