@@ -881,7 +881,7 @@ void launch_conv_out4(int dt, const void* a, const float* w, const float* bias, 
 // One thread owns a 16-byte channel vector (its weights and bias live in registers) and walks over the pixels of the
 // block's fixed range: the block partition does not depend on the batch, so the statistics are batch-invariant.
 // ------------------------------------------------------------------------------------------------
-constexpr int kCombinePixPerBlock = 1024;
+constexpr int kCombinePixPerBlock = 256;
 
 template <typename T, int PC>
 __global__ void __launch_bounds__(256) combine_kernel(const T* __restrict__ h, const float* __restrict__ pyr,
@@ -906,27 +906,39 @@ __global__ void __launch_bounds__(256) combine_kernel(const T* __restrict__ h, c
   for (int j = 0; j < V; ++j) s[j] = q[j] = 0.f;
   const size_t base = static_cast<size_t>(b) * HW;
   if (prow < rows) {
-    for (int p = p0 + prow; p < p1; p += rows) {
-      float pv[PC];
-      if constexpr (PC == 4) {
-        const float4 t = __ldg(reinterpret_cast<const float4*>(pyr) + base + p);
-        pv[0] = t.x; pv[1] = t.y; pv[2] = t.z; pv[3] = t.w;
-      } else {
-        const float2 t = __ldg(reinterpret_cast<const float2*>(pyr) + base + p);
-        pv[0] = t.x; pv[1] = t.y;
-      }
-      float f[V];
-      Vec<T>::load(h + (base + p) * C + cv * V, f);
+    constexpr int U = 4;  // independent pixel loads in flight per thread (a serial loop here is pure load latency)
+    for (int pb = p0 + prow; pb < p1; pb += U * rows) {
+      float pv[U][PC], f[U][V];
 #pragma unroll
-      for (int j = 0; j < V; ++j) {
-        float acc = bv[j];
-        if constexpr (PC == 4) acc += wv[j][0] * pv[0] + wv[j][1] * pv[1] + wv[j][2] * pv[2] + wv[j][3] * pv[3];
-        else acc += wv[j][0] * pv[0] + wv[j][1] * pv[1];
-        f[j] = acc + f[j];  // same association as conv2d then "+ h": (bias + w.p) + h
-        s[j] += f[j];
-        q[j] = fmaf(f[j], f[j], q[j]);
+      for (int u = 0; u < U; ++u) {
+        const int p = pb + u * rows;
+        if (p < p1) {
+          if constexpr (PC == 4) {
+            const float4 t = __ldg(reinterpret_cast<const float4*>(pyr) + base + p);
+            pv[u][0] = t.x; pv[u][1] = t.y; pv[u][2] = t.z; pv[u][3] = t.w;
+          } else {
+            const float2 t = __ldg(reinterpret_cast<const float2*>(pyr) + base + p);
+            pv[u][0] = t.x; pv[u][1] = t.y;
+          }
+          Vec<T>::load(h + (base + p) * C + cv * V, f[u]);
+        }
       }
-      Vec<T>::store(out + (base + p) * C + cv * V, f);
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const int p = pb + u * rows;
+        if (p < p1) {
+#pragma unroll
+          for (int j = 0; j < V; ++j) {
+            float acc = bv[j];
+            if constexpr (PC == 4) acc += wv[j][0] * pv[u][0] + wv[j][1] * pv[u][1] + wv[j][2] * pv[u][2] + wv[j][3] * pv[u][3];
+            else acc += wv[j][0] * pv[u][0] + wv[j][1] * pv[u][1];
+            f[u][j] = acc + f[u][j];  // same association as conv2d then "+ h": (bias + w.p) + h
+            s[j] += f[u][j];
+            q[j] = fmaf(f[u][j], f[u][j], q[j]);
+          }
+          Vec<T>::store(out + (base + p) * C + cv * V, f[u]);
+        }
+      }
     }
   }
   if (stats == nullptr) return;

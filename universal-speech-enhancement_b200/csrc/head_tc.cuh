@@ -104,7 +104,7 @@ __global__ void __launch_bounds__(kHeadThreads, 1) head_tc_kernel(const __grid_c
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
+    {  // the whole warp walks the loop; one elected lane issues (uniform control flow keeps the descriptors in uniform registers)
       constexpr uint32_t idesc = umma_idesc(kBf16 ? 1 : 2, 128, kHeadN);
       const uint32_t sA_addr = smem_u32(sA), sW_addr = smem_u32(sW);
       mbar_wait(w_full, 0);
@@ -117,18 +117,22 @@ __global__ void __launch_bounds__(kHeadThreads, 1) head_tc_kernel(const __grid_c
           const uint32_t as = ai % kHeadASlots, aph = (ai / kHeadASlots) & 1;
           mbar_wait(&a_full[as], aph);
           tc_fence_after();
+          if (elect_one()) {
 #pragma unroll
-          for (int sub = 0; sub < 2; ++sub) {
+            for (int sub = 0; sub < 2; ++sub) {
 #pragma unroll
-            for (int k = 0; k < 4; ++k) {
-              const uint64_t ad = umma_desc_sw128(sA_addr + as * kHeadASlot + sub * 16384 + k * 32);
-              const uint64_t bd = umma_desc_sw128(sW_addr + kc * kHeadN * 128 + k * 32);
-              umma_ss<kBf16>(tmem_base + acs * 128 + sub * 64, ad, bd, idesc, (kc == 0 && k == 0) ? 0u : 1u);
+              for (int k = 0; k < 4; ++k) {
+                const uint64_t ad = umma_desc_sw128(sA_addr + as * kHeadASlot + sub * 16384 + k * 32);
+                const uint64_t bd = umma_desc_sw128(sW_addr + kc * kHeadN * 128 + k * 32);
+                umma_ss<kBf16>(tmem_base + acs * 128 + sub * 64, ad, bd, idesc, (kc == 0 && k == 0) ? 0u : 1u);
+              }
             }
+            umma_commit(&a_empty[as]);
           }
-          umma_commit(&a_empty[as]);
+          __syncwarp();
         }
-        umma_commit(&t_full[acs]);
+        if (elect_one()) umma_commit(&t_full[acs]);
+        __syncwarp();
       }
     }
   } else {
