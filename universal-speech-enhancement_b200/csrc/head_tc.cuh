@@ -151,6 +151,35 @@ __global__ void __launch_bounds__(kHeadThreads, 1) head_tc_kernel(const __grid_c
       const int th = rem / p.tiles_w;
       const int h = th * kHeadTile + oy, w = (rem - th * p.tiles_w) * kHeadTile + ox;
       const uint32_t acs = ti & 1, acph = (ti >> 1) & 1;
+      // FIR-upsampled previous pyramid level: request its four taps BEFORE waiting for the accumulator -- the epilogue of
+      // a tile is serial (stage -> barrier -> gather -> barrier), a global-load latency inside it costs ~30 % of the tile
+      const bool live = e < kHeadTile * kHeadTile && h < p.H && w < p.W;
+      float up[4] = {0.f, 0.f, 0.f, 0.f};
+      if (live && p.prev4 != nullptr) {
+        const int Hp = p.H >> 1, Wp = p.W >> 1;
+        const int my = h >> 1, mx = w >> 1;
+        const int ya = (h & 1) ? my : my - 1, xa = (w & 1) ? mx : mx - 1;
+        const float wya = (h & 1) ? 0.75f : 0.25f, wxa = (w & 1) ? 0.75f : 0.25f;
+#pragma unroll
+        for (int dy = 0; dy < 2; ++dy) {
+          const int yy = ya + dy;
+          if (yy < 0 || yy >= Hp) continue;
+#pragma unroll
+          for (int dx = 0; dx < 2; ++dx) {
+            const int xx = xa + dx;
+            if (xx < 0 || xx >= Wp) continue;
+            const float kw = (dy ? 1.f - wya : wya) * (dx ? 1.f - wxa : wxa);
+            const float* pv = p.prev4 + ((static_cast<size_t>(b) * Hp + yy) * Wp + xx) * pc;
+            if (pc == 4) {
+              const float4 q = __ldg(reinterpret_cast<const float4*>(pv));
+              up[0] += kw * q.x; up[1] += kw * q.y; up[2] += kw * q.z; up[3] += kw * q.w;
+            } else {
+              const float2 q = __ldg(reinterpret_cast<const float2*>(pv));
+              up[0] += kw * q.x; up[1] += kw * q.y;
+            }
+          }
+        }
+      }
       mbar_wait(&t_full[acs], acph);
       tc_fence_after();
       const uint32_t trow = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + acs * 128 + sub * 64;
@@ -172,7 +201,7 @@ __global__ void __launch_bounds__(kHeadThreads, 1) head_tc_kernel(const __grid_c
       __syncwarp();
       if (lane == 0) mbar_arrive(&t_empty[acs]);
       named_bar_sync(1, 256);
-      if (e < kHeadTile * kHeadTile && h < p.H && w < p.W) {
+      if (live) {
         float o[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
         for (int co = 0; co < 4; ++co) if (co < pc) o[co] = __ldg(p.bias + co);
@@ -185,31 +214,8 @@ __global__ void __launch_bounds__(kHeadThreads, 1) head_tc_kernel(const __grid_c
             for (int co = 0; co < 4; ++co) if (co < pc) o[co] += src[co];
           }
         }
-        if (p.prev4 != nullptr) {
-          const int Hp = p.H >> 1, Wp = p.W >> 1;
-          const int my = h >> 1, mx = w >> 1;
-          const int ya = (h & 1) ? my : my - 1, xa = (w & 1) ? mx : mx - 1;
-          const float wya = (h & 1) ? 0.75f : 0.25f, wxa = (w & 1) ? 0.75f : 0.25f;
 #pragma unroll
-          for (int dy = 0; dy < 2; ++dy) {
-            const int yy = ya + dy;
-            if (yy < 0 || yy >= Hp) continue;
-#pragma unroll
-            for (int dx = 0; dx < 2; ++dx) {
-              const int xx = xa + dx;
-              if (xx < 0 || xx >= Wp) continue;
-              const float kw = (dy ? 1.f - wya : wya) * (dx ? 1.f - wxa : wxa);
-              const float* pv = p.prev4 + ((static_cast<size_t>(b) * Hp + yy) * Wp + xx) * pc;
-              if (pc == 4) {
-                const float4 q = __ldg(reinterpret_cast<const float4*>(pv));
-                o[0] += kw * q.x; o[1] += kw * q.y; o[2] += kw * q.z; o[3] += kw * q.w;
-              } else {
-                const float2 q = __ldg(reinterpret_cast<const float2*>(pv));
-                o[0] += kw * q.x; o[1] += kw * q.y;
-              }
-            }
-          }
-        }
+        for (int co = 0; co < 4; ++co) o[co] += up[co];  // (conv + bias) + upsampled pyramid, like the reference's sum
         const size_t pix = (static_cast<size_t>(b) * p.H + h) * p.W + w;
         if (pc == 4) reinterpret_cast<float4*>(p.out4)[pix] = make_float4(o[0], o[1], o[2], o[3]);
         else reinterpret_cast<float2*>(p.out4)[pix] = make_float2(o[0], o[1]);
