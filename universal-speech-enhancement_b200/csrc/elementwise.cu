@@ -532,55 +532,62 @@ __global__ void __launch_bounds__(256, 4) gn_fir_down_kernel(GnSrcT<T> s0, const
   constexpr int CH = FirDownCh<T>::value;
   constexpr int VPC = CH / V;  // 4
   constexpr int TO = 8, WIN = 18, NPX = WIN * WIN;
+  // Shared-memory layout: a pixel's slice is 64 B = half of the 32 banks, and the filter reads every OTHER pixel of a
+  // row (8 of them per warp-wide LDS.128): with a plain [row][pixel] layout all eight land in the same half (2x bank
+  // conflicts, and shared-memory wavefronts were this kernel's limiter).  Pixels 2 and 3 of every group of four are
+  // swapped (physical column = c ^ ((c >> 1) & 1)), which makes the bank half alternate along any stride-2 walk; rows
+  // are padded to 20 pixels (a multiple of 128 B).
+  constexpr int WROW = 20, NPHYS = WIN * WROW;
   extern __shared__ __align__(16) unsigned char smraw[];
-  T* sa = reinterpret_cast<T*>(smraw);  // activated [NPX][CH]
-  T* sr = sa + NPX * CH;                // raw       [NPX][CH]
-  float* saff = reinterpret_cast<float*>(sr + NPX * CH);
+  T* sa = reinterpret_cast<T*>(smraw);  // activated [WIN][WROW][CH]
+  T* sr = sa + NPHYS * CH;              // raw       [WIN][WROW][CH]
+  float* saff = reinterpret_cast<float*>(sr + NPHYS * CH);
+  auto phys = [](int wr, int wc) { return wr * WROW + (wc ^ ((wc >> 1) & 1)); };
   const int C = s0.C;
   const int Hout = Hin / 2, Wout = Win / 2;
-  const int tiles_x = (Wout + TO - 1) / TO, tiles_y = (Hout + TO - 1) / TO;
-  const int nchunk = C / CH;
-  const int ntiles = nchunk * tiles_x * tiles_y * B;  // channel slice fastest: concurrent blocks read whole DRAM rows
+  const int tiles_x = (Wout + TO - 1) / TO;
   const int v = threadIdx.x & (VPC - 1), ps = threadIdx.x / VPC;
   constexpr int PSTEP = 256 / VPC;                 // 64
   constexpr int NIT = (NPX + PSTEP - 1) / PSTEP;   // 6
-
-  // One tile per block, channel slice fastest.  (Measured alternatives at 512 x 640 x 128 x 16 clips: persistent blocks
-  // with a register-level prefetch of the next window 1.7 TB/s, 128-byte slices with 2x2 outputs per thread 1.8 TB/s,
-  // this form 2.0 TB/s: the kernel is bound by issue slots lost at the two barriers, not by bytes in flight.)
-  auto decode = [&](int t, int& b, int& c0, int& oy0, int& ox0) {
-    c0 = (t % nchunk) * CH; t /= nchunk;
-    ox0 = (t % tiles_x) * TO; t /= tiles_x;
-    oy0 = (t % tiles_y) * TO; b = t / tiles_y;
-  };
-  auto load_window = [&](int t, uint4 (&r)[NIT], uint32_t& inb) {
-    int b, c0, oy0, ox0;
-    decode(t, b, c0, oy0, ox0);
+  // One tile per block; grid = (channel slice, tile, sample): the slices of the same pixels run concurrently, so DRAM
+  // sees whole rows.  (Measured alternatives at 512 x 640 x 128 x 16 clips: persistent blocks with a register-level
+  // prefetch of the next window 1.7 TB/s, 128-byte slices with 2x2 outputs per thread 1.8 TB/s, this form 2.0 TB/s and,
+  // with the conflict-free shared-memory layout below, 2.7 TB/s in fp32.)
+  {
+    const int b = blockIdx.z, c0 = blockIdx.x * CH;
+    const int ty = blockIdx.y / tiles_x;
+    const int oy0 = ty * TO, ox0 = (blockIdx.y - ty * tiles_x) * TO;
     const int iy0 = 2 * oy0 - 1, ix0 = 2 * ox0 - 1;
     const T* src = s0.x + static_cast<size_t>(b) * Hin * Win * C + c0 + v * V;
-    inb = 0;
+    // interior tiles (all but the image border) need no bounds checks and no zero padding
+    const bool interior = iy0 >= 0 && ix0 >= 0 && iy0 + WIN <= Hin && ix0 + WIN <= Win;
+    uint4 cur[NIT];
+    uint32_t inb_cur = 0;
+    if (interior) {
+      const T* s00 = src + (static_cast<size_t>(iy0) * Win + ix0) * C;
 #pragma unroll
-    for (int k = 0; k < NIT; ++k) {
-      const int pw = ps + k * PSTEP;
-      const int wr = pw / WIN, wc = pw - wr * WIN;
-      const int iy = iy0 + wr, ix = ix0 + wc;
-      const bool in = pw < NPX && iy >= 0 && iy < Hin && ix >= 0 && ix < Win;
-      inb |= in ? (1u << k) : 0u;
-      r[k] = in ? __ldg(reinterpret_cast<const uint4*>(src + (static_cast<size_t>(iy) * Win + ix) * C)) : make_uint4(0, 0, 0, 0);
+      for (int k = 0; k < NIT; ++k) {
+        const int pw = ps + k * PSTEP;
+        const int wr = pw / WIN, wc = pw - wr * WIN;
+        const bool in = pw < NPX;
+        inb_cur |= in ? (1u << k) : 0u;
+        cur[k] = in ? __ldg(reinterpret_cast<const uint4*>(s00 + (static_cast<size_t>(wr) * Win + wc) * C)) : make_uint4(0, 0, 0, 0);
+      }
+    } else {
+#pragma unroll
+      for (int k = 0; k < NIT; ++k) {
+        const int pw = ps + k * PSTEP;
+        const int wr = pw / WIN, wc = pw - wr * WIN;
+        const int iy = iy0 + wr, ix = ix0 + wc;
+        const bool in = pw < NPX && iy >= 0 && iy < Hin && ix >= 0 && ix < Win;
+        inb_cur |= in ? (1u << k) : 0u;
+        cur[k] = in ? __ldg(reinterpret_cast<const uint4*>(src + (static_cast<size_t>(iy) * Win + ix) * C)) : make_uint4(0, 0, 0, 0);
+      }
     }
-  };
-
-  uint4 cur[NIT];
-  uint32_t inb_cur = 0;
-  for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-    int b, c0, oy0, ox0;
-    decode(tile, b, c0, oy0, ox0);
-    load_window(tile, cur, inb_cur);
     if (threadIdx.x < CH) {
       const int c = c0 + threadIdx.x;
       if (aff != nullptr) {
-        // scale / shift precomputed once per launch (launch_gn_affine): the fp64 statistics arithmetic below costs
-        // ~2.5k cycles of one warp while the other seven wait at the barrier -- per TILE, it dominated the old kernel
+        // scale / shift precomputed once per launch (launch_gn_affine)
         saff[threadIdx.x] = __ldg(aff + (static_cast<size_t>(b) * 2) * C + c);
         saff[CH + threadIdx.x] = __ldg(aff + (static_cast<size_t>(b) * 2 + 1) * C + c);
       } else {
@@ -620,8 +627,10 @@ __global__ void __launch_bounds__(256, 4) gn_fir_down_kernel(GnSrcT<T> s0, const
             const float n = fmaf(f[j], sc[j], sh[j]);
             a[j] = in ? (do_silu ? silu_act<T>(n) : n) : 0.f;  // the FIR pads the ACTIVATED tensor with zeros
           }
-          sts_vec<T>(sa + pw * CH + v * V, a);
-          *reinterpret_cast<uint4*>(sr + pw * CH + v * V) = cur[k];
+          const int wr = pw / WIN, wc = pw - wr * WIN;
+          const int pp = phys(wr, wc);
+          sts_vec<T>(sa + pp * CH + v * V, a);
+          *reinterpret_cast<uint4*>(sr + pp * CH + v * V) = cur[k];
         }
       }
     }
@@ -631,8 +640,12 @@ __global__ void __launch_bounds__(256, 4) gn_fir_down_kernel(GnSrcT<T> s0, const
     for (int it = threadIdx.x; it < TO * TO * NQ; it += 256) {
       const int q = it % NQ, px = it / NQ;
       const int oy = px / TO, ox = px - oy * TO;
-      const T* pa = sa + ((2 * oy) * WIN + 2 * ox) * CH + q * 4;
-      const T* pr = sr + ((2 * oy) * WIN + 2 * ox) * CH + q * 4;
+      // window column 2 ox + bb -> physical column c ^ ((c >> 1) & 1)
+      const T* pa = sa + ((2 * oy) * WROW) * CH + q * 4;
+      const T* pr = sr + ((2 * oy) * WROW) * CH + q * 4;
+      int colp[4];
+#pragma unroll
+      for (int bb = 0; bb < 4; ++bb) { const int c = 2 * ox + bb; colp[bb] = (c ^ ((c >> 1) & 1)) * CH; }
       float4 acc = make_float4(0.f, 0.f, 0.f, 0.f), raw = acc;
       const float k1[4] = {0.125f, 0.375f, 0.375f, 0.125f};
 #pragma unroll
@@ -640,8 +653,8 @@ __global__ void __launch_bounds__(256, 4) gn_fir_down_kernel(GnSrcT<T> s0, const
         float4 ha = make_float4(0.f, 0.f, 0.f, 0.f), hr = ha;
 #pragma unroll
         for (int bb = 0; bb < 4; ++bb) {
-          fma4(ha, k1[bb], lds4<T>(pa + (a * WIN + bb) * CH));
-          fma4(hr, k1[bb], lds4<T>(pr + (a * WIN + bb) * CH));
+          fma4(ha, k1[bb], lds4<T>(pa + a * WROW * CH + colp[bb]));
+          fma4(hr, k1[bb], lds4<T>(pr + a * WROW * CH + colp[bb]));
         }
         fma4(acc, k1[a], ha);
         fma4(raw, k1[a], hr);
@@ -662,8 +675,6 @@ __global__ void __launch_bounds__(256, 4) gn_fir_down_kernel(GnSrcT<T> s0, const
         if (out_raw != nullptr) put(out_raw, raw);
       }
     }
-    // (a block that loops: the __syncthreads at the top of the next iteration orders this filter phase before the next
-    // window's stores)
   }
 }
 
@@ -679,9 +690,8 @@ void launch_gn_apply(int dt, GnSrc s0, GnSrc s1, const float* gamma, const float
       GnSrcT<T> a{(const T*)s0.x, s0.stats, s0.C};
       if (fir == 1) {
         constexpr int CHD = FirDownCh<T>::value;
-        const long long ntiles = static_cast<long long>(s0.C / CHD) * ((Hout + 7) / 8) * ((Wout + 7) / 8) * B;
-        const int grid = static_cast<int>(std::min<long long>(ntiles, 1LL << 30));
-        const size_t sm = 2 * 18 * 18 * CHD * sizeof(T) + 2 * CHD * sizeof(float);
+        dim3 grid(s0.C / CHD, ((Hout + 7) / 8) * ((Wout + 7) / 8), B);
+        const size_t sm = 2 * 18 * 20 * CHD * sizeof(T) + 2 * CHD * sizeof(float);
         gn_fir_down_kernel<T><<<grid, 256, sm, st>>>(a, gamma, beta, eps, do_silu, as_operand, (T*)out_act, (T*)out_raw, Hin, Win, B, aff);
       } else {
         dim3 grid(((Hout + 15) / 16) * ((Wout + 15) / 16), s0.C / CH, B);
