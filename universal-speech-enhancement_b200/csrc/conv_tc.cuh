@@ -21,7 +21,7 @@
 // alternatives: global -> registers -> smem in the transform warps exposes the load latency, 70 % of the plain conv
 // speed; in place behind a 3-deep TMA ring: 92-94 %.  L2 prefetch hints made both variants slower.)
 //
-// Warp roles: warp 0 = TMA producer (1 thread), warp 1 = TMEM owner + MMA issuer (1 thread),
+// Warp roles: warp 0 = TMA producer (1 thread), warp 1 = TMEM owner + MMA issuer (the warp in lockstep, one elected lane),
 // warps 2..2+4*NSUB = epilogue (TMEM -> registers -> bias / residual / scale -> global), then 6 transform warps.
 // Accumulators are double-buffered in TMEM (2 x NSUB x N columns) so the epilogue of tile i overlaps the MMAs of
 // tile i+1.  Persistent CTAs, static round-robin over tiles (w fastest: neighbours share halos and weights in L2).
@@ -117,6 +117,7 @@ struct ConvCfg {
 // which halves that stream.  A weight slot is recycled only when the MMAs of BOTH CTAs have released it (b_empty
 // counts 2 arrivals, one of them a multicast tcgen05.commit from the peer).  A CTA whose tile index falls past the end
 // processes a "ghost" tile (loads are zero-filled out of bounds, nothing is stored) to keep the pair in lockstep.
+// Measured: no gain (a multicast to fewer than ~8 CTAs is not deduplicated in L2 on this part); off by default.
 //
 // CG2 (C_out = 128, pixel-major, MC = 2): the CTA pair issues ONE tcgen05.mma.cta_group::2 per step (M = 256 = the 128
 // pixels of a sub-tile of each CTA, N = 128): each CTA stages only HALF of every weight tile (its 64 C_out rows; the
@@ -124,7 +125,9 @@ struct ConvCfg {
 // layers -- and doubles the time the weight ring covers.  Only the leader (cluster rank 0) issues MMAs; every barrier
 // that collects both CTAs' arrivals (a_full, b_full, t_empty) lives in the leader and is signalled remotely by the
 // peer's TMA loads (cp.async.bulk.tensor.cta_group::2), transform warps and epilogue warps; the leader's
-// tcgen05.commit releases slots / publishes accumulators in both CTAs by multicast.
+// tcgen05.commit releases slots / publishes accumulators in both CTAs by multicast.  Measured: bit-correct, but slower
+// than swap-AB (1332 vs 1713 TFLOP/s, bf16 128 -> 128): the leader issues eight N = 128 MMAs per tap for two SMs and the
+// pixel-major epilogue is heavier; USE_B200_CONV_CG2=1 selects it for experiments.
 template <typename T, int N, int NSUB, bool SWAP, bool FUSE, int MC = 1, bool PROF = false, bool CG2 = false>
 __global__ void __launch_bounds__(ConvCfg<T, N, NSUB, FUSE, CG2>::THREADS, 1) conv_tc_kernel(const __grid_constant__ ConvParams p) {
   using C = ConvCfg<T, N, NSUB, FUSE, CG2>;
