@@ -77,15 +77,6 @@ static bool encode_w(CUtensorMap* m, int dt, const void* base, int taps, int N, 
   return true;
 }
 
-// swap-AB variant of the C_out = 128 kernel (see conv_tc.cuh); USE_B200_CONV_SWAP=0 selects the pixel-major one.
-static bool swap_ab_enabled() {
-  static bool on = [] {
-    const char* v = getenv("USE_B200_CONV_SWAP");
-    return !(v && v[0] == '0');
-  }();
-  return on;
-}
-
 // CTA-pair weight multicast (cluster of 2) is OFF by default: measured on B200 it changes nothing (bf16 128 -> 128 at
 // 512 x 640 x 16: 1442 TFLOP/s with it, 1462 without).  The L2 -> SM path is the limiter of these layers (the PROF build
 // gains 18 % with the weight stream removed), but a multicast to fewer than ~8 CTAs is not deduplicated in L2 on this
