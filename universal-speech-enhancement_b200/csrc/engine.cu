@@ -183,7 +183,12 @@ struct Program {
   size_t stats_bytes = 0;
   size_t pyramid_off = 0;  // final fp32 [B][F][T][4]
   char* base = nullptr;
+  // the launch sequence of one evaluation as a CUDA graph (captured on first use, replayed every step)
+  cudaGraphExec_t graph = nullptr;
+  bool graph_failed = false;
+  long long graph_launches = 0;
   ~Program() {
+    if (graph) cudaGraphExecDestroy(graph);
     for (auto* p : plans) tc_conv_plan_destroy(p);
     for (auto* p : heads) head_tc_plan_destroy(p);
   }
@@ -215,6 +220,9 @@ struct use_engine {
   // GroupNorm + SiLU applied inside the convolution kernel's operand path (no normalised tensor in HBM); off: the
   // separate gn_apply kernel feeds the same convolutions (A/B testing: both give bit-identical results)
   bool fuse_gn = true;
+  // replay the ~230 launches of an evaluation as one CUDA graph (small batches are launch-latency bound: the deep levels
+  // run dozens of kernels of a few microseconds each)
+  bool use_graphs = true;
   cudaStream_t gstream[2] = {nullptr, nullptr};
   cudaEvent_t ev_fork = nullptr, ev_join[2] = {nullptr, nullptr};
   // instrumentation
@@ -858,7 +866,7 @@ static Program* get_program(use_engine* e, int B, int F, int T, void* workspace,
 }
 
 // one network evaluation: t / gfp already in the workspace head; xr packed
-static void run_network(use_engine* e, Program* p, cudaStream_t st, const float* gfp, int gfp_bstride) {
+static void run_network(use_engine* e, Program* p, cudaStream_t st, const float* gfp, int gfp_bstride, bool allow_graph) {
   char* base = p->base;
   const int nf = e->cfg.nf;
   cudaMemsetAsync(base + e->head.stats, 0, p->stats_bytes, st);  // fixed-point accumulators start at zero
@@ -872,6 +880,31 @@ static void run_network(use_engine* e, Program* p, cudaStream_t st, const float*
     e->launches += 2;
   }
   if (!e->profiling) {
+    if (allow_graph && e->use_graphs && !p->graph && !p->graph_failed) {
+      // capture needs a non-legacy stream (use_pc_sample runs on the engine's own streams); anything that refuses to be
+      // captured falls back to plain launches for good
+      cudaGraph_t g = nullptr;
+      if (cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal) == cudaSuccess) {
+        long long n = 0;
+        for (auto& op : p->ops) { op.fn(st); n += op.launches; }
+        if (cudaStreamEndCapture(st, &g) == cudaSuccess && g != nullptr &&
+            cudaGraphInstantiate(&p->graph, g, 0) == cudaSuccess) {
+          p->graph_launches = n;
+        } else {
+          p->graph = nullptr;
+          p->graph_failed = true;
+        }
+        if (g) cudaGraphDestroy(g);
+      } else {
+        p->graph_failed = true;
+      }
+      cudaGetLastError();
+    }
+    if (allow_graph && p->graph) {
+      cudaGraphLaunch(p->graph, st);
+      e->launches += p->graph_launches;
+      return;
+    }
     for (auto& op : p->ops) { op.fn(st); e->launches += op.launches; }
     return;
   }
@@ -938,6 +971,7 @@ use_engine* use_engine_create(const use_config* cfg) {
   }
   cudaGetLastError();
   if (const char* v = getenv("USE_B200_FUSE_GN")) e->fuse_gn = v[0] != '0';
+  if (const char* v = getenv("USE_B200_GRAPHS")) e->use_graphs = v[0] != '0';
   return e;
 }
 
@@ -995,6 +1029,11 @@ int use_engine_set_option(use_engine* e, const char* key, int value) {
     e->groups = value;
     return 0;
   }
+  if (!strcmp(key, "use_graphs")) {
+    e->use_graphs = value != 0;
+    e->programs.clear();
+    return 0;
+  }
   if (!strcmp(key, "fuse_gn")) {
     e->fuse_gn = value != 0;
     e->programs.clear();
@@ -1018,7 +1057,7 @@ static int net_forward(use_engine* e, int B, int F, int T, const void* x, const 
   const size_t per = (size_t)F * T;
   launch_pack_input(e->dt, e->cfg.input_channels, (const float2*)x, (const float2*)Y, (float*)(p->base + e->head.xr),
                     p->base + e->head.xpad, per * B, st);
-  run_network(e, p, st, (const float*)(p->base + e->head.gfp), 2 * e->cfg.nf);
+  run_network(e, p, st, (const float*)(p->base + e->head.gfp), 2 * e->cfg.nf, false);  // caller's stream: plain launches
   StepArgs a{};
   a.pyramid = (const float*)(p->base + p->pyramid_off);
   a.pc = e->cfg.input_channels;
@@ -1067,7 +1106,10 @@ int use_pc_sample(use_engine* e, int B, int F, int T, const void* Y, void* x_sta
     prog[g] = get_program(e, Bg, F, T, (char*)workspace + g * slice, slice);
     if (!prog[g]) return 1;
   }
-  if (G > 1) {
+  // the loop runs on the engine's own streams: two half-batches side by side, and (also for a single group) a stream
+  // that CUDA graph capture accepts -- the caller's stream may be the legacy default stream
+  const bool own_streams = G > 1 || e->use_graphs;
+  if (own_streams) {
     for (int g = 0; g < G; ++g) {
       if (!e->gstream[g]) cudaStreamCreateWithFlags(&e->gstream[g], cudaStreamNonBlocking);
       if (!e->ev_join[g]) cudaEventCreateWithFlags(&e->ev_join[g], cudaEventDisableTiming);
@@ -1100,7 +1142,7 @@ int use_pc_sample(use_engine* e, int B, int F, int T, const void* Y, void* x_sta
       const float* gfp_dev = (const float*)(base + e->head.sched) + N + (size_t)i * nf2;
       launch_pack_input(e->dt, 4, (const float2*)x_state + o, (const float2*)Y + o, (float*)(base + e->head.xr),
                         base + e->head.xpad, n, gs[g]);
-      run_network(e, p, gs[g], gfp_dev, 0);
+      run_network(e, p, gs[g], gfp_dev, 0, own_streams);
       StepArgs a{};
       a.pyramid = (const float*)(base + p->pyramid_off);
       a.pc = 4;
@@ -1127,7 +1169,7 @@ int use_pc_sample(use_engine* e, int B, int F, int T, const void* Y, void* x_sta
       e->launches += 2;
     }
   }
-  if (G > 1) {
+  if (own_streams) {
     for (int g = 0; g < G; ++g) {
       cudaEventRecord(e->ev_join[g], gs[g]);
       cudaStreamWaitEvent(st, e->ev_join[g], 0);
