@@ -84,6 +84,27 @@ def test_engine_host_logic_discriminative_generator():
     L.use_engine_destroy(h)
 
 
+def test_engine_options():
+    """A/B switches of the engine: known keys are accepted (and both plans still fit their workspace), unknown ones and
+    out-of-range values fail with a message."""
+    L = _lib.lib()
+    h = _engine(L, O.TINY, 1)
+    _feed(L, h, O.make_state_dict(O.TINY, seed=11))
+    assert L.use_engine_pack(h, None) == 0, L.use_last_error()
+    sizes = {}
+    for fuse in (1, 0):
+        assert L.use_engine_set_option(h, b"fuse_gn", fuse) == 0
+        w = C.c_size_t()
+        assert L.use_engine_workspace_bytes(h, 2, 16, 24, C.byref(w)) == 0, L.use_last_error()
+        sizes[fuse] = w.value
+    assert sizes[0] > 0 and sizes[1] > 0
+    for key, val in ((b"use_graphs", 0), (b"use_graphs", 1), (b"overlap_groups", 1), (b"overlap_groups", 2)):
+        assert L.use_engine_set_option(h, key, val) == 0, L.use_last_error()
+    assert L.use_engine_set_option(h, b"overlap_groups", 3) != 0 and b"overlap_groups" in L.use_last_error()
+    assert L.use_engine_set_option(h, b"no_such_option", 1) != 0 and b"unknown option" in L.use_last_error()
+    L.use_engine_destroy(h)
+
+
 def test_engine_rejects_missing_and_misshaped_weights():
     L = _lib.lib()
     h = _engine(L, O.TINY, 0)
