@@ -471,11 +471,15 @@ __global__ void __launch_bounds__(ConvCfg<T, N, NSUB, FUSE, CG2>::THREADS, 1) co
           }
         }
       }
-      mbar_wait_p<PROF>(&t_full[acs], acph, w_f);
-      tc_fence_after();
+      // (the swap-AB forms request the first chunk of the residual BEFORE waiting for the accumulator)
+      auto wait_acc = [&]() {
+        mbar_wait_p<PROF>(&t_full[acs], acph, w_f);
+        tc_fence_after();
+      };
       bool dbg_skip = false, dbg_nostore = false;
       if constexpr (PROF) { dbg_skip = (p.dbg & 1) != 0; dbg_nostore = (p.dbg & 2) != 0; }
       if (dbg_skip) {
+        wait_acc();
       } else if constexpr (SWAP) {
         // channel-major accumulator: this thread = output channel quad*32 + lane; warp half `sub` owns pixel columns
         // [128*sub, 128*sub + 128) of the 256-pixel tile = tile rows [16*sub, 16*sub + 16).  Every pixel is written
@@ -502,18 +506,27 @@ __global__ void __launch_bounds__(ConvCfg<T, N, NSUB, FUSE, CG2>::THREADS, 1) co
           __nv_bfloat16* ob2 = reinterpret_cast<__nv_bfloat16*>(out) + (tile_off - c + ce);
           const __nv_bfloat16* rb2 = reinterpret_cast<const __nv_bfloat16*>(res) + (tile_off - c + ce);
           float s2[2] = {0.f, 0.f}, q2[2] = {0.f, 0.f};  // partial sums for channels ce, ce+1 over this lane's pixels
+          // residual words of the current 32-pixel chunk: chunk 0 is requested before the wait for the accumulator, the
+          // others at the top of their chunk.  (The element-wise rolling prefetch of the fp32 form below was measured
+          // here too: 16 % slower in bf16, where every element already costs a shuffle and a packed store.)
+          uint32_t rres[16];
+          auto load_res = [&](int ch, int k) -> uint32_t {
+            const int row0 = sub * 16 + ch * 4;
+            const int idx = 2 * k + (odd ? 1 : 0), i = idx >> 3, j = idx & 7;
+            const bool ok = (th0 + row0 + i < p.H) && ((wmask >> j) & 1u);
+            return ok ? __ldg(reinterpret_cast<const uint32_t*>(rb2 + (row0 + i) * rowstride + static_cast<size_t>(j) * N)) : 0u;
+          };
+          if (res != nullptr) {
+#pragma unroll
+            for (int k = 0; k < 16; ++k) rres[k] = load_res(0, k);
+          }
+          wait_acc();
 #pragma unroll 1
           for (int ch = 0; ch < 4; ++ch) {
             const int row0 = sub * 16 + ch * 4;
-            uint32_t rres[16];
-            if (res != nullptr) {
+            if (res != nullptr && ch > 0) {
 #pragma unroll
-              for (int k = 0; k < 16; ++k) {
-                const int idx = 2 * k + (odd ? 1 : 0), i = idx >> 3, j = idx & 7;
-                const bool ok = (th0 + row0 + i < p.H) && ((wmask >> j) & 1u);
-                rres[k] = ok ? __ldg(reinterpret_cast<const uint32_t*>(rb2 + (row0 + i) * rowstride + static_cast<size_t>(j) * N))
-                             : 0u;
-              }
+              for (int k = 0; k < 16; ++k) rres[k] = load_res(ch, k);
             }
             uint32_t r[32];
             tmem_ld32(tcol + ch * 32, r);
@@ -550,21 +563,25 @@ __global__ void __launch_bounds__(ConvCfg<T, N, NSUB, FUSE, CG2>::THREADS, 1) co
           }
         } else {
         float s_sum = 0.f, s_sq = 0.f;
+        // residual of the current chunk, rolling prefetch: chunk 0 is requested before the wait for the accumulator and
+        // element (i, j) of chunk ch + 1 as soon as element (i, j) of chunk ch has been consumed, so a chunk's loads are in
+        // flight during the stores of the previous one (TF32 128 -> 128 + residual: 665 -> 713 TFLOP/s)
+        float rv[32];
+        auto load_res = [&](int ch, int i, int j) -> float {
+          const int row0 = sub * 16 + ch * 4;
+          const bool ok = (th0 + row0 + i < p.H) && ((wmask >> j) & 1u);
+          return ok ? static_cast<float>(__ldg(rbase + (row0 + i) * rowstride + static_cast<size_t>(j) * N)) : 0.f;
+        };
+        if (res != nullptr) {
+#pragma unroll
+          for (int i = 0; i < 4; ++i)
+#pragma unroll
+            for (int j = 0; j < 8; ++j) rv[i * 8 + j] = load_res(0, i, j);
+        }
+        wait_acc();
 #pragma unroll 1
         for (int ch = 0; ch < 4; ++ch) {
           const int row0 = sub * 16 + ch * 4;  // first tile row of this 32-pixel chunk (4 rows x 8 columns)
-          float rv[32];
-          if (res != nullptr) {
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-              const bool rok = th0 + row0 + i < p.H;
-#pragma unroll
-              for (int j = 0; j < 8; ++j)
-                rv[i * 8 + j] = (rok && ((wmask >> j) & 1u))
-                                    ? static_cast<float>(rbase[(row0 + i) * rowstride + static_cast<size_t>(j) * N])
-                                    : 0.f;
-            }
-          }
           uint32_t r[32];
           tmem_ld32(tcol + ch * 32, r);
           tmem_ld_wait();
@@ -574,7 +591,10 @@ __global__ void __launch_bounds__(ConvCfg<T, N, NSUB, FUSE, CG2>::THREADS, 1) co
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
               float v = __uint_as_float(r[i * 8 + j]) + bias_c;
-              if (res != nullptr) v += rv[i * 8 + j];
+              if (res != nullptr) {
+                v += rv[i * 8 + j];
+                if (ch < 3) rv[i * 8 + j] = load_res(ch + 1, i, j);
+              }
               v *= p.scale;
               if (rok && ((wmask >> j) & 1u)) {
                 obase[(row0 + i) * rowstride + static_cast<size_t>(j) * N] = static_cast<T>(v);
@@ -591,6 +611,7 @@ __global__ void __launch_bounds__(ConvCfg<T, N, NSUB, FUSE, CG2>::THREADS, 1) co
         }
         }  // fp32 direct stores
       } else {
+      wait_acc();
       const uint32_t trow = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + acs * C::ACC_COLS + sub * N;
 #pragma unroll 1
       for (int c0 = 0; c0 < N; c0 += 32) {
