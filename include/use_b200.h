@@ -174,6 +174,9 @@ int use_op_fir4_down(const float* x, float* out, int B, int Hin, int Win, int pc
 int use_op_philox(void* z, uint64_t seed, uint32_t step, uint32_t clip0, int B, size_t per_clip, void* stream);
 /* pack fp32 OIHW conv weights into the tcgen05 layout [taps][O][I] of the act dtype (host -> host). */
 int use_pack_conv_weight(int dtype, const float* w_oihw, int O, int I, int ksize, void* out);
+/* pack fp32 [pc][C][3][3] pyramid-head weights into the head kernel's layout: act dtype [48][C], row tap * pc + c_out
+ * (rows >= 9 * pc are zero): the nine taps folded into the MMA's N dimension (host -> host). */
+int use_pack_head_weight(int dtype, const float* w_oihw, int pc, int C, void* out);
 
 #if defined(__GNUC__)
 #pragma GCC visibility pop

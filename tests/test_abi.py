@@ -142,6 +142,44 @@ def test_pack_conv_weight_layout():
     assert torch.equal(outb.reshape(9, 2, 3), w.reshape(2, 3, 9).permute(2, 0, 1).to(torch.bfloat16))
 
 
+def test_pack_head_weight_layout():
+    """Pyramid-head weights: [pc][C][3][3] -> [48][C] with row tap * pc + c_out, zero rows above 9 * pc."""
+    L = _lib.lib()
+    for pc in (4, 2):
+        Cc = 64
+        w = torch.randn(pc, Cc, 3, 3)
+        out = torch.full((48, Cc), float("nan"), dtype=torch.float32)
+        assert L.use_pack_head_weight(0, w.contiguous().data_ptr(), pc, Cc, out.data_ptr()) == 0
+        ref = torch.zeros(48, Cc)
+        for tap in range(9):
+            for co in range(pc):
+                ref[tap * pc + co] = w[co, :, tap // 3, tap % 3]
+        # fp32 mode stores TF32-rounded values
+        from util import round_tf32
+        assert torch.equal(out, round_tf32(ref))
+        outb = torch.empty(48, Cc, dtype=torch.bfloat16)
+        assert L.use_pack_head_weight(1, w.contiguous().data_ptr(), pc, Cc, outb.data_ptr()) == 0
+        assert torch.equal(outb, ref.to(torch.bfloat16))
+    assert L.use_pack_head_weight(0, w.data_ptr(), 3, 64, out.data_ptr()) != 0
+
+
+def test_ncu_summary_tool_reproduces_committed_summary(tmp_path):
+    """tools/summarize_ncu.py on the committed launch list gives the committed per-kernel summary (the file bench.py
+    reads `roofline.traffic` from)."""
+    import json
+    import sys
+    for d in ("fp32", "bf16"):
+        src = os.path.join(ROOT, "profiles", f"r01_ncu_launches_{d}_b2.csv")
+        out = tmp_path / f"s_{d}.json"
+        subprocess.run([sys.executable, os.path.join(ROOT, "tools", "summarize_ncu.py"), src, str(out)], check=True,
+                       capture_output=True)
+        got = json.load(open(out))["kernels"]
+        ref = json.load(open(os.path.join(ROOT, "profiles", f"r01_kernel_summary_{d}.json")))["kernels"]
+        assert got == ref
+        conv = [v for k, v in got.items() if "conv_tc_kernel" in k]
+        assert sum(v["launches"] for v in conv) == 99  # the convolutions of one NCSNppLarge evaluation
+
+
 def test_missing_library_is_a_loud_error(monkeypatch, tmp_path):
     monkeypatch.setattr(_lib, "_lib", None)
     monkeypatch.setattr(_lib, "LIB_PATH", str(tmp_path / "nope.so"))

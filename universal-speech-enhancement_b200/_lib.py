@@ -25,7 +25,7 @@ SYMBOLS = [
     "use_engine_get_profile", "use_engine_get_profile_ops", "use_score_forward", "use_net_forward", "use_pc_sample",
     "use_stft", "use_istft", "use_upfirdn2d_f32", "use_op_gn_stats", "use_op_gn_apply", "use_op_conv_tc", "use_op_gn_affine", "use_op_conv_tc_gn", "use_op_head_tc", "use_op_combine_stats", "use_op_gn_apply_aff",
     "use_op_conv_ref", "use_op_conv_in4", "use_op_conv_out4", "use_op_combine", "use_op_fir4_down", "use_op_philox",
-    "use_pack_conv_weight",
+    "use_pack_conv_weight", "use_pack_head_weight",
 ]
 
 
@@ -107,6 +107,7 @@ def lib() -> C.CDLL:
         L.use_op_fir4_down.argtypes = [vp, vp, i32, i32, i32, i32, vp]
         L.use_op_philox.argtypes = [vp, u64, u32, u32, i32, sz, vp]
         L.use_pack_conv_weight.argtypes = [i32, vp, i32, i32, i32, vp]
+        L.use_pack_head_weight.argtypes = [i32, vp, i32, i32, vp]
         for name in SYMBOLS:
             fn = getattr(L, name)  # AttributeError here = header / library mismatch
             if fn.restype is C.c_int and name not in ("use_abi_version",):

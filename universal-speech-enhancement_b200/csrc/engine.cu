@@ -1386,6 +1386,12 @@ int use_op_philox(void* z, uint64_t seed, uint32_t step, uint32_t clip0, int B, 
   launch_philox_fill((float2*)z, seed, step, clip0, B, per_clip, (cudaStream_t)stream);
   return cuda_check("use_op_philox");
 }
+int use_pack_head_weight(int dtype, const float* w_oihw, int pc, int C, void* out) {
+  if (!w_oihw || !out) return fail("null argument");
+  if (pc != 2 && pc != 4) return fail("pc must be 2 or 4");
+  pack_head_weight(dtype, w_oihw, pc, C, out);
+  return 0;
+}
 int use_pack_conv_weight(int dtype, const float* w_oihw, int O, int I, int ksize, void* out) {
   if (!w_oihw || !out) return fail("null argument");
   pack_conv_weight(dtype, w_oihw, O, I, ksize, out);
