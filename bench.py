@@ -268,6 +268,17 @@ def main():
                             f"(ncu, batch {cap_b}, {tot_n} launches of one evaluation), scaled linearly to batch {B}")
     except Exception:
         pass
+    # clock-independent utilisation of the same kernel from the committed ncu capture (L0 layers, profiles/README.md)
+    ncu_pipe = None
+    try:
+        import csv
+
+        rows = list(csv.reader(open(os.path.join(ROOT, "profiles", f"r01_ncu_conv_L0_{args.dtype}.csv"))))
+        col = rows[0].index("sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active")
+        vals = [float(r[col]) for r in rows[2:] if r and r[col]]
+        ncu_pipe = round(sum(vals) / len(vals), 2) if vals else None
+    except Exception:
+        pass
     roofline = {
         "bound": "tensor", "kernel": "conv_tc_kernel (tcgen05 implicit-GEMM 3x3/1x1 convolutions, all launches of one "
                                      "network evaluation)",
@@ -278,6 +289,7 @@ def main():
         "launches_per_eval": conv["launches"],
         "per_class_ms_per_eval": {k: round(v["ms"], 3) for k, v in prof.items() if k != "top_conv"},
         "whole_path_tflops": world * B * N * FLOP_PER_CLIP_EVAL / (ms_step * 1e-3) / 1e12,
+        "ncu_tensor_pipe_active_pct_L0": ncu_pipe,
     }
 
     cpu_baseline = None
