@@ -66,7 +66,7 @@ class ClockSampler:
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         self.proc.terminate()
-        sm, smax, reasons = [], [], set()
+        sm, smax, power, reasons = [], [], [], set()
         for l in self.lines:
             f = [x.strip() for x in l.split(",")]
             if len(f) < 8:
@@ -75,14 +75,21 @@ class ClockSampler:
                 sm.append(float(f[1])); smax.append(float(f[2]))
             except ValueError:
                 continue
+            try:
+                power.append(float(f[3]))
+            except ValueError:
+                pass
             for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[4:8]):
                 if v.lower().startswith("active"):
                     reasons.add(name)
         sm.sort()
-        # median over samples taken under load (the top half of the samples)
-        load = sm[len(sm) // 2:] if sm else []
+        # the sampler only runs during the timed region: the plain median is the clock under load (under the 1 kW cap the
+        # loaded clock is LOWER than the idle one, so "top half" would pick the wrong samples)
+        load = sm
+        power.sort()
+        pw = power
         return {"sm_mhz": load[len(load) // 2] if load else None, "sm_max_mhz": max(smax) if smax else None,
-                "samples": len(sm), "reasons": sorted(reasons)}
+                "samples": len(sm), "reasons": sorted(reasons), "power_w": pw[len(pw) // 2] if pw else None}
 
 
 def cpu_oracle_rate(n_evals: int, threads: int):
