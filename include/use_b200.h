@@ -19,6 +19,8 @@
  *   use_pc_sample            sampling.get_pc_sampler().pc_sampler (sampling/__init__.py:59-71) with
  *                            ReverseDiffusionPredictor (sampling/predictors.py:61-68), NoneCorrector
  *                            (sampling/correctors.py:101-111), RSDE.discretize (sdes.py:159-173)
+ *   use_pc_sample_ex         the same loop with EulerMaruyamaPredictor (predictors.py:40-53), LangevinCorrector /
+ *                            AnnealedLangevinDynamics (sampling/correctors.py:37-98), probability flow, denoise=False
  *   use_stft / use_istft     ScoreModel.stft + spec_fwd + pad_spec / spec_back + istft
  *                            (model_wrapper.py:92-122, util/other.py:128-135)
  *   use_op_*                 single kernels, exported for the parity tests
@@ -36,10 +38,13 @@ extern "C" {
 #pragma GCC visibility push(default)
 #endif
 
-#define USE_B200_ABI_VERSION 3
+#define USE_B200_ABI_VERSION 4
 
 #define USE_DTYPE_F32 0  /* fp32 storage, TF32 tensor-core math (PyTorch's own GPU default for conv) */
 #define USE_DTYPE_BF16 1 /* bf16 storage + bf16 tensor-core math, fp32 accumulate / statistics / SDE state */
+#define USE_DTYPE_F32X3 2 /* parity mode: fp32 storage, every tensor-core convolution evaluated as the 3xTF32 split
+                           * x_hi w_hi + x_hi w_lo + x_lo w_hi (fp32-level accuracy at a third of the TF32 rate); engine
+                           * only (use_config.act_dtype), the single-kernel exports take USE_DTYPE_F32 / _BF16 */
 
 typedef struct use_engine use_engine;
 
@@ -105,6 +110,41 @@ int use_net_forward(use_engine* e, int B, int F, int T, const void* x, const voi
 int use_pc_sample(use_engine* e, int B, int F, int T, const void* Y, void* x_state, void* x_mean, int N,
                   const float* t_host, const float* G_host, const float* gfp_host, float prior_std, const void* noise,
                   uint64_t seed, uint32_t clip0, void* workspace, size_t workspace_bytes, void* stream);
+
+/* The general predictor-corrector sampler (sampling/__init__.py:23-73): use_pc_sample with the other registered
+ * predictors / correctors fused into the same one-call loop.
+ *   predictor  reverse_diffusion (predictors.py:56-68) | euler_maruyama (predictors.py:40-53 over RSDE.rsde_parts,
+ *              sdes.py:128-150) | none (predictors.py:71-79)
+ *   corrector  none (correctors.py:101-111) | langevin (correctors.py:37-64; its batch-mean norms are a deterministic
+ *              two-pass device reduction, the batch is never split into stream groups) | ald (correctors.py:67-98)
+ * Normal draws are consumed in the reference's order: the prior, then per outer step `corrector_steps` corrector draws
+ * and one predictor draw; explicit `noise` is complex64 [1 + N * (corrector_steps_eff + predictor_eff)][B][F][T]
+ * (corrector_steps_eff = 0 for corrector none, predictor_eff = 0 for predictor none), the Philox stream of draw d is
+ * keyed (seed, d, clip0 + b).  opts == NULL: reverse_diffusion + none, denoise = 1 (= use_pc_sample). */
+#define USE_PRED_REVERSE_DIFFUSION 0
+#define USE_PRED_EULER_MARUYAMA 1
+#define USE_PRED_NONE 2
+#define USE_CORR_NONE 0
+#define USE_CORR_LANGEVIN 1
+#define USE_CORR_ALD 2
+typedef struct use_sampler_opts {
+  int predictor;              /* USE_PRED_* */
+  int corrector;              /* USE_CORR_* */
+  int corrector_steps;        /* n_steps of the corrector */
+  float snr;                  /* Langevin target SNR */
+  int probability_flow;       /* 1: score term halved, no predictor noise (sdes.py:139-143,166-170) */
+  int denoise;                /* 1: return the noise-free mean of the last step; 0: the state itself */
+  const float* g_host;        /* [N] diffusion g(t_i) (host), required by euler_maruyama */
+  const float* ald_step_host; /* [N] 2 (snr std(t_i))^2 (host), required by ald */
+  void* trace;                /* optional device complex64 [N][B][F][T]: xt_mean after every outer step (parity tests) */
+  const void* x_init;         /* optional device complex64 [B][F][T]: start from this state instead of the prior draw
+                               * (single update_fn steps of the registry classes: N = 1 tables + dt_steps = sde.N) */
+  int dt_steps;               /* > 0: dt = 1 / dt_steps instead of 1 / N */
+} use_sampler_opts;
+int use_pc_sample_ex(use_engine* e, int B, int F, int T, const void* Y, void* x_state, void* x_mean, int N,
+                     const float* t_host, const float* G_host, const float* gfp_host, float prior_std, const void* noise,
+                     uint64_t seed, uint32_t clip0, const use_sampler_opts* opts, void* workspace, size_t workspace_bytes,
+                     void* stream);
 
 /* y: device float [B][L] -> Y: device complex64 [B][n_fft/2+1][Tp], frames >= 1 + L/hop zero (pad_spec).
  * window [n_fft] and twiddle [n_fft] (cos, sin of 2 pi i / n_fft, interleaved) are device arrays. */

@@ -452,49 +452,97 @@ def draw_noise(shape, N: int, seed: int, dtype=torch.complex64) -> Tensor:
     return torch.stack([torch.randn(shape, dtype=dtype, generator=g) for _ in range(N + 1)])
 
 
+def draws_per_step(predictor: str, corrector: str, corrector_steps: int) -> int:
+    """Normal draws one outer step consumes: the corrector's inner steps, then the predictor's."""
+    return (0 if corrector == "none" else corrector_steps) + (0 if predictor == "none" else 1)
+
+
 def pc_sample_spec(score_fn, Y: Tensor, N: int, noise: Tensor, sde: SdeCfg = SdeCfg(),
-                   trace: Optional[list] = None) -> Tensor:
-    """pc_sampler() with ReverseDiffusionPredictor + NoneCorrector, explicit noise.
+                   trace: Optional[list] = None, predictor: str = "reverse_diffusion", corrector: str = "none",
+                   corrector_steps: int = 1, snr: float = 0.5, denoise: bool = True) -> Tensor:
+    """pc_sampler() (sampling/__init__.py:59-71) with explicit noise.
 
     score_fn(x, t_vec) -> complex score [B,1,F,T] (already negated net output).
-    Y complex [B,1,F,T]; noise complex [N+1,B,1,F,T].  Returns x_mean of the last step.
+    Y complex [B,1,F,T]; noise complex [1 + N * draws_per_step, B,1,F,T] in the order the reference draws:
+    prior, then per outer step the corrector's inner-step draws followed by the predictor's draw.
+    predictor: reverse_diffusion (predictors.py:56-68) | euler_maruyama (predictors.py:40-53 with the drift of
+    RSDE.rsde_parts, sdes.py:128-150) | none.  corrector: none | langevin (correctors.py:37-64) | ald (:67-98).
+    Returns x_mean of the last step (denoise) or the state.
     """
     B = Y.shape[0]
     rdt = Y.real.dtype
+    bc = lambda v: v[:, None, None, None]  # noqa: E731
     std1 = ouve_std(torch.ones((B,), dtype=rdt), sde)
-    xt = Y + noise[0] * std1[:, None, None, None]
+    xt = Y + noise[0] * bc(std1)
     ts = torch.linspace(sde.T, sde.t_eps, N, dtype=rdt)
     xt_mean = xt
+    k = 1  # next unused draw
+    n_corr = 0 if corrector == "none" else corrector_steps
     for i in range(N):
         vec_t = torch.ones(B, dtype=rdt) * ts[i]
-        # SDE.discretize (sdes.py:88-92) with dt = 1/N
+        # ---- corrector
+        if n_corr:
+            std_t = ouve_std(vec_t, sde)
+        for _ in range(n_corr):
+            grad = score_fn(xt, vec_t)
+            z = noise[k]
+            k += 1
+            if corrector == "langevin":
+                gnorm = torch.norm(grad.reshape(B, -1), dim=-1).mean()
+                znorm = torch.norm(z.reshape(B, -1), dim=-1).mean()
+                step = ((snr * znorm / gnorm) ** 2 * 2).reshape(1, 1, 1, 1)
+            elif corrector == "ald":
+                step = bc((snr * std_t) ** 2 * 2)
+            else:
+                raise NotImplementedError(corrector)
+            xt_mean = xt + step * grad
+            xt = xt_mean + z * torch.sqrt(step * 2)
+        # ---- predictor
         dt = 1 / N
-        drift = sde.theta * (Y - xt)
-        G = ouve_diffusion(vec_t, sde) * torch.sqrt(torch.tensor(dt, dtype=rdt))
-        f = drift * dt
-        Gb = G[:, None, None, None]
-        rev_f = f - Gb**2 * score_fn(xt, vec_t) * 1.0
-        xt_mean = xt - rev_f
-        xt = xt_mean + Gb * noise[i + 1]
+        g = ouve_diffusion(vec_t, sde)
+        if predictor == "reverse_diffusion":
+            # SDE.discretize (sdes.py:88-92) with dt = 1/N
+            drift = sde.theta * (Y - xt)
+            G = g * torch.sqrt(torch.tensor(dt, dtype=rdt))
+            f = drift * dt
+            Gb = bc(G)
+            rev_f = f - Gb**2 * score_fn(xt, vec_t) * 1.0
+            z = noise[k]
+            k += 1
+            xt_mean = xt - rev_f
+            xt = xt_mean + Gb * z
+        elif predictor == "euler_maruyama":
+            z = noise[k]
+            k += 1
+            gb = bc(g)
+            total = sde.theta * (Y - xt) + (-(gb**2) * score_fn(xt, vec_t) * 1.0)
+            xt_mean = xt + total * (-dt)
+            xt = xt_mean + gb * np.sqrt(dt) * z
+        elif predictor == "none":
+            xt_mean = xt
+        else:
+            raise NotImplementedError(predictor)
         if trace is not None:
             trace.append(xt_mean.clone())
-    return xt_mean
+    return xt_mean if (denoise and N) else xt
 
 
 def sample(sd: Dict[str, Tensor], y: Tensor, N: int, noise: Optional[Tensor] = None, seed: int = 42,
            net: NetCfg = LARGE, spec: SpecCfg = SpecCfg(), sde: SdeCfg = SdeCfg(),
-           return_spec: bool = False):
+           return_spec: bool = False, **sampler_kw):
     """ScoreModel.sample (model_wrapper.py:262-329): y float [B, L] -> enhanced float [B, L]."""
     with torch.no_grad():
         T_orig = y.size(1)
         Y = pad_spec(spec_fwd(stft(y, spec), spec).unsqueeze(1))
         if noise is None:
-            noise = draw_noise(tuple(Y.shape), N, seed, dtype=Y.dtype)
+            per = draws_per_step(sampler_kw.get("predictor", "reverse_diffusion"), sampler_kw.get("corrector", "none"),
+                                 sampler_kw.get("corrector_steps", 1))
+            noise = draw_noise(tuple(Y.shape), N * per, seed, dtype=Y.dtype)
 
         def score_fn(x, t):
             return -ncsnpp_forward(sd, net, torch.cat([x, Y], dim=1), t)
 
-        xm = pc_sample_spec(score_fn, Y, N, noise, sde)
+        xm = pc_sample_spec(score_fn, Y, N, noise, sde, **sampler_kw)
         out = istft(spec_back(xm.squeeze(1), spec), spec, T_orig)
     return (out, xm, Y) if return_spec else out
 

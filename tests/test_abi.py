@@ -30,7 +30,7 @@ def test_library_exports_every_declared_symbol():
     assert exported == set(header_symbols())
     for name in header_symbols():
         assert hasattr(L, name)
-    assert L.use_abi_version() == 3
+    assert L.use_abi_version() == 4
 
 
 def _engine(L, net, dt):

@@ -1,0 +1,149 @@
+"""The other registered sampler variants on the fused CUDA loop (use_pc_sample_ex),
+against goldens produced by the UNMODIFIED reference classes (tests/golden/sampler_variants_T64.npz, written by
+oracle/make_golden_variants.py, which also pins the oracle restatement bit-exactly):
+
+  reverse_diffusion + langevin   (correctors.py:37-64: batch-mean norms -> deterministic device reduction)
+  reverse_diffusion + ald        (correctors.py:67-98, two inner steps)
+  euler_maruyama   + none        (predictors.py:40-53 over RSDE.rsde_parts, sdes.py:128-150)
+
+Explicit noise in the reference's draw order (prior; per outer step the corrector's inner draws, then the predictor's).
+Tolerances as for the default sampler: waveform rel-L2 <= 2e-3 (fp32 / TF32), <= 2e-2 (bf16).
+"""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import use_b200
+from oracle import sgmse_oracle as O
+from util import GOLDEN, rel_l2
+
+pytestmark = pytest.mark.gpu
+
+TOL = {"fp32": 2e-3, "bf16": 2e-2}
+CASES = ["rd_langevin", "rd_ald", "em_none"]
+
+
+def _model(dtype, weight_seed, predictor="reverse_diffusion", corrector="none", **kw):
+    m = use_b200.ScoreModel(backbone="ncsnpplarge", sde="ouve", t_eps=3e-2, condition="noisy", sde_input="noisy",
+                            n_fft=1022, hop_length=160, num_frames=512, dtype=dtype, predictor=predictor,
+                            corrector=corrector, **kw)
+    m.score_net.load_state_dict(O.make_state_dict(O.LARGE, seed=weight_seed), strict=True)
+    return m
+
+
+@pytest.mark.parametrize("dtype", ["fp32", "bf16"])
+@pytest.mark.parametrize("case", CASES)
+def test_sampler_variant_matches_reference_golden(case, dtype):
+    g = np.load(os.path.join(GOLDEN, "sampler_variants_T64.npz"))
+    N, seed = int(g["N"]), int(g["seed"])
+    pred, corr = str(g[f"{case}.predictor"]), str(g[f"{case}.corrector"])
+    steps, snr = int(g[f"{case}.corrector_steps"]), float(g[f"{case}.snr"])
+    m = _model(dtype, int(g["weight_seed"]), pred, corr)
+    y = torch.from_numpy(g["y"])
+    per = O.draws_per_step(pred, corr, steps)
+    noise = O.draw_noise((2, 1, 512, 64), N * per, seed).cuda()
+    got = m.sample({"perturbed": y.cuda()}, N=N, corrector_steps=steps, snr=snr, noise=noise)["enhanced"].cpu()
+    ref = torch.from_numpy(g[case])
+    e = rel_l2(got, ref)
+    assert bool(torch.isfinite(got).all()) and e <= TOL[dtype], (case, dtype, e)
+    # a different variant is a different sampler: the default chain with the same leading draws must NOT match
+    if case != "em_none":
+        base = _model(dtype, int(g["weight_seed"])).sample({"perturbed": y.cuda()}, N=N, noise=noise[: N + 1].contiguous())
+        assert rel_l2(base["enhanced"].cpu(), ref) > 10 * TOL[dtype]
+
+
+def test_langevin_philox_is_deterministic_and_batch_coupled():
+    """In-kernel Philox noise: same seed -> same bits (the norm reduction is a fixed-order two-pass sum, no float
+    atomics); and the Langevin step size is a BATCH mean (correctors.py:55-57), so a clip sampled alone differs from
+    the same clip inside a batch -- the reference's semantics, unlike the default sampler which is batch-invariant."""
+    m = _model("bf16", 7, "reverse_diffusion", "langevin")
+    y = O.synthetic_clips(2, 9600).cuda()
+    a = m.sample({"perturbed": y}, N=2, snr=0.5, seed=3)["enhanced"]
+    b = m.sample({"perturbed": y}, N=2, snr=0.5, seed=3)["enhanced"]
+    assert torch.equal(a, b) and bool(torch.isfinite(a).all())
+    alone = m.sample({"perturbed": y[:1]}, N=2, snr=0.5, seed=3)["enhanced"]
+    assert not torch.equal(alone, a[:1])
+    # ALD has per-sample step sizes: batch-invariant again
+    m2 = _model("bf16", 7, "reverse_diffusion", "ald")
+    a2 = m2.sample({"perturbed": y}, N=2, snr=0.4, seed=3)["enhanced"]
+    alone2 = m2.sample({"perturbed": y[1:]}, N=2, snr=0.4, seed=3, clip0=1)["enhanced"]
+    assert torch.equal(alone2, a2[1:])
+
+
+def test_update_fn_single_steps_equal_the_fused_loop():
+    """Driving the registry classes by hand (the reference's plugin usage) runs the same kernels: N update_fn calls of
+    ReverseDiffusionPredictor with explicit zero noise reproduce the fused N-step chain's x_mean."""
+    m = _model("fp32", 7)
+    g = torch.Generator().manual_seed(21)
+    B, F, T, N = 2, 512, 64, 3
+    Y = (0.3 * torch.randn(B, 1, F, T, dtype=torch.complex64, generator=g)).cuda()
+    noise = torch.zeros(N + 1, B, 1, F, T, dtype=torch.complex64, device="cuda")  # x0 = Y, no noise: deterministic
+    fused, nfe = m.get_pc_sampler("reverse_diffusion", "none", Y, N=N, conditioning=[Y], noise=noise)()
+    assert nfe == N
+    sde = m.sde.copy()
+    sde.N = N
+    pred = use_b200.PredictorRegistry.get_by_name("reverse_diffusion")(sde, m)
+    ts = sde.step_tables(N, m.t_eps)[0]
+    x = Y
+    for i in range(N):
+        x_noisy, xm = pred.update_fn(x, torch.ones(B, device="cuda") * ts[i], Y, conditioning=[Y])
+        x = xm  # follow the noise-free mean, as the zero-noise fused chain does
+    # (not asserted bit-equal: the one-element schedule tables of a single step go through torch's scalar pow / log
+    # paths on the host, which may differ from the vectorised ones by an ulp)
+    assert rel_l2(torch.view_as_real(xm.cpu()), torch.view_as_real(fused.cpu())) < 1e-5
+    # euler_maruyama and the correctors go through the same entry point
+    em = use_b200.PredictorRegistry.get_by_name("euler_maruyama")(sde, m)
+    xs, xm_em = em.update_fn(Y, torch.ones(B, device="cuda") * ts[0], Y, conditioning=[Y])
+    assert xm_em.shape == Y.shape and rel_l2(torch.view_as_real(xm_em.cpu()), torch.view_as_real(fused.cpu())) < 1.0
+    lc = use_b200.CorrectorRegistry.get_by_name("langevin")(sde, m, snr=0.5, n_steps=1)
+    xs, xm_l = lc.update_fn(Y, torch.ones(B, device="cuda") * ts[0], Y, conditioning=[Y])
+    assert bool(torch.isfinite(torch.view_as_real(xs)).all()) and not torch.equal(xs, xm_l)
+
+
+def test_denoise_false_and_none_predictor():
+    m = _model("bf16", 7)
+    y = O.synthetic_clips(1, 9600).cuda()
+    Y = m.stft_compressed(y).unsqueeze(1)
+    noise = O.draw_noise((1, 1, 512, 64), 2, 5).cuda()
+    mean, _ = m.get_pc_sampler("reverse_diffusion", "none", Y, N=2, conditioning=[Y], noise=noise)()
+    state, _ = m.get_pc_sampler("reverse_diffusion", "none", Y, N=2, conditioning=[Y], noise=noise, denoise=False)()
+    sde = m.sde.copy()
+    sde.N = 2
+    G_last = float(sde.step_tables(2, m.t_eps)[1][-1])
+    # x = x_mean + G z of the last step
+    assert rel_l2(torch.view_as_real((state - mean).cpu()), torch.view_as_real((G_last * noise[2]).cpu())) < 1e-3
+    prior, nfe = m.get_pc_sampler("none", "none", Y, N=2, conditioning=[Y], noise=noise[:1].contiguous())()
+    std1 = sde.step_tables(2, m.t_eps)[2]
+    assert rel_l2(torch.view_as_real(prior.cpu()), torch.view_as_real((Y + std1 * noise[0]).cpu())) < 1e-6
+
+
+def test_program_cache_survives_many_shapes():
+    """the launch-program cache used to clear itself while a call still held a program pointer (two
+    stream groups -> two lookups).  Walk more distinct (shape, workspace) combinations than the cache holds with B = 4
+    (two groups), then re-run the first shape and compare bit for bit."""
+    m = _model("bf16", 7)
+    first = None
+    for k, L in enumerate([9600, 19840, 30080, 9600 + 160 * 64 * 3, 50560, 60800, 71040, 9600]):
+        y = O.synthetic_clips(4, L, seed=3).cuda()
+        out = m.sample({"perturbed": y}, N=1, seed=11)["enhanced"]
+        assert out.shape == (4, L) and bool(torch.isfinite(out).all())
+        if k == 0:
+            first = out.clone()
+    assert torch.equal(out, first)
+
+
+def test_minibatch_argument_keys_noise_by_global_clip():
+    """get_pc_sampler(minibatch=k) must give every minibatch its own Philox streams (clip0 + offset)
+    and its own slice of explicit noise: the split result equals the unsplit one bit for bit."""
+    m = _model("bf16", 7)
+    y = O.synthetic_clips(4, 9600).cuda()
+    Y = m.stft_compressed(y).unsqueeze(1)
+    whole, _ = m.get_pc_sampler("reverse_diffusion", "none", Y, N=2, conditioning=[Y], seed=9)()
+    split, ns = m.get_pc_sampler("reverse_diffusion", "none", Y, N=2, minibatch=1, conditioning=[Y], seed=9)()
+    assert torch.equal(whole, split) and ns == [2, 2, 2, 2]
+    noise = O.draw_noise((4, 1, 512, 64), 2, 5).cuda()
+    whole_n, _ = m.get_pc_sampler("reverse_diffusion", "none", Y, N=2, conditioning=[Y], noise=noise)()
+    split_n, _ = m.get_pc_sampler("reverse_diffusion", "none", Y, N=2, minibatch=3, conditioning=[Y], noise=noise)()
+    assert torch.equal(whole_n, split_n)

@@ -89,21 +89,60 @@ def test_unsupported_options_fail_loudly():
         m.get_ode_sampler(torch.zeros(1))
 
 
-def test_generic_sampler_loop_shapes_with_fake_score_fn():
-    """The host loop of the non-fused route (registry predictors / correctors) with a CPU stand-in score function."""
+def test_plugin_predictor_corrector_run_through_the_host_loop():
+    """Third-party predictors / correctors registered through the plugin API (no fused `kind`) are sequenced by the host
+    loop -- corrector then predictor per step, over linspace(T, eps, N) -- around any score function; ReverseSDE gives
+    them the reverse drift.  CPU stand-in score function: checks the API contract, not the kernels."""
+    from use_b200 import sampling
+
     sde = use_b200.OUVESDE()
     sde.N = 4
     y = torch.randn(2, 1, 8, 8, dtype=torch.complex64)
+    calls = []
 
     def score_fn(x, t, score_conditioning=None, sde_input=None):
+        assert score_conditioning[0] is y and sde_input is y
         return -(x - y)
 
-    for pred, corr in (("reverse_diffusion", "none"), ("euler_maruyama", "none"), ("reverse_diffusion", "langevin"),
-                       ("reverse_diffusion", "ald"), ("none", "none")):
-        s = use_b200.get_pc_sampler(pred, corr, sde, score_fn, y, corrector_steps=1, snr=0.5, conditioning=[y])
-        x, n = s()
-        assert x.shape == y.shape and bool(torch.isfinite(torch.view_as_real(x)).all())
-        assert n == sde.N * ((0 if corr == "none" else 1) + 1)
+    if "test_plugin_pred" not in use_b200.PredictorRegistry.get_all_names():
+        @use_b200.PredictorRegistry.register("test_plugin_pred")
+        class PluginPredictor(sampling.Predictor):
+            def update_fn(self, x, t, y_, conditioning=None):
+                calls.append(("p", float(t[0])))
+                f, G = self.rsde.discretize(x, t, y_, conditioning=conditioning)
+                return x - f, x - f  # noise-free reverse-diffusion step
+
+        @use_b200.CorrectorRegistry.register("test_plugin_corr")
+        class PluginCorrector(sampling.Corrector):
+            def update_fn(self, x, t, y_, conditioning=None):
+                calls.append(("c", float(t[0])))
+                drift, g = self.rsde.sde(x, t, y_, conditioning=conditioning)
+                assert drift.shape == x.shape and g.shape == (2, 1, 1, 1)
+                return x, x
+
+    s = use_b200.get_pc_sampler("test_plugin_pred", "test_plugin_corr", sde, score_fn, y, corrector_steps=1, snr=0.5,
+                                conditioning=[y])
+    x, n = s()
+    assert x.shape == y.shape and bool(torch.isfinite(torch.view_as_real(x)).all()) and n == 8
+    ts = [float(v) for v in torch.linspace(1, 3e-2, 4)]
+    assert calls == [(k, t) for t in ts for k in ("c", "p")]
+    # a built-in (fused) predictor refuses a score function that is not the B200 ScoreModel: there is no host fallback
+    with pytest.raises(NotImplementedError):
+        use_b200.get_pc_sampler("reverse_diffusion", "test_plugin_corr", sde, score_fn, y, conditioning=[y])()
+    # NonePredictor / NoneCorrector are pure pass-throughs
+    x0, n0 = use_b200.get_pc_sampler("none", "none", sde, score_fn, y, conditioning=[y])()
+    assert x0.shape == y.shape and n0 == 4
+
+
+def test_variant_tables_match_reference_expressions():
+    """g(t_i) and the ALD step sizes handed to the fused loop = the reference's float32 torch expressions."""
+    sde = use_b200.OUVESDE()
+    ts, G, std1 = sde.step_tables(30, 3e-2)
+    g, ald = sde.variant_tables(ts, 0.4)
+    og = O.ouve_diffusion(ts)
+    assert torch.equal(g, og.to(torch.float32))
+    assert torch.equal(ald, (0.4 * O.ouve_std(ts)) ** 2 * 2)
+    assert torch.equal(G, O.step_coefficients(30)[1])
 
 
 def test_gan_generator_host_structure():

@@ -69,3 +69,37 @@ def test_module_plan_large():
     assert len(plan) == 74
     assert sum(v.numel() for v in O.make_state_dict(O.LARGE).values()) == 64_799_782
     assert len(O.make_state_dict(O.LARGE)) == 617
+
+
+def test_sampler_variants_match_reference_golden():
+    """Langevin / ALD correctors and the Euler-Maruyama predictor of the oracle against the outputs of the reference's
+    own classes (oracle/make_golden_variants.py): one case per run of the CPU suite keeps it fast, all three are asserted
+    bit-exact by the generating script."""
+    g = np.load(os.path.join(GOLDEN, "sampler_variants_T64.npz"))
+    sd = O.make_state_dict(O.LARGE, seed=int(g["weight_seed"]))
+    y = torch.from_numpy(g["y"])
+    case = "rd_langevin"
+    kw = dict(predictor=str(g[f"{case}.predictor"]), corrector=str(g[f"{case}.corrector"]),
+              corrector_steps=int(g[f"{case}.corrector_steps"]), snr=float(g[f"{case}.snr"]))
+    out = O.sample(sd, y, int(g["N"]), seed=int(g["seed"]), **kw)
+    ref = torch.from_numpy(g[case])
+    d = float((out - ref).abs().max())
+    assert d == 0.0 or d < 1e-5 * float(ref.abs().max()), d
+    assert O.draws_per_step("reverse_diffusion", "ald", 2) == 3 and O.draws_per_step("none", "none", 5) == 0
+
+
+def test_baseline_golden_is_consistent():
+    """tests/golden/sample_large_T640_N30.npz (the BASELINE configuration, from the unmodified reference): the clip is the
+    bench's synthetic clip, shapes / schedule metadata are what the GPU test expects and the sub-sampled x_mean traces are
+    self-consistent (cheap sanity: the full 30-step chain costs the oracle ~10 min and is asserted bit-exact against
+    the reference by oracle/make_golden_large.py)."""
+    g = np.load(os.path.join(GOLDEN, "sample_large_T640_N30.npz"))
+    assert int(g["N"]) == 30 and int(g["L"]) == 96000 and int(g["B"]) == 1
+    assert torch.equal(torch.from_numpy(g["y"]), O.synthetic_clips(1, 96000))
+    assert g["xmean_re"].shape == (30, 512 // int(g["sub_f"]), 640 // int(g["sub_t"])) and g["enhanced"].shape == (1, 96000)
+    xs = np.sqrt((g["xmean_re"].astype(np.float64) ** 2 + g["xmean_im"].astype(np.float64) ** 2).sum(axis=(1, 2)))
+    assert np.allclose(xs, g["xnorm_sub"], rtol=1e-6)
+    assert np.all(np.isfinite(g["enhanced"])) and float(np.abs(g["enhanced"]).max()) > 1e-3
+    # the sub-grid is a fair sample of the full grid: energy ratio ~ 1 / (sub_f * sub_t) at every step
+    ratio = (g["xnorm_sub"] / g["xnorm"]) ** 2 * int(g["sub_f"]) * int(g["sub_t"])
+    assert np.all((ratio > 0.5) & (ratio < 2.0)), ratio

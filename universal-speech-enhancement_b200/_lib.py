@@ -17,12 +17,16 @@ CSRC = os.path.join(_HERE, "csrc")
 
 DTYPE_F32 = 0
 DTYPE_BF16 = 1
+DTYPE_F32X3 = 2  # engine only: 3xTF32 split convolutions (fp32-level accuracy; parity mode)
+
+PRED = {"reverse_diffusion": 0, "euler_maruyama": 1, "none": 2}
+CORR = {"none": 0, "langevin": 1, "ald": 2}
 
 # every symbol include/use_b200.h declares (tests check the header against this list and the .so)
 SYMBOLS = [
     "use_abi_version", "use_last_error", "use_engine_create", "use_engine_destroy", "use_engine_set_weight",
     "use_engine_pack", "use_engine_upload", "use_engine_workspace_bytes", "use_engine_set_option", "use_engine_launch_count", "use_engine_set_profiling",
-    "use_engine_get_profile", "use_engine_get_profile_ops", "use_score_forward", "use_net_forward", "use_pc_sample",
+    "use_engine_get_profile", "use_engine_get_profile_ops", "use_score_forward", "use_net_forward", "use_pc_sample", "use_pc_sample_ex",
     "use_stft", "use_istft", "use_upfirdn2d_f32", "use_op_gn_stats", "use_op_gn_apply", "use_op_conv_tc", "use_op_gn_affine", "use_op_conv_tc_gn", "use_op_head_tc", "use_op_combine_stats", "use_op_gn_apply_aff",
     "use_op_conv_ref", "use_op_conv_in4", "use_op_conv_out4", "use_op_combine", "use_op_fir4_down", "use_op_philox",
     "use_pack_conv_weight", "use_pack_head_weight",
@@ -35,6 +39,14 @@ class UseConfig(C.Structure):
         ("input_channels", C.c_int), ("act_dtype", C.c_int), ("n_fft", C.c_int), ("hop", C.c_int),
         ("spec_factor", C.c_float), ("spec_abs_exponent", C.c_float), ("theta", C.c_float),
         ("conditional", C.c_int), ("scale_by_sigma", C.c_int),
+    ]
+
+
+class UseSamplerOpts(C.Structure):
+    _fields_ = [
+        ("predictor", C.c_int), ("corrector", C.c_int), ("corrector_steps", C.c_int), ("snr", C.c_float),
+        ("probability_flow", C.c_int), ("denoise", C.c_int), ("g_host", C.c_void_p), ("ald_step_host", C.c_void_p),
+        ("trace", C.c_void_p), ("x_init", C.c_void_p), ("dt_steps", C.c_int),
     ]
 
 
@@ -85,6 +97,8 @@ def lib() -> C.CDLL:
         L.use_score_forward.argtypes = [vp, i32, i32, i32, vp, vp, vp, vp, vp, vp, sz, vp]
         L.use_net_forward.argtypes = [vp, i32, i32, i32, vp, vp, vp, vp, vp, vp, sz, vp]
         L.use_pc_sample.argtypes = [vp, i32, i32, i32, vp, vp, vp, i32, vp, vp, vp, f32, vp, u64, u32, vp, sz, vp]
+        L.use_pc_sample_ex.argtypes = [vp, i32, i32, i32, vp, vp, vp, i32, vp, vp, vp, f32, vp, u64, u32,
+                                       C.POINTER(UseSamplerOpts), vp, sz, vp]
         L.use_stft.argtypes = [vp, i32, i32, i32, vp, vp, vp, vp, vp]
         L.use_istft.argtypes = [vp, i32, i32, i32, vp, vp, vp, vp, vp, vp, vp]
         L.use_upfirdn2d_f32.argtypes = [vp, vp, i32, i32, i32, i32, vp] + [i32] * 10 + [vp]
@@ -112,7 +126,7 @@ def lib() -> C.CDLL:
             fn = getattr(L, name)  # AttributeError here = header / library mismatch
             if fn.restype is C.c_int and name not in ("use_abi_version",):
                 fn.restype = C.c_int
-        if L.use_abi_version() != 3:
+        if L.use_abi_version() != 4:
             raise RuntimeError("use_b200: ABI version mismatch between the Python layer and libuse_b200.so")
         _lib = L
         return L
@@ -132,11 +146,13 @@ def stream_ptr() -> int:
 
 def dtype_code(name) -> int:
     """'fp32' / torch.float32 / 0 -> DTYPE_F32 (TF32 MMA);  'bf16' / torch.bfloat16 / 1 -> DTYPE_BF16."""
-    if isinstance(name, int) and not isinstance(name, bool) and name in (DTYPE_F32, DTYPE_BF16):
+    if isinstance(name, int) and not isinstance(name, bool) and name in (DTYPE_F32, DTYPE_BF16, DTYPE_F32X3):
         return name
     s = str(name).replace("torch.", "").lower()
     if s in ("fp32", "float32", "tf32", "float"):
         return DTYPE_F32
     if s in ("bf16", "bfloat16"):
         return DTYPE_BF16
-    raise ValueError(f"unsupported compute dtype {name!r} (use 'fp32' or 'bf16')")
+    if s in ("fp32x3", "3xtf32", "tf32x3"):
+        return DTYPE_F32X3
+    raise ValueError(f"unsupported compute dtype {name!r} (use 'fp32', 'bf16' or 'fp32x3')")

@@ -332,8 +332,10 @@ class _Engine:
         return self.net_module.gfp_features(t_host)
 
     def pc_sample(self, Y: torch.Tensor, ts: torch.Tensor, G: torch.Tensor, prior_std: float, noise=None, seed: int = 0,
-                  clip0: int = 0) -> torch.Tensor:
-        """Fused reverse-diffusion loop; returns x_mean of the last step (complex64 [B, F, T])."""
+                  clip0: int = 0, predictor="reverse_diffusion", corrector="none", corrector_steps=1, snr=0.5,
+                  probability_flow=False, denoise=True, g=None, ald_step=None, trace=None, x_init=None, dt_steps=0):
+        """The fused predictor-corrector loop (use_pc_sample_ex); returns (x_result, x_state), complex64 [B, F, T]:
+        x_result = the noise-free mean of the last step (denoise) or the state."""
         assert Y.dtype == torch.complex64 and Y.dim() == 3 and Y.is_cuda
         B, F, T = Y.shape
         Y = Y.contiguous()
@@ -341,16 +343,41 @@ class _Engine:
         ts = ts.detach().to("cpu", torch.float32).contiguous()
         G = G.detach().to("cpu", torch.float32).contiguous()
         gfp = self.net_module.gfp_features(ts)
+        o = _lib.UseSamplerOpts()
+        o.predictor, o.corrector = _lib.PRED[predictor], _lib.CORR[corrector]
+        o.corrector_steps, o.snr = int(corrector_steps), float(snr)
+        o.probability_flow, o.denoise, o.dt_steps = int(bool(probability_flow)), int(bool(denoise)), int(dt_steps)
+        keep = []
+        if g is not None:
+            g = g.detach().to("cpu", torch.float32).contiguous()
+            assert g.numel() == N
+            o.g_host = g.data_ptr()
+        if ald_step is not None:
+            ald_step = ald_step.detach().to("cpu", torch.float32).contiguous()
+            assert ald_step.numel() == N
+            o.ald_step_host = ald_step.data_ptr()
+        n_corr = 0 if corrector == "none" else int(corrector_steps)
+        draws = 1 + N * (n_corr + (0 if predictor == "none" else 1))
         x_state, x_mean = torch.empty_like(Y), torch.empty_like(Y)
         nptr = None
         if noise is not None:
-            assert noise.dtype == torch.complex64 and tuple(noise.shape) == (N + 1, B, F, T) and noise.is_cuda
+            assert noise.dtype == torch.complex64 and tuple(noise.shape) == (draws, B, F, T) and noise.is_cuda, \
+                f"explicit noise must be complex64 [{draws}, {B}, {F}, {T}] (prior + per-step draws in the reference's order)"
             noise = noise.contiguous()
             nptr = noise.data_ptr()
+        if trace is not None:
+            assert trace.dtype == torch.complex64 and tuple(trace.shape) == (N, B, F, T) and trace.is_cuda \
+                and trace.is_contiguous()
+            o.trace = trace.data_ptr()
+        if x_init is not None:
+            x_init = x_init.to(torch.complex64).contiguous()
+            assert tuple(x_init.shape) == (B, F, T) and x_init.is_cuda
+            keep.append(x_init)
+            o.x_init = x_init.data_ptr()
         with torch.cuda.device(self.device):
             ws = self.workspace(B, F, T)
-            _lib.check(self.L.use_pc_sample(self.h, B, F, T, Y.data_ptr(), x_state.data_ptr(), x_mean.data_ptr(), N,
-                                            ts.data_ptr(), G.data_ptr(), gfp.data_ptr(), float(prior_std), nptr,
-                                            int(seed) & (2**64 - 1), int(clip0), ws.data_ptr(), ws.numel(),
-                                            _lib.stream_ptr()), "use_pc_sample")
-        return x_mean
+            _lib.check(self.L.use_pc_sample_ex(self.h, B, F, T, Y.data_ptr(), x_state.data_ptr(), x_mean.data_ptr(), N,
+                                               ts.data_ptr(), G.data_ptr(), gfp.data_ptr(), float(prior_std), nptr,
+                                               int(seed) & (2**64 - 1), int(clip0), C.byref(o), ws.data_ptr(), ws.numel(),
+                                               _lib.stream_ptr()), "use_pc_sample_ex")
+        return x_mean, x_state

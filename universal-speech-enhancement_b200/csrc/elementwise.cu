@@ -1062,6 +1062,31 @@ void launch_conv_ref(int dt, const void* x, const float* w, const float* bias, i
 }
 
 // ------------------------------------------------------------------------------------------------
+// 3xTF32 parity mode (USE_DTYPE_F32X3): split an fp32 channel window into two TF32 operands,
+// hi = rne_tf32(x), lo = rne_tf32(x - hi)  (x - hi is exact in fp32), so that
+// x w ~= x_hi w_hi + x_hi w_lo + x_lo w_hi with a relative error of ~2^-21 instead of TF32's 2^-11.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) split_tf32_kernel(const float* __restrict__ x, int Ct, int c0, int C,
+                                                          float* __restrict__ hi, float* __restrict__ lo, size_t npix) {
+  const size_t n = npix * static_cast<size_t>(C);
+  for (size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n;
+       i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const size_t pix = i / C;
+    const int c = static_cast<int>(i - pix * C);
+    const float v = x[pix * Ct + c0 + c];
+    const float h = round_tf32(v);
+    hi[i] = h;
+    lo[i] = round_tf32(v - h);
+  }
+}
+
+void launch_split_tf32(const float* x, int Ct, int c0, int C, float* hi, float* lo, size_t npix, cudaStream_t st) {
+  const size_t n = npix * static_cast<size_t>(C);
+  const int blocks = static_cast<int>(std::min<size_t>((n + 255) / 256, 148 * 32));
+  split_tf32_kernel<<<blocks, 256, 0, st>>>(x, Ct, c0, C, hi, lo, npix);
+}
+
+// ------------------------------------------------------------------------------------------------
 // upfirdn2d, the reference's own native op (op/upfirdn2d.cpp:12-23, semantics of upfirdn2d_native,
 // op/upfirdn2d.py:173-208): zero-insert upsample, pad (negative pads crop), FIR with the flipped kernel,
 // decimate.  Generic gather formulation over [major][H][W][minor]; the network itself uses the fused

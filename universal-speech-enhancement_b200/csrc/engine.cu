@@ -56,7 +56,9 @@ static inline float f32_to_tf32(float f) {
   return r;
 }
 
-static void pack_conv_weight(int dt, const float* w, int O, int I, int ks, void* out) {
+// lo = false: the operand rounding of the act dtype; lo = true (fp32 only): the second TF32 term w - tf32(w) of the
+// 3xTF32 split (USE_DTYPE_F32X3)
+static void pack_conv_weight(int dt, const float* w, int O, int I, int ks, void* out, bool lo = false) {
   const int taps = ks * ks;
   for (int tap = 0; tap < taps; ++tap)
     for (int o = 0; o < O; ++o)
@@ -64,7 +66,7 @@ static void pack_conv_weight(int dt, const float* w, int O, int I, int ks, void*
         const float v = w[((size_t)o * I + i) * taps + tap];
         const size_t idx = ((size_t)tap * O + o) * I + i;
         if (dt == kBF16) ((uint16_t*)out)[idx] = f32_to_bf16(v);
-        else ((float*)out)[idx] = f32_to_tf32(v);
+        else ((float*)out)[idx] = lo ? f32_to_tf32(v - f32_to_tf32(v)) : f32_to_tf32(v);
       }
 }
 
@@ -187,6 +189,7 @@ struct Program {
   cudaGraphExec_t graph = nullptr;
   bool graph_failed = false;
   long long graph_launches = 0;
+  unsigned long long last_use = 0;  // LRU stamp of the program cache
   ~Program() {
     if (graph) cudaGraphExecDestroy(graph);
     for (auto* p : plans) tc_conv_plan_destroy(p);
@@ -211,15 +214,20 @@ struct use_engine {
   int in_conv_idx = 3;  // index of the input convolution in all_modules (3 with the time-embedding MLP, 1 without)
   char* dev_w = nullptr;
   int num_sms = 148;
-  std::map<std::string, std::unique_ptr<Program>> programs;  // keyed by "B,F,T,base"
+  // keyed by "B,F,T,base".  shared_ptr: a call holds ("pins") its programs for its whole duration, and eviction only
+  // ever drops entries nobody holds -- a second lookup inside the same call can never free the first one's program
+  std::map<std::string, std::shared_ptr<Program>> programs;
+  unsigned long long program_tick = 0;
   // fixed head of the workspace (byte offsets)
-  struct Head { size_t xr, xpad, t, gfp, sched, temb, dense, stats, arena; } head;
+  struct Head { size_t xr, xpad, t, gfp, sched, temb, dense, score, red, stats, arena; } head;
   // concurrency: a batch is split into `groups` halves that run on their own streams, so the HBM-bound GroupNorm
   // kernels of one half overlap the tensor-bound convolutions of the other (they fit beside the persistent conv CTA)
   int groups = 2;
   // GroupNorm + SiLU applied inside the convolution kernel's operand path (no normalised tensor in HBM); off: the
   // separate gn_apply kernel feeds the same convolutions (A/B testing: both give bit-identical results)
   bool fuse_gn = true;
+  // USE_DTYPE_F32X3 (parity mode): dt = fp32 and every tensor-core convolution is the 3xTF32 split (three launches)
+  bool x3 = false;
   // replay the ~230 launches of an evaluation as one CUDA graph (small batches are launch-latency bound: the deep levels
   // run dozens of kernels of a few microseconds each)
   bool use_graphs = true;
@@ -331,10 +339,16 @@ static int pack_all(use_engine* e) {
   auto put_conv_tc = [&](const std::string& name, int O, int I, int ks, size_t* off) -> int {
     const HostTensor* t = getw(e, name, {O, I, ks, ks});
     if (!t) return 1;
-    *off = bw.reserve((size_t)ks * ks * O * I * es);
+    const size_t nb = (size_t)ks * ks * O * I * es;
+    *off = bw.reserve(e->x3 ? 2 * nb : nb);  // 3xTF32: the lo term follows the hi term
     pack_conv_weight(dt, t->data.data(), O, I, ks, e->blob.data() + *off);
+    if (e->x3) pack_conv_weight(dt, t->data.data(), O, I, ks, e->blob.data() + *off + nb, true);
     return 0;
   };
+  {
+    std::vector<float> z(1024, 0.f);
+    e->off["zeros"] = bw.put(z.data(), z.size() * 4);
+  }
   if (putf("gfp.W", P(0) + ".W", {nf})) return 1;
   if (c.conditional) {
     if (putf("l1.w", P(1) + ".weight", {D, 2 * nf}) || putf("l1.b", P(1) + ".bias", {D})) return 1;
@@ -354,7 +368,7 @@ static int pack_all(use_engine* e) {
       case K_GFP: case K_LINEAR: break;
       case K_CONV3: {
         if (putf(p + ".w", p + ".weight", {m.cout, m.cin, 3, 3}) || putf(p + ".b", p + ".bias", {m.cout})) return 1;
-        if (m.cin == c.input_channels && tc_conv_supported(dt, m.cout) && m.cout != 32) {
+        if (m.cin == c.input_channels && tc_conv_supported(dt, m.cout) && m.cout != 32 && !e->x3) {
           // input conv 4 -> nf: tcgen05 layout with the input channels zero-padded to one 128-byte chunk
           const int ck = 128 / (int)es;
           const HostTensor* t = getw(e, p + ".weight", {m.cout, m.cin, 3, 3});
@@ -366,7 +380,7 @@ static int pack_all(use_engine* e) {
           pack_conv_weight(dt, wp.data(), m.cout, ck, 3, e->blob.data() + off);
           e->off[p + ".wtc"] = off;
         }
-        if (m.cout == c.input_channels && head_tc_supported(dt, m.cin, m.cout)) {
+        if (m.cout == c.input_channels && head_tc_supported(dt, m.cin, m.cout) && !e->x3) {
           // pyramid head C -> pc: the nine taps folded into the MMA's N dimension (head_tc.cuh), rows tap * pc + co
           const HostTensor* t = getw(e, p + ".weight", {m.cout, m.cin, 3, 3});
           size_t off = bw.reserve((size_t)48 * m.cin * es);
@@ -520,13 +534,18 @@ struct Builder {
     return off;
   }
   // stat_target: the conv's output tensor when the epilogue should also produce its GroupNorm statistics
-  void conv_tc(TcConvDesc d, Act* stat_target = nullptr) {
+  // flops_alg: algorithmic FLOPs when they differ from 2 px N sum(taps C) (the input conv's K is zero-padded to one chunk)
+  void conv_tc(TcConvDesc d, Act* stat_target = nullptr, double flops_alg = 0) {
     if (stat_target) {
       stat_target->stats_off = stats_top;
       stats_top += (size_t)B * d.N * 2 * sizeof(long long);
       if (!dry) d.stats_acc = stats_ptr(stat_target->stats_off);
     }
+    if (e->x3) { conv_tc_x3(d); return; }
     if (dry) return;
+    emit_conv_plan(d, flops_alg);
+  }
+  void emit_conv_plan(const TcConvDesc& d, double flops_alg, bool count = true) {
     char msg[512];
     TcConvPlan* p = tc_conv_plan_create(e->dt, d, e->num_sms, msg, sizeof(msg));
     if (!p) { err = fail("%s", msg); return; }
@@ -534,8 +553,42 @@ struct Builder {
     double k = 0, cin = 0;
     for (int i = 0; i < d.nseg; ++i) { k += (double)d.seg[i].taps * d.seg[i].C; cin += d.seg[i].C; }
     const double px = (double)d.B * d.H * d.W;
-    emit([=](cudaStream_t s) { tc_conv_launch(p, s); }, TAG_CONV_TC, 1, 2.0 * px * d.N * k,
-         (px * (cin + d.N * (d.res ? 2 : 1))) * es());
+    const double fl = flops_alg > 0 ? flops_alg : 2.0 * px * d.N * k;
+    emit([=](cudaStream_t s) { tc_conv_launch(p, s); }, TAG_CONV_TC, 1, count ? fl : 0.0,
+         count ? (px * (cin + d.N * (d.res ? 2 : 1))) * es() : 0.0);
+  }
+  // 3xTF32 parity mode: out = ((x_hi w_hi + bias) + (x_lo w_hi + (x_hi w_lo + res))) * scale as three launches of the same
+  // tcgen05 kernel (small terms first; the fp32 adds of the epilogue chain them through its residual input)
+  void conv_tc_x3(const TcConvDesc& d) {
+    const size_t px = (size_t)d.B * d.H * d.W;
+    size_t hi[3], lo[3];
+    for (int i = 0; i < d.nseg; ++i) { hi[i] = new_f32(px * d.seg[i].C); lo[i] = new_f32(px * d.seg[i].C); }
+    const size_t t1 = new_f32(px * d.N), t2 = new_f32(px * d.N);
+    if (!dry) {
+      TcConvDesc p1 = d, p2 = d, p3 = d;
+      for (int i = 0; i < d.nseg; ++i) {
+        const TcSegDesc& sg = d.seg[i];
+        float *h = (float*)ws(hi[i]), *l = (float*)ws(lo[i]);
+        const float* src = (const float*)sg.act;
+        const int Ct = sg.C_tensor, c0 = sg.c0, C = sg.C;
+        emit([=](cudaStream_t s) { launch_split_tf32(src, Ct, c0, C, h, l, px, s); }, TAG_OTHER, 1, 0, 0);
+        const char* w_lo = (const char*)sg.w + (size_t)sg.taps * d.N * sg.Cw_total * 4;
+        TcSegDesc a = sg;
+        a.C_tensor = C; a.c0 = 0; a.aff = nullptr; a.aff_C = 0; a.aff_c0 = 0;
+        a.act = h; a.w = w_lo; p1.seg[i] = a;
+        a.act = l; a.w = sg.w; p2.seg[i] = a;
+        a.act = h; a.w = sg.w; p3.seg[i] = a;
+      }
+      const float* zeros = wf("zeros");
+      p1.bias = zeros; p1.bias_bstride = 0; p1.scale = 1.0f; p1.out = ws(t1); p1.stats_acc = nullptr;  // res = d.res
+      p2.bias = zeros; p2.bias_bstride = 0; p2.scale = 1.0f; p2.out = ws(t2); p2.stats_acc = nullptr; p2.res = ws(t1);
+      p3.res = ws(t2);
+      emit_conv_plan(p1, 0, false);
+      if (!err) emit_conv_plan(p2, 0, false);
+      if (!err) emit_conv_plan(p3, 0, true);
+    }
+    arena.release(t1); arena.release(t2);
+    for (int i = 0; i < d.nseg; ++i) { arena.release(hi[i]); arena.release(lo[i]); }
   }
 
   // ResnetBlockBigGANpp.forward (layerspp.py:282-314).  x1 != nullptr: input is cat[x0, x1].
@@ -546,7 +599,8 @@ struct Builder {
     const int fir = m.down ? 1 : (m.up ? 2 : 0);
     const int Ho = m.down ? x0.H / 2 : (m.up ? x0.H * 2 : x0.H);
     const int Wo = m.down ? x0.W / 2 : (m.up ? x0.W * 2 : x0.W);
-    const bool fuse = e->fuse_gn;
+    const bool fuse = e->fuse_gn && !e->x3;
+    const bool opnd = !e->x3;  // 3xTF32: the normalised tensors stay full fp32 and are split in front of each convolution
     const bool fuse0 = fuse && fir == 0;  // FIR blocks resample between GroupNorm/SiLU and Conv_0: separate kernel
     Act a0, raw;
     size_t aff0 = (size_t)-1;
@@ -555,7 +609,7 @@ struct Builder {
     } else {
       a0 = new_act(Cin, Ho, Wo);
       if (fir) raw = new_act(Cin, Ho, Wo);
-      gn_apply(x0, x1, w.gn0_g, w.gn0_b, fir, true, true, a0, fir ? &raw : nullptr);
+      gn_apply(x0, x1, w.gn0_g, w.gn0_b, fir, true, opnd, a0, fir ? &raw : nullptr);
     }
     Act h1 = new_act(Cout, Ho, Wo);
     {
@@ -593,7 +647,7 @@ struct Builder {
       aff1 = gn_affine(h1, nullptr, w.gn1_g, w.gn1_b);
     } else {
       a1 = new_act(Cout, Ho, Wo);
-      gn_apply(h1, nullptr, w.gn1_g, w.gn1_b, 0, true, true, a1, nullptr);
+      gn_apply(h1, nullptr, w.gn1_g, w.gn1_b, 0, true, opnd, a1, nullptr);
       free_act(h1);
     }
     Act out = new_act(Cout, Ho, Wo);
@@ -690,7 +744,7 @@ struct Builder {
         d.bias = dry ? nullptr : wf(inp + ".b");
         d.bias_bstride = 0;
         d.scale = 1.0f;
-        conv_tc(d, &h0);
+        conv_tc(d, &h0, 2.0 * B * F * T * c.nf * 9.0 * c.input_channels);  // algorithmic K = 9 * input_channels, not the padded chunk
       } else if (!dry) {
         const float *w = wf(inp + ".w"), *b = wf(inp + ".b");
         void* o = ws(h0.off);
@@ -833,6 +887,8 @@ static int plan_workspace(use_engine* e, int B, int F, int T, size_t* total, siz
   e->head.sched = off; off = align_up(off + (size_t)kMaxSteps * (2 * c.nf + 1) * 4, 1024);  // per-step t_i and Fourier features
   e->head.temb = off; off = align_up(off + (size_t)B * 4 * c.nf * 4, 1024);
   e->head.dense = off; off = align_up(off + (size_t)B * e->dense_rows * 4, 1024);
+  e->head.score = off; off = align_up(off + (size_t)B * F * T * 8, 1024);  // score of a corrector step (complex64)
+  e->head.red = off; off = align_up(off + corrector_scratch_bytes(B), 1024);
   e->head.stats = off; off = align_up(off + b.stats_top, 1024);
   e->head.arena = off;
   *total = off + b.arena.peak;
@@ -840,7 +896,23 @@ static int plan_workspace(use_engine* e, int B, int F, int T, size_t* total, siz
   return 0;
 }
 
-static Program* get_program(use_engine* e, int B, int F, int T, void* workspace, size_t workspace_bytes) {
+constexpr size_t kMaxPrograms = 8;  // cached launch programs (distinct (B, F, T, workspace) combinations)
+
+// Drop least-recently-used programs until at most kMaxPrograms - 1 remain, skipping every entry that is pinned by a
+// running call (use_count > 1).  The destructor of a Program whose graph is still executing is safe:
+// cudaGraphExecDestroy defers the release until the launch has completed.
+static void evict_programs(use_engine* e) {
+  while (e->programs.size() >= kMaxPrograms) {
+    auto victim = e->programs.end();
+    for (auto it = e->programs.begin(); it != e->programs.end(); ++it)
+      if (it->second.use_count() == 1 && (victim == e->programs.end() || it->second->last_use < victim->second->last_use))
+        victim = it;
+    if (victim == e->programs.end()) return;  // everything is pinned: let the cache grow for this call
+    e->programs.erase(victim);
+  }
+}
+
+static std::shared_ptr<Program> get_program(use_engine* e, int B, int F, int T, void* workspace, size_t workspace_bytes) {
   char key[128];
   snprintf(key, sizeof(key), "%d,%d,%d,%p", B, F, T, workspace);
   size_t need = 0;
@@ -850,19 +922,22 @@ static Program* get_program(use_engine* e, int B, int F, int T, void* workspace,
     return nullptr;
   }
   auto it = e->programs.find(key);
-  if (it != e->programs.end()) return it->second.get();
+  if (it != e->programs.end()) {
+    it->second->last_use = ++e->program_tick;
+    return it->second;
+  }
   if (!e->dev_w) { fail("weights not uploaded"); return nullptr; }
-  if (e->programs.size() > 8) e->programs.clear();
-  std::unique_ptr<Program> p(new Program());
+  evict_programs(e);
+  std::shared_ptr<Program> p(new Program());
   p->B = B; p->F = F; p->T = T; p->base = (char*)workspace;
   Builder b{e, p.get(), B, F, T};
   b.base = (char*)workspace;
   b.dry = false;
   b.build();
   if (b.err) return nullptr;
-  Program* raw = p.get();
-  e->programs[key] = std::move(p);
-  return raw;
+  p->last_use = ++e->program_tick;
+  e->programs[key] = p;
+  return p;
 }
 
 // one network evaluation: t / gfp already in the workspace head; xr packed
@@ -945,14 +1020,15 @@ const char* use_last_error(void) { return g_err; }
 use_engine* use_engine_create(const use_config* cfg) {
   if (!cfg) { fail("null config"); return nullptr; }
   if (cfg->num_levels < 1 || cfg->num_levels > 8 || cfg->nf <= 0 || (cfg->input_channels != 4 && cfg->input_channels != 2) ||
-      (cfg->act_dtype != USE_DTYPE_F32 && cfg->act_dtype != USE_DTYPE_BF16)) {
+      (cfg->act_dtype != USE_DTYPE_F32 && cfg->act_dtype != USE_DTYPE_BF16 && cfg->act_dtype != USE_DTYPE_F32X3)) {
     fail("unsupported config (levels=%d nf=%d input_channels=%d dtype=%d)", cfg->num_levels, cfg->nf,
          cfg->input_channels, cfg->act_dtype);
     return nullptr;
   }
   use_engine* e = new use_engine();
   e->cfg = *cfg;
-  e->dt = cfg->act_dtype;
+  e->x3 = cfg->act_dtype == USE_DTYPE_F32X3;
+  e->dt = e->x3 ? (int)kF32 : cfg->act_dtype;
   build_mods(e);
   for (auto& m : e->mods) {
     if (m.kind == K_RB) {
@@ -1049,8 +1125,9 @@ static int net_forward(use_engine* e, int B, int F, int T, const void* x, const 
   const bool cond = e->cfg.conditional != 0;
   if (e->cfg.input_channels == 4 && !Y) return fail("the conditioning spectrogram Y is required (input_channels = 4)");
   if ((cond || e->cfg.scale_by_sigma) && (!t_host || (cond && !gfp_host))) return fail("time inputs are required");
-  Program* p = get_program(e, B, F, T, workspace, workspace_bytes);
-  if (!p) return 1;
+  std::shared_ptr<Program> pin = get_program(e, B, F, T, workspace, workspace_bytes);
+  if (!pin) return 1;
+  Program* p = pin.get();
   cudaStream_t st = (cudaStream_t)stream;
   if (t_host) cudaMemcpyAsync(p->base + e->head.t, t_host, (size_t)B * 4, cudaMemcpyHostToDevice, st);
   if (cond) cudaMemcpyAsync(p->base + e->head.gfp, gfp_host, (size_t)B * 2 * e->cfg.nf * 4, cudaMemcpyHostToDevice, st);
@@ -1085,22 +1162,37 @@ int use_net_forward(use_engine* e, int B, int F, int T, const void* x, const voi
   return net_forward(e, B, F, T, x, Y, t_host, gfp_host, out, 1.0f, workspace, workspace_bytes, stream);
 }
 
-int use_pc_sample(use_engine* e, int B, int F, int T, const void* Y, void* x_state, void* x_mean, int N,
-                  const float* t_host, const float* G_host, const float* gfp_host, float prior_std, const void* noise,
-                  uint64_t seed, uint32_t clip0, void* workspace, size_t workspace_bytes, void* stream) {
+int use_pc_sample_ex(use_engine* e, int B, int F, int T, const void* Y, void* x_state, void* x_mean, int N,
+                     const float* t_host, const float* G_host, const float* gfp_host, float prior_std, const void* noise,
+                     uint64_t seed, uint32_t clip0, const use_sampler_opts* opts, void* workspace, size_t workspace_bytes,
+                     void* stream) {
   if (!e || !Y || !x_state || !x_mean || !t_host || !G_host || !gfp_host || !workspace) return fail("null argument");
   if (N < 1 || N > kMaxSteps) return fail("N must be in [1, %d]", kMaxSteps);
   if (e->cfg.input_channels != 4 || !e->cfg.conditional || !e->cfg.scale_by_sigma)
     return fail("use_pc_sample needs the noise-conditional score network (input_channels=4, conditional, scale_by_sigma)");
+  use_sampler_opts o{};
+  o.predictor = USE_PRED_REVERSE_DIFFUSION;
+  o.corrector = USE_CORR_NONE;
+  o.denoise = 1;
+  if (opts) o = *opts;
+  if (o.predictor < 0 || o.predictor > USE_PRED_NONE) return fail("unknown predictor %d", o.predictor);
+  if (o.corrector < 0 || o.corrector > USE_CORR_ALD) return fail("unknown corrector %d", o.corrector);
+  const int cs = o.corrector == USE_CORR_NONE ? 0 : o.corrector_steps;  // NoneCorrector.n_steps = 0 (correctors.py:106-108)
+  if (cs < 0) return fail("corrector_steps must be >= 0");
+  if (o.predictor == USE_PRED_EULER_MARUYAMA && !o.g_host) return fail("euler_maruyama needs the diffusion table g_host[N]");
+  if (o.corrector == USE_CORR_ALD && cs > 0 && !o.ald_step_host) return fail("ald needs the step-size table ald_step_host[N]");
+  const int pe = o.predictor == USE_PRED_NONE ? 0 : 1;
+  const int draws_per_step = cs + pe;  // normal draws per outer step, in the reference's order: corrector steps, predictor
   cudaStream_t st = (cudaStream_t)stream;
-  const int G = group_count(e, B), Bg = B / G;
+  // Langevin's step size is a batch mean (correctors.py:55-57): the batch must stay one group
+  const int G = (o.corrector == USE_CORR_LANGEVIN && cs > 0) ? 1 : group_count(e, B), Bg = B / G;
   const size_t per = (size_t)F * T;
   const int nf2 = 2 * e->cfg.nf;
   size_t need = 0;
   if (plan_workspace(e, Bg, F, T, &need, nullptr)) return 1;
   const size_t slice = G > 1 ? align_up(need, 4096) : need;
   if (workspace_bytes < slice * G) return fail("workspace too small: %zu bytes given, %zu needed", workspace_bytes, slice * G);
-  Program* prog[2] = {nullptr, nullptr};
+  std::shared_ptr<Program> prog[2];  // pinned for the duration of the call (the cache never evicts a held program)
   cudaStream_t gs[2] = {st, st};
   for (int g = 0; g < G; ++g) {
     prog[g] = get_program(e, Bg, F, T, (char*)workspace + g * slice, slice);
@@ -1128,45 +1220,102 @@ int use_pc_sample(use_engine* e, int B, int F, int T, const void* Y, void* x_sta
   for (int g = 0; g < G; ++g) {
     char* base = prog[g]->base;
     cudaMemcpyAsync(base + e->head.sched, sched.data(), sched.size() * 4, cudaMemcpyHostToDevice, gs[g]);
-    const size_t o = (size_t)g * Bg * per;
-    // x_0 = Y + z_0 * std(1)   (sdes.py:248-254)
-    launch_prior((const float2*)Y + o, z ? z + o : nullptr, (float2*)x_state + o, prior_std, seed, clip0 + g * Bg, Bg, per,
-                 gs[g]);
+    const size_t off = (size_t)g * Bg * per;
+    if (o.x_init) {
+      if ((const float2*)o.x_init != (const float2*)x_state)
+        cudaMemcpyAsync((float2*)x_state + off, (const float2*)o.x_init + off, per * Bg * sizeof(float2), cudaMemcpyDeviceToDevice,
+                        gs[g]);
+    } else {
+      // x_0 = Y + z_0 * std(1)   (sdes.py:248-254)
+      launch_prior((const float2*)Y + off, z ? z + off : nullptr, (float2*)x_state + off, prior_std, seed, clip0 + g * Bg, Bg,
+                   per, gs[g]);
+    }
   }
   for (int i = 0; i < N; ++i) {
     for (int g = 0; g < G; ++g) {  // interleaved enqueue: both streams always have work queued
-      Program* p = prog[g];
+      Program* p = prog[g].get();
       char* base = p->base;
-      const size_t o = (size_t)g * Bg * per, n = per * Bg;
+      const size_t off = (size_t)g * Bg * per, n = per * Bg;
       const float* t_dev = (const float*)(base + e->head.sched) + i;
       const float* gfp_dev = (const float*)(base + e->head.sched) + N + (size_t)i * nf2;
-      launch_pack_input(e->dt, 4, (const float2*)x_state + o, (const float2*)Y + o, (float*)(base + e->head.xr),
-                        base + e->head.xpad, n, gs[g]);
-      run_network(e, p, gs[g], gfp_dev, 0, own_streams);
-      StepArgs a{};
-      a.pyramid = (const float*)(base + p->pyramid_off);
-      a.pc = 4;
-      a.out_sign = -1.0f;
-      a.t = t_dev;
-      a.t_bstride = 0;
-      a.ow = (const float*)(e->dev_w + e->off.at("out.w"));
-      a.ob = (const float*)(e->dev_w + e->off.at("out.b"));
-      a.score = nullptr;
-      a.x = (const float2*)x_state + o;
-      a.Y = (const float2*)Y + o;
-      a.z = z ? z + (size_t)(i + 1) * per * B + o : nullptr;
-      a.x_mean = (float2*)x_mean + o;
-      a.x_next = (float2*)x_state + o;
-      a.theta = e->cfg.theta;
-      a.dt = 1.0f / (float)N;
-      a.G = G_host[i];
-      a.seed = seed;
-      a.step = (unsigned)i;
-      a.clip0 = clip0 + g * Bg;
-      a.B = Bg;
-      a.per_clip = per;
-      launch_final_step(a, gs[g]);
-      e->launches += 2;
+      auto evaluate = [&](StepArgs& a) {  // one network evaluation at t_i from the current state + the fused tail
+        launch_pack_input(e->dt, 4, (const float2*)x_state + off, (const float2*)Y + off, (float*)(base + e->head.xr),
+                          base + e->head.xpad, n, gs[g]);
+        run_network(e, p, gs[g], gfp_dev, 0, own_streams);
+        a.pyramid = (const float*)(base + p->pyramid_off);
+        a.pc = 4;
+        a.out_sign = -1.0f;
+        a.t = t_dev;
+        a.t_bstride = 0;
+        a.ow = (const float*)(e->dev_w + e->off.at("out.w"));
+        a.ob = (const float*)(e->dev_w + e->off.at("out.b"));
+        a.B = Bg;
+        a.per_clip = per;
+        launch_final_step(a, gs[g]);
+        e->launches += 2;
+      };
+      // ---- corrector: n_steps x (score evaluation, Langevin update)   (sampling/__init__.py:67, correctors.py:37-98)
+      for (int j = 0; j < cs; ++j) {
+        const unsigned draw = (unsigned)(i * draws_per_step + j);
+        float2* grad = (float2*)(base + e->head.score);
+        StepArgs a{};
+        a.score = grad;
+        evaluate(a);
+        CorrectorArgs c{};
+        c.x = (const float2*)x_state + off;
+        c.grad = grad;
+        c.z = z ? z + (size_t)(1 + draw) * per * B + off : nullptr;
+        c.x_mean = (float2*)x_mean + off;
+        c.x_next = (float2*)x_state + off;
+        c.langevin = o.corrector == USE_CORR_LANGEVIN;
+        c.snr = o.snr;
+        c.step = o.corrector == USE_CORR_ALD ? o.ald_step_host[i] : 0.f;
+        c.scratch = base + e->head.red;
+        c.seed = seed;
+        c.draw = draw;
+        c.clip0 = clip0 + g * Bg;
+        c.B = Bg;
+        c.per_clip = per;
+        launch_corrector_step(c, gs[g]);
+        e->launches += c.langevin ? 3 : 1;
+      }
+      // ---- predictor   (sampling/__init__.py:68, predictors.py:40-68)
+      if (pe) {
+        const unsigned draw = (unsigned)(i * draws_per_step + cs);
+        StepArgs a{};
+        a.x = (const float2*)x_state + off;
+        a.Y = (const float2*)Y + off;
+        a.z = z ? z + (size_t)(1 + draw) * per * B + off : nullptr;
+        a.x_mean = (float2*)x_mean + off;
+        a.x_next = (float2*)x_state + off;
+        a.theta = e->cfg.theta;
+        const int Ndt = o.dt_steps > 0 ? o.dt_steps : N;
+        a.dt = 1.0f / (float)Ndt;
+        a.pf = o.probability_flow ? 0.5f : 1.0f;
+        if (o.predictor == USE_PRED_EULER_MARUYAMA) {
+          a.mode = kStepEulerMaruyama;
+          a.G = o.g_host[i];
+          a.Gz = o.probability_flow ? 0.f : o.g_host[i] * sqrtf(1.0f / (float)Ndt);
+        } else {
+          a.mode = kStepReverseDiffusion;
+          a.G = G_host[i];
+          a.Gz = o.probability_flow ? 0.f : G_host[i];
+        }
+        a.seed = seed;
+        a.step = draw;
+        a.clip0 = clip0 + g * Bg;
+        evaluate(a);
+      }
+      if (o.trace)  // parity instrumentation: xt_mean after outer step i (NonePredictor returns (x, x): the state itself)
+        cudaMemcpyAsync((float2*)o.trace + (size_t)i * per * B + off, (pe ? (const float2*)x_mean : (const float2*)x_state) + off,
+                        n * sizeof(float2), cudaMemcpyDeviceToDevice, gs[g]);
+    }
+  }
+  if (!o.denoise || pe == 0) {  // x_result = xt (sampling/__init__.py:69); NonePredictor returns (x, x) (predictors.py:78-79)
+    for (int g = 0; g < G; ++g) {
+      const size_t off = (size_t)g * Bg * per;
+      cudaMemcpyAsync((float2*)x_mean + off, (const float2*)x_state + off, per * Bg * sizeof(float2), cudaMemcpyDeviceToDevice,
+                      gs[g]);
     }
   }
   if (own_streams) {
@@ -1177,6 +1326,13 @@ int use_pc_sample(use_engine* e, int B, int F, int T, const void* Y, void* x_sta
   }
   e->launches += G;
   return cuda_check("use_pc_sample");
+}
+
+int use_pc_sample(use_engine* e, int B, int F, int T, const void* Y, void* x_state, void* x_mean, int N,
+                  const float* t_host, const float* G_host, const float* gfp_host, float prior_std, const void* noise,
+                  uint64_t seed, uint32_t clip0, void* workspace, size_t workspace_bytes, void* stream) {
+  return use_pc_sample_ex(e, B, F, T, Y, x_state, x_mean, N, t_host, G_host, gfp_host, prior_std, noise, seed, clip0, nullptr,
+                          workspace, workspace_bytes, stream);
 }
 
 long long use_engine_launch_count(use_engine* e) { return e ? e->launches : -1; }

@@ -56,11 +56,15 @@ void launch_upfirdn2d(const float* in, float* out, int major, int in_h, int in_w
 void launch_conv_ref(int dt, const void* x, const float* w, const float* bias, int bias_bstride, const void* res,
                      float scale, void* out, int B, int H, int W, int Cin, int Cout, int ksize, cudaStream_t st);
 
+// 3xTF32 parity mode: hi = rne_tf32(x[:, c0:c0+C]), lo = rne_tf32(x - hi), both dense [npix][C] fp32
+void launch_split_tf32(const float* x, int Ct, int c0, int C, float* hi, float* lo, size_t npix, cudaStream_t st);
+
 // ---- network input / output, SDE arithmetic -------------------------------------------------------
 // xr[b][f][t][:] = 2*[Re x, Im x, Re Y, Im Y] - 1 (fp32 x4); xpad (optional): the same 4 values as act-dtype MMA
 // operands zero-padded to one 128-byte channel chunk per pixel (input of the tcgen05 input convolution)
 void launch_pack_input(int dt, int pc, const float2* x, const float2* Y, float* xr, void* xpad, size_t n, cudaStream_t st);
 
+enum StepMode { kStepReverseDiffusion = 0, kStepEulerMaruyama = 1 };
 struct StepArgs {
   const float* pyramid;  // fp32 [B][F][T][pc]
   int pc;                // pyramid channels: 4 (score network) or 2 (discriminative network)
@@ -76,7 +80,10 @@ struct StepArgs {
   const float2* z;       // explicit noise or nullptr -> Philox
   float2* x_mean;
   float2* x_next;
-  float theta, dt, G;
+  float theta, dt, G;    // G: reverse diffusion g(t_i) sqrt(1/N); Euler-Maruyama: g(t_i)
+  float Gz;              // noise gain: G (reverse diffusion), g sqrt(1/N) (Euler-Maruyama), 0 for the probability flow
+  float pf;              // 1, or 0.5 for the probability-flow ODE (sdes.py:139,166)
+  int mode;              // kStepReverseDiffusion | kStepEulerMaruyama
   unsigned long long seed;
   unsigned int step;
   unsigned int clip0;    // global index of sample 0 (shard-invariant RNG streams)
@@ -84,6 +91,25 @@ struct StepArgs {
   size_t per_clip;       // F*T
 };
 void launch_final_step(const StepArgs& a, cudaStream_t st);
+// One corrector update (LangevinCorrector / AnnealedLangevinDynamics, sampling/correctors.py:37-98) given grad = score(x):
+// x_mean = x + step grad ; x = x_mean + z sqrt(2 step).  langevin: step = 2 (snr mean_b||z_b|| / mean_b||grad_b||)^2 is
+// reduced on the device (deterministic two-pass sum); otherwise `step` is the host-computed 2 (snr std(t))^2 of ALD.
+struct CorrectorArgs {
+  const float2* x;
+  const float2* grad;
+  const float2* z;        // explicit noise or nullptr -> Philox stream `draw`
+  float2* x_mean;
+  float2* x_next;
+  int langevin;
+  float snr, step;
+  void* scratch;          // corrector_scratch_bytes(B) device bytes (Langevin only)
+  unsigned long long seed;
+  unsigned int draw, clip0;
+  int B;
+  size_t per_clip;
+};
+size_t corrector_scratch_bytes(int B);
+void launch_corrector_step(const CorrectorArgs& c, cudaStream_t st);
 // x0 = Y + z * std   (z explicit or Philox, step = 0xffffffff stream)
 void launch_prior(const float2* Y, const float2* z, float2* x0, float std, unsigned long long seed, unsigned int clip0,
                   int B, size_t per_clip, cudaStream_t st);

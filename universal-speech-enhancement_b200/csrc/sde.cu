@@ -107,14 +107,115 @@ __global__ void __launch_bounds__(256) final_step_kernel(StepArgs a) {
       float2 z;
       if (a.z != nullptr) z = a.z[i];
       else z = philox_cnormal(a.seed, a.step, a.clip0 + b, i - static_cast<size_t>(b) * a.per_clip);
-      // f = theta (Y - x) dt ; rev_f = f - G^2 score ; x_mean = x - rev_f ; x = x_mean + G z
-      const float fre = (a.theta * (Y.x - x.x)) * a.dt, fim = (a.theta * (Y.y - x.y)) * a.dt;
-      const float rre = fre - G2 * score.x, rim = fim - G2 * score.y;
-      const float2 xm = make_float2(x.x - rre, x.y - rim);
+      float2 xm;
+      if (a.mode == kStepEulerMaruyama) {
+        // f = theta (Y - x) - g^2 score pf ; x_mean = x + f (-1/N) ; x = x_mean + g sqrt(1/N) z   (predictors.py:40-53,
+        // RSDE.rsde_parts sdes.py:128-150); a.G = g(t_i) here, a.Gz = g sqrt(1/N) (0 for the probability flow)
+        const float dre = a.theta * (Y.x - x.x) + (-G2 * score.x) * a.pf, dim_ = a.theta * (Y.y - x.y) + (-G2 * score.y) * a.pf;
+        xm = make_float2(x.x + dre * (-a.dt), x.y + dim_ * (-a.dt));
+      } else {
+        // f = theta (Y - x) dt ; rev_f = f - G^2 score pf ; x_mean = x - rev_f ; x = x_mean + G z
+        const float fre = (a.theta * (Y.x - x.x)) * a.dt, fim = (a.theta * (Y.y - x.y)) * a.dt;
+        const float rre = fre - G2 * score.x * a.pf, rim = fim - G2 * score.y * a.pf;
+        xm = make_float2(x.x - rre, x.y - rim);
+      }
       a.x_mean[i] = xm;
-      a.x_next[i] = make_float2(xm.x + a.G * z.x, xm.y + a.G * z.y);
+      a.x_next[i] = make_float2(xm.x + a.Gz * z.x, xm.y + a.Gz * z.y);
     }
   }
+}
+
+// ---- correctors (sampling/correctors.py:37-98) ---------------------------------------------------------------
+// Langevin: the step size couples the whole batch through two batch-mean norms (correctors.py:55-57).  Deterministic
+// two-pass reduction: pass 1 = per-(clip, block) sums of |grad|^2 and |noise|^2 in a fixed order (double), pass 2 = one
+// block folds the partials in index order, takes sqrt per clip, the batch means, and writes the step coefficients.
+constexpr int kRedBlocks = 64;  // partial sums per clip
+
+__global__ void __launch_bounds__(256) sumsq_pair_kernel(const float2* __restrict__ grad, const float2* __restrict__ z,
+                                                          double* __restrict__ part, unsigned long long seed,
+                                                          unsigned int draw, unsigned int clip0, size_t per_clip) {
+  const int b = blockIdx.y, blk = blockIdx.x;
+  const size_t chunk = (per_clip + kRedBlocks - 1) / kRedBlocks;
+  const size_t lo = blk * chunk, hi = lo + chunk < per_clip ? lo + chunk : per_clip;
+  double sg = 0.0, sz = 0.0;
+  for (size_t i = lo + threadIdx.x; i < hi; i += 256) {
+    const float2 g = grad[static_cast<size_t>(b) * per_clip + i];
+    const float2 n = z ? z[static_cast<size_t>(b) * per_clip + i] : philox_cnormal(seed, draw, clip0 + b, i);
+    sg += static_cast<double>(g.x) * g.x + static_cast<double>(g.y) * g.y;
+    sz += static_cast<double>(n.x) * n.x + static_cast<double>(n.y) * n.y;
+  }
+  __shared__ double sh[2][256];
+  sh[0][threadIdx.x] = sg;
+  sh[1][threadIdx.x] = sz;
+  __syncthreads();
+  for (int s = 128; s > 0; s >>= 1) {  // fixed tree: deterministic
+    if (threadIdx.x < s) {
+      sh[0][threadIdx.x] += sh[0][threadIdx.x + s];
+      sh[1][threadIdx.x] += sh[1][threadIdx.x + s];
+    }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    part[(static_cast<size_t>(b) * kRedBlocks + blk) * 2] = sh[0][0];
+    part[(static_cast<size_t>(b) * kRedBlocks + blk) * 2 + 1] = sh[1][0];
+  }
+}
+
+// coef[0] = step_size = 2 (snr * mean_b ||z_b|| / mean_b ||grad_b||)^2 ; coef[1] = sqrt(2 step_size)
+__global__ void langevin_coef_kernel(const double* __restrict__ part, float* __restrict__ coef, float snr, int B) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  float gn = 0.f, zn = 0.f;
+  for (int b = 0; b < B; ++b) {
+    double sg = 0.0, sz = 0.0;
+    for (int k = 0; k < kRedBlocks; ++k) {
+      sg += part[(static_cast<size_t>(b) * kRedBlocks + k) * 2];
+      sz += part[(static_cast<size_t>(b) * kRedBlocks + k) * 2 + 1];
+    }
+    gn += static_cast<float>(sqrt(sg));
+    zn += static_cast<float>(sqrt(sz));
+  }
+  gn /= static_cast<float>(B);
+  zn /= static_cast<float>(B);
+  const float r = snr * zn / gn;
+  const float step = r * r * 2.f;
+  coef[0] = step;
+  coef[1] = sqrtf(step * 2.f);
+}
+
+// x_mean = x + step * grad ; x = x_mean + noise * sqrt(2 step)   (correctors.py:61-62,95-96); in place on x allowed
+__global__ void __launch_bounds__(256) corrector_update_kernel(const float2* __restrict__ x, const float2* __restrict__ grad,
+                                                                const float2* __restrict__ z, const float* __restrict__ coef_dev,
+                                                                float step_imm, float nz_imm, float2* __restrict__ x_mean,
+                                                                float2* __restrict__ x_next, unsigned long long seed,
+                                                                unsigned int draw, unsigned int clip0, size_t per_clip, size_t n) {
+  const float step = coef_dev ? coef_dev[0] : step_imm;
+  const float nz = coef_dev ? coef_dev[1] : nz_imm;
+  for (size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n;
+       i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const uint32_t b = static_cast<uint32_t>(i / per_clip);
+    const float2 zz = z ? z[i] : philox_cnormal(seed, draw, clip0 + b, i - static_cast<size_t>(b) * per_clip);
+    const float2 xv = x[i], g = grad[i];
+    const float2 xm = make_float2(xv.x + step * g.x, xv.y + step * g.y);
+    x_mean[i] = xm;
+    x_next[i] = make_float2(xm.x + zz.x * nz, xm.y + zz.y * nz);
+  }
+}
+
+size_t corrector_scratch_bytes(int B) { return static_cast<size_t>(B) * kRedBlocks * 2 * sizeof(double) + 64; }
+
+void launch_corrector_step(const CorrectorArgs& c, cudaStream_t st) {
+  const size_t n = c.per_clip * c.B;
+  const float* coef_dev = nullptr;
+  if (c.langevin) {
+    double* part = reinterpret_cast<double*>(c.scratch);
+    float* coef = reinterpret_cast<float*>(reinterpret_cast<char*>(c.scratch) + static_cast<size_t>(c.B) * kRedBlocks * 2 * sizeof(double));
+    sumsq_pair_kernel<<<dim3(kRedBlocks, c.B), 256, 0, st>>>(c.grad, c.z, part, c.seed, c.draw, c.clip0, c.per_clip);
+    langevin_coef_kernel<<<1, 32, 0, st>>>(part, coef, c.snr, c.B);
+    coef_dev = coef;
+  }
+  const int blocks = static_cast<int>(std::min<size_t>((n + 255) / 256, 148 * 16));
+  corrector_update_kernel<<<blocks, 256, 0, st>>>(c.x, c.grad, c.z, coef_dev, c.step, sqrtf(c.step * 2.f), c.x_mean, c.x_next,
+                                                   c.seed, c.draw, c.clip0, c.per_clip, n);
 }
 
 void launch_final_step(const StepArgs& a, cudaStream_t st) {

@@ -20,19 +20,29 @@ def shard_range(n: int, rank: int, world: int) -> Tuple[int, int]:
     return lo, lo + base + (1 if rank < rem else 0)
 
 
-def sample_sharded(sample_fn: Callable[[torch.Tensor, int], torch.Tensor], y: torch.Tensor, gather: bool = True):
+def sample_sharded(sample_fn: Callable[[torch.Tensor, int], torch.Tensor], y: torch.Tensor, gather: bool = True,
+                   out_shape=None):
     """Run ``sample_fn(y_local, clip0)`` on this rank's shard of ``y`` [B, L] and all-gather the results.
 
     ``clip0`` is the global index of the shard's first clip: the in-kernel Philox noise is keyed by the global clip
-    index, so the gathered result does not depend on the number of ranks.
+    index, so the gathered result does not depend on the number of ranks.  ``out_shape``: per-clip shape of
+    ``sample_fn``'s result when it differs from ``y.shape[1:]`` (only needed by ranks whose shard is empty, B < world).
     """
     if not (dist.is_available() and dist.is_initialized()):
         return sample_fn(y, 0)
     world, rank = dist.get_world_size(), dist.get_rank()
     B = y.shape[0]
     lo, hi = shard_range(B, rank, world)
-    out_local = sample_fn(y[lo:hi], lo)
+    if hi > lo:
+        out_local = sample_fn(y[lo:hi], lo)
+    else:
+        # B < world: this rank owns no clip.  Launch nothing (a B = 0 grid is an invalid launch) but still take part in
+        # the gather below, otherwise the other ranks would hang in it.
+        out_local = y.new_zeros((0,) + tuple(y.shape[1:]), dtype=torch.float32) if out_shape is None else \
+            torch.zeros((0,) + tuple(out_shape), dtype=torch.float32, device=y.device)
     if not gather:
+        return out_local
+    if B == 0:
         return out_local
     if B % world == 0:
         out = torch.empty((B,) + tuple(out_local.shape[1:]), dtype=out_local.dtype, device=out_local.device)

@@ -105,6 +105,12 @@ class GANModule(_Base):
             if hasattr(m, "invalidate_engine"):
                 m.invalidate_engine()
 
+    def load_checkpoint(self, ckpt_path: str, strict: bool = False):
+        """Load a Lightning ``.ckpt`` of the reference (``state_dict`` keys ``G.net.*`` / ``D.*``) through the lenient
+        ``load_state_dict`` above -- what ``trainer.predict(ckpt_path=...)`` does for this module (predict.py:79)."""
+        ckpt = torch.load(ckpt_path, map_location="cpu", weights_only=False)
+        return self.load_state_dict(ckpt.get("state_dict", ckpt), strict=strict)
+
     def training_step(self, batch, batch_idx):
         raise NotImplementedError("training is out of scope of the B200 predict path")
 

@@ -166,19 +166,38 @@ class ScoreModel(nn.Module):
         return self.forward_score(x, t, score_conditioning, sde_input)
 
     # ---- samplers ----------------------------------------------------------------------------------
-    def _fused_pc_sample(self, sde, y, eps, noise=None, seed=None, clip0=0):
-        """y: complex [B,1,F,T].  One C call for prior + N predictor steps."""
-        ts, G, std1 = sde.step_tables(sde.N, eps)
+    def _fused_pc_sample(self, sde, y, eps, predictor="reverse_diffusion", corrector="none", corrector_steps=1, snr=0.5,
+                         probability_flow=False, denoise=True, noise=None, seed=None, clip0=0, trace=None, x_init=None,
+                         times=None, want_state=False):
+        """y: complex [B,1,F,T].  One C call (use_pc_sample_ex) per micro-batch: prior + N x (corrector steps, predictor
+        step).  ``x_init`` + ``times`` = [t]: a single update_fn step from the given state (dt stays 1 / sde.N)."""
+        ts, G, std1 = sde.step_tables(sde.N, eps, times=times)
+        g_tab, ald_tab = sde.variant_tables(ts, snr)
         if seed is None:
             seed = int(torch.randint(0, 2**31 - 1, (1,)).item())  # consumes the global RNG like randn_like would
         nz = noise[:, :, 0] if noise is not None else None
-        mb = self.micro_batch or y.shape[0]
-        outs = []
-        for s in range(0, y.shape[0], mb):
+        B = y.shape[0]
+        mb = self.micro_batch or B
+        eng = self._engine(y.device)
+        means, states = [], []
+        for s in range(0, B, mb):
             Yc = y[s:s + mb, 0]
             nc = nz[:, s:s + mb].contiguous() if nz is not None else None
-            outs.append(self._engine(y.device).pc_sample(Yc, ts, G, std1, noise=nc, seed=seed, clip0=clip0 + s))
-        return torch.cat(outs, dim=0).unsqueeze(1) if len(outs) > 1 else outs[0].unsqueeze(1)
+            tr = None
+            if trace is not None:
+                tr = trace[:, :, 0] if mb >= B else torch.empty_like(trace[:, s:s + mb, 0]).contiguous()
+            xm, xs = eng.pc_sample(Yc, ts, G, std1, noise=nc, seed=seed, clip0=clip0 + s, predictor=predictor,
+                                   corrector=corrector, corrector_steps=corrector_steps, snr=snr,
+                                   probability_flow=probability_flow, denoise=denoise, g=g_tab, ald_step=ald_tab, trace=tr,
+                                   x_init=None if x_init is None else x_init[s:s + mb, 0], dt_steps=sde.N)
+            if trace is not None and mb < B:
+                trace[:, s:s + mb, 0] = tr
+            means.append(xm)
+            states.append(xs)
+        mean = (torch.cat(means, dim=0) if len(means) > 1 else means[0]).unsqueeze(1)
+        if not want_state:
+            return mean
+        return (torch.cat(states, dim=0) if len(states) > 1 else states[0]).unsqueeze(1), mean
 
     def get_pc_sampler(self, predictor_name, corrector_name, y, N=None, minibatch=None, **kwargs):
         N = self.sde.N if N is None else N
@@ -194,6 +213,11 @@ class ScoreModel(nn.Module):
             for i in range(int(ceil(M / minibatch))):
                 y_mini = y[i * minibatch:(i + 1) * minibatch]
                 kw = dict(kwargs)
+                kw["clip0"] = kwargs.get("clip0", 0) + i * minibatch      # global clip index keys the Philox streams
+                if kw.get("noise") is not None:
+                    kw["noise"] = kw["noise"][:, i * minibatch:(i + 1) * minibatch]
+                if kw.get("trace") is not None:
+                    raise NotImplementedError("trace is not supported together with minibatch (use micro_batch)")
                 if kw.get("conditioning") is not None:
                     kw["conditioning"] = [y_mini if c is y else c[i * minibatch:(i + 1) * minibatch]
                                           for c in kw["conditioning"]]
@@ -209,8 +233,10 @@ class ScoreModel(nn.Module):
         raise NotImplementedError("the ODE (RK45) sampler is not on the accelerated path (SURVEY.md section 8f, rank 3)")
 
     @torch.no_grad()
-    def sample(self, batch, sampler_type=None, N=None, corrector_steps=1, snr=0.5, noise=None, seed=None, clip0=0):
-        """ScoreModel.sample (model_wrapper.py:262-329)."""
+    def sample(self, batch, sampler_type=None, N=None, corrector_steps=1, snr=0.5, noise=None, seed=None, clip0=0,
+               trace=None):
+        """ScoreModel.sample (model_wrapper.py:262-329).  ``noise`` / ``seed`` / ``clip0`` / ``trace``: see
+        sampling.get_pc_sampler."""
         sampler_type = sampler_type or self.default_sampler_type or "pc"
         N = N if N is not None else (self.default_N if self.default_N is not None else 50)
         y = batch["perturbed"]
@@ -221,7 +247,7 @@ class ScoreModel(nn.Module):
             raise NotImplementedError(f"{sampler_type} is not a valid sampler type on the accelerated path (use 'pc')")
         sampler = self.get_pc_sampler(self.predictor, self.corrector, Y, N=N, corrector_steps=corrector_steps, snr=snr,
                                       intermediate=False, conditioning=score_conditioning, noise=noise, seed=seed,
-                                      clip0=clip0)
+                                      clip0=clip0, trace=trace)
         sample, nfe = sampler()
         batch["enhanced"] = self.istft_decompressed(sample.squeeze(1), T_orig)
         return batch
@@ -233,7 +259,9 @@ class ScoreModel(nn.Module):
         start = time.time()
         dev = y.device if y.is_cuda else torch.device("cuda", torch.cuda.current_device())
         y = y.to(dev, torch.float32)
-        norm_factor = y.abs().max().item()
+        # the reference divides by the peak unguarded (model.py:962-963): an all-zero input gives NaN there; here a silent
+        # clip is passed through unscaled (deliberate deviation, tests/test_gpu_entrypoints.py)
+        norm_factor = y.abs().max().item() or 1.0
         y = y / norm_factor
         T_orig = y.size(1)
         Y = self.stft_compressed(y).unsqueeze(1)

@@ -32,8 +32,8 @@ def _read_wav(path: str):
             wav = wav.astype(np.float32) / float(np.iinfo(wav.dtype).max)
         wav = wav.astype(np.float32)
     if wav.ndim > 1:
-        wav = wav.mean(axis=1)
-    return wav, int(sr)
+        wav = wav[:, 0]  # the reference keeps channel 0 (loadwav_dataset.py:96), it does not down-mix
+    return np.ascontiguousarray(wav), int(sr)
 
 
 class LoadWavDataModule:
@@ -54,7 +54,8 @@ class LoadWavDataModule:
 
             wav = resample(wav, int(round(len(wav) * self.sampling_rate / sr))).astype(np.float32)
         if self.normalize:
-            wav = wav / (np.abs(wav).max() + 1e-8) * 0.8
+            peak = float(np.abs(wav).max())
+            wav = wav / peak * 0.8 if peak > 0 else wav  # loadwav_dataset.py:99-100; an all-zero file stays zero
         return wav
 
     def predict_dataloader(self) -> Iterator[Dict]:

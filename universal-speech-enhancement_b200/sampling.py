@@ -1,171 +1,200 @@
-"""Predictor-corrector sampling (host side).
+"""Predictor-corrector sampling: the reference's plugin surface over the fused CUDA loop.
 
-Mirrors /root/reference/src/models/components/sgmse/sampling/{__init__,predictors,correctors}.py: the
-``PredictorRegistry`` / ``CorrectorRegistry`` plugin surface, ``Predictor.update_fn(x, t, *args)`` and
-``get_pc_sampler(...) -> callable`` returning ``(x_result, n_function_evaluations)``.
+Mirrors the API of /root/reference/src/models/components/sgmse/sampling/{__init__,predictors,correctors}.py -- the
+``PredictorRegistry`` / ``CorrectorRegistry`` names ("reverse_diffusion", "euler_maruyama", "none"; "langevin",
+"ald", "none"), ``update_fn(x, t, y, conditioning=...) -> (x, x_mean)`` and ``get_pc_sampler(...) -> callable``
+returning ``(x_result, n_function_evaluations)`` -- but none of the arithmetic lives here:
 
-Two execution routes, both with the score network in CUDA (libuse_b200.so):
-  * fused: predictor "reverse_diffusion" + corrector "none" + OUVESDE + a B200 ScoreModel as ``score_fn`` --
-    the configuration src/predict.py runs (model_wrapper.py:305-314).  The whole N-step loop is ONE C call
-    (``use_pc_sample``): prior draw, N x (network + fused drift/diffusion/noise-inject step).
-  * generic: any other registered predictor / corrector runs the reference's loop on the host, one C call
-    (``use_score_forward``) per score evaluation, elementwise SDE arithmetic as torch ops on the device.
+  * every built-in predictor / corrector is a *descriptor* (``kind``) of a step the C library executes; the whole
+    sampler (prior draw + N x [corrector steps, predictor step], each = one NCSN++ evaluation + one fused update
+    kernel) is ONE call of ``use_pc_sample_ex`` (include/use_b200.h) with no host synchronisation inside;
+  * ``update_fn`` of a built-in class is the same C call restricted to one step starting from the given state, so
+    third-party code that drives the classes by hand gets the same kernels;
+  * predictors / correctors registered by third parties (no ``kind``) run through ``_host_loop`` below, which only
+    sequences their ``update_fn`` calls.
+
+Reference quirks kept or documented:
+  * draws are consumed in the reference's order (prior, then per outer step the corrector's draws, then the
+    predictor's); ``noise`` makes them explicit for parity tests, otherwise Philox streams keyed by the global clip
+    index are used (shard invariant);
+  * ``LangevinCorrector`` couples the batch through two batch-mean norms (correctors.py:55-57): under sharding or
+    micro-batching the mean is over the local (micro-)batch, exactly as the reference's per-rank / ``minibatch``
+    behaviour;
+  * ``probability_flow`` never reaches the reverse SDE of a predictor in the reference (predictors.py:14-19 builds
+    ``sde.reverse(score_fn)`` without it), so it does not change the PC sampler here either (the C library's
+    ``use_sampler_opts.probability_flow`` implements the halved-score / no-noise step for callers that want it);
+  * ``euler_maruyama`` cannot run in the reference with this ScoreModel (RSDE.rsde_parts calls
+    ``score_model(x, t, conditioning)`` without ``sde_input``, sdes.py:131-134 -> TypeError); here it follows the
+    evident intent and is pinned against the reference's own classes driven with an adapter score function
+    (oracle/make_golden_variants.py).
 """
 from __future__ import annotations
 
 import abc
 
-import numpy as np
 import torch
 
-from . import sdes
+from . import _lib, sdes
 from .registry import Registry
 
 PredictorRegistry = Registry("Predictor")
 CorrectorRegistry = Registry("Corrector")
 
 
-class Predictor(abc.ABC):
+def _uniform_time(t: torch.Tensor) -> float:
+    """update_fn receives vec_t = ones(B) * t_i (sampling/__init__.py:65-66): the fused step takes the scalar."""
+    t = t.detach().reshape(-1)
+    t0 = float(t[0])
+    if t.numel() > 1 and not bool((t == t[0]).all()):
+        raise NotImplementedError("the fused sampler steps take one batch-uniform time value")
+    return t0
+
+
+class _Step(abc.ABC):
+    """Common part of the built-in predictors / correctors: one fused step through the C library."""
+
+    kind: str = None  # name of the fused step; None for host-defined plugins
+
+    def _fused_step(self, x, t, y, conditioning, **sel):
+        fn = getattr(self.score_fn, "_fused_pc_sample", None)
+        if fn is None:
+            raise NotImplementedError(f"{type(self).__name__} needs a B200 ScoreModel as score_fn")
+        if conditioning is not None and not (len(conditioning) == 1 and conditioning[0] is y):
+            raise NotImplementedError("fused steps support score_conditioning = [y] (condition='noisy')")
+        return fn(self.sde, y, None, x_init=x, times=torch.tensor([_uniform_time(t)]), want_state=True, **sel)
+
+
+class Predictor(_Step):
+    """Base class of the plugin API (predictors.py:11-38)."""
+
     def __init__(self, sde, score_fn, probability_flow=False):
-        self.sde = sde
+        # reference quirk (predictors.py:14-19): the flag is stored but the reverse SDE is always built WITHOUT it, so
+        # get_pc_sampler(probability_flow=True) samples exactly like probability_flow=False; kept.
+        self.sde, self.score_fn, self.probability_flow = sde, score_fn, probability_flow
         self.rsde = sde.reverse(score_fn)
-        self.score_fn = score_fn
-        self.probability_flow = probability_flow
 
     @abc.abstractmethod
-    def update_fn(self, x, t, *args):
+    def update_fn(self, x, t, *args, **kwargs):
         """One predictor update: returns (x, x_mean)."""
 
 
-@PredictorRegistry.register("euler_maruyama")
-class EulerMaruyamaPredictor(Predictor):
+class Corrector(_Step):
+    """Base class of the plugin API (correctors.py:11-34)."""
+
+    def __init__(self, sde, score_fn, snr, n_steps):
+        self.sde, self.score_fn, self.snr, self.n_steps = sde, score_fn, snr, n_steps
+        self.rsde = sde.reverse(score_fn)
+
+    @abc.abstractmethod
     def update_fn(self, x, t, *args, **kwargs):
-        dt = -1.0 / self.rsde.N
-        z = torch.randn_like(x)
-        f, g = self.rsde.sde(x, t, *args, **kwargs)
-        x_mean = x + f * dt
-        if g.ndim < x.ndim:
-            g = g.view(*g.size(), *((1,) * (x.ndim - g.ndim)))
-        return x_mean + g * np.sqrt(-dt) * z, x_mean
+        """One corrector update (n_steps inner steps): returns (x, x_mean)."""
+
+
+class _FusedPredictor(Predictor):
+    def update_fn(self, x, t, y, conditioning=None, **_):
+        return self._fused_step(x, t, y, conditioning, predictor=self.kind, corrector="none")
+
+
+class _FusedCorrector(Corrector):
+    def update_fn(self, x, t, y, conditioning=None, **_):
+        return self._fused_step(x, t, y, conditioning, predictor="none", corrector=self.kind,
+                                corrector_steps=self.n_steps, snr=self.snr)
+
+
+@PredictorRegistry.register("euler_maruyama")
+class EulerMaruyamaPredictor(_FusedPredictor):
+    kind = "euler_maruyama"
 
 
 @PredictorRegistry.register("reverse_diffusion")
-class ReverseDiffusionPredictor(Predictor):
-    def update_fn(self, x, t, *args, **kwargs):
-        f, g = self.rsde.discretize(x, t, *args, **kwargs)
-        z = torch.randn_like(x)
-        x_mean = x - f
-        if g.ndim < x.ndim:
-            g = g.view(*g.size(), *((1,) * (x.ndim - g.ndim)))
-        return x_mean + g * z, x_mean
+class ReverseDiffusionPredictor(_FusedPredictor):
+    kind = "reverse_diffusion"
 
 
 @PredictorRegistry.register("none")
 class NonePredictor(Predictor):
+    kind = "none"
+
     def __init__(self, *args, **kwargs):
-        pass
+        self.probability_flow = False
 
     def update_fn(self, x, t, *args, **kwargs):
         return x, x
 
 
-class Corrector(abc.ABC):
-    def __init__(self, sde, score_fn, snr, n_steps):
-        self.rsde = sde.reverse(score_fn)
-        self.score_fn = score_fn
-        self.snr = snr
-        self.n_steps = n_steps
-
-    @abc.abstractmethod
-    def update_fn(self, x, t, *args):
-        """One corrector update: returns (x, x_mean)."""
-
-    def _grad(self, x, t, *args, **kwargs):
-        if kwargs.get("conditioning") is not None:
-            return self.score_fn(x, t, score_conditioning=kwargs["conditioning"], sde_input=args[0])
-        return self.score_fn(x, t, *args)
-
-
 @CorrectorRegistry.register(name="langevin")
-class LangevinCorrector(Corrector):
-    def update_fn(self, x, t, *args, **kwargs):
-        x_mean = x
-        for _ in range(self.n_steps):
-            grad = self._grad(x, t, *args, **kwargs)
-            noise = torch.randn_like(x)
-            grad_norm = torch.norm(grad.reshape(grad.shape[0], -1), dim=-1).mean()
-            noise_norm = torch.norm(noise.reshape(noise.shape[0], -1), dim=-1).mean()
-            step_size = ((self.snr * noise_norm / grad_norm) ** 2 * 2).unsqueeze(0)
-            step_size = step_size.view(*step_size.size(), *((1,) * (x.ndim - step_size.ndim)))
-            x_mean = x + step_size * grad
-            x = x_mean + noise * torch.sqrt(step_size * 2)
-        return x, x_mean
+class LangevinCorrector(_FusedCorrector):
+    kind = "langevin"
 
 
 @CorrectorRegistry.register(name="ald")
-class AnnealedLangevinDynamics(Corrector):
+class AnnealedLangevinDynamics(_FusedCorrector):
+    kind = "ald"
+
     def __init__(self, sde, score_fn, snr, n_steps):
-        super().__init__(sde, score_fn, snr, n_steps)
         if not isinstance(sde, sdes.OUVESDE):
             raise NotImplementedError(f"SDE class {sde.__class__.__name__} not yet supported.")
-        self.sde = sde
-
-    def update_fn(self, x, t, *args, **kwargs):
-        std = self.sde.marginal_prob(x, t, *args)[1]
-        x_mean = x
-        for _ in range(self.n_steps):
-            grad = self._grad(x, t, *args, **kwargs)
-            noise = torch.randn_like(x)
-            step_size = (self.snr * std) ** 2 * 2
-            step_size = step_size.view(*step_size.size(), *((1,) * (x.ndim - step_size.ndim)))
-            x_mean = x + step_size * grad
-            x = x_mean + noise * torch.sqrt(step_size * 2)
-        return x, x_mean
+        super().__init__(sde, score_fn, snr, n_steps)
 
 
 @CorrectorRegistry.register(name="none")
 class NoneCorrector(Corrector):
+    kind = "none"
+
     def __init__(self, *args, **kwargs):
-        self.snr = 0
-        self.n_steps = 0
+        self.snr, self.n_steps = 0, 0
 
     def update_fn(self, x, t, *args, **kwargs):
         return x, x
 
 
-def _fusable(predictor_name, corrector_name, sde, score_fn, probability_flow, conditioning, y) -> bool:
-    return (predictor_name == "reverse_diffusion" and corrector_name == "none" and isinstance(sde, sdes.OUVESDE)
-            and not probability_flow and hasattr(score_fn, "_fused_pc_sample") and sde.N >= 1
+_BUILTIN = {EulerMaruyamaPredictor, ReverseDiffusionPredictor, NonePredictor, LangevinCorrector,
+            AnnealedLangevinDynamics, NoneCorrector}  # exact classes: a subclass overriding update_fn is a host plugin
+
+
+def _fusable(predictor_cls, corrector_cls, sde, score_fn, conditioning, y) -> bool:
+    return (predictor_cls in _BUILTIN and corrector_cls in _BUILTIN and isinstance(sde, sdes.OUVESDE) and hasattr(score_fn, "_fused_pc_sample") and sde.N >= 1
             and conditioning is not None and len(conditioning) == 1 and conditioning[0] is y)
+
+
+def _host_loop(predictor, corrector, sde, y, eps, denoise, conditioning):
+    """Sequencing only, for predictor / corrector classes defined outside this package: prior draw, then the
+    corrector-then-predictor order of the reference's pc_sampler over the float32 schedule linspace(T, eps, N)."""
+    state = sde.prior_sampling(y.shape, y)
+    mean = state
+    ones = torch.ones(y.shape[0], device=y.device)
+    for t_i in sde.step_tables(sde.N, eps)[0].to(y.device):
+        for stage in (corrector, predictor):
+            state, mean = stage.update_fn(state, ones * t_i, y, conditioning=conditioning)
+    return (mean if denoise and sde.N else state), sde.N * (corrector.n_steps + 1)
 
 
 def get_pc_sampler(predictor_name, corrector_name, sde, score_fn, y, denoise=True, eps=3e-2, snr=0.1,
                    corrector_steps=1, probability_flow: bool = False, conditioning=None, intermediate=False,
-                   noise=None, seed=None, clip0=0, **kwargs):
-    """Create a PC sampler (sampling/__init__.py:23-73).  ``noise`` (complex [N+1, *y.shape], explicit draws) /
-    ``seed`` / ``clip0`` are additions for reproducible and shard-invariant sampling on the fused route."""
+                   noise=None, seed=None, clip0=0, trace=None, **kwargs):
+    """Create a PC sampler (sampling/__init__.py:23-73).  Additions for reproducible / shard-invariant sampling and
+    parity tests: ``noise`` (complex [1 + N * draws_per_step, *y.shape], the explicit normal draws), ``seed`` /
+    ``clip0`` (Philox streams), ``trace`` (complex [N, *y.shape] device tensor receiving xt_mean of every step)."""
     predictor_cls = PredictorRegistry.get_by_name(predictor_name)
     corrector_cls = CorrectorRegistry.get_by_name(corrector_name)
 
-    if denoise and _fusable(predictor_name, corrector_name, sde, score_fn, probability_flow, conditioning, y):
+    if _fusable(predictor_cls, corrector_cls, sde, score_fn, conditioning, y):
+        n_corr = 0 if corrector_cls.kind == "none" else corrector_steps
+
         def fused_sampler():
-            return score_fn._fused_pc_sample(sde, y, eps, noise=noise, seed=seed, clip0=clip0), sde.N
+            out = score_fn._fused_pc_sample(sde, y, eps, predictor=predictor_cls.kind, corrector=corrector_cls.kind,
+                                            corrector_steps=corrector_steps, snr=snr, denoise=denoise, noise=noise, seed=seed, clip0=clip0, trace=trace)
+            return out, sde.N * (n_corr + 1)
 
         return fused_sampler
 
+    if noise is not None or trace is not None:
+        raise NotImplementedError("explicit noise / trace need the fused sampler (built-in predictor and corrector)")
     predictor = predictor_cls(sde, score_fn, probability_flow=probability_flow)
     corrector = corrector_cls(sde, score_fn, snr=snr, n_steps=corrector_steps)
 
     def pc_sampler():
         with torch.no_grad():
-            xt = sde.prior_sampling(y.shape, y).to(y.device)
-            timesteps = torch.linspace(sde.T, eps, sde.N).to(y.device)
-            xt_mean = xt
-            for i in range(sde.N):
-                vec_t = torch.ones(y.shape[0], device=y.device) * timesteps[i]
-                xt, xt_mean = corrector.update_fn(xt, vec_t, y, conditioning=conditioning)
-                xt, xt_mean = predictor.update_fn(xt, vec_t, y, conditioning=conditioning)
-            x_result = xt_mean if (denoise and sde.N) else xt
-            return x_result, sde.N * (corrector.n_steps + 1)
+            return _host_loop(predictor, corrector, sde, y, eps, denoise, conditioning)
 
     return pc_sampler

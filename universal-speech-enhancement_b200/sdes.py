@@ -1,7 +1,7 @@
 """SDE classes of the path (host side; scalars and schedule tables only -- tensors stay in the CUDA kernels).
 
 Mirrors /root/reference/src/models/components/sgmse/sdes.py: ``SDERegistry``, ``SDE.discretize`` (:75-92),
-``SDE.reverse`` -> RSDE (:94-175) and ``OUVESDE`` (:182-279).  OUVPSDE is out of scope (not selectable from the
+``SDE.reverse`` -> ``ReverseSDE`` (:94-175) and ``OUVESDE`` (:182-279).  OUVPSDE is out of scope (not selectable from the
 shipped configs).  The tensor methods are written with torch ops so they work on any
 device for the non-fused sampler variants; the fused predictor consumes ``step_tables`` instead.
 """
@@ -36,42 +36,47 @@ class SDE:
         G = diffusion * torch.sqrt(torch.tensor(dt, device=t.device))
         return f, G
 
-    def reverse(oself, score_model, probability_flow=False):
-        N, T, sde_fn, discretize_fn = oself.N, oself.T, oself.sde, oself.discretize
-
-        class RSDE(oself.__class__):
-            def __init__(self):
-                self.N = N
-                self.probability_flow = probability_flow
-
-            @property
-            def T(self):
-                return T
-
-            def _score(self, x, t, *args, **kwargs):
-                if kwargs.get("conditioning") is not None:
-                    return score_model(x, t, score_conditioning=kwargs["conditioning"], sde_input=args[0])
-                return score_model(x, t, *args)
-
-            def sde(self, x, t, *args, **kwargs):
-                drift, diffusion = sde_fn(x, t, *args)
-                score = self._score(x, t, *args, **kwargs)
-                if diffusion.ndim < x.ndim:
-                    diffusion = diffusion.view(*diffusion.size(), *((1,) * (x.ndim - diffusion.ndim)))
-                total = drift - diffusion**2 * score * (0.5 if self.probability_flow else 1.0)
-                return total, (torch.zeros_like(diffusion) if self.probability_flow else diffusion)
-
-            def discretize(self, x, t, *args, **kwargs):
-                f, G = discretize_fn(x, t, *args)
-                if G.ndim < x.ndim:
-                    G = G.view(*G.size(), *((1,) * (x.ndim - G.ndim)))
-                rev_f = f - G**2 * self._score(x, t, *args, **kwargs) * (0.5 if self.probability_flow else 1.0)
-                return rev_f, (torch.zeros_like(G) if self.probability_flow else G)
-
-        return RSDE()
+    def reverse(self, score_model, probability_flow=False):
+        """The reverse-time SDE / probability-flow ODE around ``score_model`` (sdes.py:94-175 of the reference)."""
+        return ReverseSDE(self, score_model, probability_flow)
 
     def copy(self):
         raise NotImplementedError
+
+
+class ReverseSDE:
+    """dx = [f(x, t) - g(t)^2 score(x, t) c] dt + g(t) dw_bar with c = 1 (SDE) or 1/2 and no noise (probability flow).
+
+    Host-side helper for third-party predictors / correctors (the built-in ones run fused in CUDA and never touch it):
+    the score comes from the B200 network (one C call), the elementwise part is torch on the device.  Same two entry
+    points as the reference's RSDE: ``sde(x, t, y, conditioning=...)`` -> (drift, diffusion) and
+    ``discretize(...)`` -> (f, G) with the forward SDE's dt = 1/N.
+    """
+
+    def __init__(self, forward_sde, score_model, probability_flow=False):
+        self.fwd, self.score_model = forward_sde, score_model
+        self.N, self.probability_flow = forward_sde.N, probability_flow
+
+    @property
+    def T(self):
+        return self.fwd.T
+
+    def _score_term(self, x, t, y, g, conditioning):
+        cond = [y] if conditioning is None else conditioning
+        score = self.score_model(x, t, score_conditioning=cond, sde_input=y)
+        g = g.reshape(g.shape + (1,) * (x.ndim - g.ndim))
+        weight = 0.5 if self.probability_flow else 1.0
+        return g, g**2 * score * weight
+
+    def sde(self, x, t, y, conditioning=None):
+        drift, g = self.fwd.sde(x, t, y)
+        g, term = self._score_term(x, t, y, g, conditioning)
+        return drift - term, (torch.zeros_like(g) if self.probability_flow else g)
+
+    def discretize(self, x, t, y, conditioning=None):
+        f, G = self.fwd.discretize(x, t, y)
+        G, term = self._score_term(x, t, y, G, conditioning)
+        return f - term, (torch.zeros_like(G) if self.probability_flow else G)
 
 
 @SDERegistry.register("ouve")
@@ -118,15 +123,25 @@ class OUVESDE(SDE):
         raise NotImplementedError("prior_logp for OU SDE not yet implemented!")
 
     # ---- what the fused CUDA sampler consumes ----------------------------------------------------
-    def step_tables(self, N: int, eps: float):
-        """(t_i, G_i, std(T)) as CPU float32: the bit-exact step schedule.
+    def step_tables(self, N: int, eps: float, times=None):
+        """(t_i, G_i, std(T)) as CPU float32: the bit-exact step schedule, plus the tables of the sampler variants.
 
         t_i = torch.linspace(T, eps, N) (sampling/__init__.py:63) and G_i = g(t_i) * sqrt(float32(1/N))
         (sdes.py:88-92,216-224) are evaluated with the SAME torch CPU expressions the reference uses, so the
         integer step index i in [0, N) maps to identical float32 bit patterns (tests/test_schedule.py).
+        ``times`` replaces the linspace (single update_fn steps); N stays the dt denominator.
         """
-        ts = torch.linspace(self.T, eps, N)
+        ts = torch.linspace(self.T, eps, N) if times is None else times.detach().to("cpu", torch.float32)
         sigma = self.sigma_min * (self.sigma_max / self.sigma_min) ** ts
         G = sigma * np.sqrt(2 * self.logsig) * torch.sqrt(torch.tensor(1 / N))
         std1 = self._std(torch.ones((1,)))
         return ts, G, float(std1[0])
+
+    def variant_tables(self, ts: torch.Tensor, snr: float):
+        """float32 tables of the other registered steps, with the reference's torch expressions:
+        g(t_i) (OUVESDE.sde, sdes.py:216-224; Euler-Maruyama) and the annealed-Langevin step size
+        2 (snr std(t_i))^2 (correctors.py:84,94)."""
+        ts = ts.detach().to("cpu", torch.float32)
+        g = self.sigma_min * (self.sigma_max / self.sigma_min) ** ts * np.sqrt(2 * self.logsig)
+        ald = (snr * self._std(ts)) ** 2 * 2
+        return g.to(torch.float32).contiguous(), ald.to(torch.float32).contiguous()
