@@ -6,8 +6,14 @@ STFT + compression -> prior draw -> N x (NCSN++ Large evaluation + fused reverse
 Default workload = BASELINE.json configs[1]: batch 32 per GPU, N = 30, fp32 storage with TF32 tensor-core
 convolutions (PyTorch's own GPU default for the reference's fp32 model).
 
-  python bench.py [--gpus N] [--steps K] [--warmup W] [--dtype fp32|bf16] [--batch B] [--N 30]
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--config 1|2|3|4] [--dtype fp32|bf16] [--batch B] [--N 30]
   python bench.py --impl reference ...     # the reference algorithm on the host CPU cores (oracle port)
+
+--config selects a BASELINE.json preset (explicit --dtype / --batch / --N / --micro-batch still override it):
+  1  configs[1]: batch 32, N = 30, fp32 storage + TF32 MMA                      (the default workload)
+  2  configs[2]: batch 256 (4 micro-batches of 64), N = 30, bf16 score net + fp32 SDE state
+  3  configs[3]: batch 64, N = 60 ("quality mode"), fp32 storage + TF32 MMA
+  4  configs[4]: batch 256 PER GPU (micro-batches of 64), N = 30, bf16: 2048 clips on 8 GPUs, 1/2/4/8-GPU weak scaling
 
 N > 1: launched by torchrun, one rank per GPU; clips shard across ranks with no collective inside the loop and ONE
 NCCL all-gather of the enhanced waveforms at the end of each step ("scaling": "weak", per-GPU batch fixed).
@@ -35,13 +41,19 @@ def parse():
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--dtype", default="fp32", choices=["fp32", "bf16"])
-    ap.add_argument("--batch", type=int, default=32, help="clips per GPU per step")
-    ap.add_argument("--N", type=int, default=30, help="reverse-diffusion steps")
-    ap.add_argument("--micro-batch", type=int, default=0)
+    ap.add_argument("--config", type=int, default=1, choices=[1, 2, 3, 4], help="BASELINE.json configs[i] preset")
+    ap.add_argument("--dtype", default=None, choices=["fp32", "bf16"])
+    ap.add_argument("--batch", type=int, default=None, help="clips per GPU per step")
+    ap.add_argument("--N", type=int, default=None, help="reverse-diffusion steps")
+    ap.add_argument("--micro-batch", type=int, default=None)
     ap.add_argument("--cpu-sample-evals", type=int, default=2, help="network evaluations timed for the CPU baseline")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    return ap.parse_args()
+    args = ap.parse_args()
+    preset = {1: ("fp32", 32, 30, 0), 2: ("bf16", 256, 30, 64), 3: ("fp32", 64, 60, 0), 4: ("bf16", 256, 30, 64)}[args.config]
+    for key, val in zip(("dtype", "batch", "N", "micro_batch"), preset):
+        if getattr(args, key) is None:
+            setattr(args, key, val)
+    return args
 
 
 class ClockSampler:
@@ -92,6 +104,32 @@ class ClockSampler:
                 "samples": len(sm), "reasons": sorted(reasons), "power_w": pw[len(pw) // 2] if pw else None}
 
 
+def measure_tf32_peak(torch, dev, seconds: float = 4.0, n: int = 8192) -> float:
+    """Sustained cuBLAS TF32 GEMM rate (TFLOP/s) on this GPU, measured like MEASURED_PEAKS.json's bf16 figure."""
+    old = torch.backends.cuda.matmul.allow_tf32
+    torch.backends.cuda.matmul.allow_tf32 = True
+    try:
+        a = torch.randn(n, n, device=dev)
+        b = torch.randn(n, n, device=dev)
+        c = torch.empty(n, n, device=dev)
+        for _ in range(3):
+            torch.matmul(a, b, out=c)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0, iters = time.time(), 0
+        e0.record()
+        while time.time() - t0 < seconds:
+            for _ in range(20):
+                torch.matmul(a, b, out=c)
+            iters += 20
+            torch.cuda.synchronize()
+        e1.record()
+        torch.cuda.synchronize()
+        return 2.0 * n ** 3 * iters / (e0.elapsed_time(e1) * 1e-3) / 1e12
+    finally:
+        torch.backends.cuda.matmul.allow_tf32 = old
+
+
 def cpu_oracle_rate(n_evals: int, threads: int):
     """The reference algorithm (oracle port, same op sequence as ScoreModel.sample) on the host cores: one 4 s clip,
     `n_evals` reverse-diffusion steps of the full-size network, extrapolated linearly to N steps."""
@@ -131,8 +169,10 @@ def run_reference(args):
         "steps": len(times), "warmup": args.warmup, "ms_per_step": 1e3 * sum(times) / len(times),
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "rtf": sec_per_clip / CLIP_SECONDS,
-        "config": {"workload": f"batch={args.batch} x 4 s clips @ 24 kHz, N={args.N} PC steps (reverse_diffusion/none), "
-                               f"NCSNppLarge, CPU oracle port", "sample": sample},
+        "config": {"workload": f"CPU arm: 1 clip x 4 s @ 24 kHz (512x640), {args.cpu_sample_evals} network evaluations timed "
+                               f"and extrapolated linearly to N={args.N} PC steps (reverse_diffusion/none), NCSNppLarge, "
+                               f"oracle port of the reference, no batch; compared with the GPU arm's batch={args.batch}",
+                   "sample": sample},
         "cpu_baseline": {"value": value, "unit": "clips/s", "cores": threads, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": "clips/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
@@ -165,24 +205,29 @@ def main():
     model.score_net.load_state_dict(O.make_state_dict(O.LARGE, seed=7), strict=True)
     module = use_b200.SGMSEModule(Score=model)
 
-    # synthetic clips: every rank owns clips [rank*B, (rank+1)*B) of one global batch
-    y_host = O.synthetic_clips(B * world, L_SAMPLES)[rank * B:(rank + 1) * B].contiguous().pin_memory()
-    y_dev = y_host.to(dev)
-    gathered = torch.empty(world * B, L_SAMPLES, device=dev) if world > 1 else None
+    # synthetic clips: ONE global batch of world * B clips; use_b200.distributed.sample_sharded gives rank r the contiguous
+    # shard [r*B, (r+1)*B) (weights replicated, no collective inside the loop) and all-gathers the enhanced waveforms once
+    from use_b200.distributed import sample_sharded, shard_range
+
+    y_all = O.synthetic_clips(B * world, L_SAMPLES)
+    lo, hi = shard_range(B * world, rank, world)
+    y_host = y_all[lo:hi].contiguous().pin_memory()   # e2e: this rank's clips start in pinned HOST memory every step
+    y_dev_all = y_all.to(dev)                          # device-timed arm: inputs already resident in HBM
 
     def step_device(i):
-        out = model.sample({"perturbed": y_dev}, N=N, seed=1000 + i, clip0=rank * B)["enhanced"]
-        if world > 1:
-            dist.all_gather_into_tensor(gathered, out)
-        return out
+        return sample_sharded(lambda yl, clip0: model.sample({"perturbed": yl}, N=N, seed=1000 + i, clip0=clip0)["enhanced"],
+                              y_dev_all)
 
     def step_e2e(i):
-        batch = {"perturbed": y_host.to(dev, non_blocking=True)}
-        out = module.predict_step(batch, i, write=False)["enhanced"]
+        # host -> device copy of this rank's clips, the reference-facing call, gather, device -> host read of the result
+        def local(_, clip0):
+            batch = {"perturbed": y_host.to(dev, non_blocking=True)}
+            return module.predict_step(batch, i, write=False)["enhanced"]
+
         if world > 1:
-            dist.all_gather_into_tensor(gathered, out)
-            return gathered.to("cpu", non_blocking=False) if rank == 0 else out[:1].cpu()
-        return out.cpu()
+            out = sample_sharded(local, y_dev_all)
+            return out.to("cpu") if rank == 0 else out[:1].cpu()
+        return local(None, 0).cpu()
 
     def barrier():
         if world > 1:
@@ -217,7 +262,7 @@ def main():
     value = world * B / (ms_step / 1e3)
 
     # end to end through the reference-facing call (SGMSEModule.predict_step) with HOST buffers
-    e2e_steps = max(1, min(args.steps, 2))
+    e2e_steps = max(1, min(args.steps, 3))
     ms_e2e, _ = timed(step_e2e, e2e_steps, 1)
     e2e_value = world * B / (ms_e2e / e2e_steps / 1e3)
 
@@ -226,7 +271,7 @@ def main():
     prof = None
     if rank == 0:
         eng.L.use_engine_set_profiling(eng.h, 1)
-        model.sample({"perturbed": y_dev}, N=1, seed=7)
+        model.sample({"perturbed": y_dev_all[lo:hi]}, N=1, seed=7)
         torch.cuda.synchronize()
         import ctypes
 
@@ -256,7 +301,11 @@ def main():
     bf16_peak = peaks.get("bf16_tflops_sustained", 1400.0)
     peak_src = "measured (MEASURED_PEAKS.json bf16_tflops_sustained)" if peaks else "fallback 1.4 PFLOP/s sustained"
     if args.dtype == "fp32":
-        peak, peak_note = bf16_peak / 2.0, peak_src + " x 0.5 (TF32 runs at half the bf16 rate; no TF32 measurement in the file)"
+        # no TF32 entry in MEASURED_PEAKS.json: measure it here, outside the timed region, with the file's own recipe
+        # (cuBLAS GEMM 8192^3 back to back for 4 s, CUDA events) -- a library GEMM as the DENOMINATOR only
+        peak = measure_tf32_peak(torch, dev)
+        peak_note = (f"measured in-run: torch.matmul fp32 8192^3 with allow_tf32 (cuBLAS TF32), back to back for 4 s, CUDA "
+                     f"events = {peak:.1f} TFLOP/s sustained (same recipe as MEASURED_PEAKS.json's bf16 {bf16_peak:.1f})")
     else:
         peak, peak_note = bf16_peak, peak_src
     conv = prof["conv_tc"]
@@ -265,13 +314,15 @@ def main():
     # DRAM traffic of the conv launches from the committed ncu capture (taken at a small batch; scales with the batch)
     traffic, traffic_note = None, "no ncu summary committed for this dtype"
     try:
-        summ = json.load(open(os.path.join(ROOT, "profiles", f"r01_kernel_summary_{args.dtype}.json")))
+        summ_path = next(p for p in (os.path.join(ROOT, "profiles", f"r0{r}_kernel_summary_{args.dtype}.json") for r in (2, 1))
+                         if os.path.exists(p))
+        summ = json.load(open(summ_path))
         tot_b = sum(v["dram_bytes_total"] for k, v in summ["kernels"].items() if "conv_tc_kernel" in k)
         tot_n = sum(v["launches"] for k, v in summ["kernels"].items() if "conv_tc_kernel" in k)
         cap_b = summ.get("batch", 2)
         if tot_n:
             traffic = tot_b / tot_n / cap_b * B
-            traffic_note = (f"dram__bytes_read+write per conv_tc launch from profiles/r01_kernel_summary_{args.dtype}.json "
+            traffic_note = (f"dram__bytes_read+write per conv_tc launch from profiles/{os.path.basename(summ_path)} "
                             f"(ncu, batch {cap_b}, {tot_n} launches of one evaluation), scaled linearly to batch {B}")
     except Exception:
         pass
@@ -280,7 +331,9 @@ def main():
     try:
         import csv
 
-        rows = list(csv.reader(open(os.path.join(ROOT, "profiles", f"r01_ncu_conv_L0_{args.dtype}.csv"))))
+        l0_path = next(p for p in (os.path.join(ROOT, "profiles", f"r0{r}_ncu_conv_L0_{args.dtype}.csv") for r in (2, 1))
+                       if os.path.exists(p))
+        rows = list(csv.reader(open(l0_path)))
         col = rows[0].index("sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active")
         vals = [float(r[col]) for r in rows[2:] if r and r[col]]
         ncu_pipe = round(sum(vals) / len(vals), 2) if vals else None
@@ -317,6 +370,7 @@ def main():
         "config": {"workload": f"batch={B} per GPU x 4 s clips @ 24 kHz (512x640 spectrogram), N={N} PC steps "
                                f"(reverse_diffusion / none), NCSNppLarge, {args.dtype} storage"
                                + (" + TF32 tensor-core convolutions" if args.dtype == "fp32" else ", fp32 SDE state"),
+                   "baseline_config": args.config, "N": N, "micro_batch": args.micro_batch or None,
                    "global_batch": world * B, "parallelism": f"dp{world} (clips sharded, one NCCL all-gather per step)",
                    "l2_policy": "inputs_exceed_l2 (activations of one step are GBs; no flush needed)",
                    "weights": "seeded random (no checkpoint offline)"},

@@ -133,7 +133,9 @@ typedef struct use_sampler_opts {
   int corrector_steps;        /* n_steps of the corrector */
   float snr;                  /* Langevin target SNR */
   int probability_flow;       /* 1: score term halved, no predictor noise (sdes.py:139-143,166-170) */
-  int denoise;                /* 1: return the noise-free mean of the last step; 0: the state itself */
+  int denoise;                /* 1: return the noise-free mean of the last step (the state itself when the predictor is
+                               * "none": NonePredictor returns (x, x)); 0: the state; 2: the mean of the last update of
+                               * any kind (a corrector-only step: Corrector.update_fn's own x_mean) */
   const float* g_host;        /* [N] diffusion g(t_i) (host), required by euler_maruyama */
   const float* ald_step_host; /* [N] 2 (snr std(t_i))^2 (host), required by ald */
   void* trace;                /* optional device complex64 [N][B][F][T]: xt_mean after every outer step (parity tests) */

@@ -346,7 +346,7 @@ class _Engine:
         o = _lib.UseSamplerOpts()
         o.predictor, o.corrector = _lib.PRED[predictor], _lib.CORR[corrector]
         o.corrector_steps, o.snr = int(corrector_steps), float(snr)
-        o.probability_flow, o.denoise, o.dt_steps = int(bool(probability_flow)), int(bool(denoise)), int(dt_steps)
+        o.probability_flow, o.denoise, o.dt_steps = int(bool(probability_flow)), int(denoise), int(dt_steps)
         keep = []
         if g is not None:
             g = g.detach().to("cpu", torch.float32).contiguous()

@@ -1311,7 +1311,7 @@ int use_pc_sample_ex(use_engine* e, int B, int F, int T, const void* Y, void* x_
                         n * sizeof(float2), cudaMemcpyDeviceToDevice, gs[g]);
     }
   }
-  if (!o.denoise || pe == 0) {  // x_result = xt (sampling/__init__.py:69); NonePredictor returns (x, x) (predictors.py:78-79)
+  if (!o.denoise || (pe == 0 && o.denoise != 2)) {  // x_result = xt (sampling/__init__.py:69); NonePredictor returns (x, x) (predictors.py:78-79)
     for (int g = 0; g < G; ++g) {
       const size_t off = (size_t)g * Bg * per;
       cudaMemcpyAsync((float2*)x_mean + off, (const float2*)x_state + off, per * Bg * sizeof(float2), cudaMemcpyDeviceToDevice,

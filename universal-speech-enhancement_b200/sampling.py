@@ -98,7 +98,7 @@ class _FusedPredictor(Predictor):
 class _FusedCorrector(Corrector):
     def update_fn(self, x, t, y, conditioning=None, **_):
         return self._fused_step(x, t, y, conditioning, predictor="none", corrector=self.kind,
-                                corrector_steps=self.n_steps, snr=self.snr)
+                                corrector_steps=self.n_steps, snr=self.snr, denoise=2)  # 2: the corrector's own x_mean
 
 
 @PredictorRegistry.register("euler_maruyama")
