@@ -21,6 +21,8 @@
  *                            (sampling/correctors.py:101-111), RSDE.discretize (sdes.py:159-173)
  *   use_pc_sample_ex         the same loop with EulerMaruyamaPredictor (predictors.py:40-53), LangevinCorrector /
  *                            AnnealedLangevinDynamics (sampling/correctors.py:37-98), probability flow, denoise=False
+ *   use_train_forward        forward half of ScoreModel.train_step (model_wrapper.py:147-208): marginal_prob perturbation,
+ *                            one score evaluation with per-sample times, denoising-score-matching loss (:124-133)
  *   use_stft / use_istft     ScoreModel.stft + spec_fwd + pad_spec / spec_back + istft
  *                            (model_wrapper.py:92-122, util/other.py:128-135)
  *   use_op_*                 single kernels, exported for the parity tests
@@ -148,6 +150,18 @@ int use_pc_sample_ex(use_engine* e, int B, int F, int T, const void* Y, void* x_
                      uint64_t seed, uint32_t clip0, const use_sampler_opts* opts, void* workspace, size_t workspace_bytes,
                      void* stream);
 
+/* Forward half of ScoreModel.train_step (model_wrapper.py:147-208; the backward pass / optimizer are out of scope):
+ *   x_t  = exp(-theta t_b) X0 + (1 - exp(-theta t_b)) Y + std(t_b) z        (OUVESDE.marginal_prob, sdes.py:225-247)
+ *   loss = mean_b 0.5 sum |score(x_t, t_b) std(t_b) + z|^2  (loss_type 0, "mse")  or  ... sum |.|  (1, "mae")  (:124-133)
+ * X0 (clean), Y (noisy): device complex64 [B][F][T] compressed spectrograms; t_host [B] per-sample times, gfp_host
+ * [B][2*nf] their Fourier features, coef_host [2][B] = (exp(-theta t_b), std(t_b)) -- host float32 arrays from the host
+ * layer's torch expressions; noise: device complex64 [B][F][T] explicit z or NULL (Philox, keyed by seed and clip0 + b).
+ * x_t (out): device complex64 [B][F][T]; loss (out): device float [1 + B] = (batch mean, per-clip terms).  The sums are
+ * deterministic two-pass reductions (no floating-point atomics). */
+int use_train_forward(use_engine* e, int B, int F, int T, const void* X0, const void* Y, const float* t_host,
+                      const float* gfp_host, const float* coef_host, const void* noise, uint64_t seed, uint32_t clip0,
+                      int loss_type, void* x_t, float* loss, void* workspace, size_t workspace_bytes, void* stream);
+
 /* y: device float [B][L] -> Y: device complex64 [B][n_fft/2+1][Tp], frames >= 1 + L/hop zero (pad_spec).
  * window [n_fft] and twiddle [n_fft] (cos, sin of 2 pi i / n_fft, interleaved) are device arrays. */
 int use_stft(use_engine* e, int B, int L, int Tp, const float* y, void* Y, const float* window, const float* twiddle,
@@ -156,6 +170,20 @@ int use_stft(use_engine* e, int B, int L, int Tp, const float* y, void* Y, const
  * envelope: device float [n_fft + hop (Tp-1)] = overlap-added squared window. */
 int use_istft(use_engine* e, int B, int L, int Tp, const void* X, float* y, float* frames_scratch, const float* window,
               const float* twiddle, const float* envelope, void* stream);
+
+/* ---- predict-side audio preparation ------------------------------------------------ */
+/* librosa.resample(y, orig_sr, target_sr, res_type="fft") of LoadWavDataset.__getitem__ (src/data/components/
+ * loadwav_dataset.py:94-98) = scipy.signal.resample(y, n_out) with n_out = ceil(n_in * target_sr / orig_sr): x device float
+ * [B][n_in] -> y[b * y_stride + j], j < n_out.  Any lengths (Bluestein chirp-z + radix-2 Stockham passes); `work`: device
+ * scratch of use_resample_workspace_bytes. */
+int use_resample_workspace_bytes(int B, int n_in, int n_out, size_t* bytes);
+int use_resample_fft_f32(const float* x, int B, int n_in, float* y, int n_out, int y_stride, void* work, size_t work_bytes,
+                         void* stream);
+/* y / max|y| * target_peak per clip over its first lengths[b] samples (loadwav_dataset.py:99-100; target_peak <= 0: no
+ * scaling; an all-zero clip stays zero) and zero padding up to `stride` (collate.pad_to_longest_monaural_inference,
+ * collate.py:42-73), in place.  lengths_dev: device int [B]; peaks_scratch: device, 4 * B bytes (holds max|y| as float). */
+int use_peak_normalize_pad_f32(float* y, const int* lengths_dev, int B, int stride, float target_peak, void* peaks_scratch,
+                               void* stream);
 
 /* ---- the reference's native op -------------------------------------------------------------------- */
 /* upfirdn2d over [major][in_h][in_w][minor] fp32 (op/upfirdn2d.cpp:12-23 argument order). */

@@ -547,6 +547,55 @@ def sample(sd: Dict[str, Tensor], y: Tensor, N: int, noise: Optional[Tensor] = N
     return (out, xm, Y) if return_spec else out
 
 
+def ouve_mean(x0: Tensor, t: Tensor, y: Tensor, sde: SdeCfg = SdeCfg()) -> Tensor:
+    """OUVESDE._mean (sdes.py:225-228)."""
+    e = torch.exp(-sde.theta * t)[:, None, None, None]
+    return e * x0 + (1 - e) * y
+
+
+def train_draws(B: int, n_freq: int, n_frames: int, seed: int, crop_range: Optional[int] = None, sde: SdeCfg = SdeCfg()):
+    """The three random draws of ScoreModel.train_step under np.random.seed(seed) / torch.manual_seed(seed), in the
+    reference's order AND memory layout: crop offset int(np.random.uniform(0, crop_range)) (model_wrapper.py:156; 0 when
+    the clip is padded instead), t = rand(B) (T - t_eps) + t_eps (:178), z = randn_like(x) (:180).  randn_like fills its
+    result in MEMORY order and x = spec_fwd(stft(.)) keeps torch.stft's frame-major strides (F*T, 1, F), so z is drawn
+    frame by frame, not bin by bin.  Returns (start, t [B], z complex64 [B,1,F,T])."""
+    start = 0
+    if crop_range is not None:
+        np.random.seed(seed)
+        start = int(np.random.uniform(0, crop_range))
+    g = torch.Generator().manual_seed(seed)
+    t = torch.rand(B, generator=g) * (sde.T - sde.t_eps) + sde.t_eps
+    z = torch.empty_strided((B, 1, n_freq, n_frames), (n_freq * n_frames, n_freq, 1, n_freq), dtype=torch.complex64)
+    z.normal_(generator=g)
+    return start, t, z
+
+
+def train_step_loss(sd: Dict[str, Tensor], x: Tensor, y: Tensor, t: Tensor, z: Tensor, start: int = 0,
+                    net: NetCfg = LARGE, spec: SpecCfg = SpecCfg(), sde: SdeCfg = SdeCfg(), num_frames: int = 512,
+                    loss_type: str = "mse"):
+    """Forward half of ScoreModel.train_step (model_wrapper.py:147-208) with the random draws made explicit:
+    ``start`` (crop offset, np.random.uniform :156), ``t`` [B] (torch.rand :178), ``z`` complex [B,1,F,T] (:180).
+    x (clean), y (noisy): float [B, L].  Returns (loss, perturbed x_t)."""
+    with torch.no_grad():
+        target_len = (num_frames - 1) * spec.hop_length
+        cur = x.size(-1)
+        pad = max(target_len - cur, 0)
+        if pad == 0:
+            x, y = x[..., start:start + target_len], y[..., start:start + target_len]
+        else:
+            x = F.pad(x, (pad // 2, pad // 2 + (pad % 2)))
+            y = F.pad(y, (pad // 2, pad // 2 + (pad % 2)))
+        X0 = spec_fwd(stft(x, spec), spec).unsqueeze(1)
+        Y = spec_fwd(stft(y, spec), spec).unsqueeze(1)
+        std = ouve_std(t, sde)[:, None, None, None]
+        x_t = ouve_mean(X0, t, Y, sde) + std * z
+        score = -ncsnpp_forward(sd, net, torch.cat([x_t, Y], dim=1), t)
+        err = score * std + z
+        per = err.abs() if loss_type == "mae" else torch.square(err.abs())
+        loss = torch.mean(0.5 * torch.sum(per.reshape(per.shape[0], -1), dim=-1))
+    return loss, x_t
+
+
 def gan_denoise(sd: Dict[str, Tensor], y: Tensor, net: NetCfg = GAN_G, spec: SpecCfg = SpecCfg()) -> Tensor:
     """NCSNPP_Wrapper.forward, inference branch (GAN/generator/ncsnpp/model_wrapper.py:114-121): one forward of the
     discriminative NCSN++ on the compressed spectrogram: y float [B, L] -> batch["fake"] float [B, L]."""

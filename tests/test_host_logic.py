@@ -162,3 +162,30 @@ def test_gan_generator_host_structure():
         G({"clean": torch.zeros(1, 8), "perturbed": torch.zeros(1, 8)})
     with pytest.raises(RuntimeError, match="CUDA"):
         G({"perturbed": torch.zeros(1, 9600)})
+
+
+def test_loadwav_datamodule_file_discovery(tmp_path):
+    """The reference's four ways to name the inputs (loadwav_dataset.py:38-77): json lines, list file, in-memory lists,
+    folder walk -- host logic only."""
+    import json
+
+    from use_b200.predict import LoadWavDataModule
+
+    (tmp_path / "a").mkdir()
+    for n in ("x.wav", "y.wav", "z.txt"):
+        (tmp_path / "a" / n).write_bytes(b"")
+    walk = LoadWavDataModule(data_folder=str(tmp_path))
+    assert sorted(os.path.basename(f) for f in walk.files) == ["x.wav", "y.wav"]
+    lst = tmp_path / "list.txt"
+    lst.write_text("/p/1.wav\n\n/p/2.wav\n")
+    assert LoadWavDataModule(list_path=str(lst)).files == ["/p/1.wav", "/p/2.wav"]
+    js = tmp_path / "m.json"
+    js.write_text(json.dumps({"audio_filepath": "/q/1.wav"}) + "\n" + json.dumps({"file_path": "/q/2.wav"}) + "\n"
+                  + json.dumps({"audio_filepath": "/q/1.wav"}) + "\n")
+    assert LoadWavDataModule(json_path=str(js)).files == ["/q/1.wav", "/q/2.wav"]
+    assert LoadWavDataModule(input_plain_list=["/r/1.wav"]).files == ["/r/1.wav"]
+    assert LoadWavDataModule(input_json_list=[json.dumps({"file_path": "/s.wav"})]).files == ["/s.wav"]
+    with pytest.raises(ValueError, match="No input list"):
+        LoadWavDataModule()
+    with pytest.raises(NotImplementedError):
+        LoadWavDataModule(data_folder=str(tmp_path), output_resample=True)

@@ -328,6 +328,30 @@ class _Engine:
                                               ws.numel(), _lib.stream_ptr()), "use_net_forward")
         return out
 
+    def train_forward(self, X0, Y, t, coef, noise=None, seed=0, clip0=0, mae=False):
+        """use_train_forward: returns (loss [1 + B] float32 device tensor, x_t complex64 [B, F, T])."""
+        assert X0.dtype == torch.complex64 and X0.shape == Y.shape and X0.dim() == 3 and X0.is_cuda
+        B, F, T = X0.shape
+        X0, Y = X0.contiguous(), Y.contiguous()
+        t_host = t.detach().to("cpu", torch.float32).contiguous()
+        coef = coef.detach().to("cpu", torch.float32).contiguous()
+        assert t_host.numel() == B and tuple(coef.shape) == (2, B)
+        gfp = self.net_module.gfp_features(t_host)
+        x_t = torch.empty_like(X0)
+        loss = torch.empty(1 + B, dtype=torch.float32, device=X0.device)
+        nptr = None
+        if noise is not None:
+            noise = noise.to(torch.complex64).contiguous()
+            assert noise.shape == X0.shape and noise.is_cuda
+            nptr = noise.data_ptr()
+        with torch.cuda.device(self.device):
+            ws = self.workspace(B, F, T)
+            _lib.check(self.L.use_train_forward(self.h, B, F, T, X0.data_ptr(), Y.data_ptr(), t_host.data_ptr(), gfp.data_ptr(),
+                                                coef.data_ptr(), nptr, int(seed) & (2**64 - 1), int(clip0), int(bool(mae)),
+                                                x_t.data_ptr(), loss.data_ptr(), ws.data_ptr(), ws.numel(),
+                                                _lib.stream_ptr()), "use_train_forward")
+        return loss, x_t
+
     def net_gfp(self, t_host):
         return self.net_module.gfp_features(t_host)
 

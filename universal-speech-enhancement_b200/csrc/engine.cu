@@ -1162,6 +1162,34 @@ int use_net_forward(use_engine* e, int B, int F, int T, const void* x, const voi
   return net_forward(e, B, F, T, x, Y, t_host, gfp_host, out, 1.0f, workspace, workspace_bytes, stream);
 }
 
+int use_train_forward(use_engine* e, int B, int F, int T, const void* X0, const void* Y, const float* t_host,
+                      const float* gfp_host, const float* coef_host, const void* noise, uint64_t seed, uint32_t clip0,
+                      int loss_type, void* x_t, float* loss, void* workspace, size_t workspace_bytes, void* stream) {
+  if (!e || !X0 || !Y || !t_host || !gfp_host || !coef_host || !x_t || !loss || !workspace) return fail("null argument");
+  if (loss_type != 0 && loss_type != 1) return fail("loss_type must be 0 (mse) or 1 (mae)");
+  if (e->cfg.input_channels != 4 || !e->cfg.conditional || !e->cfg.scale_by_sigma)
+    return fail("use_train_forward needs the noise-conditional score network");
+  cudaStream_t st = (cudaStream_t)stream;
+  const size_t per = (size_t)F * T;
+  // plan first: the head offsets (score buffer, reduction scratch, per-sample coefficient slot) belong to this shape
+  size_t need = 0;
+  if (plan_workspace(e, B, F, T, &need, nullptr)) return 1;
+  if (workspace_bytes < need) return fail("workspace too small: %zu bytes given, %zu needed", workspace_bytes, need);
+  char* base = (char*)workspace;
+  float* coef_dev = (float*)(base + e->head.gfp);  // [2][B] -- parked in the Fourier-feature slot until net_forward refills it
+  if ((size_t)2 * B > (size_t)B * 2 * e->cfg.nf) return fail("internal: coefficient slot too small");
+  cudaMemcpyAsync(coef_dev, coef_host, (size_t)2 * B * 4, cudaMemcpyHostToDevice, st);
+  launch_perturb((const float2*)X0, (const float2*)Y, (const float2*)noise, coef_dev, (float2*)x_t, seed, clip0, B, per, st);
+  float2* score = (float2*)(base + e->head.score);
+  if (net_forward(e, B, F, T, x_t, Y, t_host, gfp_host, score, -1.0f, workspace, workspace_bytes, stream)) return 1;
+  // net_forward refilled the gfp slot: upload the coefficients again (tiny) into the temb slot, free after the network ran
+  float* coef2 = (float*)(base + e->head.temb);
+  cudaMemcpyAsync(coef2, coef_host, (size_t)2 * B * 4, cudaMemcpyHostToDevice, st);
+  launch_dsm_loss(score, (const float2*)noise, coef2, base + e->head.red, loss, loss_type, seed, clip0, B, per, st);
+  e->launches += 3;
+  return cuda_check("use_train_forward");
+}
+
 int use_pc_sample_ex(use_engine* e, int B, int F, int T, const void* Y, void* x_state, void* x_mean, int N,
                      const float* t_host, const float* G_host, const float* gfp_host, float prior_std, const void* noise,
                      uint64_t seed, uint32_t clip0, const use_sampler_opts* opts, void* workspace, size_t workspace_bytes,
@@ -1397,6 +1425,30 @@ int use_upfirdn2d_f32(const float* in, float* out, int major, int in_h, int in_w
   launch_upfirdn2d(in, out, major, in_h, in_w, minor, kernel, kh, kw, up_x, up_y, down_x, down_y, pad_x0, pad_x1, pad_y0,
                    pad_y1, (cudaStream_t)stream);
   return cuda_check("use_upfirdn2d_f32");
+}
+
+// ---- predict-side audio preparation ---------------------------------------------------------------------------------
+int use_resample_workspace_bytes(int B, int n_in, int n_out, size_t* bytes) {
+  if (!bytes || B < 1 || n_in < 2 || n_out < 2) return fail("invalid resample shape (B=%d n_in=%d n_out=%d)", B, n_in, n_out);
+  if (n_in > (1 << 27) || n_out > (1 << 27)) return fail("clip too long for the resampler");
+  *bytes = resample_workspace_bytes(B, n_in, n_out);
+  return 0;
+}
+int use_resample_fft_f32(const float* x, int B, int n_in, float* y, int n_out, int y_stride, void* work, size_t work_bytes,
+                         void* stream) {
+  if (!x || !y || !work) return fail("null argument");
+  size_t need = 0;
+  if (use_resample_workspace_bytes(B, n_in, n_out, &need)) return 1;
+  if (work_bytes < need) return fail("resample workspace too small: %zu < %zu", work_bytes, need);
+  if (y_stride < n_out) return fail("y_stride %d < n_out %d", y_stride, n_out);
+  launch_resample_fft(x, y, B, n_in, n_out, y_stride, work, (cudaStream_t)stream);
+  return cuda_check("use_resample_fft_f32");
+}
+int use_peak_normalize_pad_f32(float* y, const int* lengths_dev, int B, int stride, float target_peak, void* peaks_scratch,
+                               void* stream) {
+  if (!y || !lengths_dev || !peaks_scratch || B < 1 || stride < 1) return fail("invalid argument");
+  launch_peak_normalize_pad(y, lengths_dev, B, stride, target_peak, (unsigned int*)peaks_scratch, (cudaStream_t)stream);
+  return cuda_check("use_peak_normalize_pad_f32");
 }
 
 // ---- single-kernel exports ----------------------------------------------------------------------

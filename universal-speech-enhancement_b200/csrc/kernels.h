@@ -108,6 +108,12 @@ struct CorrectorArgs {
   int B;
   size_t per_clip;
 };
+// forward half of train_step: coef = device fp32 [2][B] = (exp(-theta t_b), std(t_b)); z explicit or Philox stream 0xfffffffe
+void launch_perturb(const float2* X0, const float2* Y, const float2* z, const float* coef, float2* xt, unsigned long long seed,
+                    unsigned int clip0, int B, size_t per_clip, cudaStream_t st);
+// loss[0] = mean_b 0.5 sum |score std + z|^2 (mae: |.|), loss[1 + b] = the per-clip terms; scratch: corrector_scratch_bytes(B)
+void launch_dsm_loss(const float2* score, const float2* z, const float* coef, void* scratch, float* loss, int mae,
+                     unsigned long long seed, unsigned int clip0, int B, size_t per_clip, cudaStream_t st);
 size_t corrector_scratch_bytes(int B);
 void launch_corrector_step(const CorrectorArgs& c, cudaStream_t st);
 // x0 = Y + z * std   (z explicit or Philox, step = 0xffffffff stream)
@@ -142,6 +148,14 @@ void launch_stft(const float* y, float2* Y, const float* window, const float2* t
 void launch_istft(const float2* X, float* frames, float* y, const float* window, const float2* twiddle,
                   const float* inv_env, int B, int L, int n_fft, int hop, int Tp, float factor, float exponent,
                   cudaStream_t st);
+
+// ---- predict-side audio preparation (resample.cu) ---------------------------------------------------------------------
+// scipy.signal.resample / librosa res_type="fft" semantics: x [B][n_in] -> y[b * y_stride + j], j < n_out
+size_t resample_workspace_bytes(int B, int n_in, int n_out);
+void launch_resample_fft(const float* x, float* y, int B, int n_in, int n_out, int y_stride, void* work, cudaStream_t st);
+// y [B][stride]: clip b keeps its first lengths[b] samples scaled to peak `target` (<= 0: unscaled), the rest is zeroed
+void launch_peak_normalize_pad(float* y, const int* lengths, int B, int stride, float target, unsigned int* peaks,
+                               cudaStream_t st);
 
 // ---- tcgen05 convolution ----------------------------------------------------------------------------------
 struct TcSegDesc {

@@ -218,6 +218,78 @@ void launch_corrector_step(const CorrectorArgs& c, cudaStream_t st) {
                                                    c.seed, c.draw, c.clip0, c.per_clip, n);
 }
 
+// ---- forward half of ScoreModel.train_step (model_wrapper.py:147-208) ----------------------------------------------
+// perturbed = exp(-theta t) x0 + (1 - exp(-theta t)) y + std(t) z   (OUVESDE.marginal_prob, sdes.py:225-247); the
+// per-sample coefficients e_b = exp(-theta t_b) and std_b come from the host (the reference's float32 torch expressions)
+__global__ void __launch_bounds__(256) perturb_kernel(const float2* __restrict__ X0, const float2* __restrict__ Y,
+                                                       const float2* __restrict__ z, const float* __restrict__ coef,
+                                                       float2* __restrict__ xt, unsigned long long seed, unsigned int clip0,
+                                                       size_t per_clip, size_t n, int B) {
+  for (size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n;
+       i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const uint32_t b = static_cast<uint32_t>(i / per_clip);
+    const float e = coef[b], sd = coef[B + b];
+    const float2 zz = z ? z[i] : philox_cnormal(seed, 0xfffffffeu, clip0 + b, i - static_cast<size_t>(b) * per_clip);
+    const float2 x0 = X0[i], y = Y[i];
+    const float om = 1.f - e;
+    xt[i] = make_float2((e * x0.x + om * y.x) + sd * zz.x, (e * x0.y + om * y.y) + sd * zz.y);
+  }
+}
+
+// err = score std + z ; per-(clip, block) partial sums of |err|^2 (mse) or |err| (mae), fixed order (model_wrapper.py:124-133)
+__global__ void __launch_bounds__(256) dsm_partial_kernel(const float2* __restrict__ score, const float2* __restrict__ z,
+                                                           const float* __restrict__ coef, double* __restrict__ part, int mae,
+                                                           unsigned long long seed, unsigned int clip0, size_t per_clip, int B) {
+  const int b = blockIdx.y, blk = blockIdx.x;
+  const size_t chunk = (per_clip + kRedBlocks - 1) / kRedBlocks;
+  const size_t lo = blk * chunk, hi = lo + chunk < per_clip ? lo + chunk : per_clip;
+  const float sd = coef[B + b];
+  double acc = 0.0;
+  for (size_t i = lo + threadIdx.x; i < hi; i += 256) {
+    const float2 s = score[static_cast<size_t>(b) * per_clip + i];
+    const float2 zz = z ? z[static_cast<size_t>(b) * per_clip + i] : philox_cnormal(seed, 0xfffffffeu, clip0 + b, i);
+    const float er = s.x * sd + zz.x, ei = s.y * sd + zz.y;
+    const float a2 = er * er + ei * ei;
+    acc += mae ? static_cast<double>(sqrtf(a2)) : static_cast<double>(a2);
+  }
+  __shared__ double sh[256];
+  sh[threadIdx.x] = acc;
+  __syncthreads();
+  for (int s = 128; s > 0; s >>= 1) {
+    if (threadIdx.x < s) sh[threadIdx.x] += sh[threadIdx.x + s];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) part[static_cast<size_t>(b) * kRedBlocks + blk] = sh[0];
+}
+
+// loss[0] = mean_b 0.5 sum_b ; loss[1 + b] = 0.5 sum_b (per-clip terms, for inspection)
+__global__ void dsm_final_kernel(const double* __restrict__ part, float* __restrict__ loss, int B) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  float tot = 0.f;
+  for (int b = 0; b < B; ++b) {
+    double s = 0.0;
+    for (int k = 0; k < kRedBlocks; ++k) s += part[static_cast<size_t>(b) * kRedBlocks + k];
+    const float lb = 0.5f * static_cast<float>(s);
+    loss[1 + b] = lb;
+    tot += lb;
+  }
+  loss[0] = tot / static_cast<float>(B);
+}
+
+void launch_perturb(const float2* X0, const float2* Y, const float2* z, const float* coef, float2* xt, unsigned long long seed,
+                    unsigned int clip0, int B, size_t per_clip, cudaStream_t st) {
+  const size_t n = per_clip * B;
+  const int blocks = static_cast<int>(std::min<size_t>((n + 255) / 256, 148 * 16));
+  perturb_kernel<<<blocks, 256, 0, st>>>(X0, Y, z, coef, xt, seed, clip0, per_clip, n, B);
+}
+
+void launch_dsm_loss(const float2* score, const float2* z, const float* coef, void* scratch, float* loss, int mae,
+                     unsigned long long seed, unsigned int clip0, int B, size_t per_clip, cudaStream_t st) {
+  double* part = reinterpret_cast<double*>(scratch);
+  dsm_partial_kernel<<<dim3(kRedBlocks, B), 256, 0, st>>>(score, z, coef, part, mae, seed, clip0, per_clip, B);
+  dsm_final_kernel<<<1, 32, 0, st>>>(part, loss, B);
+}
+
 void launch_final_step(const StepArgs& a, cudaStream_t st) {
   const size_t n = a.per_clip * a.B;
   const int blocks = static_cast<int>(std::min<size_t>((n + 255) / 256, 148 * 16));

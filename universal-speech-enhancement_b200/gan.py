@@ -18,7 +18,7 @@ import torch.nn as nn
 from . import _lib
 from .backbones import NCSNpp
 from .model_wrapper import get_window
-from .sgmse_module import write_wav
+from .sgmse_module import AsyncWavWriter, write_wav
 
 try:  # pragma: no cover
     from lightning import LightningModule as _Base
@@ -115,14 +115,16 @@ class GANModule(_Base):
         raise NotImplementedError("training is out of scope of the B200 predict path")
 
     @torch.no_grad()
-    def predict_step(self, batch: dict, batch_idx: int = 0, write: bool = True) -> dict:
+    def predict_step(self, batch: dict, batch_idx: int = 0, write: bool = True, writer=None) -> dict:
         batch = self.G(batch)
         if write and "audio_path" in batch:
+            own = writer is None
+            w = AsyncWavWriter(workers=2) if own else writer
             for i in range(len(batch["fake"])):
                 noisy_path = batch["audio_path"][i]
                 n = int(batch["sample_length"][i])
                 out_path = noisy_path.replace(batch["data_folder"], batch["target_folder"])
-                os.makedirs(os.path.dirname(out_path) or ".", exist_ok=True)
-                write_wav(out_path, batch["fake"][i].detach().cpu().numpy().astype(np.float32)[:n],
-                          int(batch["sampling_rate"][i]))
+                w.submit(out_path, batch["fake"][i, :n], int(batch["sampling_rate"][i]))
+            if own:
+                w.close()
         return batch

@@ -165,6 +165,41 @@ class ScoreModel(nn.Module):
     def forward(self, x, t, score_conditioning, sde_input):
         return self.forward_score(x, t, score_conditioning, sde_input)
 
+    # ---- forward half of the training step ------------------------------------------------------------
+    @torch.no_grad()
+    def train_step(self, batch, t=None, noise=None, seed=None, return_parts=False):
+        """Forward half of ScoreModel.train_step (model_wrapper.py:147-208): random crop / centre pad to
+        (num_frames - 1) * hop samples, STFT + compression, forward diffusion x_t = mean(x0, t, y) + std(t) z with
+        t ~ U(t_eps, T), ONE score evaluation with per-sample times, loss = mean_b 0.5 sum |score std + z|^2.
+        Everything numerical is one C call (use_train_forward); no autograd graph is built -- the backward pass and the
+        optimizer are out of scope.  ``t`` / ``noise`` make the random draws explicit
+        (parity tests); otherwise t comes from torch's global RNG like the reference's and z from Philox(seed)."""
+        x, y = batch["clean"], batch["perturbed"]
+        if "fake" in batch:
+            raise NotImplementedError("the 'fake' (GAN-denoised) conditioning branch is not on the accelerated path")
+        current_len = x.size(-1)
+        pad = max(self.target_len - current_len, 0)
+        if pad == 0:
+            start = int(np.random.uniform(0, current_len - self.target_len))  # same draw as model_wrapper.py:156
+            x, y = x[..., start:start + self.target_len], y[..., start:start + self.target_len]
+        else:
+            x = torch.nn.functional.pad(x, (pad // 2, pad // 2 + (pad % 2)), mode="constant")
+            y = torch.nn.functional.pad(y, (pad // 2, pad // 2 + (pad % 2)), mode="constant")
+        X0, Y = self.stft_compressed(x.contiguous()), self.stft_compressed(y.contiguous())
+        B = X0.shape[0]
+        if t is None:
+            t = torch.rand(B) * (self.sde.T - self.t_eps) + self.t_eps
+        t = t.detach().to("cpu", torch.float32)
+        coef = torch.stack([torch.exp(-self.sde.theta * t), self.sde._std(t)])  # the reference's float32 expressions
+        if seed is None:
+            seed = int(torch.randint(0, 2**31 - 1, (1,)).item())
+        nz = noise[:, 0] if noise is not None and noise.dim() == 4 else noise
+        loss, x_t = self._engine(X0.device).train_forward(X0, Y, t, coef, noise=nz, seed=seed,
+                                                          mae=(self.loss_type == "mae"))
+        if return_parts:
+            return loss[0], dict(per_clip=loss[1:], x_t=x_t.unsqueeze(1), t=t, X0=X0.unsqueeze(1), Y=Y.unsqueeze(1))
+        return loss[0]
+
     # ---- samplers ----------------------------------------------------------------------------------
     def _fused_pc_sample(self, sde, y, eps, predictor="reverse_diffusion", corrector="none", corrector_steps=1, snr=0.5,
                          probability_flow=False, denoise=True, noise=None, seed=None, clip0=0, trace=None, x_init=None,
