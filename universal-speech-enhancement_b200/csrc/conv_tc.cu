@@ -157,12 +157,34 @@ TcConvPlan* tc_conv_plan_create(int dt, const TcConvDesc& d, int num_sms, char* 
   p->N = d.N;
   bool fuse = false;
   for (int i = 0; i < d.nseg; ++i) fuse = fuse || d.seg[i].aff != nullptr;
+  // N-split (conv_tc.cuh, ConvParams::nsplit): fewer tiles than SMs -> 64-channel slices of C_out as extra work units.
+  // Only the C_out = 256 family: its unsplit kernel is the same pixel-major form, so split and unsplit launches are
+  // bit-identical (a clip sampled alone == the same clip inside any batch).  The C_out = 128 layers run the swap-AB kernel,
+  // whose channel-major epilogue sums the GroupNorm statistics in a different order: slicing them would make the result
+  // depend on the batch size (measured: 1 ulp in the statistics, amplified to the rounding-noise floor).
+  int nsplit = 1;
+  {
+    const int base_h = d.N == 256 ? 16 : 32;
+    const int base_tiles = ((d.W + 7) / 8) * ((d.H + base_h - 1) / base_h) * d.B;
+    static const bool off = getenv("USE_B200_CONV_NSPLIT") && getenv("USE_B200_CONV_NSPLIT")[0] == '0';
+    static const int max_tiles = getenv("USE_B200_CONV_NSPLIT_MAXTILES") ? atoi(getenv("USE_B200_CONV_NSPLIT_MAXTILES")) : (1 << 30);
+    if (!off && d.N == 256 && base_tiles < num_sms && base_tiles < max_tiles && multicast_width() == 1 && !cg2_enabled() && !getenv("USE_B200_CONV_PROF"))
+      nsplit = d.N / 64;
+  }
+  if (getenv("USE_B200_CONV_DEBUG")) {
+    const int bh = d.N == 256 ? 16 : 32;
+    fprintf(stderr, "conv plan B=%d H=%d W=%d N=%d nseg=%d base_tiles=%d nsplit=%d fuse=%d\n", d.B, d.H, d.W, d.N, d.nseg,
+            ((d.W + 7) / 8) * ((d.H + bh - 1) / bh) * d.B, nsplit, (int)fuse);
+  }
+  const int kN = nsplit > 1 ? 64 : d.N;  // the kernel's N (MMA width, TMEM columns, weight-tile rows)
   if (dt == kBF16) {
-    if (d.N == 256) fill_kernel<__nv_bfloat16, 256, 1>(p, fuse);
+    if (nsplit > 1) fill_kernel<__nv_bfloat16, 64, 1>(p, fuse);
+    else if (d.N == 256) fill_kernel<__nv_bfloat16, 256, 1>(p, fuse);
     else if (d.N == 128) fill_kernel<__nv_bfloat16, 128, 2>(p, fuse);
     else fill_kernel<__nv_bfloat16, 64, 2>(p, fuse);
   } else {
-    if (d.N == 256) fill_kernel<float, 256, 1>(p, fuse);
+    if (nsplit > 1) fill_kernel<float, 64, 1>(p, fuse);
+    else if (d.N == 256) fill_kernel<float, 256, 1>(p, fuse);
     else if (d.N == 128) fill_kernel<float, 128, 2>(p, fuse);
     else fill_kernel<float, 64, 2>(p, fuse);
   }
@@ -185,8 +207,8 @@ TcConvPlan* tc_conv_plan_create(int dt, const TcConvDesc& d, int num_sms, char* 
     }
     const int rows = s.taps == 9 ? tile_h + 2 : tile_h, cols = s.taps == 9 ? 10 : 8;
     if (!encode_act(&P.seg[i].tmA, dt, s.act, d.B, d.H, d.W, s.C_tensor, cols, rows, err, errlen) ||
-        !encode_w(&P.seg[i].tmW, dt, s.w, s.taps, d.N, s.Cw_total, d.N, err, errlen) ||
-        !encode_w(&P.seg[i].tmWh, dt, s.w, s.taps, d.N, s.Cw_total, d.N / 2, err, errlen)) {
+        !encode_w(&P.seg[i].tmW, dt, s.w, s.taps, d.N, s.Cw_total, kN, err, errlen) ||
+        !encode_w(&P.seg[i].tmWh, dt, s.w, s.taps, d.N, s.Cw_total, kN / 2, err, errlen)) {
       delete p;
       return nullptr;
     }
@@ -204,9 +226,12 @@ TcConvPlan* tc_conv_plan_create(int dt, const TcConvDesc& d, int num_sms, char* 
   P.tiles_w = (d.W + 7) / 8;
   P.tiles_h = (d.H + tile_h - 1) / tile_h;
   P.ntiles = P.tiles_w * P.tiles_h * d.B;
+  P.nsplit = nsplit;
+  P.ldn = d.N;
+  P.nunits = P.ntiles * nsplit;
   P.out = d.out; P.bias = d.bias; P.bias_bstride = d.bias_bstride; P.res = d.res; P.scale = d.scale;
   P.stats_acc = d.stats_acc;
-  const int units = (P.ntiles + p->mc - 1) / p->mc;  // tile groups
+  const int units = (P.nunits + p->mc - 1) / p->mc;  // work-unit groups
   const int max_groups = num_sms / p->mc;
   p->grid = (units < max_groups ? units : max_groups) * p->mc;  // persistent CTAs, one per SM, a multiple of the cluster
   return p;

@@ -51,7 +51,12 @@ struct alignas(64) ConvParams {
   int nseg;
   int B, H, W;
   int tiles_w, tiles_h, ntiles;
-  void* out;          // T [B][H][W][N]
+  // C_out split ("N-split") for launches with fewer tiles than SMs (small batches at the deep levels, where ONE CTA
+  // would stream a whole layer's weights through one SM: 29 us per 8 x 10 layer): the kernel's N is a 64-channel SLICE
+  // of the ldn = C_out channels, a work unit is (tile, slice) and nunits = ntiles * nsplit of them are spread over the
+  // CTAs.  Every output element sees the same K sequence as in the unsplit kernel: results are bit-identical.
+  int nsplit, ldn, nunits;
+  void* out;          // T [B][H][W][ldn]
   const float* bias;  // [B or 1][N]
   int bias_bstride;   // N (per-sample bias incl. the time-embedding term) or 0
   const void* res;    // optional residual, T [B][H][W][N]
@@ -179,8 +184,10 @@ __global__ void __launch_bounds__(ConvCfg<T, N, NSUB, FUSE, CG2>::THREADS, 1) co
   // tile groups of MC consecutive tiles: CTA `crank` of a pair takes tile group * MC + crank.  T0 / TSTEP / TEND walk the
   // tile index of THIS CTA; TEND is rounded up so both CTAs of a pair run the same number of iterations.
   const int crank = MC > 1 ? static_cast<int>(cluster_ctarank()) : 0;
+  // (with an N-split the walk is over work units u = tile * nsplit + slice; nsplit = 1: u = tile)
   const int T0 = (blockIdx.x / MC) * MC + crank, TSTEP = (gridDim.x / MC) * MC;
-  const int TEND = (p.ntiles + MC - 1) / MC * MC;
+  const int TEND = (p.nunits + MC - 1) / MC * MC;
+  const int nsp = p.nsplit;
 
   if (warp == 0) {
     // ================================ TMA producer ================================
@@ -199,8 +206,9 @@ __global__ void __launch_bounds__(ConvCfg<T, N, NSUB, FUSE, CG2>::THREADS, 1) co
         if (blocking) mbar_wait_p<PROF>(&a_empty[as], aph ^ 1, w_a);
         else if (!mbar_try_wait(&a_empty[as], aph ^ 1)) return false;
         const ConvSeg& S = p.seg[a_sg];
-        const int b = a_tile / tiles_per_img;
-        const int rem = a_tile - b * tiles_per_img;
+        const int a_t = a_tile / nsp;  // a_tile walks work units
+        const int b = a_t / tiles_per_img;
+        const int rem = a_t - b * tiles_per_img;
         const int th = rem / p.tiles_w;
         const int w0 = (rem - th * p.tiles_w) * C::TILE_W, h0 = th * C::TILE_H;
         const bool k3 = S.taps == 9;
@@ -231,6 +239,7 @@ __global__ void __launch_bounds__(ConvCfg<T, N, NSUB, FUSE, CG2>::THREADS, 1) co
       };
       uint32_t bi = 0, bj = 0;  // weight tiles issued, chunks whose weights have been issued
       for (int tile = T0; tile < TEND; tile += TSTEP) {
+        const int wrow0 = (tile % nsp) * N;  // first C_out row of this unit's slice
         for (int sg = 0; sg < p.nseg; ++sg) {
           const ConvSeg& S = p.seg[sg];
           const bool k3 = S.taps == 9;
@@ -255,7 +264,7 @@ __global__ void __launch_bounds__(ConvCfg<T, N, NSUB, FUSE, CG2>::THREADS, 1) co
                 tma_load_3d_mc(sB + bs * C::B_TILE + crank * (C::B_TILE / 2), &S.tmWh, &b_full[bs], S.wc0 + kc * C::CK,
                                crank * (N / 2), wtap, uint16_t(3));
               else
-                tma_load_3d(sB + bs * C::B_TILE, &S.tmW, &b_full[bs], S.wc0 + kc * C::CK, 0, wtap);
+                tma_load_3d(sB + bs * C::B_TILE, &S.tmW, &b_full[bs], S.wc0 + kc * C::CK, wrow0, wtap);
               ++bi;
             }
           }
@@ -368,7 +377,8 @@ __global__ void __launch_bounds__(ConvCfg<T, N, NSUB, FUSE, CG2>::THREADS, 1) co
     uint32_t ai = 0, rawph = 0;  // rawph: phase parity of a_raw per slot (it only advances on fused fills)
     long long w_r = 0;
     const long long t_begin = PROF ? clock64() : 0;
-    for (int tile = T0; tile < TEND; tile += TSTEP) {
+    for (int unit = T0; unit < TEND; unit += TSTEP) {
+      const int tile = unit / nsp;
       const int b = tile / tiles_per_img;
       const int rem = tile - b * tiles_per_img;
       const int th = rem / p.tiles_w;
@@ -444,7 +454,10 @@ __global__ void __launch_bounds__(ConvCfg<T, N, NSUB, FUSE, CG2>::THREADS, 1) co
     uint32_t ti = 0;
     long long w_f = 0;
     const long long t_begin = PROF ? clock64() : 0;
-    for (int tile = T0; tile < TEND; tile += TSTEP, ++ti) {
+    for (int unit = T0; unit < TEND; unit += TSTEP, ++ti) {
+      const int tile = unit / nsp;
+      const int nb0 = (unit - tile * nsp) * N;  // first output channel of this unit's slice (0 without an N-split)
+      const int ldn = SWAP ? N : p.ldn;         // channel pitch of out / res / stats (the swap-AB form is never split)
       const bool ghost = tile >= p.ntiles;
       const int b = ghost ? 0 : tile / tiles_per_img;
       const int rem = tile - (tile / tiles_per_img) * tiles_per_img;
@@ -453,7 +466,7 @@ __global__ void __launch_bounds__(ConvCfg<T, N, NSUB, FUSE, CG2>::THREADS, 1) co
       const int h = th * C::TILE_H + hl;
       const bool valid = !ghost && (h < p.H) && (w < p.W);
       const size_t pix = (static_cast<size_t>(b) * p.H + h) * p.W + w;
-      const float* bias = p.bias + static_cast<size_t>(b) * p.bias_bstride;
+      const float* bias = p.bias + static_cast<size_t>(b) * p.bias_bstride + nb0;
       const uint32_t acs = ti & 1, acph = (ti >> 1) & 1;
       if (res != nullptr && !ghost) {
         // pull this thread's share of the residual tile into L2 while the MMAs of the tile are still running
@@ -466,7 +479,7 @@ __global__ void __launch_bounds__(ConvCfg<T, N, NSUB, FUSE, CG2>::THREADS, 1) co
           const int hh = th0p + (pixl >> 3), ww = tw0p + (pixl & 7);
           if (hh < p.H && ww < p.W) {
             const char* a = reinterpret_cast<const char*>(res) +
-                            ((static_cast<size_t>(b) * p.H + hh) * p.W + ww) * row_bytes + seg * 128;
+                            (((static_cast<size_t>(b) * p.H + hh) * p.W + ww) * ldn + nb0) * sizeof(T) + seg * 128;
             asm volatile("prefetch.global.L2 [%0];" ::"l"(a));
           }
         }
@@ -619,7 +632,7 @@ __global__ void __launch_bounds__(ConvCfg<T, N, NSUB, FUSE, CG2>::THREADS, 1) co
         uint4 rq[32 / V];
         if (res != nullptr && valid) {
 #pragma unroll
-          for (int j = 0; j < 32 / V; ++j) rq[j] = __ldg(reinterpret_cast<const uint4*>(res + pix * N + c0) + j);
+          for (int j = 0; j < 32 / V; ++j) rq[j] = __ldg(reinterpret_cast<const uint4*>(res + pix * ldn + nb0 + c0) + j);
         }
         uint32_t r[32];
         tmem_ld32(trow + c0, r);
@@ -650,7 +663,7 @@ __global__ void __launch_bounds__(ConvCfg<T, N, NSUB, FUSE, CG2>::THREADS, 1) co
             float v[V];
 #pragma unroll
             for (int q = 0; q < V; ++q) v[q] = f[j + q];
-            Vec<T>::store(out + pix * N + c0 + j, v);
+            Vec<T>::store(out + pix * ldn + nb0 + c0 + j, v);
           }
         }
         if (p.stats_acc != nullptr) {
@@ -696,7 +709,7 @@ __global__ void __launch_bounds__(ConvCfg<T, N, NSUB, FUSE, CG2>::THREADS, 1) co
         // combine the epilogue warps of this tile in a fixed order (deterministic) and publish the tile partial
         constexpr int ET = 32 * C::EPI_WARPS;
         asm volatile("bar.sync 1, %0;" ::"r"(ET) : "memory");
-        long long* dst = p.stats_acc + static_cast<size_t>(b) * N * 2;
+        long long* dst = p.stats_acc + (static_cast<size_t>(b) * ldn + nb0) * 2;
         for (int i = threadIdx.x - 64; i < N && !ghost; i += ET) {
           float sm_ = 0.f, sq_ = 0.f;
           if constexpr (SWAP) {
