@@ -144,6 +144,9 @@ typedef struct use_sampler_opts {
   const void* x_init;         /* optional device complex64 [B][F][T]: start from this state instead of the prior draw
                                * (single update_fn steps of the registry classes: N = 1 tables + dt_steps = sde.N) */
   int dt_steps;               /* > 0: dt = 1 / dt_steps instead of 1 / N */
+  const void* cond;           /* optional device complex64 [B][F][T]: the network's conditioning spectrogram when it is not
+                               * the SDE's y (condition="denoised" with sde_input="noisy" and vice versa,
+                               * model_wrapper.py:281-299); NULL: the network is conditioned on Y */
 } use_sampler_opts;
 int use_pc_sample_ex(use_engine* e, int B, int F, int T, const void* Y, void* x_state, void* x_mean, int N,
                      const float* t_host, const float* G_host, const float* gfp_host, float prior_std, const void* noise,

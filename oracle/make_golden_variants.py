@@ -34,7 +34,12 @@ CASES = {
     "rd_langevin": dict(predictor="reverse_diffusion", corrector="langevin", corrector_steps=1, snr=0.5),
     "rd_ald": dict(predictor="reverse_diffusion", corrector="ald", corrector_steps=2, snr=0.4),
     "em_none": dict(predictor="euler_maruyama", corrector="none", corrector_steps=1, snr=0.5),
+    # the GAN-refiner conditioning variants (batch["fake"] = the first stage's output; model_wrapper.py:281-299,321-328)
+    "cond_denoised": dict(predictor="reverse_diffusion", corrector="none", corrector_steps=1, snr=0.5),
+    "cond_denoised_sde_denoised": dict(predictor="reverse_diffusion", corrector="none", corrector_steps=1, snr=0.5),
 }
+COND = {"cond_denoised": ("denoised", "noisy", "enhanced"),
+        "cond_denoised_sde_denoised": ("denoised", "denoised", "fake_sde_enhanced")}
 
 
 def main():
@@ -45,11 +50,13 @@ def main():
     sdL = O.make_state_dict(O.LARGE, seed=7)
     B, L, N, seed = 2, 9600, 3, 42
     y = O.synthetic_clips(B, L)
-    out = dict(y=y.numpy(), B=B, L=L, N=N, seed=seed, weight_seed=7)
+    fake = 0.7 * y + 0.05 * O.synthetic_clips(B, L, seed=77)  # stand-in for the GAN stage's denoised output
+    out = dict(y=y.numpy(), fake=fake.numpy(), B=B, L=L, N=N, seed=seed, weight_seed=7)
     for name, kw in CASES.items():
-        m = ScoreModel(backbone="ncsnpplarge", sde="ouve", t_eps=3e-2, mode="regen-joint-training", condition="noisy",
+        condition, sde_input, key = COND.get(name, ("noisy", "noisy", "enhanced"))
+        m = ScoreModel(backbone="ncsnpplarge", sde="ouve", t_eps=3e-2, mode="regen-joint-training", condition=condition,
                        loss_type="mse", n_fft=1022, hop_length=160, num_frames=512, window="hann", spec_factor=0.15,
-                       spec_abs_exponent=0.5, sde_input="noisy", predictor=kw["predictor"],
+                       spec_abs_exponent=0.5, sde_input=sde_input, predictor=kw["predictor"],
                        corrector=kw["corrector"]).eval()
         m.score_net.load_state_dict(sdL, strict=True)
         torch.manual_seed(seed)
@@ -62,15 +69,19 @@ def main():
                                             y=Y, eps=m.t_eps, conditioning=None)
                 xm, nfe = sampler()
                 ref = m.istft(m.spec_back(xm.squeeze(1)), L)
+        elif name in COND:
+            ref = m.sample({"perturbed": y.clone(), "fake": fake.clone()}, N=N)[key]
         else:
             ref = m.sample({"perturbed": y.clone()}, N=N, corrector_steps=kw["corrector_steps"], snr=kw["snr"])["enhanced"]
-        mine = O.sample(sdL, y, N, seed=seed, **kw)
+        mine = O.sample(sdL, y, N, seed=seed, fake=fake if name in COND else None, condition=condition, sde_input=sde_input,
+                        **kw)
         d = float((ref - mine).abs().max())
         print(f"{name}: max|ref-oracle| = {d}", flush=True)
         assert d == 0.0, name
         out[name] = ref.numpy()
         for k, v in kw.items():
             out[f"{name}.{k}"] = v
+        out[f"{name}.condition"], out[f"{name}.sde_input"], out[f"{name}.key"] = condition, sde_input, key
     np.savez_compressed(os.path.join(ROOT, "tests", "golden", "sampler_variants_T64.npz"), **out)
     print("written tests/golden/sampler_variants_T64.npz")
 

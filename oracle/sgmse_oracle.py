@@ -529,18 +529,24 @@ def pc_sample_spec(score_fn, Y: Tensor, N: int, noise: Tensor, sde: SdeCfg = Sde
 
 def sample(sd: Dict[str, Tensor], y: Tensor, N: int, noise: Optional[Tensor] = None, seed: int = 42,
            net: NetCfg = LARGE, spec: SpecCfg = SpecCfg(), sde: SdeCfg = SdeCfg(),
-           return_spec: bool = False, **sampler_kw):
-    """ScoreModel.sample (model_wrapper.py:262-329): y float [B, L] -> enhanced float [B, L]."""
+           return_spec: bool = False, fake: Optional[Tensor] = None, condition: str = "noisy", sde_input: str = "noisy",
+           **sampler_kw):
+    """ScoreModel.sample (model_wrapper.py:262-329): y float [B, L] -> enhanced float [B, L].  ``fake`` (the GAN stage's
+    output, batch["fake"]) + condition / sde_input in {"noisy", "denoised"} select the network's conditioning spectrogram
+    and the SDE's y (:281-299)."""
     with torch.no_grad():
         T_orig = y.size(1)
         Y = pad_spec(spec_fwd(stft(y, spec), spec).unsqueeze(1))
+        Yd = pad_spec(spec_fwd(stft(fake, spec), spec).unsqueeze(1)) if fake is not None else None
+        cond = Yd if (condition == "denoised" and Yd is not None) else Y
+        Y = Yd if (sde_input == "denoised" and Yd is not None) else Y
         if noise is None:
             per = draws_per_step(sampler_kw.get("predictor", "reverse_diffusion"), sampler_kw.get("corrector", "none"),
                                  sampler_kw.get("corrector_steps", 1))
             noise = draw_noise(tuple(Y.shape), N * per, seed, dtype=Y.dtype)
 
         def score_fn(x, t):
-            return -ncsnpp_forward(sd, net, torch.cat([x, Y], dim=1), t)
+            return -ncsnpp_forward(sd, net, torch.cat([x, cond], dim=1), t)
 
         xm = pc_sample_spec(score_fn, Y, N, noise, sde, **sampler_kw)
         out = istft(spec_back(xm.squeeze(1), spec), spec, T_orig)

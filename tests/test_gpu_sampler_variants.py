@@ -5,6 +5,8 @@ oracle/make_golden_variants.py, which also pins the oracle restatement bit-exact
   reverse_diffusion + langevin   (correctors.py:37-64: batch-mean norms -> deterministic device reduction)
   reverse_diffusion + ald        (correctors.py:67-98, two inner steps)
   euler_maruyama   + none        (predictors.py:40-53 over RSDE.rsde_parts, sdes.py:128-150)
+  condition="denoised" (+ sde_input "noisy" / "denoised"): the network conditioned on batch["fake"], the SDE anchored on
+                                 the noisy or the denoised spectrogram (model_wrapper.py:281-299,321-328)
 
 Explicit noise in the reference's draw order (prior; per outer step the corrector's inner draws, then the predictor's).
 Tolerances as for the default sampler: waveform rel-L2 <= 2e-3 (fp32 / TF32), <= 2e-2 (bf16).
@@ -22,11 +24,11 @@ from util import GOLDEN, rel_l2
 pytestmark = pytest.mark.gpu
 
 TOL = {"fp32": 2e-3, "bf16": 2e-2}
-CASES = ["rd_langevin", "rd_ald", "em_none"]
+CASES = ["rd_langevin", "rd_ald", "em_none", "cond_denoised", "cond_denoised_sde_denoised"]
 
 
-def _model(dtype, weight_seed, predictor="reverse_diffusion", corrector="none", **kw):
-    m = use_b200.ScoreModel(backbone="ncsnpplarge", sde="ouve", t_eps=3e-2, condition="noisy", sde_input="noisy",
+def _model(dtype, weight_seed, predictor="reverse_diffusion", corrector="none", condition="noisy", sde_input="noisy", **kw):
+    m = use_b200.ScoreModel(backbone="ncsnpplarge", sde="ouve", t_eps=3e-2, condition=condition, sde_input=sde_input,
                             n_fft=1022, hop_length=160, num_frames=512, dtype=dtype, predictor=predictor,
                             corrector=corrector, **kw)
     m.score_net.load_state_dict(O.make_state_dict(O.LARGE, seed=weight_seed), strict=True)
@@ -40,16 +42,20 @@ def test_sampler_variant_matches_reference_golden(case, dtype):
     N, seed = int(g["N"]), int(g["seed"])
     pred, corr = str(g[f"{case}.predictor"]), str(g[f"{case}.corrector"])
     steps, snr = int(g[f"{case}.corrector_steps"]), float(g[f"{case}.snr"])
-    m = _model(dtype, int(g["weight_seed"]), pred, corr)
+    condition, sde_input, key = str(g[f"{case}.condition"]), str(g[f"{case}.sde_input"]), str(g[f"{case}.key"])
+    m = _model(dtype, int(g["weight_seed"]), pred, corr, condition=condition, sde_input=sde_input)
     y = torch.from_numpy(g["y"])
     per = O.draws_per_step(pred, corr, steps)
     noise = O.draw_noise((2, 1, 512, 64), N * per, seed).cuda()
-    got = m.sample({"perturbed": y.cuda()}, N=N, corrector_steps=steps, snr=snr, noise=noise)["enhanced"].cpu()
+    batch = {"perturbed": y.cuda()}
+    if condition != "noisy" or sde_input != "noisy":
+        batch["fake"] = torch.from_numpy(g["fake"]).cuda()  # the GAN stage's output (model_wrapper.py:271-272)
+    got = m.sample(batch, N=N, corrector_steps=steps, snr=snr, noise=noise)[key].cpu()
     ref = torch.from_numpy(g[case])
     e = rel_l2(got, ref)
     assert bool(torch.isfinite(got).all()) and e <= TOL[dtype], (case, dtype, e)
     # a different variant is a different sampler: the default chain with the same leading draws must NOT match
-    if case != "em_none":
+    if case in ("rd_langevin", "rd_ald"):
         base = _model(dtype, int(g["weight_seed"])).sample({"perturbed": y.cuda()}, N=N, noise=noise[: N + 1].contiguous())
         assert rel_l2(base["enhanced"].cpu(), ref) > 10 * TOL[dtype]
 

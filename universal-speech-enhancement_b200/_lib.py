@@ -47,6 +47,7 @@ class UseSamplerOpts(C.Structure):
         ("predictor", C.c_int), ("corrector", C.c_int), ("corrector_steps", C.c_int), ("snr", C.c_float),
         ("probability_flow", C.c_int), ("denoise", C.c_int), ("g_host", C.c_void_p), ("ald_step_host", C.c_void_p),
         ("trace", C.c_void_p), ("x_init", C.c_void_p), ("dt_steps", C.c_int),
+        ("cond", C.c_void_p),
     ]
 
 

@@ -357,7 +357,7 @@ class _Engine:
 
     def pc_sample(self, Y: torch.Tensor, ts: torch.Tensor, G: torch.Tensor, prior_std: float, noise=None, seed: int = 0,
                   clip0: int = 0, predictor="reverse_diffusion", corrector="none", corrector_steps=1, snr=0.5,
-                  probability_flow=False, denoise=True, g=None, ald_step=None, trace=None, x_init=None, dt_steps=0):
+                  probability_flow=False, denoise=True, g=None, ald_step=None, trace=None, x_init=None, dt_steps=0, cond=None):
         """The fused predictor-corrector loop (use_pc_sample_ex); returns (x_result, x_state), complex64 [B, F, T]:
         x_result = the noise-free mean of the last step (denoise) or the state."""
         assert Y.dtype == torch.complex64 and Y.dim() == 3 and Y.is_cuda
@@ -398,6 +398,11 @@ class _Engine:
             assert tuple(x_init.shape) == (B, F, T) and x_init.is_cuda
             keep.append(x_init)
             o.x_init = x_init.data_ptr()
+        if cond is not None:
+            cond = cond.to(torch.complex64).contiguous()
+            assert tuple(cond.shape) == (B, F, T) and cond.is_cuda
+            keep.append(cond)
+            o.cond = cond.data_ptr()
         with torch.cuda.device(self.device):
             ws = self.workspace(B, F, T)
             _lib.check(self.L.use_pc_sample_ex(self.h, B, F, T, Y.data_ptr(), x_state.data_ptr(), x_mean.data_ptr(), N,

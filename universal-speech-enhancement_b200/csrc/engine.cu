@@ -1267,8 +1267,8 @@ int use_pc_sample_ex(use_engine* e, int B, int F, int T, const void* Y, void* x_
       const float* t_dev = (const float*)(base + e->head.sched) + i;
       const float* gfp_dev = (const float*)(base + e->head.sched) + N + (size_t)i * nf2;
       auto evaluate = [&](StepArgs& a) {  // one network evaluation at t_i from the current state + the fused tail
-        launch_pack_input(e->dt, 4, (const float2*)x_state + off, (const float2*)Y + off, (float*)(base + e->head.xr),
-                          base + e->head.xpad, n, gs[g]);
+        launch_pack_input(e->dt, 4, (const float2*)x_state + off, (const float2*)(o.cond ? o.cond : Y) + off,
+                          (float*)(base + e->head.xr), base + e->head.xpad, n, gs[g]);
         run_network(e, p, gs[g], gfp_dev, 0, own_streams);
         a.pyramid = (const float*)(base + p->pyramid_off);
         a.pc = 4;

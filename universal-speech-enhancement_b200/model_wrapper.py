@@ -50,10 +50,10 @@ class ScoreModel(nn.Module):
                  corrector="none", dtype: str = "fp32", micro_batch: Optional[int] = None, N: Optional[int] = None,
                  sampler_type: Optional[str] = None):
         super().__init__()
-        if condition != "noisy" or sde_input != "noisy":
+        if condition not in ("noisy", "denoised") or sde_input not in ("noisy", "denoised"):
             raise NotImplementedError(
-                "ScoreModel(B200): only condition='noisy', sde_input='noisy' (configs/model/SGMSE_Large.yaml) is on "
-                "the accelerated path; 'both'/'denoised' belong to the GAN-refiner pipeline (SURVEY.md section 8f)")
+                "ScoreModel(B200): condition / sde_input must be 'noisy' or 'denoised' (4-channel score network, "
+                "model_wrapper.py:43-46); condition='both' (6-channel input fed by the GAN stage's output) is not built")
         self.score_net = BackboneRegistry.get_by_name(backbone)(input_channels=4, compute_dtype=dtype)
         self.sde = SDERegistry.get_by_name(sde)()
         self.t_eps = t_eps
@@ -203,7 +203,7 @@ class ScoreModel(nn.Module):
     # ---- samplers ----------------------------------------------------------------------------------
     def _fused_pc_sample(self, sde, y, eps, predictor="reverse_diffusion", corrector="none", corrector_steps=1, snr=0.5,
                          probability_flow=False, denoise=True, noise=None, seed=None, clip0=0, trace=None, x_init=None,
-                         times=None, want_state=False):
+                         times=None, want_state=False, cond=None):
         """y: complex [B,1,F,T].  One C call (use_pc_sample_ex) per micro-batch: prior + N x (corrector steps, predictor
         step).  ``x_init`` + ``times`` = [t]: a single update_fn step from the given state (dt stays 1 / sde.N)."""
         ts, G, std1 = sde.step_tables(sde.N, eps, times=times)
@@ -224,7 +224,8 @@ class ScoreModel(nn.Module):
             xm, xs = eng.pc_sample(Yc, ts, G, std1, noise=nc, seed=seed, clip0=clip0 + s, predictor=predictor,
                                    corrector=corrector, corrector_steps=corrector_steps, snr=snr,
                                    probability_flow=probability_flow, denoise=denoise, g=g_tab, ald_step=ald_tab, trace=tr,
-                                   x_init=None if x_init is None else x_init[s:s + mb, 0], dt_steps=sde.N)
+                                   x_init=None if x_init is None else x_init[s:s + mb, 0], dt_steps=sde.N,
+                                   cond=None if cond is None else cond[s:s + mb, 0])
             if trace is not None and mb < B:
                 trace[:, s:s + mb, 0] = tr
             means.append(xm)
@@ -277,14 +278,29 @@ class ScoreModel(nn.Module):
         y = batch["perturbed"]
         T_orig = y.size(1)
         Y = self.stft_compressed(y).unsqueeze(1)          # = pad_spec(spec_fwd(stft(y)).unsqueeze(1))
-        score_conditioning = [Y]
+        Y_denoised = self.stft_compressed(batch["fake"]).unsqueeze(1) if "fake" in batch else None
+        # conditioning of the network / the SDE's y (model_wrapper.py:281-299)
+        if self.condition == "noisy":
+            score_conditioning = [Y]
+        elif self.condition == "denoised" and Y_denoised is not None:
+            score_conditioning = [Y_denoised]
+        else:
+            raise NotImplementedError(f"Don't know the conditioning you have wished for: {self.condition}")
+        if self.sde_input == "denoised" and Y_denoised is not None:
+            sde_input = Y_denoised
+        elif self.sde_input == "noisy":
+            sde_input = Y
+        else:
+            raise NotImplementedError(f"Don't know the sde input you have wished for: {self.sde_input}")
         if sampler_type != "pc":
             raise NotImplementedError(f"{sampler_type} is not a valid sampler type on the accelerated path (use 'pc')")
-        sampler = self.get_pc_sampler(self.predictor, self.corrector, Y, N=N, corrector_steps=corrector_steps, snr=snr,
-                                      intermediate=False, conditioning=score_conditioning, noise=noise, seed=seed,
-                                      clip0=clip0, trace=trace)
+        sampler = self.get_pc_sampler(self.predictor, self.corrector, sde_input, N=N, corrector_steps=corrector_steps,
+                                      snr=snr, intermediate=False, conditioning=score_conditioning, noise=noise,
+                                      seed=seed, clip0=clip0, trace=trace)
         sample, nfe = sampler()
-        batch["enhanced"] = self.istft_decompressed(sample.squeeze(1), T_orig)
+        out = self.istft_decompressed(sample.squeeze(1), T_orig)
+        # output key as in the reference (model_wrapper.py:321-328)
+        batch["fake_sde_enhanced" if (self.sde_input == "denoised" and Y_denoised is not None) else "enhanced"] = out
         return batch
 
     @torch.no_grad()

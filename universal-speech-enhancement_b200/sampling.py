@@ -59,9 +59,10 @@ class _Step(abc.ABC):
         fn = getattr(self.score_fn, "_fused_pc_sample", None)
         if fn is None:
             raise NotImplementedError(f"{type(self).__name__} needs a B200 ScoreModel as score_fn")
-        if conditioning is not None and not (len(conditioning) == 1 and conditioning[0] is y):
-            raise NotImplementedError("fused steps support score_conditioning = [y] (condition='noisy')")
-        return fn(self.sde, y, None, x_init=x, times=torch.tensor([_uniform_time(t)]), want_state=True, **sel)
+        if conditioning is not None and len(conditioning) != 1:
+            raise NotImplementedError("fused steps take ONE conditioning spectrogram (condition='noisy' or 'denoised')")
+        cond = None if conditioning is None or conditioning[0] is y else conditioning[0]
+        return fn(self.sde, y, None, x_init=x, times=torch.tensor([_uniform_time(t)]), want_state=True, cond=cond, **sel)
 
 
 class Predictor(_Step):
@@ -154,7 +155,7 @@ _BUILTIN = {EulerMaruyamaPredictor, ReverseDiffusionPredictor, NonePredictor, La
 
 def _fusable(predictor_cls, corrector_cls, sde, score_fn, conditioning, y) -> bool:
     return (predictor_cls in _BUILTIN and corrector_cls in _BUILTIN and isinstance(sde, sdes.OUVESDE) and hasattr(score_fn, "_fused_pc_sample") and sde.N >= 1
-            and conditioning is not None and len(conditioning) == 1 and conditioning[0] is y)
+            and conditioning is not None and len(conditioning) == 1)
 
 
 def _host_loop(predictor, corrector, sde, y, eps, denoise, conditioning):
@@ -183,7 +184,8 @@ def get_pc_sampler(predictor_name, corrector_name, sde, score_fn, y, denoise=Tru
 
         def fused_sampler():
             out = score_fn._fused_pc_sample(sde, y, eps, predictor=predictor_cls.kind, corrector=corrector_cls.kind,
-                                            corrector_steps=corrector_steps, snr=snr, denoise=denoise, noise=noise, seed=seed, clip0=clip0, trace=trace)
+                                            corrector_steps=corrector_steps, snr=snr, denoise=denoise,
+                                            cond=None if conditioning[0] is y else conditioning[0], noise=noise, seed=seed, clip0=clip0, trace=trace)
             return out, sde.N * (n_corr + 1)
 
         return fused_sampler
