@@ -10,7 +10,11 @@
 // pixel in the epilogue.  Tile = 16 x 16 window (TMA box, zero fill outside the image) -> 14 x 14 outputs.  The packed
 // weights of all channel chunks stay resident in shared memory.  HBM-bound: one read of the operand.
 //
-// Warp roles: warp 0 = TMA producer, warp 1 = MMA issuer / TMEM owner, warps 2..9 = epilogue (thread = window pixel).
+// Warp roles: warp 0 = TMA producer, warp 1 = MMA issuer / TMEM owner, warps 2..17 = TWO epilogue groups of 8 warps
+// (thread = window pixel).  A tile's epilogue is a serial chain (accumulator ready -> tcgen05.ld -> stage in shared memory
+// -> barrier -> 3x3 gather -> store -> barrier, ~2.3 us) that one group could not hide behind the loads once the operand is
+// bf16 (half the bytes per tile: round 1 measured 48 % of the HBM roofline in bf16 vs 86 % in fp32).  Group g owns
+// accumulator slot g and staging buffer g and takes every other tile of the CTA, so two epilogues are in flight.
 #pragma once
 #include "common.cuh"
 
@@ -33,12 +37,12 @@ constexpr int kHeadN = 48;           // 9 taps x 4 outputs, padded to a multiple
 constexpr int kHeadTile = 14;        // outputs per tile edge
 constexpr int kHeadWin = 16;         // window edge
 constexpr int kHeadASlot = kHeadWin * kHeadWin * 128;  // 32 KB
-constexpr int kHeadASlots = 4;
+constexpr int kHeadASlots = 3;
 constexpr int kHeadWBytes = kHeadMaxChunks * kHeadN * 128;  // 48 KB
 constexpr int kHeadStagePitch = 37;  // floats per pixel in the staging buffer (odd: conflict-free)
-constexpr int kHeadStageBytes = 256 * kHeadStagePitch * 4;
-constexpr int kHeadThreads = 64 + 256;
-constexpr int kHeadSmem = 1024 + kHeadASlots * kHeadASlot + kHeadWBytes + kHeadStageBytes + (2 * kHeadASlots + 5) * 8 + 16;
+constexpr int kHeadStageBytes = 256 * kHeadStagePitch * 4;  // per epilogue group
+constexpr int kHeadThreads = 64 + 2 * 256;
+constexpr int kHeadSmem = 1024 + kHeadASlots * kHeadASlot + kHeadWBytes + 2 * kHeadStageBytes + (2 * kHeadASlots + 5) * 8 + 16;
 static_assert(kHeadSmem <= 232448, "shared memory budget");
 
 template <typename T>
@@ -50,7 +54,7 @@ __global__ void __launch_bounds__(kHeadThreads, 1) head_tc_kernel(const __grid_c
   uint8_t* sA = smem;
   uint8_t* sW = sA + kHeadASlots * kHeadASlot;
   float* stage = reinterpret_cast<float*>(sW + kHeadWBytes);
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sW + kHeadWBytes + kHeadStageBytes);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sW + kHeadWBytes + 2 * kHeadStageBytes);
   uint64_t* a_full = bars;
   uint64_t* a_empty = a_full + kHeadASlots;
   uint64_t* w_full = a_empty + kHeadASlots;
@@ -136,16 +140,18 @@ __global__ void __launch_bounds__(kHeadThreads, 1) head_tc_kernel(const __grid_c
       }
     }
   } else {
-    const int ew = warp - 2;
+    const int grp = (warp - 2) >> 3;  // epilogue group: tiles ti = grp, grp + 2, ... of this CTA, accumulator slot grp
+    const int ew = (warp - 2) & 7;
     const int sub = ew >> 2;
     const int quad = warp & 3;  // TMEM lane quadrant this warp may access
     const int pixel = sub * 128 + quad * 32 + lane;  // window pixel = accumulator row
-    const int e = threadIdx.x - 64;                  // gather role: output pixel e of the 14 x 14 tile (e < 196)
+    const int e = ew * 32 + lane;                    // gather role: output pixel e of the 14 x 14 tile (e < 196)
     const int oy = e / kHeadTile, ox = e - oy * kHeadTile;
     const int pc = p.pc;
     const int nd = 9 * pc;
-    uint32_t ti = 0;
-    for (int tile = g0; tile < p.ntiles; tile += gstep, ++ti) {
+    stage += grp * (256 * kHeadStagePitch);
+    const uint32_t bar_id = 1 + grp;
+    for (uint32_t ti = grp, tile = g0 + grp * gstep; tile < static_cast<uint32_t>(p.ntiles); tile += 2 * gstep, ti += 2) {
       const int b = tile / tiles_per_img;
       const int rem = tile - b * tiles_per_img;
       const int th = rem / p.tiles_w;
@@ -200,7 +206,7 @@ __global__ void __launch_bounds__(kHeadThreads, 1) head_tc_kernel(const __grid_c
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&t_empty[acs]);
-      named_bar_sync(1, 256);
+      named_bar_sync(bar_id, 256);
       if (live) {
         float o[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
@@ -220,7 +226,7 @@ __global__ void __launch_bounds__(kHeadThreads, 1) head_tc_kernel(const __grid_c
         if (pc == 4) reinterpret_cast<float4*>(p.out4)[pix] = make_float4(o[0], o[1], o[2], o[3]);
         else reinterpret_cast<float2*>(p.out4)[pix] = make_float2(o[0], o[1]);
       }
-      named_bar_sync(1, 256);  // the staging buffer is rewritten by the next tile
+      named_bar_sync(bar_id, 256);  // the staging buffer is rewritten by this group's next tile
     }
   }
 
