@@ -48,6 +48,7 @@ def parse():
     ap.add_argument("--micro-batch", type=int, default=None)
     ap.add_argument("--cpu-sample-evals", type=int, default=2, help="network evaluations timed for the CPU baseline")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--e2e-steps", type=int, default=0, help="timed steps of the host-buffer arm (default min(steps, 3))")
     args = ap.parse_args()
     preset = {1: ("fp32", 32, 30, 0), 2: ("bf16", 256, 30, 64), 3: ("fp32", 64, 60, 0), 4: ("bf16", 256, 30, 64)}[args.config]
     for key, val in zip(("dtype", "batch", "N", "micro_batch"), preset):
@@ -262,7 +263,7 @@ def main():
     value = world * B / (ms_step / 1e3)
 
     # end to end through the reference-facing call (SGMSEModule.predict_step) with HOST buffers
-    e2e_steps = max(1, min(args.steps, 3))
+    e2e_steps = args.e2e_steps if args.e2e_steps > 0 else max(1, min(args.steps, 3))
     ms_e2e, _ = timed(step_e2e, e2e_steps, 1)
     e2e_value = world * B / (ms_e2e / e2e_steps / 1e3)
 
