@@ -3,6 +3,8 @@
 // Reference semantics: nn.GroupNorm(min(C/4,32), eps=1e-6) + SiLU (layerspp.py:255-271,283,304),
 // upsample_2d / downsample_2d with k=[1,3,3,1] (up_or_down_sampling.py:202-264), Combine "sum"
 // (layerspp.py:50-55), input conv / pyramid convs (ncsnpp.py:214,377-381,440-461).
+#include <stdlib.h>
+
 #include <algorithm>
 
 #include "common.cuh"
@@ -678,6 +680,191 @@ __global__ void __launch_bounds__(256, 4) gn_fir_down_kernel(GnSrcT<T> s0, const
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// normalise + SiLU + FIR x2 DOWN (single source), third generation (round 2): a STREAMING form without shared memory.
+// The tiled kernel above is issue-bound (ncu: ~840 instructions per thread per 8 x 8 tile, 39 % of the HBM roofline):
+// every input element costs a global load, an activation, a shared-memory store and four shared-memory loads, plus
+// two block-wide barriers per tile and a 27 % halo.  Here a WARP walks down a strip of 16 input columns x 64 bytes of
+// channels: lane = (column pair pp = lane >> 2, 16-byte channel vector q = lane & 3); a lane owns input columns
+// (2j - 1, 2j) of output column j = j0 + pp, activates them ONCE, gets columns (2j + 1, 2j + 2) from lane + 4 by
+// shuffle (lane pp = 7 has no right neighbour: 7 outputs per 16 columns, 14 % column halo, no row halo inside a
+// segment), filters horizontally in registers, and keeps TWO running vertical accumulators (output rows i - 1 and i)
+// instead of a window: input row 2i - 1 adds k2 h to output i - 1 and starts output i with k0 h, row 2i adds k3 h /
+// k1 h and emits output i - 1.  No shared memory, no barriers, ~270 instructions per output pixel x 4 channels (was
+// ~840), same FMA order as the tiled kernel (bit-identical results; in bf16 mode the activated value is rounded to
+// bf16 before the filter, as the tiled kernel's staging did).
+// ------------------------------------------------------------------------------------------------
+constexpr int kFirSegRows = 32;  // output rows per warp task (halved down to 8 while the launch has < ~3 waves of warps)
+constexpr int kFirDepth = 4;     // loop iterations (pairs of input rows) in flight per warp
+constexpr int kFirSmem = 4 * kFirDepth * 4 * 32 * 16;  // 4 warps x depth x 4 pixels x 32 lanes x 16 B = 32 KB
+
+template <typename T>
+__global__ void __launch_bounds__(128, DT<T>::kIsBf16 ? 4 : 5) gn_fir_down_stream_kernel(GnSrcT<T> s0, const float* __restrict__ gamma,
+                                                                  const float* __restrict__ beta, float eps, int do_silu,
+                                                                  int as_operand, T* __restrict__ out_act,
+                                                                  T* __restrict__ out_raw, int Hin, int Win, int B,
+                                                                  const float* __restrict__ aff, int nstrips, int nsegs,
+                                                                  int seg_rows, long long ntasks) {
+  constexpr int V = Vec<T>::N;
+  constexpr int CH = 4 * V;  // channels per warp (64 bytes)
+  extern __shared__ __align__(16) uint4 ring[];
+  const int lane = threadIdx.x & 31;
+  const int q = lane & 3, pp = lane >> 2;
+  const int C = s0.C;
+  const int nsl = C / CH;
+  const int Hout = Hin >> 1, Wout = Win >> 1;
+  const float k1[4] = {0.125f, 0.375f, 0.375f, 0.125f};
+  for (long long task = static_cast<long long>(blockIdx.x) * 4 + (threadIdx.x >> 5); task < ntasks;
+       task += static_cast<long long>(gridDim.x) * 4) {
+    // channel slice fastest: the slices of the same pixels run side by side, so DRAM sees whole pixel rows
+    long long t = task;
+    const int sl = static_cast<int>(t % nsl); t /= nsl;
+    const int strip = static_cast<int>(t % nstrips); t /= nstrips;
+    const int seg = static_cast<int>(t % nsegs);
+    const int b = static_cast<int>(t / nsegs);
+    const int c0 = sl * CH + q * V;
+    const int j = strip * 7 + pp;              // output column of this lane (lane pp = 7: halo only)
+    const int xa = 2 * j - 1, xb = 2 * j;      // owned input columns
+    const bool col_a = xa >= 0 && xa < Win, col_b = xb < Win;
+    const bool emit = pp < 7 && j < Wout;
+    const int i0 = seg * seg_rows, i1 = min(i0 + seg_rows, Hout);
+    // per-channel scale / shift of this lane's V channels
+    float sc[V], sh[V];
+    if (aff != nullptr) {
+#pragma unroll
+      for (int v = 0; v < V; ++v) {
+        sc[v] = __ldg(aff + (static_cast<size_t>(b) * 2) * C + c0 + v);
+        sh[v] = __ldg(aff + (static_cast<size_t>(b) * 2 + 1) * C + c0 + v);
+      }
+    } else {
+      const int G = min(C / 4, 32), cpg = C / G;
+      const double inv_cnt = 1.0 / (static_cast<double>(Hin) * Win * cpg);
+#pragma unroll
+      for (int v = 0; v < V; ++v) {
+        const int c = c0 + v, g = c / cpg;
+        double sum = 0.0, sq = 0.0;
+        for (int cc = g * cpg; cc < (g + 1) * cpg; ++cc) {
+          const longlong2 st = __ldg(reinterpret_cast<const longlong2*>(s0.stats + (static_cast<size_t>(b) * C + cc) * 2));
+          sum += static_cast<double>(st.x) * (1.0 / kStatSumScale);
+          sq += static_cast<double>(st.y) * (1.0 / kStatSqScale);
+        }
+        const double mean = sum * inv_cnt;
+        double var = sq * inv_cnt - mean * mean;
+        if (var < 0.0) var = 0.0;
+        const float rstd = rsqrtf(static_cast<float>(var) + eps);
+        sc[v] = gamma[c] * rstd;
+        sh[v] = beta[c] - static_cast<float>(mean) * sc[v];
+      }
+    }
+    const T* src = s0.x + static_cast<size_t>(b) * Hin * Win * C + c0;
+    float acc_a[V], acc_r[V];  // running output row (activated / raw)
+#pragma unroll
+    for (int v = 0; v < V; ++v) acc_a[v] = acc_r[v] = 0.f;
+
+    // Prefetch ring: the owned pixels of the rows of the next kFirDepth iterations travel global -> shared memory by
+    // cp.async (zero-filled outside the image), each lane into its OWN 16-byte column of the ring (conflict-free, and no
+    // cross-lane hand-off: a lane reads back only what it requested).  ncu on the register-prefetch form: 47 % of the
+    // stall cycles on global loads at 12-20 resident warps per SM; the ring hides them without spending registers.
+    auto issue_row = [&](int r, uint4* dst_a, uint4* dst_b) {
+      const bool rin = r >= 0 && r < Hin;
+      const T* rowp = src + static_cast<size_t>(rin ? r : 0) * Win * C;
+      const T* pa_ = rowp + static_cast<size_t>(col_a ? xa : 0) * C;
+      const T* pb_ = rowp + static_cast<size_t>(col_b ? xb : 0) * C;
+      const unsigned na = (rin && col_a) ? 16u : 0u, nb = (rin && col_b) ? 16u : 0u;
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(smem_u32(dst_a)), "l"(pa_), "r"(na) : "memory");
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(smem_u32(dst_b)), "l"(pb_), "r"(nb) : "memory");
+    };
+    // horizontally filtered row r -> ha (activated), hr (raw); zero outside the image (the FIR pads the ACTIVATED tensor)
+    auto hrow = [&](int r, const uint4& ra, const uint4& rb, float (&ha)[V], float (&hr)[V]) {
+      const bool rin = r >= 0 && r < Hin;
+      float fa[V], fb[V], aa[V], ab[V];
+      Vec<T>::unpack(ra, fa);
+      Vec<T>::unpack(rb, fb);
+#pragma unroll
+      for (int v = 0; v < V; ++v) {
+        const float na = fmaf(fa[v], sc[v], sh[v]), nb = fmaf(fb[v], sc[v], sh[v]);
+        aa[v] = (rin && col_a) ? (do_silu ? silu_act<T>(na) : na) : 0.f;
+        ab[v] = (rin && col_b) ? (do_silu ? silu_act<T>(nb) : nb) : 0.f;
+      }
+      // the activated values pass through the act dtype (bf16 mode: rounded, exactly like a materialised tensor)
+      uint4 pa, pb;
+      if constexpr (DT<T>::kIsBf16) {
+        pa = Vec<T>::pack_operand(aa);
+        pb = Vec<T>::pack_operand(ab);
+        Vec<T>::unpack(pa, aa);
+        Vec<T>::unpack(pb, ab);
+      } else {
+        pa = make_uint4(__float_as_uint(aa[0]), __float_as_uint(aa[1]), __float_as_uint(aa[2]), __float_as_uint(aa[3]));
+        pb = make_uint4(__float_as_uint(ab[0]), __float_as_uint(ab[1]), __float_as_uint(ab[2]), __float_as_uint(ab[3]));
+      }
+      // columns 2j + 1, 2j + 2 = the owned columns of lane + 4
+      auto shfl4 = [](const uint4& x) {
+        return make_uint4(__shfl_down_sync(0xffffffffu, x.x, 4), __shfl_down_sync(0xffffffffu, x.y, 4),
+                          __shfl_down_sync(0xffffffffu, x.z, 4), __shfl_down_sync(0xffffffffu, x.w, 4));
+      };
+      const uint4 qa = shfl4(pa), qb = shfl4(pb), sa = shfl4(ra), sb = shfl4(rb);
+      float ac[V], ad[V], fc[V], fd[V];
+      Vec<T>::unpack(qa, ac);
+      Vec<T>::unpack(qb, ad);
+      Vec<T>::unpack(sa, fc);
+      Vec<T>::unpack(sb, fd);
+#pragma unroll
+      for (int v = 0; v < V; ++v) {
+        ha[v] = fmaf(k1[3], ad[v], fmaf(k1[2], ac[v], fmaf(k1[1], ab[v], k1[0] * aa[v])));
+        hr[v] = fmaf(k1[3], fd[v], fmaf(k1[2], fc[v], fmaf(k1[1], fb[v], k1[0] * fa[v])));
+      }
+    };
+
+    uint4* my = ring + static_cast<size_t>(threadIdx.x >> 5) * (kFirDepth * 4 * 32) + lane;  // entry (slot, k): my[(slot * 4 + k) * 32]
+#pragma unroll
+    for (int k = 0; k < kFirDepth; ++k) {
+      if (i0 + k <= i1) {
+        issue_row(2 * (i0 + k) - 1, my + (k * 4 + 0) * 32, my + (k * 4 + 1) * 32);
+        issue_row(2 * (i0 + k), my + (k * 4 + 2) * 32, my + (k * 4 + 3) * 32);
+      }
+      asm volatile("cp.async.commit_group;" ::: "memory");
+    }
+    for (int i = i0; i <= i1; ++i) {
+      const int slot = (i - i0) % kFirDepth;
+      asm volatile("cp.async.wait_group %0;" ::"n"(kFirDepth - 1) : "memory");
+      const uint4 c0a = my[(slot * 4 + 0) * 32], c0b = my[(slot * 4 + 1) * 32], c1a = my[(slot * 4 + 2) * 32],
+                  c1b = my[(slot * 4 + 3) * 32];
+      if (i + kFirDepth <= i1) {
+        issue_row(2 * (i + kFirDepth) - 1, my + (slot * 4 + 0) * 32, my + (slot * 4 + 1) * 32);
+        issue_row(2 * (i + kFirDepth), my + (slot * 4 + 2) * 32, my + (slot * 4 + 3) * 32);
+      }
+      asm volatile("cp.async.commit_group;" ::: "memory");
+      float ha0[V], hr0[V], ha1[V], hr1[V];
+      hrow(2 * i - 1, c0a, c0b, ha0, hr0);
+      hrow(2 * i, c1a, c1b, ha1, hr1);
+      if (i > i0) {
+        // finish output row i - 1: taps 2 and 3
+        float oa[V], orr[V];
+#pragma unroll
+        for (int v = 0; v < V; ++v) {
+          oa[v] = fmaf(k1[3], ha1[v], fmaf(k1[2], ha0[v], acc_a[v]));
+          orr[v] = fmaf(k1[3], hr1[v], fmaf(k1[2], hr0[v], acc_r[v]));
+        }
+        if (emit) {
+          const size_t o = ((static_cast<size_t>(b) * Hout + (i - 1)) * Wout + j) * C + c0;
+          if (as_operand) Vec<T>::store_operand(out_act + o, oa);
+          else Vec<T>::store(out_act + o, oa);
+          if (out_raw != nullptr) {
+            if (as_operand) Vec<T>::store_operand(out_raw + o, orr);
+            else Vec<T>::store(out_raw + o, orr);
+          }
+        }
+      }
+      // start output row i: taps 0 and 1
+#pragma unroll
+      for (int v = 0; v < V; ++v) {
+        acc_a[v] = fmaf(k1[1], ha1[v], k1[0] * ha0[v]);
+        acc_r[v] = fmaf(k1[1], hr1[v], k1[0] * hr0[v]);
+      }
+    }
+  }
+}
+
 void launch_gn_apply(int dt, GnSrc s0, GnSrc s1, const float* gamma, const float* beta, float eps, int fir, bool do_silu,
                      bool as_operand, void* out_act, void* out_raw, int B, int Hin, int Win, cudaStream_t st,
                      const float* aff) {
@@ -688,7 +875,18 @@ void launch_gn_apply(int dt, GnSrc s0, GnSrc s1, const float* gamma, const float
     DISPATCH_DT(dt, {
       constexpr int CH = FirCh<T>::value;
       GnSrcT<T> a{(const T*)s0.x, s0.stats, s0.C};
-      if (fir == 1) {
+      static const bool tiled_down = getenv("USE_B200_FIR_DOWN") && getenv("USE_B200_FIR_DOWN")[0] == 't';  // A/B switch
+      if (fir == 1 && !tiled_down) {
+        const int nstrips = (Wout + 6) / 7;
+        int seg_rows = kFirSegRows;
+        auto tasks_for = [&](int rows) { return static_cast<long long>(s0.C / (4 * Vec<T>::N)) * nstrips * ((Hout + rows - 1) / rows) * B; };
+        while (seg_rows > 8 && tasks_for(seg_rows) < 148LL * 20 * 3) seg_rows >>= 1;
+        const int nsegs = (Hout + seg_rows - 1) / seg_rows;
+        const long long ntasks = tasks_for(seg_rows);
+        const int blocks = static_cast<int>(std::min<long long>((ntasks + 3) / 4, 148LL * 128));
+        gn_fir_down_stream_kernel<T><<<blocks, 128, kFirSmem, st>>>(a, gamma, beta, eps, do_silu, as_operand, (T*)out_act,
+                                                             (T*)out_raw, Hin, Win, B, aff, nstrips, nsegs, seg_rows, ntasks);
+      } else if (fir == 1) {
         constexpr int CHD = FirDownCh<T>::value;
         dim3 grid(s0.C / CHD, ((Hout + 7) / 8) * ((Wout + 7) / 8), B);
         const size_t sm = 2 * 18 * 20 * CHD * sizeof(T) + 2 * CHD * sizeof(float);
