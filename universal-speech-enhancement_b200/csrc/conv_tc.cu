@@ -157,7 +157,9 @@ TcConvPlan* tc_conv_plan_create(int dt, const TcConvDesc& d, int num_sms, char* 
   p->N = d.N;
   bool fuse = false;
   for (int i = 0; i < d.nseg; ++i) fuse = fuse || d.seg[i].aff != nullptr;
-  // N-split (conv_tc.cuh, ConvParams::nsplit): fewer tiles than SMs -> 64-channel slices of C_out as extra work units.
+  // N-split (conv_tc.cuh, ConvParams::nsplit): at most a third as many tiles as SMs -> 64-channel slices of C_out as extra
+  // work units (measured, bf16: batch 1 162.2 -> 157.7 ms per clip; at 80-147 tiles the 4x activation re-reads cost as
+  // much as the shorter weight stream saves: batch 2 unchanged, batch 4 2 % slower, hence the threshold).
   // Only the C_out = 256 family: its unsplit kernel is the same pixel-major form, so split and unsplit launches are
   // bit-identical (a clip sampled alone == the same clip inside any batch).  The C_out = 128 layers run the swap-AB kernel,
   // whose channel-major epilogue sums the GroupNorm statistics in a different order: slicing them would make the result
@@ -168,7 +170,7 @@ TcConvPlan* tc_conv_plan_create(int dt, const TcConvDesc& d, int num_sms, char* 
     const int base_tiles = ((d.W + 7) / 8) * ((d.H + base_h - 1) / base_h) * d.B;
     static const bool off = getenv("USE_B200_CONV_NSPLIT") && getenv("USE_B200_CONV_NSPLIT")[0] == '0';
     static const int max_tiles = getenv("USE_B200_CONV_NSPLIT_MAXTILES") ? atoi(getenv("USE_B200_CONV_NSPLIT_MAXTILES")) : (1 << 30);
-    if (!off && d.N == 256 && base_tiles < num_sms && base_tiles < max_tiles && multicast_width() == 1 && !cg2_enabled() && !getenv("USE_B200_CONV_PROF"))
+    if (!off && d.N == 256 && base_tiles * 3 <= num_sms && base_tiles < max_tiles && multicast_width() == 1 && !cg2_enabled() && !getenv("USE_B200_CONV_PROF"))
       nsplit = d.N / 64;
   }
   if (getenv("USE_B200_CONV_DEBUG")) {

@@ -1091,17 +1091,38 @@ void launch_conv_out4(int dt, const void* a, const float* w, const float* bias, 
 // ------------------------------------------------------------------------------------------------
 constexpr int kCombinePixPerBlock = 256;
 
+// four consecutive channels of T <-> floats (bf16: one 8-byte access).  The Combine kernel uses 4-channel vectors for BOTH
+// dtypes: with 8 (the 16-byte bf16 vector) it needed 128 registers and ran at 18 % of the HBM roofline (ncu r02: 24 %
+// issue-active, two blocks per SM) against 68 % for the fp32 instantiation.
+template <typename T> struct Quad;
+template <> struct Quad<float> {
+  __device__ __forceinline__ static void load(const float* p, float (&v)[4]) { Vec<float>::load(p, v); }
+  __device__ __forceinline__ static void store(float* p, const float (&v)[4]) { Vec<float>::store(p, v); }
+};
+template <> struct Quad<__nv_bfloat16> {
+  __device__ __forceinline__ static void load(const __nv_bfloat16* p, float (&v)[4]) {
+    const uint2 t = __ldg(reinterpret_cast<const uint2*>(p));
+    v[0] = __uint_as_float(t.x << 16); v[1] = __uint_as_float(t.x & 0xffff0000u);
+    v[2] = __uint_as_float(t.y << 16); v[3] = __uint_as_float(t.y & 0xffff0000u);
+  }
+  __device__ __forceinline__ static void store(__nv_bfloat16* p, const float (&v)[4]) {
+    __nv_bfloat162 lo = __floats2bfloat162_rn(v[0], v[1]), hi = __floats2bfloat162_rn(v[2], v[3]);
+    *reinterpret_cast<uint2*>(p) = make_uint2(*reinterpret_cast<uint32_t*>(&lo), *reinterpret_cast<uint32_t*>(&hi));
+  }
+};
+
 template <typename T, int PC>
 __global__ void __launch_bounds__(256) combine_kernel(const T* __restrict__ h, const float* __restrict__ pyr,
                                                        const float* __restrict__ w, const float* __restrict__ bias,
-                                                       T* __restrict__ out, long long* __restrict__ stats, int HW, int C) {
-  constexpr int V = Vec<T>::N;
+                                                       T* __restrict__ out, long long* __restrict__ stats, int HW, int C,
+                                                       int pix_per_block) {
+  constexpr int V = 4;
   extern __shared__ float sred[];  // [rows][C][2]
   const int vpp = C / V;
   const int rows = blockDim.x / vpp;
   const int cv = threadIdx.x % vpp, prow = threadIdx.x / vpp;
   const int b = blockIdx.y;
-  const int p0 = blockIdx.x * kCombinePixPerBlock, p1 = min(HW, p0 + kCombinePixPerBlock);
+  const int p0 = blockIdx.x * pix_per_block, p1 = min(HW, p0 + pix_per_block);
   float wv[V][PC], bv[V];
 #pragma unroll
   for (int j = 0; j < V; ++j) {
@@ -1114,7 +1135,9 @@ __global__ void __launch_bounds__(256) combine_kernel(const T* __restrict__ h, c
   for (int j = 0; j < V; ++j) s[j] = q[j] = 0.f;
   const size_t base = static_cast<size_t>(b) * HW;
   if (prow < rows) {
-    constexpr int U = 4;  // independent pixel loads in flight per thread (a serial loop here is pure load latency)
+    // independent pixel loads in flight per thread (a serial loop here is pure load latency); bf16 moves half the bytes
+    // per load, so it keeps twice as many in flight
+    constexpr int U = DT<T>::kIsBf16 ? 8 : 4;
     for (int pb = p0 + prow; pb < p1; pb += U * rows) {
       float pv[U][PC], f[U][V];
 #pragma unroll
@@ -1128,7 +1151,7 @@ __global__ void __launch_bounds__(256) combine_kernel(const T* __restrict__ h, c
             const float2 t = __ldg(reinterpret_cast<const float2*>(pyr) + base + p);
             pv[u][0] = t.x; pv[u][1] = t.y;
           }
-          Vec<T>::load(h + (base + p) * C + cv * V, f[u]);
+          Quad<T>::load(h + (base + p) * C + cv * V, f[u]);
         }
       }
 #pragma unroll
@@ -1144,7 +1167,7 @@ __global__ void __launch_bounds__(256) combine_kernel(const T* __restrict__ h, c
             s[j] += f[u][j];
             q[j] = fmaf(f[u][j], f[u][j], q[j]);
           }
-          Vec<T>::store(out + (base + p) * C + cv * V, f[u]);
+          Quad<T>::store(out + (base + p) * C + cv * V, f[u]);
         }
       }
     }
@@ -1171,14 +1194,18 @@ __global__ void __launch_bounds__(256) combine_kernel(const T* __restrict__ h, c
 void launch_combine(int dt, const void* h, const float* pyr, const float* w, const float* bias, void* out, long long* stats,
                     int B, int HW, int C, int pc, cudaStream_t st) {
   DISPATCH_DT(dt, {
-    constexpr int V = Vec<T>::N;
+    constexpr int V = 4;
     const int vpp = C / V;
     const int threads = vpp >= 256 ? vpp : (256 / vpp) * vpp;
     const int rows = threads / vpp;
-    dim3 grid((HW + kCombinePixPerBlock - 1) / kCombinePixPerBlock, B);
+    // pixels per block: never a function of the batch, so the per-block partial sums -- and with them the fixed-point
+    // statistics -- do not depend on how many clips are in flight.  (1024-pixel blocks were measured: no gain in fp32,
+    // slower in bf16 -- 320 blocks are barely one wave.)
+    const int ppb = kCombinePixPerBlock;
+    dim3 grid((HW + ppb - 1) / ppb, B);
     const size_t sm = static_cast<size_t>(rows) * C * 2 * sizeof(float);
-    if (pc == 4) combine_kernel<T, 4><<<grid, threads, sm, st>>>((const T*)h, pyr, w, bias, (T*)out, stats, HW, C);
-    else combine_kernel<T, 2><<<grid, threads, sm, st>>>((const T*)h, pyr, w, bias, (T*)out, stats, HW, C);
+    if (pc == 4) combine_kernel<T, 4><<<grid, threads, sm, st>>>((const T*)h, pyr, w, bias, (T*)out, stats, HW, C, ppb);
+    else combine_kernel<T, 2><<<grid, threads, sm, st>>>((const T*)h, pyr, w, bias, (T*)out, stats, HW, C, ppb);
   });
 }
 
