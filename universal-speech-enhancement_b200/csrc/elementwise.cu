@@ -1135,9 +1135,8 @@ __global__ void __launch_bounds__(256) combine_kernel(const T* __restrict__ h, c
   for (int j = 0; j < V; ++j) s[j] = q[j] = 0.f;
   const size_t base = static_cast<size_t>(b) * HW;
   if (prow < rows) {
-    // independent pixel loads in flight per thread (a serial loop here is pure load latency); bf16 moves half the bytes
-    // per load, so it keeps twice as many in flight
-    constexpr int U = DT<T>::kIsBf16 ? 8 : 4;
+    constexpr int U = 4;  // independent pixel loads in flight per thread (a serial loop here is pure load latency; 8 costs
+                          // 128 registers and a block per SM: no gain)
     for (int pb = p0 + prow; pb < p1; pb += U * rows) {
       float pv[U][PC], f[U][V];
 #pragma unroll
