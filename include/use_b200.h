@@ -55,7 +55,8 @@ typedef struct use_config {
   int num_levels;       /* len(ch_mult) (7) */
   int ch_mult[8];       /* (1,1,2,2,2,2,2) */
   int num_res_blocks;   /* 2 */
-  int input_channels;   /* 4 = [Re x, Im x, Re Y, Im Y] (score network); 2 = [Re x, Im x] (discriminative network) */
+  int input_channels;   /* 4 = [Re x, Im x, Re Y, Im Y] (score network); 2 = [Re x, Im x] (discriminative network);
+                         * 6 = [x, Y, Y2] (condition="both", model_wrapper.py:43-46: noisy + GAN-denoised conditioning) */
   int act_dtype;        /* USE_DTYPE_* */
   int n_fft, hop;       /* 1022, 160 */
   float spec_factor;    /* 0.15 */
@@ -97,6 +98,10 @@ int use_engine_get_profile_ops(use_engine* e, char* csv, size_t cap);
  * evaluated by the host layer with torch so the embedding is bit-identical to the reference's). */
 int use_score_forward(use_engine* e, int B, int F, int T, const void* x, const void* Y, const float* t_host,
                       const float* gfp_host, void* score, void* workspace, size_t workspace_bytes, void* stream);
+
+/* The same for the 6-channel network (condition="both"): score = -net(cat[x, Y, Y2], t). */
+int use_score_forward2(use_engine* e, int B, int F, int T, const void* x, const void* Y, const void* Y2, const float* t_host,
+                       const float* gfp_host, void* score, void* workspace, size_t workspace_bytes, void* stream);
 
 /* out = +net(...): NCSNpp.forward itself (ncsnpp.py:324-501).  For the discriminative generator of the LSGAN stage
  * (GAN/generator/ncsnpp/model_wrapper.py:54,114-121: input_channels = 2, conditional = 0, scale_by_sigma = 0) pass
@@ -147,6 +152,8 @@ typedef struct use_sampler_opts {
   const void* cond;           /* optional device complex64 [B][F][T]: the network's conditioning spectrogram when it is not
                                * the SDE's y (condition="denoised" with sde_input="noisy" and vice versa,
                                * model_wrapper.py:281-299); NULL: the network is conditioned on Y */
+  const void* cond2;          /* 6-channel network (condition="both"): the second conditioning spectrogram (the
+                               * GAN-denoised one, model_wrapper.py:287-288); required there, ignored otherwise */
 } use_sampler_opts;
 int use_pc_sample_ex(use_engine* e, int B, int F, int T, const void* Y, void* x_state, void* x_mean, int N,
                      const float* t_host, const float* G_host, const float* gfp_host, float prior_std, const void* noise,

@@ -37,9 +37,14 @@ CASES = {
     # the GAN-refiner conditioning variants (batch["fake"] = the first stage's output; model_wrapper.py:281-299,321-328)
     "cond_denoised": dict(predictor="reverse_diffusion", corrector="none", corrector_steps=1, snr=0.5),
     "cond_denoised_sde_denoised": dict(predictor="reverse_diffusion", corrector="none", corrector_steps=1, snr=0.5),
+    # the reference ScoreModel's DEFAULT ctor: condition="both" (6-channel network input), sde_input="denoised"
+    "cond_both_sde_denoised": dict(predictor="reverse_diffusion", corrector="none", corrector_steps=1, snr=0.5),
+    "cond_both_sde_noisy": dict(predictor="reverse_diffusion", corrector="none", corrector_steps=1, snr=0.5),
 }
 COND = {"cond_denoised": ("denoised", "noisy", "enhanced"),
-        "cond_denoised_sde_denoised": ("denoised", "denoised", "fake_sde_enhanced")}
+        "cond_denoised_sde_denoised": ("denoised", "denoised", "fake_sde_enhanced"),
+        "cond_both_sde_denoised": ("both", "denoised", "fake_sde_enhanced"),
+        "cond_both_sde_noisy": ("both", "noisy", "enhanced")}
 
 
 def main():
@@ -47,7 +52,7 @@ def main():
     ScoreModel, _, _, _ = import_reference()
     from src.models.components.sgmse import sampling as RS  # type: ignore
 
-    sdL = O.make_state_dict(O.LARGE, seed=7)
+    sd4, sd6 = O.make_state_dict(O.LARGE, seed=7), O.make_state_dict(O.LARGE6, seed=7)
     B, L, N, seed = 2, 9600, 3, 42
     y = O.synthetic_clips(B, L)
     fake = 0.7 * y + 0.05 * O.synthetic_clips(B, L, seed=77)  # stand-in for the GAN stage's denoised output
@@ -58,6 +63,7 @@ def main():
                        loss_type="mse", n_fft=1022, hop_length=160, num_frames=512, window="hann", spec_factor=0.15,
                        spec_abs_exponent=0.5, sde_input=sde_input, predictor=kw["predictor"],
                        corrector=kw["corrector"]).eval()
+        sdL, net = (sd6, O.LARGE6) if condition == "both" else (sd4, O.LARGE)
         m.score_net.load_state_dict(sdL, strict=True)
         torch.manual_seed(seed)
         if name == "em_none":
@@ -73,8 +79,8 @@ def main():
             ref = m.sample({"perturbed": y.clone(), "fake": fake.clone()}, N=N)[key]
         else:
             ref = m.sample({"perturbed": y.clone()}, N=N, corrector_steps=kw["corrector_steps"], snr=kw["snr"])["enhanced"]
-        mine = O.sample(sdL, y, N, seed=seed, fake=fake if name in COND else None, condition=condition, sde_input=sde_input,
-                        **kw)
+        mine = O.sample(sdL, y, N, seed=seed, net=net, fake=fake if name in COND else None, condition=condition,
+                        sde_input=sde_input, **kw)
         d = float((ref - mine).abs().max())
         print(f"{name}: max|ref-oracle| = {d}", flush=True)
         assert d == 0.0, name

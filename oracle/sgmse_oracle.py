@@ -90,6 +90,7 @@ class SdeCfg:
 LARGE = NetCfg()
 TINY = NetCfg(nf=64, ch_mult=(1, 2), num_res_blocks=1)
 # NCSNpp(discriminative=True) with the class defaults: the LSGAN generator (GAN/generator/ncsnpp/model_wrapper.py:54)
+LARGE6 = NetCfg(nf=128, ch_mult=(1, 1, 2, 2, 2, 2, 2), num_res_blocks=2, input_channels=6)  # condition="both"
 GAN_G = NetCfg(nf=128, ch_mult=(1, 2, 2, 2), num_res_blocks=1, input_channels=2, conditional=False, scale_by_sigma=False)
 GAN_TINY = NetCfg(nf=64, ch_mult=(1, 2), num_res_blocks=1, input_channels=2, conditional=False, scale_by_sigma=False)
 
@@ -538,7 +539,7 @@ def sample(sd: Dict[str, Tensor], y: Tensor, N: int, noise: Optional[Tensor] = N
         T_orig = y.size(1)
         Y = pad_spec(spec_fwd(stft(y, spec), spec).unsqueeze(1))
         Yd = pad_spec(spec_fwd(stft(fake, spec), spec).unsqueeze(1)) if fake is not None else None
-        cond = Yd if (condition == "denoised" and Yd is not None) else Y
+        cond = [Yd] if (condition == "denoised" and Yd is not None) else ([Y, Yd] if condition == "both" else [Y])
         Y = Yd if (sde_input == "denoised" and Yd is not None) else Y
         if noise is None:
             per = draws_per_step(sampler_kw.get("predictor", "reverse_diffusion"), sampler_kw.get("corrector", "none"),
@@ -546,7 +547,7 @@ def sample(sd: Dict[str, Tensor], y: Tensor, N: int, noise: Optional[Tensor] = N
             noise = draw_noise(tuple(Y.shape), N * per, seed, dtype=Y.dtype)
 
         def score_fn(x, t):
-            return -ncsnpp_forward(sd, net, torch.cat([x, cond], dim=1), t)
+            return -ncsnpp_forward(sd, net, torch.cat([x] + cond, dim=1), t)
 
         xm = pc_sample_spec(score_fn, Y, N, noise, sde, **sampler_kw)
         out = istft(spec_back(xm.squeeze(1), spec), spec, T_orig)

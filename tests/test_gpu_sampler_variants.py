@@ -7,6 +7,8 @@ oracle/make_golden_variants.py, which also pins the oracle restatement bit-exact
   euler_maruyama   + none        (predictors.py:40-53 over RSDE.rsde_parts, sdes.py:128-150)
   condition="denoised" (+ sde_input "noisy" / "denoised"): the network conditioned on batch["fake"], the SDE anchored on
                                  the noisy or the denoised spectrogram (model_wrapper.py:281-299,321-328)
+  condition="both" (the reference ScoreModel's default ctor): 6-channel network input cat[x, Y, Y_denoised]
+                                 (model_wrapper.py:43-46,287-288), run as a 4 + 2 channel pyramid pair on the engine
 
 Explicit noise in the reference's draw order (prior; per outer step the corrector's inner draws, then the predictor's).
 Tolerances as for the default sampler: waveform rel-L2 <= 2e-3 (fp32 / TF32), <= 2e-2 (bf16).
@@ -24,14 +26,15 @@ from util import GOLDEN, rel_l2
 pytestmark = pytest.mark.gpu
 
 TOL = {"fp32": 2e-3, "bf16": 2e-2}
-CASES = ["rd_langevin", "rd_ald", "em_none", "cond_denoised", "cond_denoised_sde_denoised"]
+CASES = ["rd_langevin", "rd_ald", "em_none", "cond_denoised", "cond_denoised_sde_denoised", "cond_both_sde_denoised",
+         "cond_both_sde_noisy"]
 
 
 def _model(dtype, weight_seed, predictor="reverse_diffusion", corrector="none", condition="noisy", sde_input="noisy", **kw):
     m = use_b200.ScoreModel(backbone="ncsnpplarge", sde="ouve", t_eps=3e-2, condition=condition, sde_input=sde_input,
                             n_fft=1022, hop_length=160, num_frames=512, dtype=dtype, predictor=predictor,
                             corrector=corrector, **kw)
-    m.score_net.load_state_dict(O.make_state_dict(O.LARGE, seed=weight_seed), strict=True)
+    m.score_net.load_state_dict(O.make_state_dict(O.LARGE6 if condition == "both" else O.LARGE, seed=weight_seed), strict=True)
     return m
 
 

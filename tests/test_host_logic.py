@@ -77,7 +77,11 @@ def test_config_surface_composes_and_instantiates():
 
 def test_unsupported_options_fail_loudly():
     with pytest.raises(NotImplementedError):
-        use_b200.ScoreModel(backbone="ncsnpplarge", condition="both", sde_input="denoised")
+        use_b200.ScoreModel(backbone="ncsnpplarge", condition="neither", sde_input="denoised")
+    both = use_b200.ScoreModel(backbone="ncsnpplarge")  # the reference's default ctor: condition="both" -> 6 input channels
+    assert both.score_net.input_channels == 6 and tuple(both.score_net.all_modules[3].weight.shape) == (128, 6, 3, 3)
+    sd6 = O.make_state_dict(O.LARGE6)  # names / shapes validated against the reference by oracle/make_golden_variants.py
+    assert {k: tuple(v.shape) for k, v in both.score_net.state_dict().items()} == {k: tuple(v.shape) for k, v in sd6.items()}
     with pytest.raises(ValueError, match="unknown"):
         use_b200.ScoreModel(backbone="does_not_exist", condition="noisy", sde_input="noisy")
     with pytest.raises(NotImplementedError):

@@ -131,9 +131,9 @@ class NCSNpp(nn.Module):
                 raise NotImplementedError(f"NCSNpp(B200): {k}={v!r} is not supported on this path (only {want!r})")
         if tuple(attn_resolutions) != (0,):
             raise NotImplementedError("NCSNpp(B200): only attn_resolutions=(0,) (bottleneck attention) is supported")
-        if input_channels != (2 if self.discriminative else 4):
-            raise NotImplementedError("NCSNpp(B200): only condition='noisy' (4 input channels) or the discriminative "
-                                      "2-channel generator are supported")
+        if input_channels not in ((2,) if self.discriminative else (4, 6)):
+            raise NotImplementedError("NCSNpp(B200): 4 input channels (one conditioning spectrogram), 6 (condition='both') "
+                                      "or the discriminative 2-channel generator are supported")
         self.conditional = not self.discriminative
         self.scale_by_sigma = not self.discriminative
         self.nf, self.ch_mult, self.num_res_blocks = nf, tuple(ch_mult), num_res_blocks
@@ -210,13 +210,15 @@ class NCSNpp(nn.Module):
         return torch.cat([torch.sin(x_proj), torch.cos(x_proj)], dim=-1).contiguous()
 
     def forward(self, x: torch.Tensor, time_cond: torch.Tensor = None) -> torch.Tensor:
-        """x: complex64 [B, 2, F, T] = cat[x_t, Y] on a CUDA device (discriminative: [B, 1, F, T], no time);
-        returns complex64 [B, 1, F, T]."""
+        """x: complex64 [B, 2, F, T] = cat[x_t, Y] (or [B, 3, F, T] = cat[x_t, Y, Y2], 6 input channels) on a CUDA device
+        (discriminative: [B, 1, F, T], no time); returns complex64 [B, 1, F, T]."""
         if not x.is_cuda:
             raise RuntimeError("NCSNpp(B200) runs on CUDA tensors only; there is no CPU path")
         if self.discriminative:
             return self.engine(x.device).net(x[:, 0].contiguous(), None, None).unsqueeze(1)
         xt, Y = x[:, 0].contiguous(), x[:, 1].contiguous()
+        if self.input_channels == 6:
+            return -self.engine(x.device).score(xt, Y, time_cond, Y2=x[:, 2].contiguous()).unsqueeze(1)
         return self.engine(x.device).net(xt, Y, time_cond).unsqueeze(1)
 
 
@@ -291,8 +293,8 @@ class _Engine:
             self._ws_key = key
         return self._ws
 
-    def score(self, x: torch.Tensor, Y: torch.Tensor, t: torch.Tensor) -> torch.Tensor:
-        """-net(cat[x, Y], t) for complex64 [B, F, T] CUDA tensors."""
+    def score(self, x: torch.Tensor, Y: torch.Tensor, t: torch.Tensor, Y2: torch.Tensor = None) -> torch.Tensor:
+        """-net(cat[x, Y (, Y2)], t) for complex64 [B, F, T] CUDA tensors (Y2: the 6-channel network's second conditioning)."""
         assert x.dtype == torch.complex64 and Y.dtype == torch.complex64 and x.shape == Y.shape and x.dim() == 3
         B, F, T = x.shape
         x, Y = x.contiguous(), Y.contiguous()
@@ -301,9 +303,16 @@ class _Engine:
         out = torch.empty_like(x)
         with torch.cuda.device(self.device):
             ws = self.workspace(B, F, T)
-            _lib.check(self.L.use_score_forward(self.h, B, F, T, x.data_ptr(), Y.data_ptr(), t_host.data_ptr(),
-                                                gfp.data_ptr(), out.data_ptr(), ws.data_ptr(), ws.numel(),
-                                                _lib.stream_ptr()), "use_score_forward")
+            if Y2 is not None:
+                Y2 = Y2.to(torch.complex64).contiguous()
+                assert Y2.shape == x.shape
+                _lib.check(self.L.use_score_forward2(self.h, B, F, T, x.data_ptr(), Y.data_ptr(), Y2.data_ptr(),
+                                                     t_host.data_ptr(), gfp.data_ptr(), out.data_ptr(), ws.data_ptr(),
+                                                     ws.numel(), _lib.stream_ptr()), "use_score_forward2")
+            else:
+                _lib.check(self.L.use_score_forward(self.h, B, F, T, x.data_ptr(), Y.data_ptr(), t_host.data_ptr(),
+                                                    gfp.data_ptr(), out.data_ptr(), ws.data_ptr(), ws.numel(),
+                                                    _lib.stream_ptr()), "use_score_forward")
         return out
 
     def net(self, x: torch.Tensor, Y, t) -> torch.Tensor:
@@ -357,7 +366,8 @@ class _Engine:
 
     def pc_sample(self, Y: torch.Tensor, ts: torch.Tensor, G: torch.Tensor, prior_std: float, noise=None, seed: int = 0,
                   clip0: int = 0, predictor="reverse_diffusion", corrector="none", corrector_steps=1, snr=0.5,
-                  probability_flow=False, denoise=True, g=None, ald_step=None, trace=None, x_init=None, dt_steps=0, cond=None):
+                  probability_flow=False, denoise=True, g=None, ald_step=None, trace=None, x_init=None, dt_steps=0, cond=None,
+                  cond2=None):
         """The fused predictor-corrector loop (use_pc_sample_ex); returns (x_result, x_state), complex64 [B, F, T]:
         x_result = the noise-free mean of the last step (denoise) or the state."""
         assert Y.dtype == torch.complex64 and Y.dim() == 3 and Y.is_cuda
@@ -403,6 +413,11 @@ class _Engine:
             assert tuple(cond.shape) == (B, F, T) and cond.is_cuda
             keep.append(cond)
             o.cond = cond.data_ptr()
+        if cond2 is not None:
+            cond2 = cond2.to(torch.complex64).contiguous()
+            assert tuple(cond2.shape) == (B, F, T) and cond2.is_cuda
+            keep.append(cond2)
+            o.cond2 = cond2.data_ptr()
         with torch.cuda.device(self.device):
             ws = self.workspace(B, F, T)
             _lib.check(self.L.use_pc_sample_ex(self.h, B, F, T, Y.data_ptr(), x_state.data_ptr(), x_mean.data_ptr(), N,

@@ -183,7 +183,8 @@ struct Program {
   std::vector<TcConvPlan*> plans;
   std::vector<HeadPlan*> heads;
   size_t stats_bytes = 0;
-  size_t pyramid_off = 0;  // final fp32 [B][F][T][4]
+  size_t pyramid_off = 0;   // final fp32 pyramid [B][F][T][4 or 2]
+  size_t pyramid2_off = 0;  // 6-channel networks: channels 4, 5 as a second fp32 [B][F][T][2] tensor
   char* base = nullptr;
   // the launch sequence of one evaluation as a CUDA graph (captured on first use, replayed every step)
   cudaGraphExec_t graph = nullptr;
@@ -380,12 +381,19 @@ static int pack_all(use_engine* e) {
           pack_conv_weight(dt, wp.data(), m.cout, ck, 3, e->blob.data() + off);
           e->off[p + ".wtc"] = off;
         }
-        if (m.cout == c.input_channels && head_tc_supported(dt, m.cin, m.cout) && !e->x3) {
-          // pyramid head C -> pc: the nine taps folded into the MMA's N dimension (head_tc.cuh), rows tap * pc + co
+        if (m.cout == c.input_channels && head_tc_supported(dt, m.cin, m.cout == 6 ? 4 : m.cout) && !e->x3) {
+          // pyramid head C -> pc: the nine taps folded into the MMA's N dimension (head_tc.cuh), rows tap * pc + co.
+          // A 6-channel head (condition="both") is a 4-channel head (rows 0..3) + a 2-channel head (rows 4, 5)
           const HostTensor* t = getw(e, p + ".weight", {m.cout, m.cin, 3, 3});
+          const int pc0 = m.cout == 6 ? 4 : m.cout;
           size_t off = bw.reserve((size_t)48 * m.cin * es);
-          pack_head_weight(dt, t->data.data(), m.cout, m.cin, e->blob.data() + off);
+          pack_head_weight(dt, t->data.data(), pc0, m.cin, e->blob.data() + off);
           e->off[p + ".whd"] = off;
+          if (m.cout == 6) {
+            size_t off2 = bw.reserve((size_t)48 * m.cin * es);
+            pack_head_weight(dt, t->data.data() + (size_t)4 * m.cin * 9, 2, m.cin, e->blob.data() + off2);
+            e->off[p + ".whd2"] = off2;
+          }
         }
         break;
       }
@@ -395,6 +403,16 @@ static int pack_all(use_engine* e) {
       }
       case K_COMBINE: {
         if (putf(p + ".w", p + ".Conv_0.weight", {m.cout, m.cin, 1, 1}) || putf(p + ".b", p + ".Conv_0.bias", {m.cout})) return 1;
+        if (m.cin == 6) {  // 6 input channels = a [C][4] and a [C][2] matrix for the 4- / 2-channel Combine kernels
+          const HostTensor* t = getw(e, p + ".Conv_0.weight", {m.cout, m.cin, 1, 1});
+          std::vector<float> w4((size_t)m.cout * 4), w2((size_t)m.cout * 2);
+          for (int o = 0; o < m.cout; ++o) {
+            for (int k = 0; k < 4; ++k) w4[(size_t)o * 4 + k] = t->data[(size_t)o * 6 + k];
+            for (int k = 0; k < 2; ++k) w2[(size_t)o * 2 + k] = t->data[(size_t)o * 6 + 4 + k];
+          }
+          e->off[p + ".w4"] = bw.put(w4.data(), w4.size() * 4);
+          e->off[p + ".w2"] = bw.put(w2.data(), w2.size() * 4);
+        }
         break;
       }
       case K_ATTN: {
@@ -755,7 +773,12 @@ struct Builder {
       hs.push_back(h0);
       idx = e->in_conv_idx + 1;
     }
-    size_t pyr_off = (size_t)-1;  // fp32 input pyramid of the current level (arena), level 0 = xr
+    // A 6-channel pyramid (condition="both") is kept as a 4-channel + a 2-channel tensor: every pyramid op is channel-wise
+    // (FIR, sums) or linear in the channels (Combine, heads, output layer), so the 4- / 2-channel kernels do the work
+    const int nparts = npc == 6 ? 2 : 1;
+    const int part_pc[2] = {npc == 6 ? 4 : npc, 2};
+    const int part_c0[2] = {0, 4};
+    size_t pyr_off[2] = {(size_t)-1, (size_t)-1};  // fp32 input pyramid of the current level (arena), level 0 = xr
     int pH = F, pW = T;
     for (int l = 0; l < L; ++l) {
       for (int r = 0; r < c.num_res_blocks; ++r) {
@@ -765,34 +788,40 @@ struct Builder {
       if (l != L - 1) {
         Act h = resblock(idx++, hs.back(), nullptr);
         // input_pyramid = FIR-down(input_pyramid); h = Conv1x1(input_pyramid) + h  (ncsnpp.py:404-406)
-        size_t np = new_f32((size_t)B * (pH / 2) * (pW / 2) * npc);
+        size_t np[2] = {(size_t)-1, (size_t)-1};
+        for (int k = 0; k < nparts; ++k) np[k] = new_f32((size_t)B * (pH / 2) * (pW / 2) * part_pc[k]);
+        // the Combine kernel also produces the GroupNorm statistics of its output (the next ResBlock's GroupNorm_0)
+        h.stats_off = stats_top;
         if (!dry) {
-          const float* src = (pyr_off == (size_t)-1) ? xr : (const float*)ws(pyr_off);
-          float* dst = (float*)ws(np);
-          const int H = pH, W = pW;
           const std::string p = "all_modules." + std::to_string(idx);
-          const float *cw = wf(p + ".w"), *cb = wf(p + ".b");
           void* hp = ws(h.off);
-          const int HW = h.H * h.W, C = h.C;
-          // the Combine kernel also produces the GroupNorm statistics of its output (the next ResBlock's GroupNorm_0)
-          h.stats_off = stats_top;
+          const int HW = h.H * h.W, C = h.C, H = pH, W = pW;
           long long* hst = stats_ptr(h.stats_off);
-          emit([=](cudaStream_t s) {
-            launch_fir4_down(src, dst, Bn, H, W, npc, s);
-            launch_combine(dt, hp, dst, cw, cb, hp, hst, Bn, HW, C, npc, s);
-          }, TAG_SMALL_CONV, 2, 2.0 * Bn * HW * C * 4, 2.0 * Bn * HW * C * es());
-        } else {
-          h.stats_off = stats_top;
+          for (int k = 0; k < nparts; ++k) {
+            const float* src = (pyr_off[k] == (size_t)-1) ? xr + (size_t)B * F * T * part_c0[k] : (const float*)ws(pyr_off[k]);
+            float* dst = (float*)ws(np[k]);
+            const int pc = part_pc[k];
+            const float* cw = npc == 6 ? wf(k == 0 ? p + ".w4" : p + ".w2") : wf(p + ".w");
+            const float* cb = k == 0 ? wf(p + ".b") : wf("zeros");      // (bias + w4 p4 + h) + w2 p2
+            long long* st_k = k == nparts - 1 ? hst : nullptr;          // statistics of the FINAL sum only
+            emit([=](cudaStream_t s) {
+              launch_fir4_down(src, dst, Bn, H, W, pc, s);
+              launch_combine(dt, hp, dst, cw, cb, hp, st_k, Bn, HW, C, pc, s);
+            }, TAG_SMALL_CONV, 2, 2.0 * Bn * HW * C * pc, 2.0 * Bn * HW * C * es());
+          }
         }
         stats_top += (size_t)B * h.C * 2 * sizeof(long long);
-        if (pyr_off != (size_t)-1) arena.release(pyr_off);
-        pyr_off = np;
+        for (int k = 0; k < nparts; ++k) {
+          if (pyr_off[k] != (size_t)-1) arena.release(pyr_off[k]);
+          pyr_off[k] = np[k];
+        }
         pH /= 2; pW /= 2;
         idx++;
         hs.push_back(h);
       }
     }
-    if (pyr_off != (size_t)-1) arena.release(pyr_off);
+    for (int k = 0; k < nparts; ++k)
+      if (pyr_off[k] != (size_t)-1) arena.release(pyr_off[k]);
     // bottleneck
     Act h = resblock(idx++, hs.back(), nullptr);
     {
@@ -806,7 +835,7 @@ struct Builder {
       h = r;
     }
     // up path
-    size_t opyr = (size_t)-1;  // fp32 output pyramid [B][H][W][4]
+    size_t opyr[2] = {(size_t)-1, (size_t)-1};  // fp32 output pyramid [B][H][W][4 or 2] (+ [B][H][W][2] for 6 channels)
     for (int l = L - 1; l >= 0; --l) {
       for (int r = 0; r < c.num_res_blocks + 1; ++r) {
         Act skip = hs.back();
@@ -816,39 +845,44 @@ struct Builder {
         free_act(skip);
         h = o;
       }
-      // pyramid: GN -> SiLU -> conv3x3 C->4 (+ FIR-up of the previous pyramid)   (ncsnpp.py:440-461)
+      // pyramid: GN -> SiLU -> conv3x3 C->pc (+ FIR-up of the previous pyramid)   (ncsnpp.py:440-461)
       {
         const std::string pg = "all_modules." + std::to_string(idx), pc = "all_modules." + std::to_string(idx + 1);
         Act a = new_act(h.C, h.H, h.W);
         const bool head_tc = e->off.count(pc + ".whd") != 0;
         gn_apply(h, nullptr, e->off.at(pg + ".g"), e->off.at(pg + ".b"), 0, true, head_tc, a, nullptr);
-        size_t np = new_f32((size_t)B * h.H * h.W * npc);
+        size_t np[2] = {(size_t)-1, (size_t)-1};
+        for (int k = 0; k < nparts; ++k) np[k] = new_f32((size_t)B * h.H * h.W * part_pc[k]);
         if (head_tc) {
-          if (!dry) {
+          for (int k = 0; k < nparts && !dry; ++k) {
             char msg[512];
-            HeadPlan* hp = head_tc_plan_create(e->dt, ws(a.off), wt(e->off.at(pc + ".whd")), wf(pc + ".b"),
-                                               opyr == (size_t)-1 ? nullptr : (const float*)ws(opyr), (float*)ws(np), B, h.H,
-                                               h.W, h.C, npc, e->num_sms, msg, sizeof(msg));
+            HeadPlan* hp = head_tc_plan_create(e->dt, ws(a.off), wt(e->off.at(k == 0 ? pc + ".whd" : pc + ".whd2")),
+                                               wf(pc + ".b") + part_c0[k],
+                                               opyr[k] == (size_t)-1 ? nullptr : (const float*)ws(opyr[k]), (float*)ws(np[k]), B,
+                                               h.H, h.W, h.C, part_pc[k], e->num_sms, msg, sizeof(msg));
             if (!hp) { err = fail("%s", msg); return; }
             prog->heads.push_back(hp);
             const double px = (double)B * h.H * h.W;
-            emit([=](cudaStream_t s) { head_tc_launch(hp, s); }, TAG_SMALL_CONV, 1, 2.0 * px * h.C * 9 * npc,
-                 px * (h.C * es() + 4.0 * npc));
+            emit([=](cudaStream_t s) { head_tc_launch(hp, s); }, TAG_SMALL_CONV, 1, 2.0 * px * h.C * 9 * part_pc[k],
+                 px * (h.C * es() + 4.0 * part_pc[k]));
           }
         } else if (npc != 4) {
-          err = fail("pyramid head with %d channels needs C %% %d == 0", npc, 128 / (int)es());
+          err = fail("pyramid head with %d channels needs the tensor-core head (C %% %d == 0, not the fp32x3 mode)", npc,
+                     128 / (int)es());
         } else if (!dry) {
           const void* ap = ws(a.off);
           const float *w = wf(pc + ".w"), *b = wf(pc + ".b");
-          const float* prev = (opyr == (size_t)-1) ? nullptr : (const float*)ws(opyr);
-          float* o = (float*)ws(np);
+          const float* prev = (opyr[0] == (size_t)-1) ? nullptr : (const float*)ws(opyr[0]);
+          float* o = (float*)ws(np[0]);
           const int H = h.H, W = h.W, C = h.C;
           emit([=](cudaStream_t s) { launch_conv_out4(dt, ap, w, b, prev, o, Bn, H, W, C, s); }, TAG_SMALL_CONV, 1,
                2.0 * Bn * H * W * C * 36, (double)Bn * H * W * (C * es() + 16));
         }
         free_act(a);
-        if (opyr != (size_t)-1) arena.release(opyr);
-        opyr = np;
+        for (int k = 0; k < nparts; ++k) {
+          if (opyr[k] != (size_t)-1) arena.release(opyr[k]);
+          opyr[k] = np[k];
+        }
         idx += 2;
       }
       if (l != 0) {
@@ -858,7 +892,10 @@ struct Builder {
       }
     }
     free_act(h);
-    if (!dry) prog->pyramid_off = e->head.arena + opyr;
+    if (!dry) {
+      prog->pyramid_off = e->head.arena + opyr[0];
+      prog->pyramid2_off = nparts > 1 ? e->head.arena + opyr[1] : 0;
+    }
     if (!dry) prog->stats_bytes = stats_top;
     if ((size_t)idx != e->mods.size() || !hs.empty()) err = fail("internal: module walk mismatch (%d of %zu)", idx, e->mods.size());
   }
@@ -1019,7 +1056,7 @@ const char* use_last_error(void) { return g_err; }
 
 use_engine* use_engine_create(const use_config* cfg) {
   if (!cfg) { fail("null config"); return nullptr; }
-  if (cfg->num_levels < 1 || cfg->num_levels > 8 || cfg->nf <= 0 || (cfg->input_channels != 4 && cfg->input_channels != 2) ||
+  if (cfg->num_levels < 1 || cfg->num_levels > 8 || cfg->nf <= 0 || (cfg->input_channels != 4 && cfg->input_channels != 2 && cfg->input_channels != 6) ||
       (cfg->act_dtype != USE_DTYPE_F32 && cfg->act_dtype != USE_DTYPE_BF16 && cfg->act_dtype != USE_DTYPE_F32X3)) {
     fail("unsupported config (levels=%d nf=%d input_channels=%d dtype=%d)", cfg->num_levels, cfg->nf,
          cfg->input_channels, cfg->act_dtype);
@@ -1029,6 +1066,11 @@ use_engine* use_engine_create(const use_config* cfg) {
   e->cfg = *cfg;
   e->x3 = cfg->act_dtype == USE_DTYPE_F32X3;
   e->dt = e->x3 ? (int)kF32 : cfg->act_dtype;
+  if (e->x3 && cfg->input_channels == 6) {
+    fail("the fp32x3 parity mode is not built for the 6-channel (condition=\"both\") network");
+    delete e;
+    return nullptr;
+  }
   build_mods(e);
   for (auto& m : e->mods) {
     if (m.kind == K_RB) {
@@ -1120,10 +1162,12 @@ int use_engine_set_option(use_engine* e, const char* key, int value) {
 
 // one evaluation of the network; sign = -1 gives the score (-net), +1 the raw network output
 static int net_forward(use_engine* e, int B, int F, int T, const void* x, const void* Y, const float* t_host,
-                       const float* gfp_host, void* out, float sign, void* workspace, size_t workspace_bytes, void* stream) {
+                       const float* gfp_host, void* out, float sign, void* workspace, size_t workspace_bytes, void* stream,
+                       const void* Y2 = nullptr) {
   if (!e || !x || !out || !workspace) return fail("null argument");
   const bool cond = e->cfg.conditional != 0;
-  if (e->cfg.input_channels == 4 && !Y) return fail("the conditioning spectrogram Y is required (input_channels = 4)");
+  if (e->cfg.input_channels >= 4 && !Y) return fail("the conditioning spectrogram Y is required (input_channels >= 4)");
+  if (e->cfg.input_channels == 6 && !Y2) return fail("the second conditioning spectrogram is required (input_channels = 6)");
   if ((cond || e->cfg.scale_by_sigma) && (!t_host || (cond && !gfp_host))) return fail("time inputs are required");
   std::shared_ptr<Program> pin = get_program(e, B, F, T, workspace, workspace_bytes);
   if (!pin) return 1;
@@ -1132,11 +1176,12 @@ static int net_forward(use_engine* e, int B, int F, int T, const void* x, const 
   if (t_host) cudaMemcpyAsync(p->base + e->head.t, t_host, (size_t)B * 4, cudaMemcpyHostToDevice, st);
   if (cond) cudaMemcpyAsync(p->base + e->head.gfp, gfp_host, (size_t)B * 2 * e->cfg.nf * 4, cudaMemcpyHostToDevice, st);
   const size_t per = (size_t)F * T;
-  launch_pack_input(e->dt, e->cfg.input_channels, (const float2*)x, (const float2*)Y, (float*)(p->base + e->head.xr),
-                    p->base + e->head.xpad, per * B, st);
+  launch_pack_input(e->dt, e->cfg.input_channels, (const float2*)x, (const float2*)Y, (const float2*)Y2,
+                    (float*)(p->base + e->head.xr), p->base + e->head.xpad, per * B, st);
   run_network(e, p, st, (const float*)(p->base + e->head.gfp), 2 * e->cfg.nf, false);  // caller's stream: plain launches
   StepArgs a{};
   a.pyramid = (const float*)(p->base + p->pyramid_off);
+  a.pyramid2 = (const float*)(p->base + p->pyramid2_off);
   a.pc = e->cfg.input_channels;
   a.out_sign = sign;
   a.t = e->cfg.scale_by_sigma ? (const float*)(p->base + e->head.t) : nullptr;
@@ -1157,6 +1202,11 @@ int use_score_forward(use_engine* e, int B, int F, int T, const void* x, const v
   return net_forward(e, B, F, T, x, Y, t_host, gfp_host, score, -1.0f, workspace, workspace_bytes, stream);
 }
 
+int use_score_forward2(use_engine* e, int B, int F, int T, const void* x, const void* Y, const void* Y2, const float* t_host,
+                       const float* gfp_host, void* score, void* workspace, size_t workspace_bytes, void* stream) {
+  return net_forward(e, B, F, T, x, Y, t_host, gfp_host, score, -1.0f, workspace, workspace_bytes, stream, Y2);
+}
+
 int use_net_forward(use_engine* e, int B, int F, int T, const void* x, const void* Y, const float* t_host,
                     const float* gfp_host, void* out, void* workspace, size_t workspace_bytes, void* stream) {
   return net_forward(e, B, F, T, x, Y, t_host, gfp_host, out, 1.0f, workspace, workspace_bytes, stream);
@@ -1168,7 +1218,7 @@ int use_train_forward(use_engine* e, int B, int F, int T, const void* X0, const 
   if (!e || !X0 || !Y || !t_host || !gfp_host || !coef_host || !x_t || !loss || !workspace) return fail("null argument");
   if (loss_type != 0 && loss_type != 1) return fail("loss_type must be 0 (mse) or 1 (mae)");
   if (e->cfg.input_channels != 4 || !e->cfg.conditional || !e->cfg.scale_by_sigma)
-    return fail("use_train_forward needs the noise-conditional score network");
+    return fail("use_train_forward needs the 4-channel noise-conditional score network");
   cudaStream_t st = (cudaStream_t)stream;
   const size_t per = (size_t)F * T;
   // plan first: the head offsets (score buffer, reduction scratch, per-sample coefficient slot) belong to this shape
@@ -1196,8 +1246,8 @@ int use_pc_sample_ex(use_engine* e, int B, int F, int T, const void* Y, void* x_
                      void* stream) {
   if (!e || !Y || !x_state || !x_mean || !t_host || !G_host || !gfp_host || !workspace) return fail("null argument");
   if (N < 1 || N > kMaxSteps) return fail("N must be in [1, %d]", kMaxSteps);
-  if (e->cfg.input_channels != 4 || !e->cfg.conditional || !e->cfg.scale_by_sigma)
-    return fail("use_pc_sample needs the noise-conditional score network (input_channels=4, conditional, scale_by_sigma)");
+  if ((e->cfg.input_channels != 4 && e->cfg.input_channels != 6) || !e->cfg.conditional || !e->cfg.scale_by_sigma)
+    return fail("use_pc_sample needs the noise-conditional score network (input_channels=4 or 6, conditional, scale_by_sigma)");
   use_sampler_opts o{};
   o.predictor = USE_PRED_REVERSE_DIFFUSION;
   o.corrector = USE_CORR_NONE;
@@ -1209,6 +1259,7 @@ int use_pc_sample_ex(use_engine* e, int B, int F, int T, const void* Y, void* x_
   if (cs < 0) return fail("corrector_steps must be >= 0");
   if (o.predictor == USE_PRED_EULER_MARUYAMA && !o.g_host) return fail("euler_maruyama needs the diffusion table g_host[N]");
   if (o.corrector == USE_CORR_ALD && cs > 0 && !o.ald_step_host) return fail("ald needs the step-size table ald_step_host[N]");
+  if (e->cfg.input_channels == 6 && !o.cond2) return fail("the 6-channel network needs the second conditioning spectrogram (cond2)");
   const int pe = o.predictor == USE_PRED_NONE ? 0 : 1;
   const int draws_per_step = cs + pe;  // normal draws per outer step, in the reference's order: corrector steps, predictor
   cudaStream_t st = (cudaStream_t)stream;
@@ -1267,11 +1318,13 @@ int use_pc_sample_ex(use_engine* e, int B, int F, int T, const void* Y, void* x_
       const float* t_dev = (const float*)(base + e->head.sched) + i;
       const float* gfp_dev = (const float*)(base + e->head.sched) + N + (size_t)i * nf2;
       auto evaluate = [&](StepArgs& a) {  // one network evaluation at t_i from the current state + the fused tail
-        launch_pack_input(e->dt, 4, (const float2*)x_state + off, (const float2*)(o.cond ? o.cond : Y) + off,
-                          (float*)(base + e->head.xr), base + e->head.xpad, n, gs[g]);
+        launch_pack_input(e->dt, e->cfg.input_channels, (const float2*)x_state + off, (const float2*)(o.cond ? o.cond : Y) + off,
+                          o.cond2 ? (const float2*)o.cond2 + off : nullptr, (float*)(base + e->head.xr), base + e->head.xpad,
+                          n, gs[g]);
         run_network(e, p, gs[g], gfp_dev, 0, own_streams);
         a.pyramid = (const float*)(base + p->pyramid_off);
-        a.pc = 4;
+        a.pyramid2 = (const float*)(base + p->pyramid2_off);
+        a.pc = e->cfg.input_channels;
         a.out_sign = -1.0f;
         a.t = t_dev;
         a.t_bstride = 0;

@@ -62,16 +62,19 @@ void launch_split_tf32(const float* x, int Ct, int c0, int C, float* hi, float* 
 // ---- network input / output, SDE arithmetic -------------------------------------------------------
 // xr[b][f][t][:] = 2*[Re x, Im x, Re Y, Im Y] - 1 (fp32 x4); xpad (optional): the same 4 values as act-dtype MMA
 // operands zero-padded to one 128-byte channel chunk per pixel (input of the tcgen05 input convolution)
-void launch_pack_input(int dt, int pc, const float2* x, const float2* Y, float* xr, void* xpad, size_t n, cudaStream_t st);
+// pc = 6 (condition="both"): Y2 = the second conditioning spectrogram; xr = a [n][4] block followed by a [n][2] block
+void launch_pack_input(int dt, int pc, const float2* x, const float2* Y, const float2* Y2, float* xr, void* xpad, size_t n,
+                       cudaStream_t st);
 
 enum StepMode { kStepReverseDiffusion = 0, kStepEulerMaruyama = 1 };
 struct StepArgs {
-  const float* pyramid;  // fp32 [B][F][T][pc]
-  int pc;                // pyramid channels: 4 (score network) or 2 (discriminative network)
+  const float* pyramid;  // fp32 [B][F][T][pc]  (pc = 6: the first four channels, [B][F][T][4])
+  const float* pyramid2; // pc = 6 only: channels 4, 5 as fp32 [B][F][T][2]
+  int pc;                // pyramid channels: 4 (score network), 2 (discriminative network) or 6 (condition="both")
   float out_sign;        // -1: score = -net(x) (ScoreModel.forward_score); +1: the raw network output
   const float* t;        // time value of sample b at t[b * t_bstride] (divides the pyramid: scale_by_sigma) or nullptr
   int t_bstride;         // 1 = per-sample times, 0 = one batch-uniform time
-  const float* ow;       // output_layer weight [2][pc]
+  const float* ow;       // output_layer weight [2][pc] (pc <= 6)
   const float* ob;       // output_layer bias [2]
   float2* score;         // optional out: -net(x)   (ScoreModel.forward)
   // fused ReverseDiffusionPredictor step (all optional as a group; enabled when x != nullptr)

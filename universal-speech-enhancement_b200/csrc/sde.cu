@@ -35,12 +35,15 @@ __device__ __forceinline__ float2 philox_cnormal(unsigned long long seed, uint32
   return make_float2(r * cs, r * sn);
 }
 
-// xr: fp32 [n][PC] (input pyramid level 0), PC = 4: [Re x, Im x, Re Y, Im Y], PC = 2: [Re x, Im x] (discriminative
-// network, no conditioning).  xpad (optional): act dtype [n][128 B of channels], channels 0..PC-1 = the same values as
-// MMA operands, the rest zero -- the tcgen05 input convolution reads it as one K chunk.
+// xr: fp32 input pyramid level 0.  PC = 4: [n][4] = [Re x, Im x, Re Y, Im Y]; PC = 2: [n][2] = [Re x, Im x]
+// (discriminative network, no conditioning); PC = 6 (condition="both", model_wrapper.py:43-46,287-288): the 4-channel
+// block [n][4] followed by a 2-channel block [n][2] = [Re Y2, Im Y2] (the engine keeps 6-channel pyramids as a 4 + 2
+// pair so that every 4- / 2-channel kernel is reused).  xpad (optional): act dtype [n][128 B of channels], channels
+// 0..PC-1 = the same values as MMA operands, the rest zero -- the tcgen05 input convolution reads it as one K chunk.
 template <typename T, int PC>
 __global__ void __launch_bounds__(256) pack_input_kernel(const float2* __restrict__ x, const float2* __restrict__ Y,
-                                                          float* __restrict__ xr, T* __restrict__ xpad, size_t n) {
+                                                          const float2* __restrict__ Y2, float* __restrict__ xr,
+                                                          T* __restrict__ xpad, size_t n) {
   constexpr int V = Vec<T>::N;
   constexpr int VPP = 8;  // 16-byte vectors per padded pixel (128 B)
   for (size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n * VPP;
@@ -54,7 +57,7 @@ __global__ void __launch_bounds__(256) pack_input_kernel(const float2* __restric
       const float2 a = x[pix];
       f[0] = 2.f * a.x - 1.0f;
       f[1] = 2.f * a.y - 1.0f;
-      if constexpr (PC == 4) {
+      if constexpr (PC >= 4) {
         const float2 b = Y[pix];
         f[2] = 2.f * b.x - 1.0f;
         f[3] = 2.f * b.y - 1.0f;
@@ -63,24 +66,37 @@ __global__ void __launch_bounds__(256) pack_input_kernel(const float2* __restric
         reinterpret_cast<float2*>(xr)[pix] = make_float2(f[0], f[1]);
       }
     }
+    if constexpr (PC == 6) {
+      // channels 4, 5: vector 0 of a bf16 pixel (8 channels per vector), vector 1 of an fp32 pixel (4 per vector)
+      if (v == (V == 8 ? 0 : 1)) {
+        const float2 c = Y2[pix];
+        const float g0 = 2.f * c.x - 1.0f, g1 = 2.f * c.y - 1.0f;
+        f[4 % V] = g0;
+        f[5 % V] = g1;
+        reinterpret_cast<float2*>(xr + n * 4)[pix] = make_float2(g0, g1);
+      }
+    }
     if (xpad != nullptr) Vec<T>::store_operand(xpad + pix * (VPP * V) + v * V, f);
   }
 }
 
-void launch_pack_input(int dt, int pc, const float2* x, const float2* Y, float* xr, void* xpad, size_t n, cudaStream_t st) {
+void launch_pack_input(int dt, int pc, const float2* x, const float2* Y, const float2* Y2, float* xr, void* xpad, size_t n,
+                       cudaStream_t st) {
   const int blocks = static_cast<int>(std::min<size_t>((n * 8 + 255) / 256, 148 * 32));
   if (dt == kBF16) {
-    if (pc == 4) pack_input_kernel<__nv_bfloat16, 4><<<blocks, 256, 0, st>>>(x, Y, xr, (__nv_bfloat16*)xpad, n);
-    else pack_input_kernel<__nv_bfloat16, 2><<<blocks, 256, 0, st>>>(x, Y, xr, (__nv_bfloat16*)xpad, n);
+    if (pc == 6) pack_input_kernel<__nv_bfloat16, 6><<<blocks, 256, 0, st>>>(x, Y, Y2, xr, (__nv_bfloat16*)xpad, n);
+    else if (pc == 4) pack_input_kernel<__nv_bfloat16, 4><<<blocks, 256, 0, st>>>(x, Y, Y2, xr, (__nv_bfloat16*)xpad, n);
+    else pack_input_kernel<__nv_bfloat16, 2><<<blocks, 256, 0, st>>>(x, Y, Y2, xr, (__nv_bfloat16*)xpad, n);
   } else {
-    if (pc == 4) pack_input_kernel<float, 4><<<blocks, 256, 0, st>>>(x, Y, xr, (float*)xpad, n);
-    else pack_input_kernel<float, 2><<<blocks, 256, 0, st>>>(x, Y, xr, (float*)xpad, n);
+    if (pc == 6) pack_input_kernel<float, 6><<<blocks, 256, 0, st>>>(x, Y, Y2, xr, (float*)xpad, n);
+    else if (pc == 4) pack_input_kernel<float, 4><<<blocks, 256, 0, st>>>(x, Y, Y2, xr, (float*)xpad, n);
+    else pack_input_kernel<float, 2><<<blocks, 256, 0, st>>>(x, Y, Y2, xr, (float*)xpad, n);
   }
 }
 
 __global__ void __launch_bounds__(256) final_step_kernel(StepArgs a) {
   const size_t n = a.per_clip * a.B;
-  float w0[4] = {0.f, 0.f, 0.f, 0.f}, w1[4] = {0.f, 0.f, 0.f, 0.f};
+  float w0[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f}, w1[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
   for (int j = 0; j < a.pc; ++j) { w0[j] = a.ow[j]; w1[j] = a.ow[a.pc + j]; }
   const float b0 = a.ob[0], b1 = a.ob[1];
   const float G2 = a.G * a.G;
@@ -88,8 +104,10 @@ __global__ void __launch_bounds__(256) final_step_kernel(StepArgs a) {
        i += static_cast<size_t>(gridDim.x) * blockDim.x) {
     const int b = static_cast<int>(i / a.per_clip);
     float4 p = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (a.pc == 4) {
+    float2 p2 = make_float2(0.f, 0.f);  // channels 4, 5 of a 6-channel pyramid (kept as a separate 2-channel tensor)
+    if (a.pc >= 4) {
       p = __ldg(reinterpret_cast<const float4*>(a.pyramid) + i);
+      if (a.pc == 6) p2 = __ldg(reinterpret_cast<const float2*>(a.pyramid2) + i);
     } else {
       const float2 q = __ldg(reinterpret_cast<const float2*>(a.pyramid) + i);
       p.x = q.x; p.y = q.y;
@@ -97,9 +115,14 @@ __global__ void __launch_bounds__(256) final_step_kernel(StepArgs a) {
     if (a.t != nullptr) {  // scale_by_sigma: divide by the TIME value (ncsnpp.py:492-494)
       const float t = a.t[static_cast<size_t>(b) * a.t_bstride];
       p.x /= t; p.y /= t; p.z /= t; p.w /= t;
+      p2.x /= t; p2.y /= t;
     }
-    const float ore = b0 + w0[0] * p.x + w0[1] * p.y + w0[2] * p.z + w0[3] * p.w;
-    const float oim = b1 + w1[0] * p.x + w1[1] * p.y + w1[2] * p.z + w1[3] * p.w;
+    float ore = b0 + w0[0] * p.x + w0[1] * p.y + w0[2] * p.z + w0[3] * p.w;
+    float oim = b1 + w1[0] * p.x + w1[1] * p.y + w1[2] * p.z + w1[3] * p.w;
+    if (a.pc == 6) {
+      ore += w0[4] * p2.x + w0[5] * p2.y;
+      oim += w1[4] * p2.x + w1[5] * p2.y;
+    }
     const float2 score = make_float2(a.out_sign * ore, a.out_sign * oim);
     if (a.score != nullptr) a.score[i] = score;
     if (a.x != nullptr) {

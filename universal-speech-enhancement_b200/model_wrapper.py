@@ -50,11 +50,11 @@ class ScoreModel(nn.Module):
                  corrector="none", dtype: str = "fp32", micro_batch: Optional[int] = None, N: Optional[int] = None,
                  sampler_type: Optional[str] = None):
         super().__init__()
-        if condition not in ("noisy", "denoised") or sde_input not in ("noisy", "denoised"):
-            raise NotImplementedError(
-                "ScoreModel(B200): condition / sde_input must be 'noisy' or 'denoised' (4-channel score network, "
-                "model_wrapper.py:43-46); condition='both' (6-channel input fed by the GAN stage's output) is not built")
-        self.score_net = BackboneRegistry.get_by_name(backbone)(input_channels=4, compute_dtype=dtype)
+        if condition not in ("noisy", "denoised", "both") or sde_input not in ("noisy", "denoised"):
+            raise NotImplementedError(f"ScoreModel(B200): unknown condition {condition!r} / sde_input {sde_input!r}")
+        # model_wrapper.py:43-46: both conditioning spectrograms -> a 6-channel network input
+        self.score_net = BackboneRegistry.get_by_name(backbone)(input_channels=6 if condition == "both" else 4,
+                                                                compute_dtype=dtype)
         self.sde = SDERegistry.get_by_name(sde)()
         self.t_eps = t_eps
         self.condition, self.mode, self.loss_type = condition, mode, loss_type
@@ -156,10 +156,11 @@ class ScoreModel(nn.Module):
     # ---- score network -----------------------------------------------------------------------------
     def forward_score(self, x, t, score_conditioning, sde_input):
         """score = -score_net(cat[x, Y], t)  (model_wrapper.py:135-141); x, Y complex [B,1,F,T]."""
-        if len(score_conditioning) != 1:
-            raise NotImplementedError("exactly one conditioning tensor (condition='noisy') is supported")
+        if len(score_conditioning) not in (1, 2):
+            raise NotImplementedError("one (condition='noisy' / 'denoised') or two (condition='both') conditioning tensors")
         Y = score_conditioning[0]
-        s = self._engine(x.device).score(x[:, 0], Y[:, 0], t)
+        Y2 = score_conditioning[1][:, 0] if len(score_conditioning) == 2 else None
+        s = self._engine(x.device).score(x[:, 0], Y[:, 0], t, Y2=Y2)
         return s.unsqueeze(1)
 
     def forward(self, x, t, score_conditioning, sde_input):
@@ -203,7 +204,7 @@ class ScoreModel(nn.Module):
     # ---- samplers ----------------------------------------------------------------------------------
     def _fused_pc_sample(self, sde, y, eps, predictor="reverse_diffusion", corrector="none", corrector_steps=1, snr=0.5,
                          probability_flow=False, denoise=True, noise=None, seed=None, clip0=0, trace=None, x_init=None,
-                         times=None, want_state=False, cond=None):
+                         times=None, want_state=False, cond=None, cond2=None):
         """y: complex [B,1,F,T].  One C call (use_pc_sample_ex) per micro-batch: prior + N x (corrector steps, predictor
         step).  ``x_init`` + ``times`` = [t]: a single update_fn step from the given state (dt stays 1 / sde.N)."""
         ts, G, std1 = sde.step_tables(sde.N, eps, times=times)
@@ -225,7 +226,8 @@ class ScoreModel(nn.Module):
                                    corrector=corrector, corrector_steps=corrector_steps, snr=snr,
                                    probability_flow=probability_flow, denoise=denoise, g=g_tab, ald_step=ald_tab, trace=tr,
                                    x_init=None if x_init is None else x_init[s:s + mb, 0], dt_steps=sde.N,
-                                   cond=None if cond is None else cond[s:s + mb, 0])
+                                   cond=None if cond is None else cond[s:s + mb, 0],
+                                   cond2=None if cond2 is None else cond2[s:s + mb, 0])
             if trace is not None and mb < B:
                 trace[:, s:s + mb, 0] = tr
             means.append(xm)
@@ -284,6 +286,8 @@ class ScoreModel(nn.Module):
             score_conditioning = [Y]
         elif self.condition == "denoised" and Y_denoised is not None:
             score_conditioning = [Y_denoised]
+        elif self.condition == "both" and Y_denoised is not None:
+            score_conditioning = [Y, Y_denoised]
         else:
             raise NotImplementedError(f"Don't know the conditioning you have wished for: {self.condition}")
         if self.sde_input == "denoised" and Y_denoised is not None:

@@ -59,10 +59,12 @@ class _Step(abc.ABC):
         fn = getattr(self.score_fn, "_fused_pc_sample", None)
         if fn is None:
             raise NotImplementedError(f"{type(self).__name__} needs a B200 ScoreModel as score_fn")
-        if conditioning is not None and len(conditioning) != 1:
-            raise NotImplementedError("fused steps take ONE conditioning spectrogram (condition='noisy' or 'denoised')")
+        if conditioning is not None and len(conditioning) not in (1, 2):
+            raise NotImplementedError("fused steps take one or two conditioning spectrograms")
         cond = None if conditioning is None or conditioning[0] is y else conditioning[0]
-        return fn(self.sde, y, None, x_init=x, times=torch.tensor([_uniform_time(t)]), want_state=True, cond=cond, **sel)
+        cond2 = conditioning[1] if conditioning is not None and len(conditioning) == 2 else None
+        return fn(self.sde, y, None, x_init=x, times=torch.tensor([_uniform_time(t)]), want_state=True, cond=cond, cond2=cond2,
+                  **sel)
 
 
 class Predictor(_Step):
@@ -155,7 +157,7 @@ _BUILTIN = {EulerMaruyamaPredictor, ReverseDiffusionPredictor, NonePredictor, La
 
 def _fusable(predictor_cls, corrector_cls, sde, score_fn, conditioning, y) -> bool:
     return (predictor_cls in _BUILTIN and corrector_cls in _BUILTIN and isinstance(sde, sdes.OUVESDE) and hasattr(score_fn, "_fused_pc_sample") and sde.N >= 1
-            and conditioning is not None and len(conditioning) == 1)
+            and conditioning is not None and len(conditioning) in (1, 2))
 
 
 def _host_loop(predictor, corrector, sde, y, eps, denoise, conditioning):
@@ -185,7 +187,8 @@ def get_pc_sampler(predictor_name, corrector_name, sde, score_fn, y, denoise=Tru
         def fused_sampler():
             out = score_fn._fused_pc_sample(sde, y, eps, predictor=predictor_cls.kind, corrector=corrector_cls.kind,
                                             corrector_steps=corrector_steps, snr=snr, denoise=denoise,
-                                            cond=None if conditioning[0] is y else conditioning[0], noise=noise, seed=seed, clip0=clip0, trace=trace)
+                                            cond=None if conditioning[0] is y else conditioning[0],
+                                            cond2=conditioning[1] if len(conditioning) == 2 else None, noise=noise, seed=seed, clip0=clip0, trace=trace)
             return out, sde.N * (n_corr + 1)
 
         return fused_sampler
