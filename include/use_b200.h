@@ -21,6 +21,8 @@
  *                            (sampling/correctors.py:101-111), RSDE.discretize (sdes.py:159-173)
  *   use_pc_sample_ex         the same loop with EulerMaruyamaPredictor (predictors.py:40-53), LangevinCorrector /
  *                            AnnealedLangevinDynamics (sampling/correctors.py:37-98), probability flow, denoise=False
+ *   use_reverse_drift        RSDE.sde()[0] (sdes.py:122-150): the drift function of get_ode_sampler
+ *                            (sampling/__init__.py:76-159)
  *   use_train_forward        forward half of ScoreModel.train_step (model_wrapper.py:147-208): marginal_prob perturbation,
  *                            one score evaluation with per-sample times, denoising-score-matching loss (:124-133)
  *   use_stft / use_istft     ScoreModel.stft + spec_fwd + pad_spec / spec_back + istft
@@ -102,6 +104,15 @@ int use_score_forward(use_engine* e, int B, int F, int T, const void* x, const v
 /* The same for the 6-channel network (condition="both"): score = -net(cat[x, Y, Y2], t). */
 int use_score_forward2(use_engine* e, int B, int F, int T, const void* x, const void* Y, const void* Y2, const float* t_host,
                        const float* gfp_host, void* score, void* workspace, size_t workspace_bytes, void* stream);
+
+/* Reverse-time drift of the SDE / probability-flow ODE at a batch-uniform time t (RSDE.sde(x, t, y)[0], sdes.py:122-150):
+ *   drift = theta (sde_y - x) - g^2 score(x, t) c,  c = 1/2 with probability_flow (the ODE's right-hand side,
+ *   sampling/__init__.py:112-114), 1 otherwise.  cond / cond2: the network's conditioning when it is not sde_y / the
+ * 6-channel network's second conditioning (NULL otherwise).  g = g(t) from the host (OUVESDE.sde).  One network
+ * evaluation + one fused kernel; the ODE solver itself (scipy RK45 in the reference) stays on the host. */
+int use_reverse_drift(use_engine* e, int B, int F, int T, const void* x, const void* sde_y, const void* cond,
+                      const void* cond2, const float* t_host, const float* gfp_host, float g, int probability_flow, void* drift,
+                      void* workspace, size_t workspace_bytes, void* stream);
 
 /* out = +net(...): NCSNpp.forward itself (ncsnpp.py:324-501).  For the discriminative generator of the LSGAN stage
  * (GAN/generator/ncsnpp/model_wrapper.py:54,114-121: input_channels = 2, conditional = 0, scale_by_sigma = 0) pass

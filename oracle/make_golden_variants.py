@@ -40,6 +40,9 @@ CASES = {
     # the reference ScoreModel's DEFAULT ctor: condition="both" (6-channel network input), sde_input="denoised"
     "cond_both_sde_denoised": dict(predictor="reverse_diffusion", corrector="none", corrector_steps=1, snr=0.5),
     "cond_both_sde_noisy": dict(predictor="reverse_diffusion", corrector="none", corrector_steps=1, snr=0.5),
+    # probability-flow ODE sampler (sampling/__init__.py:76-159): scipy RK45 on the host, rtol = atol = 1e-3 to bound the
+    # number of function evaluations; like euler_maruyama it only runs in the reference around an adapter score function
+    "ode": dict(sampler_type="ode", rtol=1e-3, atol=1e-3),
 }
 COND = {"cond_denoised": ("denoised", "noisy", "enhanced"),
         "cond_denoised_sde_denoised": ("denoised", "denoised", "fake_sde_enhanced"),
@@ -61,8 +64,8 @@ def main():
         condition, sde_input, key = COND.get(name, ("noisy", "noisy", "enhanced"))
         m = ScoreModel(backbone="ncsnpplarge", sde="ouve", t_eps=3e-2, mode="regen-joint-training", condition=condition,
                        loss_type="mse", n_fft=1022, hop_length=160, num_frames=512, window="hann", spec_factor=0.15,
-                       spec_abs_exponent=0.5, sde_input=sde_input, predictor=kw["predictor"],
-                       corrector=kw["corrector"]).eval()
+                       spec_abs_exponent=0.5, sde_input=sde_input, predictor=kw.get("predictor", "reverse_diffusion"),
+                       corrector=kw.get("corrector", "none")).eval()
         sdL, net = (sd6, O.LARGE6) if condition == "both" else (sd4, O.LARGE)
         m.score_net.load_state_dict(sdL, strict=True)
         torch.manual_seed(seed)
@@ -74,6 +77,17 @@ def main():
                 sampler = RS.get_pc_sampler("euler_maruyama", "none", sde=sde, score_fn=lambda x, t, yy: m(x, t, [yy], yy),
                                             y=Y, eps=m.t_eps, conditioning=None)
                 xm, nfe = sampler()
+                ref = m.istft(m.spec_back(xm.squeeze(1)), L)
+        elif name == "ode":
+            with torch.no_grad():
+                Y = O.pad_spec(m.spec_fwd(m.stft(y)).unsqueeze(1))
+                sde = m.sde.copy()
+                sde.N = N
+                sampler = RS.get_ode_sampler(sde, lambda x, t, yy: m(x, t, [yy], yy), y=Y, eps=m.t_eps, rtol=kw["rtol"],
+                                             atol=kw["atol"], device="cpu")
+                xm, nfe = sampler()
+                print("ode nfe =", nfe, flush=True)
+                out["ode.nfe"] = nfe
                 ref = m.istft(m.spec_back(xm.squeeze(1)), L)
         elif name in COND:
             ref = m.sample({"perturbed": y.clone(), "fake": fake.clone()}, N=N)[key]

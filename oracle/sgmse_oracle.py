@@ -528,6 +528,38 @@ def pc_sample_spec(score_fn, Y: Tensor, N: int, noise: Tensor, sde: SdeCfg = Sde
     return xt_mean if (denoise and N) else xt
 
 
+def ode_sample_spec(score_fn, Y: Tensor, N: int, noise0: Tensor, sde: SdeCfg = SdeCfg(), rtol: float = 1e-5,
+                    atol: float = 1e-5, method: str = "RK45", denoise: bool = True):
+    """get_ode_sampler() (sampling/__init__.py:76-159): the probability-flow ODE dx/dt = theta (Y - x) - g(t)^2 score / 2
+    (RSDE.sde with probability_flow=True, sdes.py:122-150) integrated from T to t_eps by scipy's solve_ivp over the
+    flattened complex64 state, then one noise-free ReverseDiffusionPredictor step at t = t_eps (dt = 1/N).
+    noise0: the prior draw, complex [B,1,F,T].  Returns (x, number of function evaluations)."""
+    from scipy import integrate
+
+    B = Y.shape[0]
+    rdt = Y.real.dtype
+    std1 = ouve_std(torch.ones((B,), dtype=rdt), sde)
+    x = Y + noise0 * std1[:, None, None, None]
+
+    def ode_func(t, x_flat):
+        xt = torch.from_numpy(x_flat.reshape(tuple(Y.shape))).type(torch.complex64)
+        vec_t = torch.ones(B) * t
+        g = ouve_diffusion(vec_t, sde)[:, None, None, None]
+        drift = sde.theta * (Y - xt) + (-(g**2) * score_fn(xt, vec_t) * 0.5)
+        return drift.detach().numpy().reshape((-1,))
+
+    sol = integrate.solve_ivp(ode_func, (sde.T, sde.t_eps), x.detach().numpy().reshape((-1,)), rtol=rtol, atol=atol,
+                              method=method)
+    x = torch.tensor(sol.y[:, -1]).reshape(Y.shape).type(torch.complex64)
+    if denoise:
+        vec_eps = torch.ones(B) * sde.t_eps
+        dt = 1 / N
+        G = (ouve_diffusion(vec_eps, sde) * torch.sqrt(torch.tensor(dt, dtype=rdt)))[:, None, None, None]
+        f = sde.theta * (Y - x) * dt
+        x = x - (f - G**2 * score_fn(x, vec_eps) * 1.0)
+    return x, sol.nfev
+
+
 def sample(sd: Dict[str, Tensor], y: Tensor, N: int, noise: Optional[Tensor] = None, seed: int = 42,
            net: NetCfg = LARGE, spec: SpecCfg = SpecCfg(), sde: SdeCfg = SdeCfg(),
            return_spec: bool = False, fake: Optional[Tensor] = None, condition: str = "noisy", sde_input: str = "noisy",
@@ -549,7 +581,12 @@ def sample(sd: Dict[str, Tensor], y: Tensor, N: int, noise: Optional[Tensor] = N
         def score_fn(x, t):
             return -ncsnpp_forward(sd, net, torch.cat([x] + cond, dim=1), t)
 
-        xm = pc_sample_spec(score_fn, Y, N, noise, sde, **sampler_kw)
+        if sampler_kw.get("sampler_type") == "ode":
+            xm, _ = ode_sample_spec(score_fn, Y, N, noise[0], sde, rtol=sampler_kw.get("rtol", 1e-5),
+                                    atol=sampler_kw.get("atol", 1e-5))
+        else:
+            sampler_kw.pop("sampler_type", None)
+            xm = pc_sample_spec(score_fn, Y, N, noise, sde, **sampler_kw)
         out = istft(spec_back(xm.squeeze(1), spec), spec, T_orig)
     return (out, xm, Y) if return_spec else out
 

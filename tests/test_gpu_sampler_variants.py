@@ -156,3 +156,33 @@ def test_minibatch_argument_keys_noise_by_global_clip():
     whole_n, _ = m.get_pc_sampler("reverse_diffusion", "none", Y, N=2, conditioning=[Y], noise=noise)()
     split_n, _ = m.get_pc_sampler("reverse_diffusion", "none", Y, N=2, minibatch=3, conditioning=[Y], noise=noise)()
     assert torch.equal(whole_n, split_n)
+
+
+@pytest.mark.parametrize("dtype,tol", [("fp32", 5e-3), ("bf16", 3e-2)])
+def test_ode_sampler_matches_reference_golden(dtype, tol):
+    """sampler_type="ode" (sampling/__init__.py:76-159): scipy RK45 on the host around use_reverse_drift (one network
+    evaluation + the fused probability-flow drift kernel per function evaluation), then the noise-free predictor step at
+    t = eps.  Golden: the reference's own get_ode_sampler around an adapter score function (it raises with the
+    reference's ScoreModel), rtol = atol = 1e-3.  The adaptive solver takes its step decisions from values that differ at
+    the operand-rounding level, so the tolerance is the solver's own (a few 1e-3), not the network's."""
+    g = np.load(os.path.join(GOLDEN, "sampler_variants_T64.npz"))
+    N, seed = int(g["N"]), int(g["seed"])
+    m = _model(dtype, int(g["weight_seed"]))
+    y = torch.from_numpy(g["y"])
+    noise = O.draw_noise((2, 1, 512, 64), 0, seed).cuda()  # the prior draw
+    out = m.sample({"perturbed": y.cuda()}, sampler_type="ode", N=N, noise=noise,
+                   ode_kwargs=dict(rtol=float(g["ode.rtol"]), atol=float(g["ode.atol"])))["enhanced"].cpu()
+    e = rel_l2(out, torch.from_numpy(g["ode"]))
+    assert bool(torch.isfinite(out).all()) and e <= tol, (dtype, e)
+    # the drift entry point itself against the oracle's formula at one time
+    Y = m.stft_compressed(y.cuda()).unsqueeze(1)
+    x = Y + 0.2 * noise[0]
+    sde = m.sde.copy()
+    drift = m._reverse_drift(sde, x, Y, 0.4, [Y]).cpu()
+    sd = O.make_state_dict(O.LARGE, seed=int(g["weight_seed"]))
+    tt = torch.full((2,), 0.4)
+    with torch.no_grad():
+        score = -O.ncsnpp_forward(sd, O.LARGE, torch.cat([x.cpu(), Y.cpu()], 1), tt)
+    gg = O.ouve_diffusion(tt)[:, None, None, None]
+    ref = 1.5 * (Y.cpu() - x.cpu()) - gg**2 * score * 0.5
+    assert rel_l2(torch.view_as_real(drift), torch.view_as_real(ref)) <= (5e-3 if dtype == "fp32" else 5e-2)

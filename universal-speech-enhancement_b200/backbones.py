@@ -337,6 +337,24 @@ class _Engine:
                                               ws.numel(), _lib.stream_ptr()), "use_net_forward")
         return out
 
+    def reverse_drift(self, x, sde_y, t: float, g: float, cond=None, cond2=None, probability_flow=True):
+        """use_reverse_drift: theta (y - x) - g^2 score c at the batch-uniform time t; complex64 [B, F, T]."""
+        assert x.dtype == torch.complex64 and x.dim() == 3 and x.shape == sde_y.shape
+        B, F, T = x.shape
+        x, sde_y = x.contiguous(), sde_y.contiguous()
+        t_host = torch.full((B,), float(t), dtype=torch.float32)
+        gfp = self.net_module.gfp_features(t_host)
+        keep = [c.to(torch.complex64).contiguous() if c is not None else None for c in (cond, cond2)]
+        out = torch.empty_like(x)
+        with torch.cuda.device(self.device):
+            ws = self.workspace(B, F, T)
+            _lib.check(self.L.use_reverse_drift(self.h, B, F, T, x.data_ptr(), sde_y.data_ptr(),
+                                                keep[0].data_ptr() if keep[0] is not None else None,
+                                                keep[1].data_ptr() if keep[1] is not None else None, t_host.data_ptr(),
+                                                gfp.data_ptr(), float(g), int(bool(probability_flow)), out.data_ptr(),
+                                                ws.data_ptr(), ws.numel(), _lib.stream_ptr()), "use_reverse_drift")
+        return out
+
     def train_forward(self, X0, Y, t, coef, noise=None, seed=0, clip0=0, mae=False):
         """use_train_forward: returns (loss [1 + B] float32 device tensor, x_t complex64 [B, F, T])."""
         assert X0.dtype == torch.complex64 and X0.shape == Y.shape and X0.dim() == 3 and X0.is_cuda

@@ -1124,7 +1124,13 @@ int use_engine_upload(use_engine* e, void* dev_weights, size_t bytes, void* stre
   return cuda_check("use_engine_upload");
 }
 
-static int group_count(const use_engine* e, int B) { return (e->groups >= 2 && !e->profiling && B >= 4 && B % 2 == 0) ? 2 : 1; }
+static int min_group_batch() {
+  static const int v = getenv("USE_B200_GROUP_MIN_BATCH") ? atoi(getenv("USE_B200_GROUP_MIN_BATCH")) : 4;
+  return v < 2 ? 2 : v;
+}
+static int group_count(const use_engine* e, int B) {
+  return (e->groups >= 2 && !e->profiling && B >= min_group_batch() && B % 2 == 0) ? 2 : 1;
+}
 
 int use_engine_workspace_bytes(use_engine* e, int B, int F, int T, size_t* bytes) {
   if (!e || !bytes) return fail("null argument");
@@ -1132,7 +1138,7 @@ int use_engine_workspace_bytes(use_engine* e, int B, int F, int T, size_t* bytes
   // large enough for one program over B and for two half-batch programs side by side
   size_t whole = 0, half = 0;
   if (plan_workspace(e, B, F, T, &whole, nullptr)) return 1;
-  if (B >= 4 && B % 2 == 0) {
+  if (B >= min_group_batch() && B % 2 == 0) {
     if (plan_workspace(e, B / 2, F, T, &half, nullptr)) return 1;
     half = 2 * align_up(half, 4096);
   }
@@ -1163,7 +1169,7 @@ int use_engine_set_option(use_engine* e, const char* key, int value) {
 // one evaluation of the network; sign = -1 gives the score (-net), +1 the raw network output
 static int net_forward(use_engine* e, int B, int F, int T, const void* x, const void* Y, const float* t_host,
                        const float* gfp_host, void* out, float sign, void* workspace, size_t workspace_bytes, void* stream,
-                       const void* Y2 = nullptr) {
+                       const void* Y2 = nullptr, const void* sde_y = nullptr, float drift_g = 0.f, float drift_pf = 1.f) {
   if (!e || !x || !out || !workspace) return fail("null argument");
   const bool cond = e->cfg.conditional != 0;
   if (e->cfg.input_channels >= 4 && !Y) return fail("the conditioning spectrogram Y is required (input_channels >= 4)");
@@ -1190,6 +1196,17 @@ static int net_forward(use_engine* e, int B, int F, int T, const void* x, const 
   a.ob = (const float*)(e->dev_w + e->off.at("out.b"));
   a.score = (float2*)out;
   a.x = nullptr;
+  if (sde_y) {  // reverse-time drift instead of the score: out = theta (y - x) - g^2 score pf
+    a.score = nullptr;
+    a.x = (const float2*)x;
+    a.Y = (const float2*)sde_y;
+    a.x_mean = (float2*)out;
+    a.x_next = (float2*)out;
+    a.mode = kStepDrift;
+    a.theta = e->cfg.theta;
+    a.G = drift_g;
+    a.pf = drift_pf;
+  }
   a.B = B;
   a.per_clip = per;
   launch_final_step(a, st);
@@ -1205,6 +1222,14 @@ int use_score_forward(use_engine* e, int B, int F, int T, const void* x, const v
 int use_score_forward2(use_engine* e, int B, int F, int T, const void* x, const void* Y, const void* Y2, const float* t_host,
                        const float* gfp_host, void* score, void* workspace, size_t workspace_bytes, void* stream) {
   return net_forward(e, B, F, T, x, Y, t_host, gfp_host, score, -1.0f, workspace, workspace_bytes, stream, Y2);
+}
+
+int use_reverse_drift(use_engine* e, int B, int F, int T, const void* x, const void* sde_y, const void* cond,
+                      const void* cond2, const float* t_host, const float* gfp_host, float g, int probability_flow, void* drift,
+                      void* workspace, size_t workspace_bytes, void* stream) {
+  if (!sde_y) return fail("null argument");
+  return net_forward(e, B, F, T, x, cond ? cond : sde_y, t_host, gfp_host, drift, -1.0f, workspace, workspace_bytes, stream, cond2,
+                     sde_y, g, probability_flow ? 0.5f : 1.0f);
 }
 
 int use_net_forward(use_engine* e, int B, int F, int T, const void* x, const void* Y, const float* t_host,

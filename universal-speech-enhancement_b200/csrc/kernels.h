@@ -66,7 +66,9 @@ void launch_split_tf32(const float* x, int Ct, int c0, int C, float* hi, float* 
 void launch_pack_input(int dt, int pc, const float2* x, const float2* Y, const float2* Y2, float* xr, void* xpad, size_t n,
                        cudaStream_t st);
 
-enum StepMode { kStepReverseDiffusion = 0, kStepEulerMaruyama = 1 };
+// kStepDrift: no update -- x_mean receives the reverse-time drift theta (Y - x) - g^2 score pf itself (RSDE.sde()[0],
+// sdes.py:122-150; the right-hand side of the probability-flow ODE when pf = 0.5)
+enum StepMode { kStepReverseDiffusion = 0, kStepEulerMaruyama = 1, kStepDrift = 2 };
 struct StepArgs {
   const float* pyramid;  // fp32 [B][F][T][pc]  (pc = 6: the first four channels, [B][F][T][4])
   const float* pyramid2; // pc = 6 only: channels 4, 5 as fp32 [B][F][T][2]

@@ -131,6 +131,10 @@ __global__ void __launch_bounds__(256) final_step_kernel(StepArgs a) {
       if (a.z != nullptr) z = a.z[i];
       else z = philox_cnormal(a.seed, a.step, a.clip0 + b, i - static_cast<size_t>(b) * a.per_clip);
       float2 xm;
+      if (a.mode == kStepDrift) {
+        a.x_mean[i] = make_float2(a.theta * (Y.x - x.x) + (-G2 * score.x) * a.pf, a.theta * (Y.y - x.y) + (-G2 * score.y) * a.pf);
+        continue;
+      }
       if (a.mode == kStepEulerMaruyama) {
         // f = theta (Y - x) - g^2 score pf ; x_mean = x + f (-1/N) ; x = x_mean + g sqrt(1/N) z   (predictors.py:40-53,
         // RSDE.rsde_parts sdes.py:128-150); a.G = g(t_i) here, a.Gz = g sqrt(1/N) (0 for the probability flow)

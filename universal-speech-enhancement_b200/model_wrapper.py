@@ -267,12 +267,45 @@ class ScoreModel(nn.Module):
 
         return batched_sampling_fn
 
-    def get_ode_sampler(self, y, N=None, minibatch=1, **kwargs):
-        raise NotImplementedError("the ODE (RK45) sampler is not on the accelerated path (SURVEY.md section 8f, rank 3)")
+    def _reverse_drift(self, sde, x, y, t: float, conditioning):
+        """theta (y - x) - g(t)^2 score / 2 (the probability-flow drift) for complex [B,1,F,T]: one C call."""
+        ts = torch.tensor([t], dtype=torch.float32)
+        g = float(sde.variant_tables(ts, 0.0)[0][0])
+        cond = None if conditioning[0] is y else conditioning[0][:, 0]
+        cond2 = conditioning[1][:, 0] if len(conditioning) == 2 else None
+        return self._engine(x.device).reverse_drift(x[:, 0], y[:, 0], t, g, cond=cond, cond2=cond2,
+                                                    probability_flow=True).unsqueeze(1)
+
+    def get_ode_sampler(self, y, N=None, minibatch=None, **kwargs):
+        """sampling.get_ode_sampler around this model (model_wrapper.py:238-260).  ``minibatch`` splits the batch like the
+        reference does (its default there is 1; None = the whole batch in one solve)."""
+        N = self.sde.N if N is None else N
+        sde = self.sde.copy()
+        sde.N = N
+        kwargs = {"eps": self.t_eps, **kwargs}
+        if minibatch is None:
+            return sampling.get_ode_sampler(sde, self, y=y, **kwargs)
+        M = y.shape[0]
+
+        def batched_sampling_fn():
+            samples, ns = [], []
+            for i in range(int(ceil(M / minibatch))):
+                sl = slice(i * minibatch, (i + 1) * minibatch)
+                kw = dict(kwargs)
+                if kw.get("conditioning") is not None:
+                    kw["conditioning"] = [c[sl] for c in kw["conditioning"]]
+                if kw.get("noise") is not None:
+                    kw["noise"] = kw["noise"][:, sl]
+                sample, n = sampling.get_ode_sampler(sde, self, y=y[sl], **kw)()
+                samples.append(sample)
+                ns.append(n)
+            return torch.cat(samples, dim=0), ns
+
+        return batched_sampling_fn
 
     @torch.no_grad()
     def sample(self, batch, sampler_type=None, N=None, corrector_steps=1, snr=0.5, noise=None, seed=None, clip0=0,
-               trace=None):
+               trace=None, ode_kwargs=None):
         """ScoreModel.sample (model_wrapper.py:262-329).  ``noise`` / ``seed`` / ``clip0`` / ``trace``: see
         sampling.get_pc_sampler."""
         sampler_type = sampler_type or self.default_sampler_type or "pc"
@@ -296,11 +329,14 @@ class ScoreModel(nn.Module):
             sde_input = Y
         else:
             raise NotImplementedError(f"Don't know the sde input you have wished for: {self.sde_input}")
-        if sampler_type != "pc":
-            raise NotImplementedError(f"{sampler_type} is not a valid sampler type on the accelerated path (use 'pc')")
-        sampler = self.get_pc_sampler(self.predictor, self.corrector, sde_input, N=N, corrector_steps=corrector_steps,
-                                      snr=snr, intermediate=False, conditioning=score_conditioning, noise=noise,
-                                      seed=seed, clip0=clip0, trace=trace)
+        if sampler_type == "pc":
+            sampler = self.get_pc_sampler(self.predictor, self.corrector, sde_input, N=N, corrector_steps=corrector_steps,
+                                          snr=snr, intermediate=False, conditioning=score_conditioning, noise=noise,
+                                          seed=seed, clip0=clip0, trace=trace)
+        elif sampler_type == "ode":
+            sampler = self.get_ode_sampler(sde_input, N=N, conditioning=score_conditioning, noise=noise, **(ode_kwargs or {}))
+        else:
+            raise NotImplementedError(f"{sampler_type} is not a valid sampler type!")
         sample, nfe = sampler()
         out = self.istft_decompressed(sample.squeeze(1), T_orig)
         # output key as in the reference (model_wrapper.py:321-328)
