@@ -89,8 +89,11 @@ def test_unsupported_options_fail_loudly():
     m = use_b200.ScoreModel(backbone="ncsnpplarge", condition="noisy", sde_input="noisy", n_fft=1022, hop_length=160)
     with pytest.raises(RuntimeError, match="CUDA"):
         m.sample({"perturbed": torch.zeros(1, 9600)}, N=1)  # CPU tensors: no CPU path, no silent fallback
+    with pytest.raises(NotImplementedError):  # the ODE sampler needs the B200 model's drift entry point, not any callable
+        from use_b200 import sampling
+        sampling.get_ode_sampler(m.sde.copy(), lambda x, t, y: x, torch.zeros(1, 1, 8, 8, dtype=torch.complex64))
     with pytest.raises(NotImplementedError):
-        m.get_ode_sampler(torch.zeros(1))
+        m.sample({"perturbed": torch.zeros(1, 9600)}, sampler_type="bogus")
 
 
 def test_plugin_predictor_corrector_run_through_the_host_loop():

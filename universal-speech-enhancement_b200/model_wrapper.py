@@ -310,6 +310,8 @@ class ScoreModel(nn.Module):
         sampling.get_pc_sampler."""
         sampler_type = sampler_type or self.default_sampler_type or "pc"
         N = N if N is not None else (self.default_N if self.default_N is not None else 50)
+        if sampler_type not in ("pc", "ode"):
+            raise NotImplementedError(f"{sampler_type} is not a valid sampler type!")
         y = batch["perturbed"]
         T_orig = y.size(1)
         Y = self.stft_compressed(y).unsqueeze(1)          # = pad_spec(spec_fwd(stft(y)).unsqueeze(1))
