@@ -84,7 +84,10 @@ int use_engine_upload(use_engine* e, void* dev_weights, size_t bytes, void* stre
 /* Workspace (device bytes) a forward / sample over B spectrograms of F x T (T % 2^(levels-1) == 0) needs. */
 int use_engine_workspace_bytes(use_engine* e, int B, int F, int T, size_t* bytes);
 /* Options: "overlap_groups" = 1 | 2 (default 2): use_pc_sample splits an even batch >= 4 into two halves that run
- * on their own streams so the HBM-bound kernels of one half overlap the tensor-bound convolutions of the other. */
+ * on their own streams so the HBM-bound kernels of one half overlap the tensor-bound convolutions of the other.
+ * A/B switches whose two settings give bit-identical results: "fuse_gn" (GroupNorm + SiLU inside the convolution's
+ * operand path), "use_graphs" (CUDA-graph replay of an evaluation), "inline_gn" (GroupNorm scale / shift tables computed
+ * inside the consumer kernels instead of one gn_affine_kernel launch per GroupNorm). */
 int use_engine_set_option(use_engine* e, const char* key, int value);
 
 /* Instrumentation: kernels launched so far by this engine; per-op-class CUDA-event timing of network evaluations

@@ -211,13 +211,14 @@ def test_full_size_properties_bf16():
 def test_engine_switches_are_bit_identical(dtype):
     """The engine's A/B switches change HOW the same arithmetic is scheduled, never the result: GroupNorm + SiLU fused
     into the convolution's operand path vs the separate gn_apply kernel, CUDA-graph replay vs plain launches, one vs
-    two half-batch streams -- all bit-identical on the NCSNppLarge sampler (0.4 s clips, N = 3)."""
+    two half-batch streams, GroupNorm scale / shift tables computed inside the consumer kernels vs by gn_affine_kernel
+    launches -- all bit-identical on the NCSNppLarge sampler (0.4 s clips, N = 3)."""
     m, _ = large_model(dtype)
     y = O.synthetic_clips(4, 9600).cuda()
     eng = m.score_net.engine(y.device, dtype)
     ref = m.sample({"perturbed": y}, N=3, seed=9)["enhanced"]
     assert bool(torch.isfinite(ref).all())
-    for key, val, back in (("fuse_gn", 0, 1), ("use_graphs", 0, 1), ("overlap_groups", 1, 2)):
+    for key, val, back in (("fuse_gn", 0, 1), ("use_graphs", 0, 1), ("overlap_groups", 1, 2), ("inline_gn", 1, 0)):
         eng.set_option(key, val)
         got = m.sample({"perturbed": y}, N=3, seed=9)["enhanced"]
         eng.set_option(key, back)

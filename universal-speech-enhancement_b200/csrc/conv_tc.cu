@@ -228,6 +228,14 @@ TcConvPlan* tc_conv_plan_create(int dt, const TcConvDesc& d, int num_sms, char* 
   P.tiles_w = (d.W + 7) / 8;
   P.tiles_h = (d.H + tile_h - 1) / tile_h;
   P.ntiles = P.tiles_w * P.tiles_h * d.B;
+  P.gn_st0 = fuse ? d.gn_st0 : nullptr;
+  P.gn_st1 = d.gn_st1; P.gn_gamma = d.gn_gamma; P.gn_beta = d.gn_beta;
+  P.gn_C0 = d.gn_C0; P.gn_C1 = d.gn_st1 ? d.gn_C1 : 0; P.gn_HW = d.gn_HW; P.gn_eps = d.gn_eps;
+  if (P.gn_st0 && P.gn_C0 + P.gn_C1 > 512) {
+    snprintf(err, errlen, "tcgen05 conv: inline GroupNorm over %d channels (max 512)", P.gn_C0 + P.gn_C1);
+    delete p;
+    return nullptr;
+  }
   P.nsplit = nsplit;
   P.ldn = d.N;
   P.nunits = P.ntiles * nsplit;

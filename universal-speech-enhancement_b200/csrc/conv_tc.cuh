@@ -56,6 +56,16 @@ struct alignas(64) ConvParams {
   // of the ldn = C_out channels, a work unit is (tile, slice) and nunits = ntiles * nsplit of them are spread over the
   // CTAs.  Every output element sees the same K sequence as in the unsplit kernel: results are bit-identical.
   int nsplit, ldn, nunits;
+  // Inline GroupNorm (fused segments only; gn_st0 != nullptr): the scale / shift table of GroupNorm(cat[s0, s1]) is NOT read
+  // from global memory (seg[].aff, one gn_affine_kernel launch per convolution: 98 launches of ~6 us per evaluation) but
+  // computed by the transform warps into shared memory whenever the CTA moves on to another sample -- the arithmetic of
+  // gn_affine_kernel, bit for bit.  Channel c of the concatenation = channel c of s0 (c < gn_C0) or c - gn_C0 of s1.
+  const long long* gn_st0;
+  const long long* gn_st1;
+  const float* gn_gamma;
+  const float* gn_beta;
+  int gn_C0, gn_C1, gn_HW;
+  float gn_eps;
   void* out;          // T [B][H][W][ldn]
   const float* bias;  // [B or 1][N]
   int bias_bstride;   // N (per-sample bias incl. the time-embedding term) or 0
@@ -102,7 +112,9 @@ struct ConvCfg {
   static constexpr int THREADS = XF_T0 + XF_THREADS;
   static constexpr int NBARS = 3 * A_SLOTS + 2 * B_SLOTS + 4;
   static constexpr int STAT_BYTES = EPI_WARPS * N * 2 * 4;  // per-warp column statistics of the current tile
-  static constexpr int SMEM_BYTES = 1024 + A_SLOTS * A_SLOT + B_SLOTS * B_TILE + STAT_BYTES + NBARS * 8 + 16;
+  static constexpr int GN_MAXC = 512;                       // channels of an inline GroupNorm (cat of two 256-channel tensors)
+  static constexpr int GN_BYTES = FUSE ? 2 * GN_MAXC * 4 : 0;  // scale row, shift row
+  static constexpr int SMEM_BYTES = 1024 + A_SLOTS * A_SLOT + B_SLOTS * B_TILE + STAT_BYTES + GN_BYTES + NBARS * 8 + 16;
   static_assert(TMEM_COLS <= 512 && (TMEM_COLS & (TMEM_COLS - 1)) == 0, "TMEM columns must be a power of two <= 512");
   static_assert(SMEM_BYTES <= 232448, "shared memory budget");
   static_assert(N % 32 == 0 && N <= 256, "N");
@@ -144,7 +156,8 @@ __global__ void __launch_bounds__(ConvCfg<T, N, NSUB, FUSE, CG2>::THREADS, 1) co
   uint8_t* sA = smem;
   uint8_t* sB = sA + C::A_SLOTS * C::A_SLOT;
   float* stat_s = reinterpret_cast<float*>(sB + C::B_SLOTS * C::B_TILE);
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sB + C::B_SLOTS * C::B_TILE + C::STAT_BYTES);
+  float* gn_s = reinterpret_cast<float*>(sB + C::B_SLOTS * C::B_TILE + C::STAT_BYTES);  // [2][GN_MAXC] (FUSE)
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sB + C::B_SLOTS * C::B_TILE + C::STAT_BYTES + C::GN_BYTES);
   uint64_t* a_full = bars;
   uint64_t* a_empty = a_full + C::A_SLOTS;
   uint64_t* a_raw = a_empty + C::A_SLOTS;  // fused segments: raw window landed (TMA -> transform warps)
@@ -375,6 +388,7 @@ __global__ void __launch_bounds__(ConvCfg<T, N, NSUB, FUSE, CG2>::THREADS, 1) co
     const int tt = threadIdx.x - C::XF_T0;
     const int v = tt & 7, pb = tt >> 3;
     uint32_t ai = 0, rawph = 0;  // rawph: phase parity of a_raw per slot (it only advances on fused fills)
+    int gn_b = -1;               // sample whose inline GroupNorm table is in gn_s
     long long w_r = 0;
     const long long t_begin = PROF ? clock64() : 0;
     for (int unit = T0; unit < TEND; unit += TSTEP) {
@@ -392,21 +406,57 @@ __global__ void __launch_bounds__(ConvCfg<T, N, NSUB, FUSE, CG2>::THREADS, 1) co
         const int hh = h0 - 1 + row, ww = w0 - 1 + col;
         if (tile < p.ntiles && q < C::NPIX && hh >= 0 && hh < p.H && ww >= 0 && ww < p.W) inside |= 1u << i;
       }
+      if (p.gn_st0 != nullptr && tile < p.ntiles && b != gn_b) {
+        // a new sample: rebuild the scale / shift table (every transform thread is past the previous tile's last chunk
+        // barrier, so nobody still reads the old table).  Same arithmetic as gn_affine_kernel.
+        const int Ct = p.gn_C0 + p.gn_C1;
+        const int G = min(Ct / 4, 32), cpg = Ct / G;
+        const double inv_cnt = 1.0 / (static_cast<double>(p.gn_HW) * cpg);
+        for (int c = tt; c < Ct; c += XT) {
+          const int g = c / cpg;
+          double sum = 0.0, sq = 0.0;
+          for (int cc = g * cpg; cc < (g + 1) * cpg; ++cc) {
+            const longlong2 st = __ldg(reinterpret_cast<const longlong2*>(
+                (cc < p.gn_C0) ? p.gn_st0 + (static_cast<size_t>(b) * p.gn_C0 + cc) * 2
+                               : p.gn_st1 + (static_cast<size_t>(b) * p.gn_C1 + (cc - p.gn_C0)) * 2));
+            sum += static_cast<double>(st.x) * (1.0 / kStatSumScale);
+            sq += static_cast<double>(st.y) * (1.0 / kStatSqScale);
+          }
+          const double mean = sum * inv_cnt;
+          double var = sq * inv_cnt - mean * mean;
+          if (var < 0.0) var = 0.0;
+          const float rstd = rsqrtf(static_cast<float>(var) + p.gn_eps);
+          const float sc = p.gn_gamma[c] * rstd;
+          gn_s[c] = sc;
+          gn_s[C::GN_MAXC + c] = p.gn_beta[c] - static_cast<float>(mean) * sc;
+        }
+        gn_b = b;
+        named_bar_sync(2, XT);
+      }
       for (int sg = 0; sg < p.nseg; ++sg) {
         const ConvSeg& S = p.seg[sg];
         if (S.raw == nullptr) { ai += S.nchunks; continue; }
-        const float* aff = S.aff + static_cast<size_t>(b) * 2 * S.aff_C + S.aff_c0 + v * V;
+        const bool inl = p.gn_st0 != nullptr;
+        const float* aff = inl ? gn_s + S.aff_c0 + v * V : S.aff + static_cast<size_t>(b) * 2 * S.aff_C + S.aff_c0 + v * V;
+        const int aff_row = inl ? C::GN_MAXC : S.aff_C;  // distance between the scale row and the shift row
         for (int kc = 0; kc < S.nchunks; ++kc, ++ai) {
           float sc[V], sh[V];
 #pragma unroll
           for (int j = 0; j < V; ++j) sc[j] = sh[j] = 0.f;
-          if (inside != 0)  // (a ghost tile has no pixel inside the image and no sample to take the table from)
+          if (inside != 0) {  // (a ghost tile has no pixel inside the image and no sample to take the table from)
 #pragma unroll
-          for (int j = 0; j < V; j += 4) {
-            const float4 a = __ldg(reinterpret_cast<const float4*>(aff + kc * C::CK + j));
-            const float4 c = __ldg(reinterpret_cast<const float4*>(aff + S.aff_C + kc * C::CK + j));
-            sc[j] = a.x; sc[j + 1] = a.y; sc[j + 2] = a.z; sc[j + 3] = a.w;
-            sh[j] = c.x; sh[j + 1] = c.y; sh[j + 2] = c.z; sh[j + 3] = c.w;
+            for (int j = 0; j < V; j += 4) {
+              float4 a, c;
+              if (inl) {
+                a = *reinterpret_cast<const float4*>(aff + kc * C::CK + j);
+                c = *reinterpret_cast<const float4*>(aff + aff_row + kc * C::CK + j);
+              } else {
+                a = __ldg(reinterpret_cast<const float4*>(aff + kc * C::CK + j));
+                c = __ldg(reinterpret_cast<const float4*>(aff + aff_row + kc * C::CK + j));
+              }
+              sc[j] = a.x; sc[j + 1] = a.y; sc[j + 2] = a.z; sc[j + 3] = a.w;
+              sh[j] = c.x; sh[j + 1] = c.y; sh[j + 2] = c.z; sh[j + 3] = c.w;
+            }
           }
           const uint32_t as = ai % C::A_SLOTS;
           mbar_wait_p<PROF>(&a_raw[as], (rawph >> as) & 1u, w_r);

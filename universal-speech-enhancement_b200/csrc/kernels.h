@@ -180,6 +180,15 @@ struct TcSegDesc {
 struct TcConvDesc {
   TcSegDesc seg[3];
   int nseg;
+  // inline GroupNorm: when gn_st0 != nullptr the fused segments' scale / shift table (GroupNorm over cat[s0, s1] with the
+  // fixed-point statistics st0 [B][C0][2], st1 [B][C1][2]) is computed INSIDE the convolution kernel; the segments then only
+  // use aff_c0 (their first channel inside the concatenation) and must set aff to any non-null value
+  const long long* gn_st0;
+  const long long* gn_st1;
+  int gn_C0, gn_C1, gn_HW;
+  const float* gn_gamma;
+  const float* gn_beta;
+  float gn_eps;
   int B, H, W, N;
   void* out;
   const float* bias;
