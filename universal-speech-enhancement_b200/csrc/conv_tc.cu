@@ -35,6 +35,7 @@ struct TcConvPlan {
   int dt, N, nsub, mc;
   int grid, threads, smem;
   const void* kernel;
+  TcConvPlan* tail = nullptr;  // sliced launch over the last (ntiles mod SMs) tiles, run right after this one
 };
 
 static bool encode_act(CUtensorMap* m, int dt, const void* base, int B, int H, int W, int Ct, int cols, int rows,
@@ -146,7 +147,35 @@ static void fill_kernel(TcConvPlan* p, bool fuse) {
 
 bool tc_conv_supported(int dt, int N) { return N == 64 || N == 128 || N == 256; }
 
+// tile_base / tile_count: the tile range of this launch (count < 0: all); force_split: run the range as 64-channel slices
+static TcConvPlan* plan_create_range(int dt, const TcConvDesc& d, int num_sms, char* err, int errlen, int tile_base,
+                                     int tile_count, bool force_split);
+
 TcConvPlan* tc_conv_plan_create(int dt, const TcConvDesc& d, int num_sms, char* err, int errlen) {
+  // Tail split (C_out = 256 family, single-CTA form): with T tiles on S persistent CTAs the last wave holds only T mod S
+  // tiles (batch 1 at 128 x 160: 160 tiles on 148 SMs = two waves for 1.08 waves of work).  When that remainder is small,
+  // the first T - (T mod S) tiles run as an exactly balanced launch and the remainder as 64-channel slices (4x the work
+  // units, a quarter of the time each) right behind it.  Slices are bit-identical to whole tiles (see N-split).
+  // MEASURED (bf16, batch 1 / 2 / 4): 159.9 vs 155.9, 222.4 vs 220.9, 393.3 vs 384.7 ms per step -- SLOWER: a second launch
+  // costs ~10 us of fixed latency (TMEM allocation, barrier set-up, pipeline fill, drain), as much as the tile it saves.
+  // Off unless USE_B200_CONV_TAILSPLIT=1.
+  if (d.N == 256 && multicast_width() == 1 && !cg2_enabled() && !getenv("USE_B200_CONV_PROF")) {
+    static const bool off = !(getenv("USE_B200_CONV_TAILSPLIT") && getenv("USE_B200_CONV_TAILSPLIT")[0] == '1');
+    const int tiles = ((d.W + 7) / 8) * ((d.H + 15) / 16) * d.B;
+    const int tail = tiles % num_sms;
+    if (!off && tiles > num_sms && tail > 0 && tail * 3 <= num_sms) {
+      TcConvPlan* main = plan_create_range(dt, d, num_sms, err, errlen, 0, tiles - tail, false);
+      if (!main) return nullptr;
+      main->tail = plan_create_range(dt, d, num_sms, err, errlen, tiles - tail, tail, true);
+      if (!main->tail) { delete main; return nullptr; }
+      return main;
+    }
+  }
+  return plan_create_range(dt, d, num_sms, err, errlen, 0, -1, false);
+}
+
+static TcConvPlan* plan_create_range(int dt, const TcConvDesc& d, int num_sms, char* err, int errlen, int tile_base,
+                                     int tile_count, bool force_split) {
   if (!tc_conv_supported(dt, d.N)) {
     snprintf(err, errlen, "tcgen05 conv: unsupported C_out=%d", d.N);
     return nullptr;
@@ -172,6 +201,7 @@ TcConvPlan* tc_conv_plan_create(int dt, const TcConvDesc& d, int num_sms, char* 
     static const int max_tiles = getenv("USE_B200_CONV_NSPLIT_MAXTILES") ? atoi(getenv("USE_B200_CONV_NSPLIT_MAXTILES")) : (1 << 30);
     if (!off && d.N == 256 && base_tiles * 3 <= num_sms && base_tiles < max_tiles && multicast_width() == 1 && !cg2_enabled() && !getenv("USE_B200_CONV_PROF"))
       nsplit = d.N / 64;
+    if (force_split) nsplit = d.N / 64;
   }
   if (getenv("USE_B200_CONV_DEBUG")) {
     const int bh = d.N == 256 ? 16 : 32;
@@ -228,6 +258,8 @@ TcConvPlan* tc_conv_plan_create(int dt, const TcConvDesc& d, int num_sms, char* 
   P.tiles_w = (d.W + 7) / 8;
   P.tiles_h = (d.H + tile_h - 1) / tile_h;
   P.ntiles = P.tiles_w * P.tiles_h * d.B;
+  P.tile_base = tile_base;
+  if (tile_count >= 0) P.ntiles = tile_base + tile_count;  // the END of this launch's range
   P.gn_st0 = fuse ? d.gn_st0 : nullptr;
   P.gn_st1 = d.gn_st1; P.gn_gamma = d.gn_gamma; P.gn_beta = d.gn_beta;
   P.gn_C0 = d.gn_C0; P.gn_C1 = d.gn_st1 ? d.gn_C1 : 0; P.gn_HW = d.gn_HW; P.gn_eps = d.gn_eps;
@@ -238,7 +270,7 @@ TcConvPlan* tc_conv_plan_create(int dt, const TcConvDesc& d, int num_sms, char* 
   }
   P.nsplit = nsplit;
   P.ldn = d.N;
-  P.nunits = P.ntiles * nsplit;
+  P.nunits = (P.ntiles - P.tile_base) * nsplit;
   P.out = d.out; P.bias = d.bias; P.bias_bstride = d.bias_bstride; P.res = d.res; P.scale = d.scale;
   P.stats_acc = d.stats_acc;
   const int units = (P.nunits + p->mc - 1) / p->mc;  // work-unit groups
@@ -248,6 +280,7 @@ TcConvPlan* tc_conv_plan_create(int dt, const TcConvDesc& d, int num_sms, char* 
 }
 
 void tc_conv_plan_destroy(TcConvPlan* p) {
+  if (p && p->tail) tc_conv_plan_destroy(p->tail);
   if (p && p->params.prof) {
     unsigned long long h[16];
     cudaMemcpy(h, p->params.prof, sizeof(h), cudaMemcpyDeviceToHost);
@@ -345,6 +378,7 @@ void tc_conv_launch(const TcConvPlan* p, cudaStream_t st) {
   cfg.attrs = attr;
   cfg.numAttrs = 1;
   cudaLaunchKernelExC(&cfg, p->kernel, args);
+  if (p->tail) tc_conv_launch(p->tail, st);
 }
 
 }  // namespace use

@@ -56,6 +56,8 @@ struct alignas(64) ConvParams {
   // of the ldn = C_out channels, a work unit is (tile, slice) and nunits = ntiles * nsplit of them are spread over the
   // CTAs.  Every output element sees the same K sequence as in the unsplit kernel: results are bit-identical.
   int nsplit, ldn, nunits;
+  int tile_base;  // first tile of this launch (a layer can be run as a balanced main launch + a sliced tail launch);
+                  // ntiles is the END of this launch's tile range, nunits = (ntiles - tile_base) * nsplit
   // Inline GroupNorm (fused segments only; gn_st0 != nullptr): the scale / shift table of GroupNorm(cat[s0, s1]) is NOT read
   // from global memory (seg[].aff, one gn_affine_kernel launch per convolution: 98 launches of ~6 us per evaluation) but
   // computed by the transform warps into shared memory whenever the CTA moves on to another sample -- the arithmetic of
@@ -219,7 +221,7 @@ __global__ void __launch_bounds__(ConvCfg<T, N, NSUB, FUSE, CG2>::THREADS, 1) co
         if (blocking) mbar_wait_p<PROF>(&a_empty[as], aph ^ 1, w_a);
         else if (!mbar_try_wait(&a_empty[as], aph ^ 1)) return false;
         const ConvSeg& S = p.seg[a_sg];
-        const int a_t = a_tile / nsp;  // a_tile walks work units
+        const int a_t = p.tile_base + a_tile / nsp;  // a_tile walks work units
         const int b = a_t / tiles_per_img;
         const int rem = a_t - b * tiles_per_img;
         const int th = rem / p.tiles_w;
@@ -392,7 +394,7 @@ __global__ void __launch_bounds__(ConvCfg<T, N, NSUB, FUSE, CG2>::THREADS, 1) co
     long long w_r = 0;
     const long long t_begin = PROF ? clock64() : 0;
     for (int unit = T0; unit < TEND; unit += TSTEP) {
-      const int tile = unit / nsp;
+      const int tile = p.tile_base + unit / nsp;
       const int b = tile / tiles_per_img;
       const int rem = tile - b * tiles_per_img;
       const int th = rem / p.tiles_w;
@@ -505,8 +507,8 @@ __global__ void __launch_bounds__(ConvCfg<T, N, NSUB, FUSE, CG2>::THREADS, 1) co
     long long w_f = 0;
     const long long t_begin = PROF ? clock64() : 0;
     for (int unit = T0; unit < TEND; unit += TSTEP, ++ti) {
-      const int tile = unit / nsp;
-      const int nb0 = (unit - tile * nsp) * N;  // first output channel of this unit's slice (0 without an N-split)
+      const int tile = p.tile_base + unit / nsp;
+      const int nb0 = (unit % nsp) * N;  // first output channel of this unit's slice (0 without an N-split)
       const int ldn = SWAP ? N : p.ldn;         // channel pitch of out / res / stats (the swap-AB form is never split)
       const bool ghost = tile >= p.ntiles;
       const int b = ghost ? 0 : tile / tiles_per_img;
