@@ -381,6 +381,14 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
+// Programmatic dependent launch (PDL).  A kernel launched with cudaLaunchAttributeProgrammaticStreamSerialization may be
+// scheduled while its predecessor in the stream still runs: pdl_launch_dependents() (called by the predecessor, here at
+// its very start) allows that, pdl_wait() (called by the successor after its local set-up -- barrier init, TMEM
+// allocation, tensor-map prefetch -- and before ANY access to global memory another kernel may write or still read)
+// blocks until the predecessor grid has completed and its writes are visible.  Both are no-ops without the attribute.
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
 __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }

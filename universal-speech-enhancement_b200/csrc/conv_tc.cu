@@ -370,13 +370,19 @@ void tc_conv_launch(const TcConvPlan* p, cudaStream_t st) {
   cfg.blockDim = dim3(p->threads);
   cfg.dynamicSmemBytes = p->smem;
   cfg.stream = st;
-  cudaLaunchAttribute attr[1];
+  cudaLaunchAttribute attr[2];
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = p->mc;
   attr[0].val.clusterDim.y = 1;
   attr[0].val.clusterDim.z = 1;
+  // programmatic dependent launch: the prologue of this kernel may overlap the tail of its predecessor (conv_tc.cuh).
+  // Measured with the gn_affine kernels in between chained the same way (bf16, CUDA graphs): batch 1 155.5 vs 158.7 ms per
+  // clip, batch 4 393.3 vs 388.3 ms per step -- inside run-to-run noise, so it stays opt-in (USE_B200_PDL=1)
+  static const bool pdl = getenv("USE_B200_PDL") && getenv("USE_B200_PDL")[0] == '1';  // opt-in: measured within noise
+  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[1].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
-  cfg.numAttrs = 1;
+  cfg.numAttrs = (pdl && p->mc == 1) ? 2 : 1;
   cudaLaunchKernelExC(&cfg, p->kernel, args);
   if (p->tail) tc_conv_launch(p->tail, st);
 }

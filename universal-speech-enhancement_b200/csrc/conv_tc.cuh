@@ -172,6 +172,9 @@ __global__ void __launch_bounds__(ConvCfg<T, N, NSUB, FUSE, CG2>::THREADS, 1) co
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
 
+  // PDL: let the next kernel of the stream be scheduled now (its CTAs only do local set-up before their own pdl_wait);
+  // everything up to pdl_wait() below touches nothing but kernel parameters, shared memory and TMEM
+  pdl_launch_dependents();
   if (threadIdx.x == 0) {
     for (int i = 0; i < p.nseg; ++i) {
       prefetch_tmap(&p.seg[i].tmA);
@@ -194,6 +197,7 @@ __global__ void __launch_bounds__(ConvCfg<T, N, NSUB, FUSE, CG2>::THREADS, 1) co
   if constexpr (MC > 1) cluster_sync_all();  // the peer's barriers are initialised before anything targets them
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();  // the predecessor's outputs (activations, statistics, scale / shift tables) are complete from here on
 
   const int tiles_per_img = p.tiles_w * p.tiles_h;
   // tile groups of MC consecutive tiles: CTA `crank` of a pair takes tile group * MC + crank.  T0 / TSTEP / TEND walk the

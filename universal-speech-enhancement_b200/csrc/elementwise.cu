@@ -103,6 +103,10 @@ __global__ void __launch_bounds__(256) gn_affine_kernel(const long long* __restr
                                                          const long long* __restrict__ st1, int C1,
                                                          const float* __restrict__ gamma, const float* __restrict__ beta,
                                                          float eps, int HW, float* __restrict__ aff) {
+  // PDL: this kernel sits between two convolutions; it lets the consumer convolution start its set-up now, and (being
+  // launched with the attribute itself) is already resident when the producer convolution finishes
+  pdl_launch_dependents();
+  pdl_wait();
   const int Ct = C0 + C1;
   const int G = min(Ct / 4, 32);
   const int cpg = Ct / G;
@@ -129,7 +133,17 @@ __global__ void __launch_bounds__(256) gn_affine_kernel(const long long* __restr
 
 void launch_gn_affine(GnSrc s0, GnSrc s1, const float* gamma, const float* beta, float eps, int HW, float* aff, int B,
                       cudaStream_t st) {
-  gn_affine_kernel<<<B, 256, 0, st>>>(s0.stats, s0.C, s1.stats, s1.C, gamma, beta, eps, HW, aff);
+  static const bool pdl = getenv("USE_B200_PDL") && getenv("USE_B200_PDL")[0] == '1';  // opt-in: measured within noise
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(B);
+  cfg.blockDim = dim3(256);
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl ? 1 : 0;
+  cudaLaunchKernelEx(&cfg, gn_affine_kernel, s0.stats, s0.C, s1.stats, s1.C, gamma, beta, eps, HW, aff);
 }
 
 // One thread owns a fixed 16-byte channel vector (scale / shift live in registers) and walks over pixels;
