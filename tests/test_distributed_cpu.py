@@ -37,7 +37,7 @@ def _worker(rank, world, port, n_clips, q):
     dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("n_clips", [8, 7])
+@pytest.mark.parametrize("n_clips", [8, 7, 1])  # even split, ragged, and B < world (rank 1 owns nothing: ADVICE r1)
 def test_two_rank_gloo_shard_and_gather(n_clips):
     with socket.socket() as s:
         s.bind(("127.0.0.1", 0))

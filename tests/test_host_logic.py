@@ -196,3 +196,18 @@ def test_loadwav_datamodule_file_discovery(tmp_path):
         LoadWavDataModule()
     with pytest.raises(NotImplementedError):
         LoadWavDataModule(data_folder=str(tmp_path), output_resample=True)
+
+
+@pytest.mark.parametrize("model_cfg", ["SGMSE_Large", "LSGAN"])
+def test_load_checkpoint_for_both_module_kinds(tmp_path, model_cfg):
+    """predict() calls model.load_checkpoint(ckpt_path) for whatever `model=` selects (GANModule had none):
+    a Lightning-style .ckpt ({"state_dict": ...}) round-trips through both module classes."""
+    cfg = compose(os.path.join(ROOT, "configs"), "predict.yaml", [f"model={model_cfg}"])
+    m = instantiate(cfg["model"])
+    sd = {k: torch.full_like(v, 0.25) if v.is_floating_point() else v for k, v in m.state_dict().items()}
+    path = str(tmp_path / "fake.ckpt")
+    torch.save({"state_dict": sd, "epoch": 3}, path)
+    m.load_checkpoint(path)
+    got = m.state_dict()
+    k = next(k for k in got if k.endswith("weight"))
+    assert float(got[k].flatten()[0]) == 0.25 and set(got.keys()) == set(sd.keys())
