@@ -104,10 +104,9 @@ struct ConvCfg {
   static constexpr int B_TILE = CG2 ? N * 64 : N * 128;  // CTA pair: each CTA stages half of the C_out rows
   // plain: 2 windows (loading / consumed).  fused: 3 (TMA loading the raw window / being normalised in place / consumed)
   static constexpr int A_SLOTS = FUSE ? 3 : 2;
-  // N <= 64: 8 KB weight tiles.  The 128-pixel form (NSUB = 1) is the N-split slice kernel of the small launches, whose K
-  // loop is bound by the TMA round trip, not by bandwidth: 16 tiles in flight instead of 8
+  // (N <= 64: 8 slots of 8 KB.  16 slots for the N-split slice kernel were measured: batch 1 158.6 vs 158.3 ms -- no gain)
   static constexpr int B_SLOTS = CG2 ? (FUSE ? 10 : 16)
-                                     : (N == 256) ? (FUSE ? 4 : 5) : (N == 128 ? (FUSE ? 5 : 8) : (NSUB == 1 ? 16 : 8));
+                                     : (N == 256) ? (FUSE ? 4 : 5) : (N == 128 ? (FUSE ? 5 : 8) : 8);
   static constexpr int ACC_COLS = NSUB * N;
   static constexpr int TMEM_COLS = (2 * ACC_COLS < 32) ? 32 : 2 * ACC_COLS;
   static constexpr int EPI_WARPS = 4 * NSUB;
