@@ -1214,7 +1214,9 @@ void launch_combine(int dt, const void* h, const float* pyr, const float* w, con
     // pixels per block: never a function of the batch, so the per-block partial sums -- and with them the fixed-point
     // statistics -- do not depend on how many clips are in flight.  (1024-pixel blocks were measured: no gain in fp32,
     // slower in bf16 -- 320 blocks are barely one wave.)
-    const int ppb = kCombinePixPerBlock;
+    // The low-resolution levels (<= 64 x 80) take shorter blocks: with 256 pixels a thread walks 32-64 pixels serially and
+    // a 2-block launch is pure load latency (batch 1: 34 us for 0.3 MB); a function of the LEVEL only, never of the batch.
+    const int ppb = HW >= 16384 ? kCombinePixPerBlock : (HW >= 4096 ? 64 : 32);
     dim3 grid((HW + ppb - 1) / ppb, B);
     const size_t sm = static_cast<size_t>(rows) * C * 2 * sizeof(float);
     if (pc == 4) combine_kernel<T, 4><<<grid, threads, sm, st>>>((const T*)h, pyr, w, bias, (T*)out, stats, HW, C, ppb);

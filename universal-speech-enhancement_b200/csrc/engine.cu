@@ -735,30 +735,25 @@ struct Builder {
     Act hn = new_act(C, x.H, x.W);
     gn_apply(x, nullptr, e->off.at(p + ".g"), e->off.at(p + ".gb"), 0, false, false, hn, nullptr);
     const size_t n = (size_t)M * C;
-    size_t hf = new_f32(n), q = new_f32(n), k = new_f32(n), v = new_f32(n), att = new_f32(n), proj = new_f32(n);
+    size_t q = new_f32(n), k = new_f32(n), v = new_f32(n), att = new_f32(n);
     Act out = new_act(C, x.H, x.W);
     if (!dry) {
       const int dt = e->dt, Bn = B;
       const void* hnp = ws(hn.off);
-      float *hfp = (float*)ws(hf), *qp = (float*)ws(q), *kp = (float*)ws(k), *vp = (float*)ws(v), *ap = (float*)ws(att),
-            *pp = (float*)ws(proj);
+      float *qp = (float*)ws(q), *kp = (float*)ws(k), *vp = (float*)ws(v), *ap = (float*)ws(att);
       const float *W0 = wf(p + ".NIN_0.W"), *b0 = wf(p + ".NIN_0.b"), *W1 = wf(p + ".NIN_1.W"), *b1 = wf(p + ".NIN_1.b");
       const float *W2 = wf(p + ".NIN_2.W"), *b2 = wf(p + ".NIN_2.b"), *W3 = wf(p + ".NIN_3.W"), *b3 = wf(p + ".NIN_3.b");
       const void* xp = ws(x.off);
       void* op = ws(out.off);
       const float sc = kInvSqrt2;
       emit([=](cudaStream_t s) {
-        launch_act_to_f32(dt, hnp, hfp, n, s);
-        launch_linear(hfp, W0, b0, qp, M, C, C, s);
-        launch_linear(hfp, W1, b1, kp, M, C, C, s);
-        launch_linear(hfp, W2, b2, vp, M, C, C, s);
+        launch_nin_qkv(dt, hnp, W0, b0, qp, W1, b1, kp, W2, b2, vp, M, C, s);
         launch_attn_core(qp, kp, vp, ap, Bn, Pn, C, s);
-        launch_linear(ap, W3, b3, pp, M, C, C, s);
-        launch_add_scale(dt, xp, pp, sc, op, n, s);
-      }, TAG_ATTN, 7, 8.0 * M * C * C + 4.0 * Bn * Pn * Pn * C, 0);
+        launch_nin_proj(dt, ap, W3, b3, xp, sc, op, M, C, s);
+      }, TAG_ATTN, 3, 8.0 * M * C * C + 4.0 * Bn * Pn * Pn * C, 0);
     }
     free_act(hn);
-    arena.release(hf); arena.release(q); arena.release(k); arena.release(v); arena.release(att); arena.release(proj);
+    arena.release(q); arena.release(k); arena.release(v); arena.release(att);
     return out;
   }
 

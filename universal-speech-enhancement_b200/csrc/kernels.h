@@ -137,13 +137,14 @@ void launch_dense_all(const float* temb, const float* W, const float* base, floa
                       cudaStream_t st);
 
 // ---- attention block (bottleneck only) ----------------------------------------------------------------
-// out[m][n] = sum_k in[m][k] * W[k][n] + b[n], fp32
-void launch_linear(const float* in, const float* W, const float* b, float* out, int M, int K, int N, cudaStream_t st);
-// act -> fp32 group-normalised (no SiLU) rows
+// q, k, v = NIN_0/1/2(in) in one launch: in is [M][C] in the activation dtype, W [C][C] ([in][out]), outputs fp32 [M][C]
+void launch_nin_qkv(int dt, const void* in, const float* W0, const float* b0, float* q, const float* W1, const float* b1,
+                    float* k, const float* W2, const float* b2, float* v, int M, int C, cudaStream_t st);
+// softmax(q k^T / sqrt(C)) v per sample over its P positions, fp32
 void launch_attn_core(const float* q, const float* k, const float* v, float* out, int B, int P, int C, cudaStream_t st);
-// out_act = (x + h + 0) * scale with h fp32 [rows][C]
-void launch_add_scale(int dt, const void* x, const float* h, float scale, void* out, size_t n, cudaStream_t st);
-void launch_act_to_f32(int dt, const void* x, float* out, size_t n, cudaStream_t st);
+// out_act = (x + NIN_3(att)) * scale
+void launch_nin_proj(int dt, const float* att, const float* W, const float* b, const void* x, float scale, void* out, int M,
+                     int C, cudaStream_t st);
 
 // ---- STFT front / back end ------------------------------------------------------------------------------
 // y [B][L] -> Y complex [B][F][Tp] with spectral compression (|S|^e e^{j angle} * factor), zero for frames >= T

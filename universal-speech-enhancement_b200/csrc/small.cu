@@ -68,37 +68,120 @@ void launch_dense_all(const float* temb, const float* W, const float* base, floa
   dense_all_kernel<<<blocks, 256, 0, st>>>(temb, W, base, out, B, rows, K);
 }
 
-// out[m][n] = in[m][:] . W[:][n] + b[n]   (NIN: W is [in][out])
-constexpr int LIN_RM = 8;
-__global__ void __launch_bounds__(256) linear_kernel(const float* __restrict__ in, const float* __restrict__ W,
-                                                      const float* __restrict__ b, float* __restrict__ out, int M, int K,
-                                                      int N) {
-  extern __shared__ float sin_[];  // [LIN_RM][K]
-  const int m0 = blockIdx.x * LIN_RM;
-  for (int i = threadIdx.x; i < LIN_RM * K; i += blockDim.x) {
-    const int r = i / K, k = i % K;
-    sin_[i] = (m0 + r < M) ? in[static_cast<size_t>(m0 + r) * K + k] : 0.f;
+// NIN layers of the attention block: out[m][n] = in[m][:] . W[:][n] + b[n]   (W is [in][out], layers.py:639-650).
+// A block owns NIN_RM rows x NIN_CN columns; its 256 threads are (column, K quarter): four partial dot products per
+// output run in parallel and are summed in a fixed order (deterministic).  At batch 1 the 80 x 256 x 256 product is
+// spread over 10 x 4 (x 3 for q, k, v) blocks with 64-step loops; the round-1 kernel walked K = 256 serially in 10 blocks
+// and the seven launches of the attention block cost 0.2 ms per evaluation (3.5 % of a batch-1 step).
+constexpr int NIN_RM = 8;
+constexpr int NIN_CN = 64;
+constexpr int NIN_KP = 4;
+
+struct NinJob {
+  const float* W;
+  const float* b;
+  float* out;
+};
+
+template <typename TIn>
+__device__ __forceinline__ void nin_block_partial(const TIn* __restrict__ in, const float* __restrict__ W, int M, int K, int N,
+                                                  int m0, int n, int kp, float* sin_, float (&acc)[NIN_RM]) {
+  for (int i = threadIdx.x; i < NIN_RM * K; i += blockDim.x) {
+    const int r = i / K, k = i - r * K;
+    sin_[i] = (m0 + r < M) ? static_cast<float>(in[static_cast<size_t>(m0 + r) * K + k]) : 0.f;
   }
   __syncthreads();
-  for (int n = blockIdx.y * blockDim.x + threadIdx.x; n < N; n += gridDim.y * blockDim.x) {
-    float acc[LIN_RM];
 #pragma unroll
-    for (int r = 0; r < LIN_RM; ++r) acc[r] = 0.f;
-    for (int k = 0; k < K; ++k) {
-      const float w = W[static_cast<size_t>(k) * N + n];
+  for (int r = 0; r < NIN_RM; ++r) acc[r] = 0.f;
+  const int kq = (K + NIN_KP - 1) / NIN_KP;
+  const int k0 = kp * kq, k1 = min(K, k0 + kq);
+  if (n < N) {
+#pragma unroll 8
+    for (int k = k0; k < k1; ++k) {
+      const float w = __ldg(W + static_cast<size_t>(k) * N + n);
 #pragma unroll
-      for (int r = 0; r < LIN_RM; ++r) acc[r] += sin_[r * K + k] * w;
+      for (int r = 0; r < NIN_RM; ++r) acc[r] = fmaf(sin_[r * K + k], w, acc[r]);
     }
-    const float bb = b[n];
-#pragma unroll
-    for (int r = 0; r < LIN_RM; ++r)
-      if (m0 + r < M) out[static_cast<size_t>(m0 + r) * N + n] = acc[r] + bb;
   }
 }
 
-void launch_linear(const float* in, const float* W, const float* b, float* out, int M, int K, int N, cudaStream_t st) {
-  dim3 grid((M + LIN_RM - 1) / LIN_RM, (N + 255) / 256);
-  linear_kernel<<<grid, 256, LIN_RM * K * sizeof(float), st>>>(in, W, b, out, M, K, N);
+// q, k, v = NIN_0/1/2(GroupNorm(x)): blockIdx.z selects the layer; the input is read in the activation dtype
+template <typename TIn>
+__global__ void __launch_bounds__(NIN_CN * NIN_KP) nin_qkv_kernel(const TIn* __restrict__ in, NinJob j0, NinJob j1, NinJob j2,
+                                                                   int M, int K, int N) {
+  extern __shared__ float nsm[];  // in[NIN_RM][K], part[NIN_KP][NIN_RM][NIN_CN]
+  float* sin_ = nsm;
+  float* part = nsm + NIN_RM * K;
+  const NinJob J = blockIdx.z == 0 ? j0 : (blockIdx.z == 1 ? j1 : j2);
+  const int m0 = blockIdx.x * NIN_RM;
+  const int nl = threadIdx.x % NIN_CN, kp = threadIdx.x / NIN_CN;
+  const int n = blockIdx.y * NIN_CN + nl;
+  float acc[NIN_RM];
+  nin_block_partial<TIn>(in, J.W, M, K, N, m0, n, kp, sin_, acc);
+#pragma unroll
+  for (int r = 0; r < NIN_RM; ++r) part[(kp * NIN_RM + r) * NIN_CN + nl] = acc[r];
+  __syncthreads();
+  for (int i = threadIdx.x; i < NIN_RM * NIN_CN; i += blockDim.x) {
+    const int r = i / NIN_CN, c = i - r * NIN_CN;
+    const int nn = blockIdx.y * NIN_CN + c;
+    if (m0 + r < M && nn < N) {
+      float v = part[r * NIN_CN + c];
+#pragma unroll
+      for (int q = 1; q < NIN_KP; ++q) v += part[(q * NIN_RM + r) * NIN_CN + c];
+      J.out[static_cast<size_t>(m0 + r) * N + nn] = v + __ldg(J.b + nn);
+    }
+  }
+}
+
+// out = (x + NIN_3(att)) * scale in the activation dtype (layerspp.py:89-93)
+template <typename T>
+__global__ void __launch_bounds__(NIN_CN * NIN_KP) nin_proj_kernel(const float* __restrict__ in, const float* __restrict__ W,
+                                                                    const float* __restrict__ b, const T* __restrict__ x,
+                                                                    float scale, T* __restrict__ out, int M, int K, int N) {
+  extern __shared__ float nsm[];
+  float* sin_ = nsm;
+  float* part = nsm + NIN_RM * K;
+  const int m0 = blockIdx.x * NIN_RM;
+  const int nl = threadIdx.x % NIN_CN, kp = threadIdx.x / NIN_CN;
+  const int n = blockIdx.y * NIN_CN + nl;
+  float acc[NIN_RM];
+  nin_block_partial<float>(in, W, M, K, N, m0, n, kp, sin_, acc);
+#pragma unroll
+  for (int r = 0; r < NIN_RM; ++r) part[(kp * NIN_RM + r) * NIN_CN + nl] = acc[r];
+  __syncthreads();
+  for (int i = threadIdx.x; i < NIN_RM * NIN_CN; i += blockDim.x) {
+    const int r = i / NIN_CN, c = i - r * NIN_CN;
+    const int nn = blockIdx.y * NIN_CN + c;
+    if (m0 + r < M && nn < N) {
+      float v = part[r * NIN_CN + c];
+#pragma unroll
+      for (int q = 1; q < NIN_KP; ++q) v += part[(q * NIN_RM + r) * NIN_CN + c];
+      const size_t o = static_cast<size_t>(m0 + r) * N + nn;
+      out[o] = static_cast<T>((static_cast<float>(x[o]) + (v + __ldg(b + nn))) * scale);
+    }
+  }
+}
+
+static size_t nin_smem(int K) { return (static_cast<size_t>(NIN_RM) * K + NIN_KP * NIN_RM * NIN_CN) * sizeof(float); }
+
+void launch_nin_qkv(int dt, const void* in, const float* W0, const float* b0, float* q, const float* W1, const float* b1,
+                    float* k, const float* W2, const float* b2, float* v, int M, int C, cudaStream_t st) {
+  dim3 grid((M + NIN_RM - 1) / NIN_RM, (C + NIN_CN - 1) / NIN_CN, 3);
+  const NinJob j0{W0, b0, q}, j1{W1, b1, k}, j2{W2, b2, v};
+  if (dt == kBF16)
+    nin_qkv_kernel<__nv_bfloat16><<<grid, NIN_CN * NIN_KP, nin_smem(C), st>>>((const __nv_bfloat16*)in, j0, j1, j2, M, C, C);
+  else
+    nin_qkv_kernel<float><<<grid, NIN_CN * NIN_KP, nin_smem(C), st>>>((const float*)in, j0, j1, j2, M, C, C);
+}
+
+void launch_nin_proj(int dt, const float* att, const float* W, const float* b, const void* x, float scale, void* out, int M,
+                     int C, cudaStream_t st) {
+  dim3 grid((M + NIN_RM - 1) / NIN_RM, (C + NIN_CN - 1) / NIN_CN);
+  if (dt == kBF16)
+    nin_proj_kernel<__nv_bfloat16><<<grid, NIN_CN * NIN_KP, nin_smem(C), st>>>(att, W, b, (const __nv_bfloat16*)x, scale,
+                                                                              (__nv_bfloat16*)out, M, C, C);
+  else
+    nin_proj_kernel<float><<<grid, NIN_CN * NIN_KP, nin_smem(C), st>>>(att, W, b, (const float*)x, scale, (float*)out, M, C, C);
 }
 
 // softmax(q k^T / sqrt(C)) v over all P = H*W positions, one block per (sample, query position)
@@ -155,35 +238,6 @@ __global__ void __launch_bounds__(256) attn_core_kernel(const float* __restrict_
 void launch_attn_core(const float* q, const float* k, const float* v, float* out, int B, int P, int C, cudaStream_t st) {
   dim3 grid(P, B);
   attn_core_kernel<<<grid, 256, (C + P + 32) * sizeof(float), st>>>(q, k, v, out, P, C);
-}
-
-template <typename T>
-__global__ void __launch_bounds__(256) add_scale_kernel(const T* __restrict__ x, const float* __restrict__ h, float scale,
-                                                         T* __restrict__ out, size_t n) {
-  for (size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n;
-       i += static_cast<size_t>(gridDim.x) * blockDim.x)
-    out[i] = static_cast<T>((static_cast<float>(x[i]) + h[i]) * scale);
-}
-template <typename T>
-__global__ void __launch_bounds__(256) act_to_f32_kernel(const T* __restrict__ x, float* __restrict__ out, size_t n) {
-  for (size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n;
-       i += static_cast<size_t>(gridDim.x) * blockDim.x)
-    out[i] = static_cast<float>(x[i]);
-}
-
-void launch_add_scale(int dt, const void* x, const float* h, float scale, void* out, size_t n, cudaStream_t st) {
-  const int blocks = static_cast<int>(std::min<size_t>((n + 255) / 256, 148 * 16));
-  if (dt == kBF16)
-    add_scale_kernel<__nv_bfloat16><<<blocks, 256, 0, st>>>((const __nv_bfloat16*)x, h, scale, (__nv_bfloat16*)out, n);
-  else
-    add_scale_kernel<float><<<blocks, 256, 0, st>>>((const float*)x, h, scale, (float*)out, n);
-}
-void launch_act_to_f32(int dt, const void* x, float* out, size_t n, cudaStream_t st) {
-  const int blocks = static_cast<int>(std::min<size_t>((n + 255) / 256, 148 * 16));
-  if (dt == kBF16)
-    act_to_f32_kernel<__nv_bfloat16><<<blocks, 256, 0, st>>>((const __nv_bfloat16*)x, out, n);
-  else
-    act_to_f32_kernel<float><<<blocks, 256, 0, st>>>((const float*)x, out, n);
 }
 
 }  // namespace use
