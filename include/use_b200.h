@@ -42,7 +42,7 @@ extern "C" {
 #pragma GCC visibility push(default)
 #endif
 
-#define USE_B200_ABI_VERSION 4
+#define USE_B200_ABI_VERSION 5
 
 #define USE_DTYPE_F32 0  /* fp32 storage, TF32 tensor-core math (PyTorch's own GPU default for conv) */
 #define USE_DTYPE_BF16 1 /* bf16 storage + bf16 tensor-core math, fp32 accumulate / statistics / SDE state */
@@ -259,6 +259,10 @@ int use_op_conv_out4(int dtype, const void* a, const float* w, const float* bias
  * w_oihw_host: fp32 [pc][C][3][3] on the HOST; w_packed_dev: device scratch of 48 * C * sizeof(act) bytes. */
 int use_op_head_tc(int dtype, const void* a, const float* w_oihw_host, const float* bias, const float* prev, float* out,
                    int B, int H, int W, int C, int pc, void* w_packed_dev, void* stream);
+/* The same head over the RAW tensor x with GroupNorm + SiLU fused into its operand path (layerspp.py / ncsnpp.py:440-446:
+ * `act(GroupNorm(h))` in front of the pyramid conv): aff = fp32 [B][2][C] scale row / shift row from use_op_gn_affine. */
+int use_op_head_tc_gn(int dtype, const void* x, const float* aff, const float* w_oihw_host, const float* bias,
+                      const float* prev, float* out, int B, int H, int W, int C, int pc, void* w_packed_dev, void* stream);
 int use_op_combine(int dtype, const void* h, const float* pyr, const float* w, const float* bias, void* out, int B, int HW,
                    int C, int pc, void* stream);
 /* Combine that also accumulates the fixed-point GroupNorm statistics [B][C][2] of its output (zero `stats` first). */

@@ -30,7 +30,7 @@ def test_library_exports_every_declared_symbol():
     assert exported == set(header_symbols())
     for name in header_symbols():
         assert hasattr(L, name)
-    assert L.use_abi_version() == 4
+    assert L.use_abi_version() == 5
 
 
 def _engine(L, net, dt):
@@ -98,7 +98,7 @@ def test_engine_options():
         assert L.use_engine_workspace_bytes(h, 2, 16, 24, C.byref(w)) == 0, L.use_last_error()
         sizes[fuse] = w.value
     assert sizes[0] > 0 and sizes[1] > 0
-    for key, val in ((b"use_graphs", 0), (b"use_graphs", 1), (b"overlap_groups", 1), (b"overlap_groups", 2)):
+    for key, val in ((b"use_graphs", 0), (b"use_graphs", 1), (b"overlap_groups", 1), (b"overlap_groups", 2), (b"fuse_head", 0), (b"fuse_head", 1)):
         assert L.use_engine_set_option(h, key, val) == 0, L.use_last_error()
     assert L.use_engine_set_option(h, b"overlap_groups", 3) != 0 and b"overlap_groups" in L.use_last_error()
     assert L.use_engine_set_option(h, b"no_such_option", 1) != 0 and b"unknown option" in L.use_last_error()

@@ -218,7 +218,7 @@ def test_engine_switches_are_bit_identical(dtype):
     eng = m.score_net.engine(y.device, dtype)
     ref = m.sample({"perturbed": y}, N=3, seed=9)["enhanced"]
     assert bool(torch.isfinite(ref).all())
-    for key, val, back in (("fuse_gn", 0, 1), ("use_graphs", 0, 1), ("overlap_groups", 1, 2), ("inline_gn", 1, 0)):
+    for key, val, back in (("fuse_gn", 0, 1), ("fuse_head", 0, 1), ("use_graphs", 0, 1), ("overlap_groups", 1, 2), ("inline_gn", 1, 0)):
         eng.set_option(key, val)
         got = m.sample({"perturbed": y}, N=3, seed=9)["enhanced"]
         eng.set_option(key, back)

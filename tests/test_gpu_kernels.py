@@ -453,6 +453,55 @@ def test_head_tc(case, dt):
     assert float((got - ref).abs().max()) <= 2e-5 * float(ref.abs().max()), describe_mismatch(got, ref)
 
 
+@pytest.mark.parametrize("dt", [F32, BF16], ids=["tf32", "bf16"])
+@pytest.mark.parametrize("case", HEAD_CASES, ids=[f"B{c[0]}_{c[1]}x{c[2]}_C{c[3]}_pc{c[4]}_{'prev' if c[5] else 'noprev'}" for c in HEAD_CASES])
+def test_head_tc_fused_groupnorm_operand(case, dt):
+    """Pyramid head with GroupNorm + SiLU applied inside its operand path (transform warps, head_tc.cuh FUSE) == gn_apply
+    followed by the plain head, BIT FOR BIT, and both match torch group_norm -> silu -> conv2d (+ FIR-up) within the
+    operand-rounding tolerance (ncsnpp.py:440-461)."""
+    B, H, W, Cc, pc, with_prev = case
+    L = _lib.lib()
+    g = torch.Generator().manual_seed(B * 977 + H + W + Cc + pc)
+    x = to_operand(1.5 * torch.randn(B, Cc, H, W, generator=g) + 0.3, dt)
+    gamma, beta = 1 + 0.1 * torch.randn(Cc, generator=g), 0.1 * torch.randn(Cc, generator=g)
+    w = torch.randn(pc, Cc, 3, 3, generator=g) / np.sqrt(9 * Cc)
+    bias = torch.randn(pc, generator=g)
+    prev = torch.randn(B, pc, H // 2, W // 2, generator=g) if with_prev and H % 2 == 0 and W % 2 == 0 else None
+    xd = act_tensor(x, dt)
+    st = gn_stats_raw(L, dt, xd, B, H * W, Cc)
+    gd, btd, bd = gamma.cuda(), beta.cuda(), bias.cuda()
+    wh = w.contiguous()
+    pd = prev.permute(0, 2, 3, 1).contiguous().cuda() if prev is not None else None
+    scratch = torch.empty(48 * Cc * 4, dtype=torch.uint8, device="cuda")
+    # (1) unfused: gn_apply materialises the activated operand, then the plain head
+    a_act = torch.empty_like(xd)
+    rc = L.use_op_gn_apply(dt, xd.data_ptr(), st.data_ptr(), Cc, None, None, 0, gd.data_ptr(), btd.data_ptr(), 1e-6, 0, 1, 1,
+                           a_act.data_ptr(), None, B, H, W, stream())
+    assert rc == 0, L.use_last_error()
+    out_u = torch.full((B, H, W, pc), float("nan"), device="cuda")
+    rc = L.use_op_head_tc(dt, a_act.data_ptr(), wh.data_ptr(), bd.data_ptr(), pd.data_ptr() if pd is not None else None,
+                          out_u.data_ptr(), B, H, W, Cc, pc, scratch.data_ptr(), stream())
+    assert rc == 0, L.use_last_error()
+    # (2) fused: the head reads the raw tensor + the scale / shift table
+    afft = torch.empty(B, 2, Cc, device="cuda", dtype=torch.float32)
+    rc = L.use_op_gn_affine(st.data_ptr(), Cc, None, 0, gd.data_ptr(), btd.data_ptr(), 1e-6, H * W, afft.data_ptr(), B, stream())
+    assert rc == 0, L.use_last_error()
+    out_f = torch.full((B, H, W, pc), float("nan"), device="cuda")
+    rc = L.use_op_head_tc_gn(dt, xd.data_ptr(), afft.data_ptr(), wh.data_ptr(), bd.data_ptr(),
+                             pd.data_ptr() if pd is not None else None, out_f.data_ptr(), B, H, W, Cc, pc, scratch.data_ptr(),
+                             stream())
+    assert rc == 0, L.use_last_error()
+    _sync()
+    assert torch.equal(out_u, out_f), describe_mismatch(out_f.cpu(), out_u.cpu())
+    ref_a = to_operand(_gn_ref(x, gamma, beta, True), dt)
+    ref = Fnn.conv2d(ref_a.double(), to_operand(w, dt).double(), bias.double(), padding=1).float()
+    if prev is not None:
+        ref = ref + O.fir_upsample_2d(prev)
+    got = out_f.permute(0, 3, 1, 2).cpu()
+    tol = (2e-3 if dt == F32 else 1.5e-2) * float(ref.abs().max())
+    assert float((got - ref).abs().max()) <= tol, describe_mismatch(got, ref)
+
+
 @pytest.mark.parametrize("dt", [F32, BF16], ids=["fp32", "bf16"])
 def test_combine_and_fir4(dt):
     L = _lib.lib()

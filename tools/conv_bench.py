@@ -28,7 +28,23 @@ CASES = [
 ]
 
 
+SMALL_CASES = [
+    ("L6 conv 256->256 (8x10)", 8, 10, 256, [256], [], []),
+    ("L6 conv 64->256 (8x10)", 8, 10, 256, [64], [], []),
+    ("L6 conv cat(256,256)->256 (8x10)", 8, 10, 256, [256, 256], [], []),
+    ("L5 conv 256->256 (16x20)", 16, 20, 256, [256], [], []),
+    ("L4 conv 256->256 (32x40)", 32, 40, 256, [256], [], []),
+    ("L3 conv 256->256 (64x80)", 64, 80, 256, [256], [], []),
+    ("L3 conv 64->256 (64x80)", 64, 80, 256, [64], [], []),
+    ("L3 conv cat(256,256)->256 (64x80)", 64, 80, 256, [256, 256], [], []),
+    ("L2 conv 256->256 (128x160)", 128, 160, 256, [256], [], []),
+]
+
+
 def main():
+    global CASES
+    if os.environ.get("CONV_BENCH_SMALL"):
+        CASES = SMALL_CASES
     ap = argparse.ArgumentParser()
     ap.add_argument("--batch", type=int, default=16)
     ap.add_argument("--reps", type=int, default=10)
@@ -99,7 +115,7 @@ def main():
         assert rc == 0, L.use_last_error()
         torch.cuda.synchronize()
 
-    def run_head(dtn, H, W, Cc):
+    def run_head(dtn, H, W, Cc, fused=False):
         dt = BF16 if dtn == "bf16" else F32
         B = args.batch
         tdt = torch.bfloat16 if dt == BF16 else torch.float32
@@ -109,8 +125,13 @@ def main():
         prev = torch.randn(B, H // 2, W // 2, 4, device="cuda")
         out = torch.empty(B, H, W, 4, device="cuda")
         scratch = torch.empty(48 * Cc * 4, dtype=torch.uint8, device="cuda")
-        rc = L.use_op_head_tc(dt, a.data_ptr(), w.data_ptr(), bias.data_ptr(), prev.data_ptr(), out.data_ptr(), B, H, W, Cc, 4,
-                              scratch.data_ptr(), stream())
+        if fused:
+            afft = torch.ones(B, 2, Cc, device="cuda", dtype=torch.float32)
+            rc = L.use_op_head_tc_gn(dt, a.data_ptr(), afft.data_ptr(), w.data_ptr(), bias.data_ptr(), prev.data_ptr(), out.data_ptr(),
+                                     B, H, W, Cc, 4, scratch.data_ptr(), stream())
+        else:
+            rc = L.use_op_head_tc(dt, a.data_ptr(), w.data_ptr(), bias.data_ptr(), prev.data_ptr(), out.data_ptr(), B, H, W, Cc, 4,
+                                  scratch.data_ptr(), stream())
         assert rc == 0, L.use_last_error()
         torch.cuda.synchronize()
 
@@ -149,6 +170,16 @@ def main():
         print(f"{dtn} gn_apply fir={fir} {H}x{W} C{Cc}: {ms:7.3f} ms  {nbytes / ms / 1e6:7.1f} GB/s (algorithmic)", flush=True)
 
     dts = ["fp32", "bf16"] if args.dtype == "both" else [args.dtype]
+    if os.environ.get("CONV_BENCH_ONLY_HEAD"):
+        cases = [(dtn, H, W, Cc, fused) for dtn in dts for (H, W, Cc) in ((512, 640, 128), (256, 320, 128), (64, 80, 256))
+                 for fused in (False, True)]
+        for c in cases:
+            run_head(*c)
+        ms = [float(l.split("ms_per_launch=")[1].split()[0]) for l in open(log) if "USE_B200_CONV_TIME" in l]
+        for (dtn, H, W, Cc, fused), t in zip(cases, ms):
+            gb = args.batch * H * W * Cc * (2 if dtn == "bf16" else 4) / 1e9
+            print(f"{dtn} head {H}x{W} C{Cc} {'fused' if fused else 'plain'}: {t:7.3f} ms  {gb / t * 1e3:7.1f} GB/s (operand read)", flush=True)
+        return
     if os.environ.get("CONV_BENCH_ONLY_FIR"):
         for dtn in dts:
             for (H, W, Cc, fir) in ((512, 640, 128, 1), (256, 320, 128, 1), (128, 160, 256, 1), (256, 320, 128, 2), (128, 160, 128, 2),
@@ -159,9 +190,10 @@ def main():
         for ci in range(len(CASES)):
             for fused in (0, 1):
                 run_case(dtn, ci, fused)
-    for dtn in dts:
-        run_head(dtn, 512, 640, 128)
-        run_head(dtn, 256, 320, 128)
+    if not os.environ.get("CONV_BENCH_SMALL"):
+        for dtn in dts:
+            run_head(dtn, 512, 640, 128)
+            run_head(dtn, 256, 320, 128)
     report(args)
 
 
@@ -179,7 +211,7 @@ def report(args):
                     line += f" | {'fused' if fused else 'plain'} {ms[k]:7.3f} ms {flops / ms[k] / 1e9:7.1f} TF/s"
                 k += 1
             print(line, flush=True)
-    for dtn in (["fp32", "bf16"] if args.dtype == "both" else [args.dtype]):
+    for dtn in ([] if os.environ.get("CONV_BENCH_SMALL") else (["fp32", "bf16"] if args.dtype == "both" else [args.dtype])):
         for (H, W, Cc) in ((512, 640, 128), (256, 320, 128)):
             if k < len(ms):
                 gb = args.batch * H * W * Cc * (2 if dtn == "bf16" else 4) / 1e9

@@ -269,7 +269,7 @@ class _Engine:
         self._ws_key = None
 
     def set_option(self, key: str, value: int) -> None:
-        """Engine A/B switches (`fuse_gn`, `use_graphs`, `overlap_groups`): results are bit-identical either way; the
+        """Engine A/B switches (`fuse_gn`, `fuse_head`, `use_graphs`, `overlap_groups`): results are bit-identical either way; the
         workspace plan may change, so the cached workspace is dropped."""
         _lib.check(self.L.use_engine_set_option(self.h, key.encode(), int(value)), "use_engine_set_option")
         self._ws = None

@@ -186,9 +186,10 @@ static TcConvPlan* plan_create_range(int dt, const TcConvDesc& d, int num_sms, c
   p->N = d.N;
   bool fuse = false;
   for (int i = 0; i < d.nseg; ++i) fuse = fuse || d.seg[i].aff != nullptr;
-  // N-split (conv_tc.cuh, ConvParams::nsplit): at most a third as many tiles as SMs -> 64-channel slices of C_out as extra
-  // work units (measured, bf16: batch 1 162.2 -> 157.7 ms per clip; at 80-147 tiles the 4x activation re-reads cost as
-  // much as the shorter weight stream saves: batch 2 unchanged, batch 4 2 % slower, hence the threshold).
+  // N-split (conv_tc.cuh, ConvParams::nsplit): a launch with few tiles runs 64- or 128-channel slices of C_out as extra
+  // work units, as many as still fit ONE wave of CTAs (first version, slices whenever tiles <= SMs / 3: batch 1
+  // 162.2 -> 157.7 ms per clip; at 80-147 tiles the 4x activation re-reads cost as much as the shorter weight stream
+  // saves: batch 2 unchanged, batch 4 2 % slower).
   // Only the C_out = 256 family: its unsplit kernel is the same pixel-major form, so split and unsplit launches are
   // bit-identical (a clip sampled alone == the same clip inside any batch).  The C_out = 128 layers run the swap-AB kernel,
   // whose channel-major epilogue sums the GroupNorm statistics in a different order: slicing them would make the result
@@ -199,8 +200,17 @@ static TcConvPlan* plan_create_range(int dt, const TcConvDesc& d, int num_sms, c
     const int base_tiles = ((d.W + 7) / 8) * ((d.H + base_h - 1) / base_h) * d.B;
     static const bool off = getenv("USE_B200_CONV_NSPLIT") && getenv("USE_B200_CONV_NSPLIT")[0] == '0';
     static const int max_tiles = getenv("USE_B200_CONV_NSPLIT_MAXTILES") ? atoi(getenv("USE_B200_CONV_NSPLIT_MAXTILES")) : (1 << 30);
-    if (!off && d.N == 256 && base_tiles * 3 <= num_sms && base_tiles < max_tiles && multicast_width() == 1 && !cg2_enabled() && !getenv("USE_B200_CONV_PROF"))
-      nsplit = d.N / 64;
+    // Slices are only worth it while ALL work units fit one wave: measured in isolation (bf16, batch 1, tools/conv_bench.py
+    // CONV_BENCH_SMALL): a single-tile K loop is bound by the latency of the dependent MMA chain (~0.3 us per tap for N = 64,
+    // 128 and 256 alike), so a unit costs the same whatever its width and a second wave doubles the launch.  64 x 80 (40
+    // tiles): unsplit 21 us, four slices (160 units = 2 waves) 26 us -> two 128-channel slices (80 units, one wave).
+    if (!off && d.N == 256 && base_tiles < max_tiles && multicast_width() == 1 && !cg2_enabled() && !getenv("USE_B200_CONV_PROF")) {
+      if (base_tiles * 4 <= num_sms) nsplit = 4;
+      else if (base_tiles * 2 <= num_sms) nsplit = 2;
+    }
+    // (Also slicing launches whose last wave is mostly empty -- batch 1 at 128 x 160: 160 tiles on 148 CTAs -- was measured:
+    // batch 1 148.8 -> 162.4 ms, batch 2 214.1 -> 249.9 ms.  A slice repeats the window load AND the GroupNorm transform of
+    // its tile, so four slices cost far more than the half-empty wave they fill.)
     if (force_split) nsplit = d.N / 64;
   }
   if (getenv("USE_B200_CONV_DEBUG")) {
@@ -208,14 +218,16 @@ static TcConvPlan* plan_create_range(int dt, const TcConvDesc& d, int num_sms, c
     fprintf(stderr, "conv plan B=%d H=%d W=%d N=%d nseg=%d base_tiles=%d nsplit=%d fuse=%d\n", d.B, d.H, d.W, d.N, d.nseg,
             ((d.W + 7) / 8) * ((d.H + bh - 1) / bh) * d.B, nsplit, (int)fuse);
   }
-  const int kN = nsplit > 1 ? 64 : d.N;  // the kernel's N (MMA width, TMEM columns, weight-tile rows)
+  const int kN = d.N / nsplit;  // the kernel's N (MMA width, TMEM columns, weight-tile rows)
   if (dt == kBF16) {
-    if (nsplit > 1) fill_kernel<__nv_bfloat16, 64, 1>(p, fuse);
+    if (nsplit == 4) fill_kernel<__nv_bfloat16, 64, 1>(p, fuse);
+    else if (nsplit == 2) fill_kernel<__nv_bfloat16, 128, 1>(p, fuse);
     else if (d.N == 256) fill_kernel<__nv_bfloat16, 256, 1>(p, fuse);
     else if (d.N == 128) fill_kernel<__nv_bfloat16, 128, 2>(p, fuse);
     else fill_kernel<__nv_bfloat16, 64, 2>(p, fuse);
   } else {
-    if (nsplit > 1) fill_kernel<float, 64, 1>(p, fuse);
+    if (nsplit == 4) fill_kernel<float, 64, 1>(p, fuse);
+    else if (nsplit == 2) fill_kernel<float, 128, 1>(p, fuse);
     else if (d.N == 256) fill_kernel<float, 256, 1>(p, fuse);
     else if (d.N == 128) fill_kernel<float, 128, 2>(p, fuse);
     else fill_kernel<float, 64, 2>(p, fuse);
@@ -306,7 +318,8 @@ bool head_tc_supported(int dt, int C, int pc) {
 }
 
 HeadPlan* head_tc_plan_create(int dt, const void* act, const void* w_packed, const float* bias, const float* prev4,
-                              float* out4, int B, int H, int W, int C, int pc, int num_sms, char* err, int errlen) {
+                              float* out4, int B, int H, int W, int C, int pc, int num_sms, char* err, int errlen,
+                              const float* aff) {
   if (!head_tc_supported(dt, C, pc)) {
     snprintf(err, errlen, "pyramid head: unsupported C=%d pc=%d", C, pc);
     return nullptr;
@@ -345,17 +358,27 @@ HeadPlan* head_tc_plan_create(int dt, const void* act, const void* w_packed, con
   P.tiles_h = (H + kHeadTile - 1) / kHeadTile;
   P.ntiles = P.tiles_w * P.tiles_h * B;
   P.bias = bias; P.out4 = out4; P.prev4 = prev4; P.pc = pc;
+  P.aff = aff; P.C = C;
   p->grid = P.ntiles < num_sms ? P.ntiles : num_sms;
-  if (dt == kBF16) cudaFuncSetAttribute(head_tc_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, kHeadSmem);
-  else cudaFuncSetAttribute(head_tc_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, kHeadSmem);
+  cudaFuncSetAttribute(head_tc_kernel<__nv_bfloat16, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kHeadSmem);
+  cudaFuncSetAttribute(head_tc_kernel<__nv_bfloat16, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kHeadSmem);
+  cudaFuncSetAttribute(head_tc_kernel<float, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kHeadSmem);
+  cudaFuncSetAttribute(head_tc_kernel<float, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kHeadSmem);
   return p;
 }
 
 void head_tc_plan_destroy(HeadPlan* p) { delete p; }
 
 void head_tc_launch(const HeadPlan* p, cudaStream_t st) {
-  if (p->dt == kBF16) head_tc_kernel<__nv_bfloat16><<<p->grid, kHeadThreads, kHeadSmem, st>>>(p->params);
-  else head_tc_kernel<float><<<p->grid, kHeadThreads, kHeadSmem, st>>>(p->params);
+  const bool fuse = p->params.aff != nullptr;
+  const int threads = kHeadThreads + (fuse ? kHeadXfThreads : 0);
+  if (p->dt == kBF16) {
+    if (fuse) head_tc_kernel<__nv_bfloat16, true><<<p->grid, threads, kHeadSmem, st>>>(p->params);
+    else head_tc_kernel<__nv_bfloat16, false><<<p->grid, threads, kHeadSmem, st>>>(p->params);
+  } else {
+    if (fuse) head_tc_kernel<float, true><<<p->grid, threads, kHeadSmem, st>>>(p->params);
+    else head_tc_kernel<float, false><<<p->grid, threads, kHeadSmem, st>>>(p->params);
+  }
 }
 
 int tc_conv_tiles_per_image(int dt, int N, int H, int W) {
@@ -375,10 +398,9 @@ void tc_conv_launch(const TcConvPlan* p, cudaStream_t st) {
   attr[0].val.clusterDim.x = p->mc;
   attr[0].val.clusterDim.y = 1;
   attr[0].val.clusterDim.z = 1;
-  // programmatic dependent launch: the prologue of this kernel may overlap the tail of its predecessor (conv_tc.cuh).
-  // Measured with the gn_affine kernels in between chained the same way (bf16, CUDA graphs): batch 1 155.5 vs 158.7 ms per
-  // clip, batch 4 393.3 vs 388.3 ms per step -- inside run-to-run noise, so it stays opt-in (USE_B200_PDL=1)
-  static const bool pdl = getenv("USE_B200_PDL") && getenv("USE_B200_PDL")[0] == '1';  // opt-in: measured within noise
+  // programmatic dependent launch: the prologue of this kernel may overlap the tail of its predecessor (conv_tc.cuh);
+  // small batches only, see pdl_enabled (kernels.h)
+  const bool pdl = pdl_enabled(p->params.B);
   attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   attr[1].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;

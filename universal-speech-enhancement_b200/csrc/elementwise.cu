@@ -131,9 +131,18 @@ __global__ void __launch_bounds__(256) gn_affine_kernel(const long long* __restr
   }
 }
 
+bool pdl_enabled(int B) {
+  static const int force = [] {
+    const char* v = getenv("USE_B200_PDL");
+    return !v ? -1 : (v[0] == '1' ? 1 : 0);
+  }();
+  static const int maxb = getenv("USE_B200_PDL_MAXB") ? atoi(getenv("USE_B200_PDL_MAXB")) : 2;
+  return force >= 0 ? force == 1 : B <= maxb;
+}
+
 void launch_gn_affine(GnSrc s0, GnSrc s1, const float* gamma, const float* beta, float eps, int HW, float* aff, int B,
                       cudaStream_t st) {
-  static const bool pdl = getenv("USE_B200_PDL") && getenv("USE_B200_PDL")[0] == '1';  // opt-in: measured within noise
+  const bool pdl = pdl_enabled(B);
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3(B);
   cfg.blockDim = dim3(256);

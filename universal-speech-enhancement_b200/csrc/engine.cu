@@ -220,13 +220,15 @@ struct use_engine {
   std::map<std::string, std::shared_ptr<Program>> programs;
   unsigned long long program_tick = 0;
   // fixed head of the workspace (byte offsets)
-  struct Head { size_t xr, xpad, t, gfp, sched, temb, dense, score, red, stats, arena; } head;
+  struct Head { size_t xr, xpad, t, gfp, sched, temb, temb_steps, dense, score, red, stats, arena; } head;
   // concurrency: a batch is split into `groups` halves that run on their own streams, so the HBM-bound GroupNorm
   // kernels of one half overlap the tensor-bound convolutions of the other (they fit beside the persistent conv CTA)
   int groups = 2;
   // GroupNorm + SiLU applied inside the convolution kernel's operand path (no normalised tensor in HBM); off: the
   // separate gn_apply kernel feeds the same convolutions (A/B testing: both give bit-identical results)
   bool fuse_gn = true;
+  // the same for the pyramid heads (head_tc.cuh, round 2): the head reads the raw ResBlock output; off: gn_apply + plain head
+  bool fuse_head = true;
   // scale / shift tables of the fused GroupNorms computed inside the consumer kernels (no gn_affine_kernel launches: 40 %
   // fewer launches per evaluation); off (default): one gn_affine_kernel launch per GroupNorm.  Bit-identical results.
   // Measured (bf16, CUDA graphs): batch 1 157.8 vs 157.1 ms per clip, batch 4 387.6 vs 377.5 ms per step -- inside a graph
@@ -865,18 +867,29 @@ struct Builder {
       // pyramid: GN -> SiLU -> conv3x3 C->pc (+ FIR-up of the previous pyramid)   (ncsnpp.py:440-461)
       {
         const std::string pg = "all_modules." + std::to_string(idx), pc = "all_modules." + std::to_string(idx + 1);
-        Act a = new_act(h.C, h.H, h.W);
         const bool head_tc = e->off.count(pc + ".whd") != 0;
-        gn_apply(h, nullptr, e->off.at(pg + ".g"), e->off.at(pg + ".b"), 0, true, head_tc, a, nullptr);
+        // fused GroupNorm operand (head_tc.cuh): the head reads the RAW ResBlock output and normalises it in shared memory
+        // (from 4 clips on: measured bf16, 16 clips 1404.6 -> 1399.7 ms per step, but batch 1 145.6 -> 146.3 ms per clip -- with
+        // one 32 KB window in flight instead of two the fused head itself runs at 1.8 TB/s against 5.3-6.3 TB/s plain)
+        const bool head_fuse = head_tc && e->fuse_gn && e->fuse_head && B >= 4;
+        Act a;
+        size_t haff = (size_t)-1;
+        if (head_fuse) {
+          haff = gn_affine(h, nullptr, e->off.at(pg + ".g"), e->off.at(pg + ".b"));
+        } else {
+          a = new_act(h.C, h.H, h.W);
+          gn_apply(h, nullptr, e->off.at(pg + ".g"), e->off.at(pg + ".b"), 0, true, head_tc, a, nullptr);
+        }
         size_t np[2] = {(size_t)-1, (size_t)-1};
         for (int k = 0; k < nparts; ++k) np[k] = new_f32((size_t)B * h.H * h.W * part_pc[k]);
         if (head_tc) {
           for (int k = 0; k < nparts && !dry; ++k) {
             char msg[512];
-            HeadPlan* hp = head_tc_plan_create(e->dt, ws(a.off), wt(e->off.at(k == 0 ? pc + ".whd" : pc + ".whd2")),
-                                               wf(pc + ".b") + part_c0[k],
+            HeadPlan* hp = head_tc_plan_create(e->dt, head_fuse ? ws(h.off) : ws(a.off),
+                                               wt(e->off.at(k == 0 ? pc + ".whd" : pc + ".whd2")), wf(pc + ".b") + part_c0[k],
                                                opyr[k] == (size_t)-1 ? nullptr : (const float*)ws(opyr[k]), (float*)ws(np[k]), B,
-                                               h.H, h.W, h.C, part_pc[k], e->num_sms, msg, sizeof(msg));
+                                               h.H, h.W, h.C, part_pc[k], e->num_sms, msg, sizeof(msg),
+                                               head_fuse ? (const float*)ws(haff) : nullptr);
             if (!hp) { err = fail("%s", msg); return; }
             prog->heads.push_back(hp);
             const double px = (double)B * h.H * h.W;
@@ -895,7 +908,8 @@ struct Builder {
           emit([=](cudaStream_t s) { launch_conv_out4(dt, ap, w, b, prev, o, Bn, H, W, C, s); }, TAG_SMALL_CONV, 1,
                2.0 * Bn * H * W * C * 36, (double)Bn * H * W * (C * es() + 16));
         }
-        free_act(a);
+        if (head_fuse) arena.release(haff);
+        else free_act(a);
         for (int k = 0; k < nparts; ++k) {
           if (opyr[k] != (size_t)-1) arena.release(opyr[k]);
           opyr[k] = np[k];
@@ -940,6 +954,7 @@ static int plan_workspace(use_engine* e, int B, int F, int T, size_t* total, siz
   e->head.gfp = off; off = align_up(off + (size_t)B * 2 * c.nf * 4, 1024);
   e->head.sched = off; off = align_up(off + (size_t)kMaxSteps * (2 * c.nf + 1) * 4, 1024);  // per-step t_i and Fourier features
   e->head.temb = off; off = align_up(off + (size_t)B * 4 * c.nf * 4, 1024);
+  e->head.temb_steps = off; off = align_up(off + (size_t)kMaxSteps * 4 * c.nf * 4, 1024);  // time embedding of every step
   e->head.dense = off; off = align_up(off + (size_t)B * e->dense_rows * 4, 1024);
   e->head.score = off; off = align_up(off + (size_t)B * F * T * 8, 1024);  // score of a corrector step (complex64)
   e->head.red = off; off = align_up(off + corrector_scratch_bytes(B), 1024);
@@ -995,18 +1010,26 @@ static std::shared_ptr<Program> get_program(use_engine* e, int B, int F, int T, 
 }
 
 // one network evaluation: t / gfp already in the workspace head; xr packed
-static void run_network(use_engine* e, Program* p, cudaStream_t st, const float* gfp, int gfp_bstride, bool allow_graph) {
+// silu(Linear(silu(Linear(gfp)))) for `rows` Fourier-feature rows (ncsnpp.py:349-368)
+static void run_temb_mlp(use_engine* e, const float* gfp, int gfp_bstride, float* temb, int rows, cudaStream_t st) {
+  launch_temb_mlp(gfp, gfp_bstride, (const float*)(e->dev_w + e->off.at("l1.w")), (const float*)(e->dev_w + e->off.at("l1.b")),
+                  (const float*)(e->dev_w + e->off.at("l2.w")), (const float*)(e->dev_w + e->off.at("l2.b")), temb, rows,
+                  e->cfg.nf, st);
+  e->launches += 1;
+}
+
+// temb_shared != nullptr: the time embedding of this evaluation was computed ahead of the loop (one row for the whole batch)
+static void run_network(use_engine* e, Program* p, cudaStream_t st, const float* gfp, int gfp_bstride, bool allow_graph,
+                        const float* temb_shared = nullptr) {
   char* base = p->base;
   const int nf = e->cfg.nf;
   cudaMemsetAsync(base + e->head.stats, 0, p->stats_bytes, st);  // fixed-point accumulators start at zero
   if (e->cfg.conditional) {
-    launch_temb_mlp(gfp, gfp_bstride, (const float*)(e->dev_w + e->off.at("l1.w")),
-                    (const float*)(e->dev_w + e->off.at("l1.b")), (const float*)(e->dev_w + e->off.at("l2.w")),
-                    (const float*)(e->dev_w + e->off.at("l2.b")), (float*)(base + e->head.temb), p->B, nf, st);
-    launch_dense_all((const float*)(base + e->head.temb), (const float*)(e->dev_w + e->off.at("dense.W")),
-                     (const float*)(e->dev_w + e->off.at("dense.base")), (float*)(base + e->head.dense), p->B,
-                     e->dense_rows, 4 * nf, st);
-    e->launches += 2;
+    if (!temb_shared) run_temb_mlp(e, gfp, gfp_bstride, (float*)(base + e->head.temb), p->B, st);
+    launch_dense_all(temb_shared ? temb_shared : (const float*)(base + e->head.temb), temb_shared ? 0 : 4 * nf,
+                     (const float*)(e->dev_w + e->off.at("dense.W")), (const float*)(e->dev_w + e->off.at("dense.base")),
+                     (float*)(base + e->head.dense), p->B, e->dense_rows, 4 * nf, st);
+    e->launches += 1;
   }
   if (!e->profiling) {
     if (allow_graph && e->use_graphs && !p->graph && !p->graph_failed) {
@@ -1106,6 +1129,7 @@ use_engine* use_engine_create(const use_config* cfg) {
   }
   cudaGetLastError();
   if (const char* v = getenv("USE_B200_FUSE_GN")) e->fuse_gn = v[0] != '0';
+  if (const char* v = getenv("USE_B200_FUSE_HEAD")) e->fuse_head = v[0] != '0';
   if (const char* v = getenv("USE_B200_GRAPHS")) e->use_graphs = v[0] != '0';
   if (const char* v = getenv("USE_B200_INLINE_GN")) e->inline_gn = v[0] != '0';
   return e;
@@ -1178,6 +1202,11 @@ int use_engine_set_option(use_engine* e, const char* key, int value) {
   }
   if (!strcmp(key, "fuse_gn")) {
     e->fuse_gn = value != 0;
+    e->programs.clear();
+    return 0;
+  }
+  if (!strcmp(key, "fuse_head")) {
+    e->fuse_head = value != 0;
     e->programs.clear();
     return 0;
   }
@@ -1347,6 +1376,9 @@ int use_pc_sample_ex(use_engine* e, int B, int F, int T, const void* Y, void* x_
   for (int g = 0; g < G; ++g) {
     char* base = prog[g]->base;
     cudaMemcpyAsync(base + e->head.sched, sched.data(), sched.size() * 4, cudaMemcpyHostToDevice, gs[g]);
+    // the time embedding depends on t_i only: all N of them in one launch ahead of the loop (it was a 2-GEMV chain in ONE
+    // block per sample at the head of every evaluation: ~40 us of a 5.1 ms batch-1 step, B times the same numbers)
+    run_temb_mlp(e, (const float*)(base + e->head.sched) + N, nf2, (float*)(base + e->head.temb_steps), N, gs[g]);
     const size_t off = (size_t)g * Bg * per;
     if (o.x_init) {
       if ((const float2*)o.x_init != (const float2*)x_state)
@@ -1369,7 +1401,7 @@ int use_pc_sample_ex(use_engine* e, int B, int F, int T, const void* Y, void* x_
         launch_pack_input(e->dt, e->cfg.input_channels, (const float2*)x_state + off, (const float2*)(o.cond ? o.cond : Y) + off,
                           o.cond2 ? (const float2*)o.cond2 + off : nullptr, (float*)(base + e->head.xr), base + e->head.xpad,
                           n, gs[g]);
-        run_network(e, p, gs[g], gfp_dev, 0, own_streams);
+        run_network(e, p, gs[g], gfp_dev, 0, own_streams, (const float*)(base + e->head.temb_steps) + (size_t)i * 2 * nf2);
         a.pyramid = (const float*)(base + p->pyramid_off);
         a.pyramid2 = (const float*)(base + p->pyramid2_off);
         a.pc = e->cfg.input_channels;
@@ -1641,8 +1673,8 @@ int use_op_conv_out4(int dtype, const void* a, const float* w, const float* bias
   launch_conv_out4(dtype, a, w, bias, prev, out, B, H, W, C, (cudaStream_t)stream);
   return cuda_check("use_op_conv_out4");
 }
-int use_op_head_tc(int dtype, const void* a, const float* w_oihw_host, const float* bias, const float* prev, float* out,
-                   int B, int H, int W, int C, int pc, void* w_packed_dev, void* stream) {
+static int op_head_tc(int dtype, const void* a, const float* aff, const float* w_oihw_host, const float* bias,
+                      const float* prev, float* out, int B, int H, int W, int C, int pc, void* w_packed_dev, void* stream) {
   if (!a || !w_oihw_host || !bias || !out || !w_packed_dev) return fail("null argument");
   if (!head_tc_supported(dtype, C, pc)) return fail("pyramid head: unsupported C=%d pc=%d", C, pc);
   std::vector<uint8_t> packed((size_t)48 * C * act_size(dtype));
@@ -1653,7 +1685,7 @@ int use_op_head_tc(int dtype, const void* a, const float* w_oihw_host, const flo
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   char msg[512];
-  HeadPlan* p = head_tc_plan_create(dtype, a, w_packed_dev, bias, prev, out, B, H, W, C, pc, sms, msg, sizeof(msg));
+  HeadPlan* p = head_tc_plan_create(dtype, a, w_packed_dev, bias, prev, out, B, H, W, C, pc, sms, msg, sizeof(msg), aff);
   if (!p) return fail("%s", msg);
   head_tc_launch(p, (cudaStream_t)stream);
   if (const char* reps_s = getenv("USE_B200_CONV_TIME")) {
@@ -1674,6 +1706,15 @@ int use_op_head_tc(int dtype, const void* a, const float* w_oihw_host, const flo
   cudaStreamSynchronize((cudaStream_t)stream);
   head_tc_plan_destroy(p);
   return cuda_check("use_op_head_tc");
+}
+int use_op_head_tc(int dtype, const void* a, const float* w_oihw_host, const float* bias, const float* prev, float* out,
+                   int B, int H, int W, int C, int pc, void* w_packed_dev, void* stream) {
+  return op_head_tc(dtype, a, nullptr, w_oihw_host, bias, prev, out, B, H, W, C, pc, w_packed_dev, stream);
+}
+int use_op_head_tc_gn(int dtype, const void* x, const float* aff, const float* w_oihw_host, const float* bias,
+                      const float* prev, float* out, int B, int H, int W, int C, int pc, void* w_packed_dev, void* stream) {
+  if (!aff) return fail("null argument");
+  return op_head_tc(dtype, x, aff, w_oihw_host, bias, prev, out, B, H, W, C, pc, w_packed_dev, stream);
 }
 int use_op_combine(int dtype, const void* h, const float* pyr, const float* w, const float* bias, void* out, int B, int HW,
                    int C, int pc, void* stream) {

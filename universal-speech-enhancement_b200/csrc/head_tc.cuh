@@ -1,5 +1,9 @@
 // Pyramid-head convolution: 3x3 pad 1, C -> pc (4 or 2) channels, fp32 output (+ FIR-upsample of the previous pyramid
-// level), ncsnpp.py:440-461.  The operand is the already normalised + activated tensor (launch_gn_apply).
+// level), ncsnpp.py:440-461.  The operand is the already normalised + activated tensor (launch_gn_apply) or, FUSE, the
+// RAW ResBlock output: six transform warps apply GroupNorm (per-sample scale / shift table) + SiLU + operand rounding in
+// place in shared memory behind the TMA, exactly like the convolution's fused operand path (conv_tc.cuh) -- the
+// normalised tensor of `GroupNorm -> SiLU -> conv3x3 C->4` never exists in HBM (one write + one read of C x H x W saved
+// per level; bit-identical to gn_apply + the plain head).
 //
 // A C -> 4 convolution has no N dimension to speak of: as nine shifted MMAs it is bound by reading the activation tile
 // from shared memory nine times (measured: 7.5 ms at 512 x 640 x 32 clips, 16 % of HBM speed).  Here the nine taps are
@@ -30,6 +34,8 @@ struct alignas(64) HeadParams {
   float* out4;         // fp32 [B][H][W][pc]
   const float* prev4;  // optional fp32 [B][H/2][W/2][pc]
   int pc;
+  const float* aff;    // FUSE: fp32 [B][2][C] scale row / shift row (launch_gn_affine)
+  int C;               // FUSE: row length of aff
 };
 
 constexpr int kHeadMaxChunks = 8;
@@ -42,11 +48,12 @@ constexpr int kHeadWBytes = kHeadMaxChunks * kHeadN * 128;  // 48 KB
 constexpr int kHeadStagePitch = 37;  // floats per pixel in the staging buffer (odd: conflict-free)
 constexpr int kHeadStageBytes = 256 * kHeadStagePitch * 4;  // per epilogue group
 constexpr int kHeadThreads = 64 + 2 * 256;
-constexpr int kHeadSmem = 1024 + kHeadASlots * kHeadASlot + kHeadWBytes + 2 * kHeadStageBytes + (2 * kHeadASlots + 5) * 8 + 16;
+constexpr int kHeadXfThreads = 256;  // FUSE: eight transform warps behind the epilogue groups (six cannot keep up with a bf16 window per 1200 cycles)
+constexpr int kHeadSmem = 1024 + kHeadASlots * kHeadASlot + kHeadWBytes + 2 * kHeadStageBytes + (3 * kHeadASlots + 5) * 8 + 16;
 static_assert(kHeadSmem <= 232448, "shared memory budget");
 
-template <typename T>
-__global__ void __launch_bounds__(kHeadThreads, 1) head_tc_kernel(const __grid_constant__ HeadParams p) {
+template <typename T, bool FUSE>
+__global__ void __launch_bounds__(kHeadThreads + (FUSE ? kHeadXfThreads : 0), 1) head_tc_kernel(const __grid_constant__ HeadParams p) {
   constexpr bool kBf16 = DT<T>::kIsBf16;
   constexpr int CK = 128 / sizeof(T);
   extern __shared__ uint8_t smem_raw[];
@@ -57,7 +64,8 @@ __global__ void __launch_bounds__(kHeadThreads, 1) head_tc_kernel(const __grid_c
   uint64_t* bars = reinterpret_cast<uint64_t*>(sW + kHeadWBytes + 2 * kHeadStageBytes);
   uint64_t* a_full = bars;
   uint64_t* a_empty = a_full + kHeadASlots;
-  uint64_t* w_full = a_empty + kHeadASlots;
+  uint64_t* a_raw = a_empty + kHeadASlots;  // FUSE: raw window landed (TMA -> transform warps)
+  uint64_t* w_full = a_raw + kHeadASlots;
   uint64_t* t_full = w_full + 1;
   uint64_t* t_empty = t_full + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(t_empty + 2);
@@ -67,7 +75,7 @@ __global__ void __launch_bounds__(kHeadThreads, 1) head_tc_kernel(const __grid_c
   if (threadIdx.x == 0) {
     prefetch_tmap(&p.tmA);
     prefetch_tmap(&p.tmW);
-    for (int i = 0; i < kHeadASlots; ++i) { mbar_init(&a_full[i], 1); mbar_init(&a_empty[i], 1); }
+    for (int i = 0; i < kHeadASlots; ++i) { mbar_init(&a_full[i], 1); mbar_init(&a_empty[i], 1); mbar_init(&a_raw[i], 1); }
     mbar_init(w_full, 1);
     for (int i = 0; i < 2; ++i) { mbar_init(&t_full[i], 1); mbar_init(&t_empty[i], 8); }
     fence_barrier_init();
@@ -102,8 +110,9 @@ __global__ void __launch_bounds__(kHeadThreads, 1) head_tc_kernel(const __grid_c
         for (int kc = 0; kc < p.nchunks; ++kc, ++ai) {
           const uint32_t as = ai % kHeadASlots, aph = (ai / kHeadASlots) & 1;
           mbar_wait(&a_empty[as], aph ^ 1);
-          mbar_arrive_expect_tx(&a_full[as], kHeadASlot);
-          tma_load_4d(sA + as * kHeadASlot, &p.tmA, &a_full[as], kc * CK, w0 - 1, h0 - 1, b);
+          uint64_t* landed = FUSE ? &a_raw[as] : &a_full[as];
+          mbar_arrive_expect_tx(landed, kHeadASlot);
+          tma_load_4d(sA + as * kHeadASlot, &p.tmA, landed, kc * CK, w0 - 1, h0 - 1, b);
         }
       }
     }
@@ -137,6 +146,62 @@ __global__ void __launch_bounds__(kHeadThreads, 1) head_tc_kernel(const __grid_c
         }
         if (elect_one()) umma_commit(&t_full[acs]);
         __syncwarp();
+      }
+    }
+  } else if (threadIdx.x >= kHeadThreads) {
+    if constexpr (FUSE) {
+      // ================================ transform warps ================================
+      // thread = one 16-byte channel vector (v) of the window pixels pb, pb + 32, ...; the window is 16 pixels x 128 B per
+      // row = 1024-byte aligned rows of 8 pixels, so the swizzle phase of window pixel q is q & 7.  Pixels outside the
+      // image keep the TMA's zero fill: the convolution pads the ACTIVATED tensor.
+      constexpr int V = DT<T>::kVec;
+      constexpr int PSTEP = kHeadXfThreads / 8;
+      constexpr int NPIX = kHeadWin * kHeadWin;
+      constexpr int NIT = (NPIX + PSTEP - 1) / PSTEP;
+      const int tt = threadIdx.x - kHeadThreads;
+      const int v = tt & 7, pb = tt >> 3;
+      uint32_t ai = 0;
+      for (int tile = g0; tile < p.ntiles; tile += gstep) {
+        const int b = tile / tiles_per_img;
+        const int rem = tile - b * tiles_per_img;
+        const int th = rem / p.tiles_w;
+        const int w0 = (rem - th * p.tiles_w) * kHeadTile, h0 = th * kHeadTile;
+        uint32_t inside = 0;
+#pragma unroll
+        for (int i = 0; i < NIT; ++i) {
+          const int q = pb + PSTEP * i;
+          const int hh = h0 - 1 + (q >> 4), ww = w0 - 1 + (q & 15);
+          if (q < NPIX && hh >= 0 && hh < p.H && ww >= 0 && ww < p.W) inside |= 1u << i;
+        }
+        const float* aff = p.aff + static_cast<size_t>(b) * 2 * p.C + v * V;
+        for (int kc = 0; kc < p.nchunks; ++kc, ++ai) {
+          float sc[V], sh[V];
+#pragma unroll
+          for (int j = 0; j < V; j += 4) {
+            const float4 a = __ldg(reinterpret_cast<const float4*>(aff + kc * CK + j));
+            const float4 c = __ldg(reinterpret_cast<const float4*>(aff + p.C + kc * CK + j));
+            sc[j] = a.x; sc[j + 1] = a.y; sc[j + 2] = a.z; sc[j + 3] = a.w;
+            sh[j] = c.x; sh[j + 1] = c.y; sh[j + 2] = c.z; sh[j + 3] = c.w;
+          }
+          const uint32_t as = ai % kHeadASlots, aph = (ai / kHeadASlots) & 1;
+          mbar_wait(&a_raw[as], aph);
+          uint8_t* slot = sA + as * kHeadASlot;
+#pragma unroll
+          for (int i = 0; i < NIT; ++i) {
+            if ((inside >> i) & 1u) {
+              const int q = pb + PSTEP * i;
+              uint4* ptr = reinterpret_cast<uint4*>(slot + q * 128 + ((v ^ (q & 7)) << 4));
+              float f[V];
+              Vec<T>::unpack(*ptr, f);
+#pragma unroll
+              for (int j = 0; j < V; ++j) f[j] = silu_act<T>(fmaf(f[j], sc[j], sh[j]));
+              *ptr = Vec<T>::pack_operand(f);
+            }
+          }
+          fence_proxy_async();  // generic-proxy writes -> visible to the tensor core's async-proxy reads
+          named_bar_sync(3, kHeadXfThreads);
+          if (tt == 0) mbar_arrive(&a_full[as]);
+        }
       }
     }
   } else {

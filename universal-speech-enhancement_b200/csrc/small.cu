@@ -46,26 +46,30 @@ void launch_temb_mlp(const float* gfp, int gfp_bstride, const float* w1, const f
   temb_mlp_kernel<<<B, 512, 6 * nf * sizeof(float), st>>>(gfp, gfp_bstride, w1, b1, w2, b2, out, nf);
 }
 
-// out[b][n] = base[n] + W[n][:] . temb[b][:]   (all Dense_0 of all ResBlocks stacked along n)
-__global__ void __launch_bounds__(256) dense_all_kernel(const float* __restrict__ temb, const float* __restrict__ W,
-                                                         const float* __restrict__ base, float* __restrict__ out, int B,
-                                                         int rows, int K) {
+// out[b][n] = base[n] + W[n][:] . temb[b][:]   (all Dense_0 of all ResBlocks stacked along n).  temb_bstride = 0: every
+// sample shares one time (the sampling loop): the row is computed once and written B times.
+__global__ void __launch_bounds__(256) dense_all_kernel(const float* __restrict__ temb, int temb_bstride,
+                                                         const float* __restrict__ W, const float* __restrict__ base,
+                                                         float* __restrict__ out, int B, int rows, int K) {
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   if (warp >= rows) return;
   const float* wr = W + static_cast<size_t>(warp) * K;
   const float bs = base[warp];
+  float last = 0.f;
   for (int b = 0; b < B; ++b) {
-    float acc = 0.f;
-    for (int k = lane; k < K; k += 32) acc += wr[k] * temb[b * K + k];
-    acc = warp_sum(acc);
-    if (lane == 0) out[static_cast<size_t>(b) * rows + warp] = acc + bs;
+    if (b == 0 || temb_bstride != 0) {
+      float acc = 0.f;
+      for (int k = lane; k < K; k += 32) acc += wr[k] * temb[static_cast<size_t>(b) * temb_bstride + k];
+      last = warp_sum(acc) + bs;
+    }
+    if (lane == 0) out[static_cast<size_t>(b) * rows + warp] = last;
   }
 }
 
-void launch_dense_all(const float* temb, const float* W, const float* base, float* out, int B, int rows, int K,
-                      cudaStream_t st) {
+void launch_dense_all(const float* temb, int temb_bstride, const float* W, const float* base, float* out, int B, int rows,
+                      int K, cudaStream_t st) {
   const int blocks = (rows * 32 + 255) / 256;
-  dense_all_kernel<<<blocks, 256, 0, st>>>(temb, W, base, out, B, rows, K);
+  dense_all_kernel<<<blocks, 256, 0, st>>>(temb, temb_bstride, W, base, out, B, rows, K);
 }
 
 // NIN layers of the attention block: out[m][n] = in[m][:] . W[:][n] + b[n]   (W is [in][out], layers.py:639-650).
