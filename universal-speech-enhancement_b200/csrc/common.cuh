@@ -146,6 +146,21 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
       : "memory");
   return ok != 0;
 }
+// NON-blocking phase test.  mbarrier.try_wait may SUSPEND the thread for a system-dependent time before it reports
+// "not complete" (PTX ISA); measured on B200 (PROF build, round 2): a failed try_wait costs the polling thread ~470 cycles,
+// which made the convolution's TMA producer -- it polls for a free window slot before every weight tile -- the slowest
+// role of the kernel (MMA issuer waiting for weights 22 % of the time).  A poll must use test_wait.
+__device__ __forceinline__ bool mbar_test_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
 // Bounded wait: a protocol bug must trap (reported as a CUDA error) instead of hanging the GPU box.
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   for (uint32_t spin = 0; spin < (1u << 22); ++spin) {

@@ -224,7 +224,7 @@ __global__ void __launch_bounds__(ConvCfg<T, N, NSUB, FUSE, CG2>::THREADS, 1) co
       auto a_issue = [&](bool blocking) -> bool {
         const uint32_t as = ai % C::A_SLOTS, aph = (ai / C::A_SLOTS) & 1;
         if (blocking) mbar_wait_p<PROF>(&a_empty[as], aph ^ 1, w_a);
-        else if (!mbar_try_wait(&a_empty[as], aph ^ 1)) return false;
+        else if (!mbar_test_wait(&a_empty[as], aph ^ 1)) return false;
         const ConvSeg& S = p.seg[a_sg];
         const int a_t = p.tile_base + a_tile / nsp;  // a_tile walks work units
         const int b = a_t / tiles_per_img;
