@@ -6,6 +6,7 @@
 #include <mutex>
 
 #include "conv_tc.cuh"
+#include "conv_tc_ks.cuh"
 #include "head_tc.cuh"
 #include "kernels.h"
 
@@ -32,7 +33,8 @@ static EncodeTiledFn get_encode() {
 
 struct TcConvPlan {
   ConvParams params;
-  int dt, N, nsub, mc;
+  int dt, N, nsub, mc;  // mc: cluster width of the launch (weight multicast pairs, CTA-pair MMAs or split-K clusters)
+  int ks = 1;           // split-K cluster width (conv_tc_ks.cuh); 1: conv_tc_kernel
   int grid, threads, smem;
   const void* kernel;
   TcConvPlan* tail = nullptr;  // sliced launch over the last (ntiles mod SMs) tiles, run right after this one
@@ -100,6 +102,24 @@ static void set_kernel(TcConvPlan* p) {
   p->smem = C::SMEM_BYTES;
   p->nsub = NSUB;
   p->mc = MC;
+}
+
+template <typename T, bool FUSE, int KS>
+static void set_ks_kernel(TcConvPlan* p) {
+  auto k = &conv_tc_ks_kernel<T, 64, FUSE, KS>;
+  p->kernel = reinterpret_cast<const void*>(k);
+  cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, ConvKsCfg<T, 64, FUSE, KS>::SMEM_BYTES);
+  cudaFuncSetAttribute(k, cudaFuncAttributeNonPortableClusterSizeAllowed, 0);
+  p->threads = ConvCfg<T, 64, 1, FUSE, false>::THREADS;
+  p->smem = ConvKsCfg<T, 64, FUSE, KS>::SMEM_BYTES;
+  p->nsub = 1;
+  p->mc = KS;
+  p->ks = KS;
+}
+template <typename T>
+static void fill_ks_kernel(TcConvPlan* p, bool fuse, int ks) {
+  if (ks == 4) { if (fuse) set_ks_kernel<T, true, 4>(p); else set_ks_kernel<T, false, 4>(p); }
+  else { if (fuse) set_ks_kernel<T, true, 2>(p); else set_ks_kernel<T, false, 2>(p); }
 }
 
 // CTA-pair MMAs (tcgen05 cta_group::2) for the C_out = 128 layers: USE_B200_CONV_CG2=1 / 0
@@ -213,13 +233,32 @@ static TcConvPlan* plan_create_range(int dt, const TcConvDesc& d, int num_sms, c
     // its tile, so four slices cost far more than the half-empty wave they fill.)
     if (force_split) nsplit = d.N / 64;
   }
+  // Split-K clusters (conv_tc_ks.cuh) for the low-resolution levels: chosen by the LEVEL GEOMETRY only (tiles per clip),
+  // never by the batch, because the partial-sum association differs from conv_tc_kernel's single accumulator: a layer
+  // that runs this form runs it at every batch size.  <= 3 tiles per clip (16 x 20, 8 x 10): 4 CTAs per work unit;
+  // <= 10 (32 x 40): 2, so that batch 1 still fits one wave (10 tiles x 4 slices x 2 = 80 CTAs).
+  int ks = 1;
+  {
+    static const bool ks_off = getenv("USE_B200_CONV_KSPLIT") && getenv("USE_B200_CONV_KSPLIT")[0] == '0';
+    const int tiles_img = ((d.W + 7) / 8) * ((d.H + 15) / 16);
+    int ktot = 0;
+    for (int i = 0; i < d.nseg; ++i) ktot += d.seg[i].taps * (d.seg[i].C / (128 / (int)act_size(dt)));
+    if (!ks_off && !force_split && tile_count < 0 && d.N == 256 && tiles_img <= 10 && ktot >= 4 && multicast_width() == 1 &&
+        !cg2_enabled() && !getenv("USE_B200_CONV_PROF")) {
+      ks = tiles_img <= 3 ? 4 : 2;
+      nsplit = 4;
+    }
+  }
   if (getenv("USE_B200_CONV_DEBUG")) {
     const int bh = d.N == 256 ? 16 : 32;
-    fprintf(stderr, "conv plan B=%d H=%d W=%d N=%d nseg=%d base_tiles=%d nsplit=%d fuse=%d\n", d.B, d.H, d.W, d.N, d.nseg,
-            ((d.W + 7) / 8) * ((d.H + bh - 1) / bh) * d.B, nsplit, (int)fuse);
+    fprintf(stderr, "conv plan B=%d H=%d W=%d N=%d nseg=%d base_tiles=%d nsplit=%d ks=%d fuse=%d\n", d.B, d.H, d.W, d.N, d.nseg,
+            ((d.W + 7) / 8) * ((d.H + bh - 1) / bh) * d.B, nsplit, ks, (int)fuse);
   }
   const int kN = d.N / nsplit;  // the kernel's N (MMA width, TMEM columns, weight-tile rows)
-  if (dt == kBF16) {
+  if (ks > 1) {
+    if (dt == kBF16) fill_ks_kernel<__nv_bfloat16>(p, fuse, ks);
+    else fill_ks_kernel<float>(p, fuse, ks);
+  } else if (dt == kBF16) {
     if (nsplit == 4) fill_kernel<__nv_bfloat16, 64, 1>(p, fuse);
     else if (nsplit == 2) fill_kernel<__nv_bfloat16, 128, 1>(p, fuse);
     else if (d.N == 256) fill_kernel<__nv_bfloat16, 256, 1>(p, fuse);
@@ -285,6 +324,26 @@ static TcConvPlan* plan_create_range(int dt, const TcConvDesc& d, int num_sms, c
   P.nunits = (P.ntiles - P.tile_base) * nsplit;
   P.out = d.out; P.bias = d.bias; P.bias_bstride = d.bias_bstride; P.res = d.res; P.scale = d.scale;
   P.stats_acc = d.stats_acc;
+  if (p->ks > 1) {
+    // one cluster per work unit, as many clusters as can be resident (one CTA per SM; GPC boundaries cost a few)
+    int max_clusters = num_sms / p->ks;
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(num_sms / p->ks * p->ks);
+    cfg.blockDim = dim3(p->threads);
+    cfg.dynamicSmemBytes = p->smem;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = p->ks;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    int n = 0;
+    if (cudaOccupancyMaxActiveClusters(&n, p->kernel, &cfg) == cudaSuccess && n > 0 && n < max_clusters) max_clusters = n;
+    cudaGetLastError();
+    p->grid = (P.nunits < max_clusters ? P.nunits : max_clusters) * p->ks;
+    return p;
+  }
   const int units = (P.nunits + p->mc - 1) / p->mc;  // work-unit groups
   const int max_groups = num_sms / p->mc;
   p->grid = (units < max_groups ? units : max_groups) * p->mc;  // persistent CTAs, one per SM, a multiple of the cluster
@@ -404,7 +463,7 @@ void tc_conv_launch(const TcConvPlan* p, cudaStream_t st) {
   attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   attr[1].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
-  cfg.numAttrs = (pdl && p->mc == 1) ? 2 : 1;
+  cfg.numAttrs = (pdl && (p->mc == 1 || p->ks > 1)) ? 2 : 1;
   cudaLaunchKernelExC(&cfg, p->kernel, args);
   if (p->tail) tc_conv_launch(p->tail, st);
 }
