@@ -216,8 +216,8 @@ def main():
     y_dev_all = y_all.to(dev)                          # device-timed arm: inputs already resident in HBM
 
     def step_device(i):
-        return sample_sharded(lambda yl, clip0: model.sample({"perturbed": yl}, N=N, seed=1000 + i, clip0=clip0)["enhanced"],
-                              y_dev_all)
+        return sample_sharded(lambda yl, clip0: model.sample({"perturbed": yl}, N=N, seed=1000 + i, clip0=clip0,
+                                                             job_clips=y_dev_all.shape[0])["enhanced"], y_dev_all)
 
     def step_e2e(i):
         # host -> device copy of this rank's clips, the reference-facing call, gather, device -> host read of the result

@@ -86,8 +86,15 @@ int use_engine_workspace_bytes(use_engine* e, int B, int F, int T, size_t* bytes
 /* Options: "overlap_groups" = 1 | 2 (default 2): use_pc_sample splits an even batch >= 4 into two halves that run
  * on their own streams so the HBM-bound kernels of one half overlap the tensor-bound convolutions of the other.
  * A/B switches whose two settings give bit-identical results: "fuse_gn" (GroupNorm + SiLU inside the convolution's
- * operand path), "use_graphs" (CUDA-graph replay of an evaluation), "inline_gn" (GroupNorm scale / shift tables computed
- * inside the consumer kernels instead of one gn_affine_kernel launch per GroupNorm). */
+ * operand path), "fuse_head" (the same inside the pyramid heads), "use_graphs" (CUDA-graph replay of an evaluation),
+ * "inline_gn" (GroupNorm scale / shift tables computed inside the consumer kernels instead of one gn_affine_kernel
+ * launch per GroupNorm).
+ * "ksplit" = 0 | 1 | 2 (default 2 = auto): LATENCY mode.  The convolutions of the low-resolution levels (<= 32 x 40
+ * pixels per clip) run as split-K clusters of 2 / 4 CTAs with a DSMEM reduction in rank order: batch 1 -6 % (bf16) /
+ * -9 % (TF32), but 2 % slower from ~16 clips on.  auto = calls of at most two clips.  The mode is a property of the whole
+ * launch program: inside a mode per-clip results are bit-identical for every batch size; the two modes differ in the
+ * last bits (same tolerance to the reference).  A caller that splits one job over several calls (micro-batches, ranks)
+ * sets 0 / 1 explicitly from the size of the whole job (the Python layer does: ScoreModel.sample(job_clips=...)). */
 int use_engine_set_option(use_engine* e, const char* key, int value);
 
 /* Instrumentation: kernels launched so far by this engine; per-op-class CUDA-event timing of network evaluations
@@ -248,6 +255,9 @@ int use_op_conv_tc_gn(int dtype, int nseg, const void* const* seg_act, const int
                       const float* const* seg_aff, const int* seg_aff_c, const int* seg_aff_c0, int B, int H, int W, int N,
                       const float* bias, int bias_bstride, const void* res, float scale, void* out, long long* stats,
                       void* stream);
+/* Test hook: the use_op_conv_tc* entry points plan their launches like a latency-mode program (split-K clusters for images
+ * of at most 10 tiles, see use_engine_set_option "ksplit"). */
+int use_op_set_latency(int on);
 int use_op_conv_ref(int dtype, const void* x, const float* w, const float* bias, int bias_bstride, const void* res,
                     float scale, void* out, int B, int H, int W, int Cin, int Cout, int ksize, void* stream);
 int use_op_conv_in4(int dtype, const float* x, const float* w, const float* bias, void* out, int B, int H, int W, int N,

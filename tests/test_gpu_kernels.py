@@ -103,6 +103,51 @@ def test_conv_tc(case, dt):
     assert float((got - ref).abs().max()) <= tol, f"{name}: " + describe_mismatch(got, ref)
 
 
+KS_CASES = [
+    # name, B, H, W, [(Cin, ks), ...], per-sample bias, residual   (C_out = 256: the only family with a split-K form)
+    ("ks4_bottleneck_8x10", 3, 8, 10, [(256, 3)], True, True),            # 1 tile per clip -> clusters of 4
+    ("ks4_16x20_cat", 2, 16, 20, [(256, 3), (256, 3)], True, False),      # 3 tiles, two 3x3 segments (concatenated input)
+    ("ks4_16x20_skip", 2, 16, 20, [(256, 3), (256, 1), (256, 1)], False, False),  # 3x3 + two 1x1 skip segments
+    ("ks2_32x40", 2, 32, 40, [(256, 3)], True, True),                     # 10 tiles -> clusters of 2
+    ("ks2_32x24_ragged", 3, 30, 20, [(128, 3), (256, 1)], False, False),  # ragged edges, odd tap split
+    ("ks4_one_chunk", 1, 8, 8, [(64, 3)], False, False),                  # 9 taps over 4 ranks (fp32: 18 over 4)
+]
+
+
+@pytest.mark.parametrize("dt", [F32, BF16], ids=["tf32", "bf16"])
+@pytest.mark.parametrize("case", KS_CASES, ids=[c[0] for c in KS_CASES])
+def test_conv_tc_latency_split_k(case, dt):
+    """conv_tc_ks.cuh: the split-K cluster form of the low-resolution levels (latency-mode programs): clusters of 2 / 4
+    CTAs accumulate disjoint tap ranges and the leader adds the partial sums in rank order through DSMEM.  vs fp64 torch,
+    vs the single-accumulator kernel (same operands, another association: fp32 rounding only), statistics of the output,
+    and batch invariance INSIDE the mode (a clip alone == the same clip in a batch, bit for bit)."""
+    name, B, H, W, seg_spec, per_sample, with_res = case
+    N = 256
+    L = _lib.lib()
+    g = torch.Generator().manual_seed(len(name) * 7 + H)
+    segs = [make_seg(g, dt, B, cin, N, H, W, ks) for cin, ks in seg_spec]
+    bias = torch.randn(B, N, generator=g) if per_sample else torch.randn(N, generator=g)
+    res = torch.randn(B, N, H, W, generator=g) if with_res else None
+    scale = 0.70710678
+    plain, st_plain = run_conv_tc(dt, segs, B, H, W, N, bias, res, scale, want_stats=True)
+    assert L.use_op_set_latency(1) == 0
+    try:
+        got, st = run_conv_tc(dt, segs, B, H, W, N, bias, res, scale, want_stats=True)
+        got2, st2 = run_conv_tc(dt, segs, B, H, W, N, bias, res, scale, want_stats=True)
+        one = run_conv_tc(dt, [(x[B - 1:], w, ks) for x, w, ks in segs], 1, H, W, N, bias[B - 1:] if per_sample else bias,
+                          res[B - 1:] if res is not None else None, scale)
+    finally:
+        L.use_op_set_latency(0)
+    ref = ref_conv(dt, segs, bias, res, scale)
+    mx = float(ref.abs().max())
+    assert float((got - ref).abs().max()) <= OUT_TOL[dt] * mx, f"{name}: " + describe_mismatch(got, ref)
+    # another association of the same fp32 products: the outputs agree to fp32 rounding (one output ulp in bf16)
+    assert float((got - plain).abs().max()) <= (1e-5 if dt == F32 else 8e-3) * mx, describe_mismatch(got, plain)
+    assert torch.equal(got, got2) and torch.equal(st, st2)          # deterministic
+    assert torch.equal(got[B - 1:], one)                              # batch-invariant inside the mode
+    assert torch.allclose(st, st_plain, rtol=1e-3, atol=1e-2 * mx)   # GroupNorm statistics of the output
+
+
 @pytest.mark.parametrize("dt", [F32, BF16], ids=["tf32", "bf16"])
 @pytest.mark.parametrize("shape", [(2, 40, 20, 128, 128), (2, 24, 10, 256, 128), (1, 128, 160, 128, 128)])
 def test_conv_tc_fused_groupnorm_stats(dt, shape):

@@ -27,7 +27,7 @@ SYMBOLS = [
     "use_abi_version", "use_last_error", "use_engine_create", "use_engine_destroy", "use_engine_set_weight",
     "use_engine_pack", "use_engine_upload", "use_engine_workspace_bytes", "use_engine_set_option", "use_engine_launch_count", "use_engine_set_profiling",
     "use_engine_get_profile", "use_engine_get_profile_ops", "use_score_forward", "use_score_forward2", "use_reverse_drift", "use_net_forward", "use_pc_sample", "use_pc_sample_ex", "use_train_forward",
-    "use_stft", "use_istft", "use_resample_workspace_bytes", "use_resample_fft_f32", "use_peak_normalize_pad_f32", "use_upfirdn2d_f32", "use_op_gn_stats", "use_op_gn_apply", "use_op_conv_tc", "use_op_gn_affine", "use_op_conv_tc_gn", "use_op_head_tc", "use_op_head_tc_gn", "use_op_combine_stats", "use_op_gn_apply_aff",
+    "use_stft", "use_istft", "use_resample_workspace_bytes", "use_resample_fft_f32", "use_peak_normalize_pad_f32", "use_upfirdn2d_f32", "use_op_gn_stats", "use_op_gn_apply", "use_op_conv_tc", "use_op_gn_affine", "use_op_conv_tc_gn", "use_op_head_tc", "use_op_head_tc_gn", "use_op_set_latency", "use_op_combine_stats", "use_op_gn_apply_aff",
     "use_op_conv_ref", "use_op_conv_in4", "use_op_conv_out4", "use_op_combine", "use_op_fir4_down", "use_op_philox",
     "use_pack_conv_weight", "use_pack_head_weight",
 ]
@@ -123,6 +123,7 @@ def lib() -> C.CDLL:
         L.use_op_conv_in4.argtypes = [i32, vp, vp, vp, vp, i32, i32, i32, i32, vp]
         L.use_op_conv_out4.argtypes = [i32, vp, vp, vp, vp, vp, i32, i32, i32, i32, vp]
         L.use_op_head_tc.argtypes = [i32, vp, vp, vp, vp, vp, i32, i32, i32, i32, i32, vp, vp]
+        L.use_op_set_latency.argtypes = [i32]
         L.use_op_head_tc_gn.argtypes = [i32, vp, vp, vp, vp, vp, vp, i32, i32, i32, i32, i32, vp, vp]
         L.use_op_combine.argtypes = [i32, vp, vp, vp, vp, vp, i32, i32, i32, i32, vp]
         L.use_op_combine_stats.argtypes = [i32, vp, vp, vp, vp, vp, vp, i32, i32, i32, i32, vp]

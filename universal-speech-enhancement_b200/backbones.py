@@ -272,8 +272,18 @@ class _Engine:
         """Engine A/B switches (`fuse_gn`, `fuse_head`, `use_graphs`, `overlap_groups`): results are bit-identical either way; the
         workspace plan may change, so the cached workspace is dropped."""
         _lib.check(self.L.use_engine_set_option(self.h, key.encode(), int(value)), "use_engine_set_option")
-        self._ws = None
-        self._ws_key = None
+        if key != "ksplit":  # (the latency mode is part of the program key and does not change the workspace plan)
+            self._ws = None
+            self._ws_key = None
+
+    def latency_mode(self, job_clips):
+        """Pin the engine's latency mode (split-K clusters at the low-resolution levels, include/use_b200.h "ksplit") from
+        the size of the WHOLE job for the calls that follow: a job that is cut into micro-batches or shards must run every
+        piece in the same mode, otherwise the pieces would differ from the unsplit job in the last bits.  ``None`` = back
+        to auto (decided per call: at most two clips).  USE_B200_KSPLIT=0|1 overrides."""
+        if os.environ.get("USE_B200_KSPLIT") in ("0", "1"):
+            return
+        self.set_option("ksplit", 2 if job_clips is None else (1 if int(job_clips) <= 2 else 0))
 
     def __del__(self):
         try:

@@ -233,17 +233,22 @@ static TcConvPlan* plan_create_range(int dt, const TcConvDesc& d, int num_sms, c
     // its tile, so four slices cost far more than the half-empty wave they fill.)
     if (force_split) nsplit = d.N / 64;
   }
-  // Split-K clusters (conv_tc_ks.cuh) for the low-resolution levels: chosen by the LEVEL GEOMETRY only (tiles per clip),
-  // never by the batch, because the partial-sum association differs from conv_tc_kernel's single accumulator: a layer
-  // that runs this form runs it at every batch size.  <= 3 tiles per clip (16 x 20, 8 x 10): 4 CTAs per work unit;
-  // <= 10 (32 x 40): 2, so that batch 1 still fits one wave (10 tiles x 4 slices x 2 = 80 CTAs).
+  // Split-K clusters (conv_tc_ks.cuh) for the low-resolution levels of a LATENCY-mode program (TcConvDesc::latency, set
+  // by the engine for jobs of at most two clips): <= 3 tiles per clip (16 x 20, 8 x 10): 4 CTAs per 64-channel work unit;
+  // <= 10 (32 x 40): 2, so that one clip still fits one wave (10 tiles x 4 slices x 2 = 80 CTAs).  The partial-sum
+  // association differs from conv_tc_kernel's single accumulator, hence a mode of the whole program and never a per-launch
+  // heuristic: inside a mode, results do not depend on the batch.  Measured (bf16 / TF32, round 2): batch 1 140.0 -> 131.1 /
+  // 235.5 -> 214.0 ms per clip, batch 2 215.9 -> 211.9 ms per step; but 16 clips 1394 -> 1421 ms and 32 clips (TF32)
+  // 4990 -> 5103 ms per step (the 64-channel slices repeat window loads and GroupNorm transforms four times, the
+  // reduction adds a cluster round trip per unit): throughput-mode programs keep the single-accumulator kernels.
   int ks = 1;
   {
     static const bool ks_off = getenv("USE_B200_CONV_KSPLIT") && getenv("USE_B200_CONV_KSPLIT")[0] == '0';
     const int tiles_img = ((d.W + 7) / 8) * ((d.H + 15) / 16);
     int ktot = 0;
     for (int i = 0; i < d.nseg; ++i) ktot += d.seg[i].taps * (d.seg[i].C / (128 / (int)act_size(dt)));
-    if (!ks_off && !force_split && tile_count < 0 && d.N == 256 && tiles_img <= 10 && ktot >= 4 && multicast_width() == 1 &&
+    static const int ks_max_tiles = getenv("USE_B200_CONV_KSPLIT_MAXTILES") ? atoi(getenv("USE_B200_CONV_KSPLIT_MAXTILES")) : 10;
+    if (d.latency && !ks_off && !force_split && tile_count < 0 && d.N == 256 && tiles_img <= ks_max_tiles && ktot >= 4 && multicast_width() == 1 &&
         !cg2_enabled() && !getenv("USE_B200_CONV_PROF")) {
       ks = tiles_img <= 3 ? 4 : 2;
       nsplit = 4;

@@ -229,6 +229,10 @@ struct use_engine {
   bool fuse_gn = true;
   // the same for the pyramid heads (head_tc.cuh, round 2): the head reads the raw ResBlock output; off: gn_apply + plain head
   bool fuse_head = true;
+  // latency mode (split-K clusters at the low-resolution levels, conv_tc_ks.cuh): 0 = never, 1 = always, 2 = auto: calls
+  // with at most two clips.  A mode of the whole PROGRAM (part of its cache key): inside a mode per-clip results do not
+  // depend on the batch; between the modes they differ in the last bits (same tolerance to the reference).
+  int ksplit = 2;
   // scale / shift tables of the fused GroupNorms computed inside the consumer kernels (no gn_affine_kernel launches: 40 %
   // fewer launches per evaluation); off (default): one gn_affine_kernel launch per GroupNorm.  Bit-identical results.
   // Measured (bf16, CUDA graphs): batch 1 157.8 vs 157.1 ms per clip, batch 4 387.6 vs 377.5 ms per step -- inside a graph
@@ -480,6 +484,7 @@ struct Builder {
   char* base;      // workspace base (nullptr on the dry run)
   bool dry;
   int err = 0;
+  bool latency = false;  // latency-mode program: split-K clusters at the low-resolution levels (use_engine::ksplit)
   const float kInvSqrt2 = 0.70710678118654752440f;
 
   size_t es() const { return act_size(e->dt); }
@@ -584,8 +589,10 @@ struct Builder {
     if (dry) return;
     emit_conv_plan(d, flops_alg);
   }
-  void emit_conv_plan(const TcConvDesc& d, double flops_alg, bool count = true) {
+  void emit_conv_plan(const TcConvDesc& d0, double flops_alg, bool count = true) {
     char msg[512];
+    TcConvDesc d = d0;
+    d.latency = latency ? 1 : 0;
     TcConvPlan* p = tc_conv_plan_create(e->dt, d, e->num_sms, msg, sizeof(msg));
     if (!p) { err = fail("%s", msg); return; }
     prog->plans.push_back(p);
@@ -981,9 +988,13 @@ static void evict_programs(use_engine* e) {
   }
 }
 
-static std::shared_ptr<Program> get_program(use_engine* e, int B, int F, int T, void* workspace, size_t workspace_bytes) {
+static bool latency_mode(const use_engine* e, int B_call) { return e->ksplit == 1 || (e->ksplit == 2 && B_call <= 2); }
+
+// latency: build / fetch the latency-mode program (use_engine::ksplit; decided by the CALL's batch, not the group's)
+static std::shared_ptr<Program> get_program(use_engine* e, int B, int F, int T, void* workspace, size_t workspace_bytes,
+                                            bool latency) {
   char key[128];
-  snprintf(key, sizeof(key), "%d,%d,%d,%p", B, F, T, workspace);
+  snprintf(key, sizeof(key), "%d,%d,%d,%p,%d", B, F, T, workspace, (int)latency);
   size_t need = 0;
   if (plan_workspace(e, B, F, T, &need, nullptr)) return nullptr;
   if (workspace_bytes < need) {
@@ -1002,6 +1013,7 @@ static std::shared_ptr<Program> get_program(use_engine* e, int B, int F, int T, 
   Builder b{e, p.get(), B, F, T};
   b.base = (char*)workspace;
   b.dry = false;
+  b.latency = latency;
   b.build();
   if (b.err) return nullptr;
   p->last_use = ++e->program_tick;
@@ -1089,6 +1101,8 @@ static void run_network(use_engine* e, Program* p, cudaStream_t st, const float*
 // =================================================================================================
 // C ABI
 // =================================================================================================
+static int g_op_latency = 0;  // use_op_set_latency (test hook)
+
 extern "C" {
 
 int use_abi_version(void) { return USE_B200_ABI_VERSION; }
@@ -1132,6 +1146,7 @@ use_engine* use_engine_create(const use_config* cfg) {
   if (const char* v = getenv("USE_B200_FUSE_HEAD")) e->fuse_head = v[0] != '0';
   if (const char* v = getenv("USE_B200_GRAPHS")) e->use_graphs = v[0] != '0';
   if (const char* v = getenv("USE_B200_INLINE_GN")) e->inline_gn = v[0] != '0';
+  if (const char* v = getenv("USE_B200_KSPLIT")) e->ksplit = (v[0] >= '0' && v[0] <= '2') ? v[0] - '0' : 2;
   return e;
 }
 
@@ -1205,6 +1220,11 @@ int use_engine_set_option(use_engine* e, const char* key, int value) {
     e->programs.clear();
     return 0;
   }
+  if (!strcmp(key, "ksplit")) {
+    if (value < 0 || value > 2) return fail("ksplit must be 0 (off), 1 (on) or 2 (auto: calls with at most two clips)");
+    e->ksplit = value;  // part of the program key: nothing to drop
+    return 0;
+  }
   if (!strcmp(key, "fuse_head")) {
     e->fuse_head = value != 0;
     e->programs.clear();
@@ -1227,7 +1247,7 @@ static int net_forward(use_engine* e, int B, int F, int T, const void* x, const 
   if (e->cfg.input_channels >= 4 && !Y) return fail("the conditioning spectrogram Y is required (input_channels >= 4)");
   if (e->cfg.input_channels == 6 && !Y2) return fail("the second conditioning spectrogram is required (input_channels = 6)");
   if ((cond || e->cfg.scale_by_sigma) && (!t_host || (cond && !gfp_host))) return fail("time inputs are required");
-  std::shared_ptr<Program> pin = get_program(e, B, F, T, workspace, workspace_bytes);
+  std::shared_ptr<Program> pin = get_program(e, B, F, T, workspace, workspace_bytes, latency_mode(e, B));
   if (!pin) return 1;
   Program* p = pin.get();
   cudaStream_t st = (cudaStream_t)stream;
@@ -1351,7 +1371,7 @@ int use_pc_sample_ex(use_engine* e, int B, int F, int T, const void* Y, void* x_
   std::shared_ptr<Program> prog[2];  // pinned for the duration of the call (the cache never evicts a held program)
   cudaStream_t gs[2] = {st, st};
   for (int g = 0; g < G; ++g) {
-    prog[g] = get_program(e, Bg, F, T, (char*)workspace + g * slice, slice);
+    prog[g] = get_program(e, Bg, F, T, (char*)workspace + g * slice, slice, latency_mode(e, B));
     if (!prog[g]) return 1;
   }
   // the loop runs on the engine's own streams: two half-batches side by side, and (also for a single group) a stream
@@ -1625,6 +1645,7 @@ int use_op_conv_tc_gn(int dtype, int nseg, const void* const* seg_act, const int
   d.B = B; d.H = H; d.W = W; d.N = N;
   d.out = out; d.bias = bias; d.bias_bstride = bias_bstride; d.res = res; d.scale = scale;
   d.stats_acc = stats;  // fixed-point accumulators, zeroed by the caller
+  d.latency = g_op_latency;  // test hook (use_op_set_latency): the split-K cluster form for <= 10-tile images
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
@@ -1657,6 +1678,10 @@ int use_op_conv_tc(int dtype, int nseg, const void* const* seg_act, const int* s
                    long long* stats, void* stream) {
   return use_op_conv_tc_gn(dtype, nseg, seg_act, seg_ctensor, seg_c0, seg_c, seg_w, seg_cw, seg_wc0, seg_taps, nullptr,
                            nullptr, nullptr, B, H, W, N, bias, bias_bstride, res, scale, out, stats, stream);
+}
+int use_op_set_latency(int on) {
+  g_op_latency = on != 0;
+  return 0;
 }
 int use_op_conv_ref(int dtype, const void* x, const float* w, const float* bias, int bias_bstride, const void* res,
                     float scale, void* out, int B, int H, int W, int Cin, int Cout, int ksize, void* stream) {

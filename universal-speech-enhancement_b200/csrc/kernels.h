@@ -204,6 +204,9 @@ struct TcConvDesc {
   const void* res;
   float scale;
   long long* stats_acc;  // optional fixed-point GroupNorm statistics of `out`, [B][N][2], zero on entry
+  // latency kernels: the low-resolution levels (<= 3 tiles per clip) run the split-K cluster form (conv_tc_ks.cuh), whose
+  // partial-sum association differs from the single-accumulator form in the last bits
+  int latency;
 };
 struct TcConvPlan;  // opaque: tensor maps + launch geometry
 // Build (host) the launch plan; returns nullptr and fills err on failure.

@@ -25,7 +25,9 @@ def sample_sharded(sample_fn: Callable[[torch.Tensor, int], torch.Tensor], y: to
     """Run ``sample_fn(y_local, clip0)`` on this rank's shard of ``y`` [B, L] and all-gather the results.
 
     ``clip0`` is the global index of the shard's first clip: the in-kernel Philox noise is keyed by the global clip
-    index, so the gathered result does not depend on the number of ranks.  ``out_shape``: per-clip shape of
+    index, so the gathered result does not depend on the number of ranks (a model-backed ``sample_fn`` should also pass
+    ``job_clips=y.shape[0]`` to ``ScoreModel.sample`` so that every shard runs the kernel mode of the whole job).
+    ``out_shape``: per-clip shape of
     ``sample_fn``'s result when it differs from ``y.shape[1:]`` (only needed by ranks whose shard is empty, B < world).
     """
     if not (dist.is_available() and dist.is_initialized()):

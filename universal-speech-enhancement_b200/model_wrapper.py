@@ -204,9 +204,11 @@ class ScoreModel(nn.Module):
     # ---- samplers ----------------------------------------------------------------------------------
     def _fused_pc_sample(self, sde, y, eps, predictor="reverse_diffusion", corrector="none", corrector_steps=1, snr=0.5,
                          probability_flow=False, denoise=True, noise=None, seed=None, clip0=0, trace=None, x_init=None,
-                         times=None, want_state=False, cond=None, cond2=None):
+                         times=None, want_state=False, cond=None, cond2=None, job_clips=None):
         """y: complex [B,1,F,T].  One C call (use_pc_sample_ex) per micro-batch: prior + N x (corrector steps, predictor
-        step).  ``x_init`` + ``times`` = [t]: a single update_fn step from the given state (dt stays 1 / sde.N)."""
+        step).  ``x_init`` + ``times`` = [t]: a single update_fn step from the given state (dt stays 1 / sde.N).
+        ``job_clips``: clips of the whole job when this call only sees a piece of it (a shard, a minibatch): it selects
+        the engine's latency / throughput kernels (default: this call's batch)."""
         ts, G, std1 = sde.step_tables(sde.N, eps, times=times)
         g_tab, ald_tab = sde.variant_tables(ts, snr)
         if seed is None:
@@ -215,6 +217,7 @@ class ScoreModel(nn.Module):
         B = y.shape[0]
         mb = self.micro_batch or B
         eng = self._engine(y.device)
+        eng.latency_mode(B if job_clips is None else job_clips)  # one mode for every micro-batch of the job
         means, states = [], []
         for s in range(0, B, mb):
             Yc = y[s:s + mb, 0]
@@ -232,6 +235,7 @@ class ScoreModel(nn.Module):
                 trace[:, s:s + mb, 0] = tr
             means.append(xm)
             states.append(xs)
+        eng.latency_mode(None)
         mean = (torch.cat(means, dim=0) if len(means) > 1 else means[0]).unsqueeze(1)
         if not want_state:
             return mean
@@ -252,6 +256,7 @@ class ScoreModel(nn.Module):
                 y_mini = y[i * minibatch:(i + 1) * minibatch]
                 kw = dict(kwargs)
                 kw["clip0"] = kwargs.get("clip0", 0) + i * minibatch      # global clip index keys the Philox streams
+                kw["job_clips"] = kwargs.get("job_clips") or M            # one kernel mode for all minibatches of the job
                 if kw.get("noise") is not None:
                     kw["noise"] = kw["noise"][:, i * minibatch:(i + 1) * minibatch]
                 if kw.get("trace") is not None:
@@ -305,9 +310,10 @@ class ScoreModel(nn.Module):
 
     @torch.no_grad()
     def sample(self, batch, sampler_type=None, N=None, corrector_steps=1, snr=0.5, noise=None, seed=None, clip0=0,
-               trace=None, ode_kwargs=None):
-        """ScoreModel.sample (model_wrapper.py:262-329).  ``noise`` / ``seed`` / ``clip0`` / ``trace``: see
-        sampling.get_pc_sampler."""
+               trace=None, ode_kwargs=None, job_clips=None):
+        """ScoreModel.sample (model_wrapper.py:262-329).  ``noise`` / ``seed`` / ``clip0`` / ``trace`` / ``job_clips``: see
+        sampling.get_pc_sampler (a rank of a sharded job passes ``clip0`` = its first global clip index and ``job_clips``
+        = the size of the whole job)."""
         sampler_type = sampler_type or self.default_sampler_type or "pc"
         N = N if N is not None else (self.default_N if self.default_N is not None else 50)
         if sampler_type not in ("pc", "ode"):
@@ -334,7 +340,7 @@ class ScoreModel(nn.Module):
         if sampler_type == "pc":
             sampler = self.get_pc_sampler(self.predictor, self.corrector, sde_input, N=N, corrector_steps=corrector_steps,
                                           snr=snr, intermediate=False, conditioning=score_conditioning, noise=noise,
-                                          seed=seed, clip0=clip0, trace=trace)
+                                          seed=seed, clip0=clip0, trace=trace, job_clips=job_clips)
         elif sampler_type == "ode":
             sampler = self.get_ode_sampler(sde_input, N=N, conditioning=score_conditioning, noise=noise, **(ode_kwargs or {}))
         else:

@@ -174,10 +174,12 @@ def _host_loop(predictor, corrector, sde, y, eps, denoise, conditioning):
 
 def get_pc_sampler(predictor_name, corrector_name, sde, score_fn, y, denoise=True, eps=3e-2, snr=0.1,
                    corrector_steps=1, probability_flow: bool = False, conditioning=None, intermediate=False,
-                   noise=None, seed=None, clip0=0, trace=None, **kwargs):
+                   noise=None, seed=None, clip0=0, trace=None, job_clips=None, **kwargs):
     """Create a PC sampler (sampling/__init__.py:23-73).  Additions for reproducible / shard-invariant sampling and
     parity tests: ``noise`` (complex [1 + N * draws_per_step, *y.shape], the explicit normal draws), ``seed`` /
-    ``clip0`` (Philox streams), ``trace`` (complex [N, *y.shape] device tensor receiving xt_mean of every step)."""
+    ``clip0`` (Philox streams), ``trace`` (complex [N, *y.shape] device tensor receiving xt_mean of every step),
+    ``job_clips`` (clips of the whole job when ``y`` is one shard / minibatch of it: selects the latency or the
+    throughput kernels for the whole job, so that its pieces stay bit-identical to the unsplit job)."""
     predictor_cls = PredictorRegistry.get_by_name(predictor_name)
     corrector_cls = CorrectorRegistry.get_by_name(corrector_name)
 
@@ -188,7 +190,8 @@ def get_pc_sampler(predictor_name, corrector_name, sde, score_fn, y, denoise=Tru
             out = score_fn._fused_pc_sample(sde, y, eps, predictor=predictor_cls.kind, corrector=corrector_cls.kind,
                                             corrector_steps=corrector_steps, snr=snr, denoise=denoise,
                                             cond=None if conditioning[0] is y else conditioning[0],
-                                            cond2=conditioning[1] if len(conditioning) == 2 else None, noise=noise, seed=seed, clip0=clip0, trace=trace)
+                                            cond2=conditioning[1] if len(conditioning) == 2 else None, noise=noise, seed=seed, clip0=clip0, trace=trace,
+                                            job_clips=job_clips)
             return out, sde.N * (n_corr + 1)
 
         return fused_sampler
