@@ -9,7 +9,13 @@
 // [r K / KS, (r + 1) K / KS) of the linearised (segment, channel chunk, tap) sequence into its own TMEM accumulator;
 // the partial sums P_1 .. P_{KS-1} are staged as fp32 in the owners' shared memory and the leader (rank 0) adds them to its
 // own accumulator in rank order through distributed shared memory (ld.shared::cluster) before the usual epilogue
-// (bias, residual, scale, rounding, GroupNorm statistics of the output).
+// (bias, residual, scale, rounding, GroupNorm statistics of the output).  The hand-off is two CLUSTER barriers per work
+// unit, executed by every thread of every CTA of the cluster: #1 "all partial sums are staged" (arrive.release after a
+// role's work on the unit, wait.acquire before the leader's remote reads), #2 "the leader has read them" (before a stage
+// is rewritten or its CTA exits).  A first version signalled the leader with remote mbarrier arrives (release.cluster /
+// try_wait.acquire.cluster) and kept the next unit's loads and MMAs running under the reduction; compute-sanitizer's
+// racecheck does not model that as cluster-wide synchronisation (it flagged every staged word), and a latency-mode
+// cluster almost always has ONE unit to do, so the barrier form costs nothing measurable and is checkable.
 //
 // Determinism / batch invariance: ((P0 + P1) + P2) + P3 is a fixed association, and WHICH layers run this form depends on
 // the level geometry only (tiles per clip, conv_tc.cu), never on the batch: a clip sampled alone is still bit-identical to
@@ -26,7 +32,7 @@ struct ConvKsCfg {
   static constexpr int STAGE_BYTES = 128 * N * 4;  // this CTA's partial sums, fp32, [N / 4][128 pixels] float4 (conflict-free)
   static constexpr int KR_MAX = 64;                // channel chunks of one work unit (3 segments x <= 16 chunks)
   static constexpr int LIST_BYTES = KR_MAX * 16;
-  static constexpr int NBARS = Base::NBARS + 2;    // + red_full (leader), red_empty (owners)
+  static constexpr int NBARS = Base::NBARS;
   static constexpr int SMEM_BYTES = 1024 + Base::A_SLOTS * Base::A_SLOT + Base::B_SLOTS * Base::B_TILE + STAGE_BYTES +
                                     Base::STAT_BYTES + Base::GN_BYTES + LIST_BYTES + NBARS * 8 + 16;
   static_assert(SMEM_BYTES <= 232448, "shared memory budget");
@@ -60,9 +66,7 @@ __global__ void __launch_bounds__(ConvCfg<T, N, 1, FUSE, false>::THREADS, 1) con
   uint64_t* b_empty = b_full + C::B_SLOTS;
   uint64_t* t_full = b_empty + C::B_SLOTS;
   uint64_t* t_empty = t_full + 2;
-  uint64_t* red_full = t_empty + 2;   // leader: every owner's epilogue warps have staged their partial sums
-  uint64_t* red_empty = red_full + 1; // owner: the leader's epilogue warps have read the stage
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(red_empty + 1);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(t_empty + 2);
   int* kr_n_s = reinterpret_cast<int*>(tmem_slot + 1);
 
   const int warp = threadIdx.x >> 5;
@@ -78,8 +82,6 @@ __global__ void __launch_bounds__(ConvCfg<T, N, 1, FUSE, false>::THREADS, 1) con
     for (int i = 0; i < C::A_SLOTS; ++i) { mbar_init(&a_full[i], 1); mbar_init(&a_empty[i], 1); mbar_init(&a_raw[i], 1); }
     for (int i = 0; i < C::B_SLOTS; ++i) { mbar_init(&b_full[i], 1); mbar_init(&b_empty[i], 1); }
     for (int i = 0; i < 2; ++i) { mbar_init(&t_full[i], 1); mbar_init(&t_empty[i], C::EPI_WARPS); }
-    mbar_init(red_full, (KS - 1) * C::EPI_WARPS);
-    mbar_init(red_empty, C::EPI_WARPS);
     fence_barrier_init();
     // this CTA's share of the K sequence: taps [q0, q1) of the linearised (segment, chunk, tap) order
     int ktot = 0;
@@ -101,7 +103,7 @@ __global__ void __launch_bounds__(ConvCfg<T, N, 1, FUSE, false>::THREADS, 1) con
   }
   tc_fence_before();
   __syncthreads();
-  cluster_sync_all();  // every CTA's barriers are initialised before anything targets them remotely
+  cluster_sync_all();  // the whole cluster is resident before anything reads a peer's shared memory
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   const int kr_n = *kr_n_s;
@@ -114,32 +116,33 @@ __global__ void __launch_bounds__(ConvCfg<T, N, 1, FUSE, false>::THREADS, 1) con
 
   if (warp == 0) {
     // ================================ TMA producer ================================
-    if (lane == 0) {
-      int a_tile = T0, a_c = 0;
-      uint32_t ai = 0;
-      auto a_pending = [&]() { return a_tile < TEND; };
-      auto a_issue = [&](bool blocking) -> bool {
-        const uint32_t as = ai % C::A_SLOTS, aph = (ai / C::A_SLOTS) & 1;
-        if (blocking) mbar_wait(&a_empty[as], aph ^ 1);
-        else if (!mbar_test_wait(&a_empty[as], aph ^ 1)) return false;
-        const int4 e = klist[a_c];
-        const ConvSeg& S = p.seg[e.x];
-        const int a_t = p.tile_base + a_tile / nsp;
-        const int b = a_t / tiles_per_img;
-        const int rem = a_t - b * tiles_per_img;
-        const int th = rem / p.tiles_w;
-        const int w0 = (rem - th * p.tiles_w) * C::TILE_W, h0 = th * C::TILE_H;
-        const bool k3 = S.taps == 9;
-        const uint32_t a_bytes = (k3 ? C::NPIX : C::TILE_H * 8) * 128;
-        uint64_t* landed = (FUSE && S.raw != nullptr) ? &a_raw[as] : &a_full[as];
-        mbar_arrive_expect_tx(landed, a_bytes);
-        tma_load_4d(sA + as * C::A_SLOT, &S.tmA, landed, S.ac0 + e.y * C::CK, k3 ? (w0 - 1) : w0, k3 ? (h0 - 1) : h0, b);
-        ++ai;
-        if (++a_c == kr_n) { a_c = 0; a_tile += TSTEP; }
-        return true;
-      };
-      uint32_t bi = 0, bj = 0;
-      for (int unit = T0; unit < TEND; unit += TSTEP) {
+    // (lane 0 issues; the whole warp walks the unit loop because every thread takes part in the cluster barriers)
+    int a_tile = T0, a_c = 0;
+    uint32_t ai = 0;
+    auto a_pending = [&]() { return a_tile < TEND; };
+    auto a_issue = [&](bool blocking) -> bool {
+      const uint32_t as = ai % C::A_SLOTS, aph = (ai / C::A_SLOTS) & 1;
+      if (blocking) mbar_wait(&a_empty[as], aph ^ 1);
+      else if (!mbar_test_wait(&a_empty[as], aph ^ 1)) return false;
+      const int4 e = klist[a_c];
+      const ConvSeg& S = p.seg[e.x];
+      const int a_t = p.tile_base + a_tile / nsp;
+      const int b = a_t / tiles_per_img;
+      const int rem = a_t - b * tiles_per_img;
+      const int th = rem / p.tiles_w;
+      const int w0 = (rem - th * p.tiles_w) * C::TILE_W, h0 = th * C::TILE_H;
+      const bool k3 = S.taps == 9;
+      const uint32_t a_bytes = (k3 ? C::NPIX : C::TILE_H * 8) * 128;
+      uint64_t* landed = (FUSE && S.raw != nullptr) ? &a_raw[as] : &a_full[as];
+      mbar_arrive_expect_tx(landed, a_bytes);
+      tma_load_4d(sA + as * C::A_SLOT, &S.tmA, landed, S.ac0 + e.y * C::CK, k3 ? (w0 - 1) : w0, k3 ? (h0 - 1) : h0, b);
+      ++ai;
+      if (++a_c == kr_n) { a_c = 0; a_tile += TSTEP; }
+      return true;
+    };
+    uint32_t bi = 0, bj = 0;
+    for (int unit = T0; unit < TEND; unit += TSTEP) {
+      if (lane == 0) {
         const int wrow0 = (unit % nsp) * N;
         for (int c = 0; c < kr_n; ++c, ++bj) {
           const int4 e = klist[c];
@@ -157,6 +160,9 @@ __global__ void __launch_bounds__(ConvCfg<T, N, 1, FUSE, false>::THREADS, 1) con
           }
         }
       }
+      __syncwarp();
+      cluster_sync_all();  // #1: partial sums staged
+      cluster_sync_all();  // #2: the leader has read them
     }
   } else if (warp == 1) {
     // ================================ MMA issuer ================================
@@ -197,6 +203,8 @@ __global__ void __launch_bounds__(ConvCfg<T, N, 1, FUSE, false>::THREADS, 1) con
       }
       if (elect_one()) umma_commit(&t_full[acs]);
       __syncwarp();
+      cluster_sync_all();  // #1
+      cluster_sync_all();  // #2
     }
   } else if (threadIdx.x >= C::XF_T0) {
     if constexpr (FUSE) {
@@ -292,6 +300,8 @@ __global__ void __launch_bounds__(ConvCfg<T, N, 1, FUSE, false>::THREADS, 1) con
           named_bar_sync(2, XT);
           if (tt == 0) mbar_arrive(&a_full[as]);
         }
+        cluster_sync_all();  // #1
+        cluster_sync_all();  // #2
       }
     }
   } else {
@@ -311,8 +321,7 @@ __global__ void __launch_bounds__(ConvCfg<T, N, 1, FUSE, false>::THREADS, 1) con
       const uint32_t acs = ti & 1, acph = (ti >> 1) & 1;
       const uint32_t trow = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + acs * C::ACC_COLS;
       if (krank != 0) {
-        // ---- owner of a partial sum: TMEM -> own shared memory, then tell the leader ----
-        mbar_wait_cluster(red_empty, (ti & 1) ^ 1);  // the leader has read the previous unit's stage (free at the start)
+        // ---- owner of a partial sum: TMEM -> own shared memory ----
         mbar_wait(&t_full[acs], acph);
         tc_fence_after();
 #pragma unroll 1
@@ -327,10 +336,10 @@ __global__ void __launch_bounds__(ConvCfg<T, N, 1, FUSE, false>::THREADS, 1) con
         }
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) {
-          mbar_arrive(&t_empty[acs]);
-          mbar_arrive_cluster(mapa_u32(smem_u32(red_full), 0));  // release.cluster: the stage writes above are visible
-        }
+        if (lane == 0) mbar_arrive(&t_empty[acs]);
+        __syncwarp();
+        cluster_sync_all();  // #1: staged (release) -- the leader reads after its wait (acquire)
+        cluster_sync_all();  // #2: the leader is done with this stage
         continue;
       }
       // ---- leader ----
@@ -346,7 +355,7 @@ __global__ void __launch_bounds__(ConvCfg<T, N, 1, FUSE, false>::THREADS, 1) con
       const float* bias = p.bias + static_cast<size_t>(b) * p.bias_bstride + nb0;
       mbar_wait(&t_full[acs], acph);
       tc_fence_after();
-      mbar_wait_cluster(red_full, ti & 1);  // acquire.cluster: every owner's partial sums are staged
+      cluster_sync_all();  // #1: every owner's partial sums are staged
 #pragma unroll 1
       for (int c0 = 0; c0 < N; c0 += 32) {
         constexpr int V = DT<T>::kVec;
@@ -429,11 +438,9 @@ __global__ void __launch_bounds__(ConvCfg<T, N, 1, FUSE, false>::THREADS, 1) con
       }
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) {
-        mbar_arrive(&t_empty[acs]);
-#pragma unroll
-        for (int rk = 1; rk < KS; ++rk) mbar_arrive_cluster(mapa_u32(smem_u32(red_empty), rk));  // their stages are free again
-      }
+      if (lane == 0) mbar_arrive(&t_empty[acs]);
+      __syncwarp();
+      cluster_arrive();  // #2 (arrive): the remote reads of this unit are done; the stores below need no peer
       if (p.stats_acc != nullptr) {
         constexpr int ET = 32 * C::EPI_WARPS;
         asm volatile("bar.sync 1, %0;" ::"r"(ET) : "memory");
@@ -446,14 +453,13 @@ __global__ void __launch_bounds__(ConvCfg<T, N, 1, FUSE, false>::THREADS, 1) con
         }
         asm volatile("bar.sync 1, %0;" ::"r"(ET) : "memory");
       }
+      cluster_wait();  // #2 (wait)
     }
-    // an owner may not leave (its shared memory would be released) before the leader has read its last stage
-    if (krank != 0 && ti > 0) mbar_wait_cluster(red_empty, (ti - 1) & 1);
   }
 
+  // (barrier #2 of the last unit is the exit guard: no owner leaves before the leader has read its stage)
   tc_fence_before();
   __syncthreads();
-  cluster_sync_all();  // no CTA leaves while a peer may still signal one of its barriers
   if (warp == 1) tmem_dealloc(tmem_base, C::TMEM_COLS);
 }
 
