@@ -353,6 +353,9 @@ __global__ void __launch_bounds__(ConvCfg<T, N, 1, FUSE, false>::THREADS, 1) con
       const bool valid = (h < p.H) && (w < p.W);
       const size_t pix = (static_cast<size_t>(b) * p.H + h) * p.W + w;
       const float* bias = p.bias + static_cast<size_t>(b) * p.bias_bstride + nb0;
+      // pull the unit's bias row (and below: nothing else is read from global memory before the stores) towards the SM
+      // while the MMAs still run: a single-unit launch would otherwise meet an L2 round trip per 32-column chunk
+      if (lane < N / 4) asm volatile("prefetch.global.L1 [%0];" ::"l"(bias + lane * 4));
       mbar_wait(&t_full[acs], acph);
       tc_fence_after();
       cluster_sync_all();  // #1: every owner's partial sums are staged

@@ -234,7 +234,8 @@ __global__ void __launch_bounds__(256) attn_core_kernel(const float* __restrict_
   const float inv = 1.0f / sum;
   for (int c = threadIdx.x; c < C; c += blockDim.x) {
     float acc = 0.f;
-    for (int j = 0; j < P; ++j) acc += sw[j] * vb[static_cast<size_t>(j) * C + c];
+#pragma unroll 8
+    for (int j = 0; j < P; ++j) acc += sw[j] * vb[static_cast<size_t>(j) * C + c];  // (same order; the loads of 8 rows in flight)
     out[(static_cast<size_t>(b) * P + i) * C + c] = acc * inv;
   }
 }
