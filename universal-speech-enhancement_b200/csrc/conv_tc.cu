@@ -221,8 +221,9 @@ static TcConvPlan* plan_create_range(int dt, const TcConvDesc& d, int num_sms, c
     static const bool off = getenv("USE_B200_CONV_NSPLIT") && getenv("USE_B200_CONV_NSPLIT")[0] == '0';
     static const int max_tiles = getenv("USE_B200_CONV_NSPLIT_MAXTILES") ? atoi(getenv("USE_B200_CONV_NSPLIT_MAXTILES")) : (1 << 30);
     // Slices are only worth it while ALL work units fit one wave: measured in isolation (bf16, batch 1, tools/conv_bench.py
-    // CONV_BENCH_SMALL): a single-tile K loop is bound by the latency of the dependent MMA chain (~0.3 us per tap for N = 64,
-    // 128 and 256 alike), so a unit costs the same whatever its width and a second wave doubles the launch.  64 x 80 (40
+    // CONV_BENCH_SMALL): in a single-tile K loop every tcgen05.mma of N <= 128 costs its issuer ~110 cycles whatever its
+    // width (~0.3 us per tap for N = 64, 128 and 256 alike; alternating two accumulators changed nothing, so it is not the
+    // accumulator dependency), so a unit costs the same whatever its width and a second wave doubles the launch.  64 x 80 (40
     // tiles): unsplit 21 us, four slices (160 units = 2 waves) 26 us -> two 128-channel slices (80 units, one wave).
     if (!off && d.N == 256 && base_tiles < max_tiles && multicast_width() == 1 && !cg2_enabled() && !getenv("USE_B200_CONV_PROF")) {
       if (base_tiles * 4 <= num_sms) nsplit = 4;
