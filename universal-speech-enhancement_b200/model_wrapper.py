@@ -219,23 +219,25 @@ class ScoreModel(nn.Module):
         eng = self._engine(y.device)
         eng.latency_mode(B if job_clips is None else job_clips)  # one mode for every micro-batch of the job
         means, states = [], []
-        for s in range(0, B, mb):
-            Yc = y[s:s + mb, 0]
-            nc = nz[:, s:s + mb].contiguous() if nz is not None else None
-            tr = None
-            if trace is not None:
-                tr = trace[:, :, 0] if mb >= B else torch.empty_like(trace[:, s:s + mb, 0]).contiguous()
-            xm, xs = eng.pc_sample(Yc, ts, G, std1, noise=nc, seed=seed, clip0=clip0 + s, predictor=predictor,
-                                   corrector=corrector, corrector_steps=corrector_steps, snr=snr,
-                                   probability_flow=probability_flow, denoise=denoise, g=g_tab, ald_step=ald_tab, trace=tr,
-                                   x_init=None if x_init is None else x_init[s:s + mb, 0], dt_steps=sde.N,
-                                   cond=None if cond is None else cond[s:s + mb, 0],
-                                   cond2=None if cond2 is None else cond2[s:s + mb, 0])
-            if trace is not None and mb < B:
-                trace[:, s:s + mb, 0] = tr
-            means.append(xm)
-            states.append(xs)
-        eng.latency_mode(None)
+        try:
+            for s in range(0, B, mb):
+                Yc = y[s:s + mb, 0]
+                nc = nz[:, s:s + mb].contiguous() if nz is not None else None
+                tr = None
+                if trace is not None:
+                    tr = trace[:, :, 0] if mb >= B else torch.empty_like(trace[:, s:s + mb, 0]).contiguous()
+                xm, xs = eng.pc_sample(Yc, ts, G, std1, noise=nc, seed=seed, clip0=clip0 + s, predictor=predictor,
+                                       corrector=corrector, corrector_steps=corrector_steps, snr=snr,
+                                       probability_flow=probability_flow, denoise=denoise, g=g_tab, ald_step=ald_tab, trace=tr,
+                                       x_init=None if x_init is None else x_init[s:s + mb, 0], dt_steps=sde.N,
+                                       cond=None if cond is None else cond[s:s + mb, 0],
+                                       cond2=None if cond2 is None else cond2[s:s + mb, 0])
+                if trace is not None and mb < B:
+                    trace[:, s:s + mb, 0] = tr
+                means.append(xm)
+                states.append(xs)
+        finally:
+            eng.latency_mode(None)  # back to auto (decided per call) also when a call fails
         mean = (torch.cat(means, dim=0) if len(means) > 1 else means[0]).unsqueeze(1)
         if not want_state:
             return mean
