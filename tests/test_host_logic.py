@@ -211,3 +211,51 @@ def test_load_checkpoint_for_both_module_kinds(tmp_path, model_cfg):
     got = m.state_dict()
     k = next(k for k in got if k.endswith("weight"))
     assert float(got[k].flatten()[0]) == 0.25 and set(got.keys()) == set(sd.keys())
+
+
+class _FakeEngine:
+    """Records what the sampler asks of the engine (no kernels): latency-mode pinning and per-call batch sizes."""
+
+    def __init__(self, fail_on_call=None):
+        self.modes, self.calls, self.fail_on_call = [], [], fail_on_call
+
+    def latency_mode(self, job_clips):
+        self.modes.append(job_clips)
+
+    def pc_sample(self, Y, ts, G, std1, **kw):
+        self.calls.append((int(Y.shape[0]), int(kw["clip0"])))
+        if self.fail_on_call is not None and len(self.calls) == self.fail_on_call:
+            raise RuntimeError("boom")
+        return torch.zeros_like(Y), torch.zeros_like(Y)
+
+
+def _fake_model(monkeypatch, eng, **kw):
+    m = use_b200.ScoreModel(backbone="ncsnpplarge", condition="noisy", sde_input="noisy", n_fft=1022, hop_length=160, **kw)
+    monkeypatch.setattr(m, "_engine", lambda device: eng)
+    return m
+
+
+def test_latency_mode_is_pinned_from_the_whole_job(monkeypatch):
+    """One job = one kernel mode (include/use_b200.h "ksplit"): micro-batches, minibatches and shards of a job pin the
+    engine's latency mode from the size of the WHOLE job and release it afterwards, also when a call fails."""
+    Y = torch.zeros(5, 1, 512, 64, dtype=torch.complex64)
+    eng = _FakeEngine()
+    m = _fake_model(monkeypatch, eng, micro_batch=2)
+    m.get_pc_sampler("reverse_diffusion", "none", Y, N=2, conditioning=[Y], seed=1)()
+    assert eng.modes == [5, None] and eng.calls == [(2, 0), (2, 2), (1, 4)]   # 2 + 2 + 1 clips, one mode (5 clips)
+    # a shard of a larger job names the job's size; a job of two clips runs in latency mode by its own size
+    eng.modes.clear(); eng.calls.clear()
+    m.micro_batch = None
+    m.get_pc_sampler("reverse_diffusion", "none", Y[:1], N=2, conditioning=[Y[:1]], seed=1, clip0=3, job_clips=4)()
+    m.get_pc_sampler("reverse_diffusion", "none", Y[:2], N=2, conditioning=[Y[:2]], seed=1)()
+    assert eng.modes == [4, None, 2, None] and eng.calls == [(1, 3), (2, 0)]
+    # the reference's minibatch argument: every minibatch carries the whole batch as its job
+    eng.modes.clear(); eng.calls.clear()
+    m.get_pc_sampler("reverse_diffusion", "none", Y, N=2, minibatch=2, conditioning=[Y], seed=1)()
+    assert eng.modes == [5, None, 5, None, 5, None] and eng.calls == [(2, 0), (2, 2), (1, 4)]
+    # released in a finally block
+    bad = _FakeEngine(fail_on_call=1)
+    m2 = _fake_model(monkeypatch, bad)
+    with pytest.raises(RuntimeError, match="boom"):
+        m2.get_pc_sampler("reverse_diffusion", "none", Y, N=2, conditioning=[Y], seed=1)()
+    assert bad.modes == [5, None]
