@@ -93,9 +93,12 @@ __device__ __forceinline__ float silu_fast(float x) { return __fdividef(x, 1.0f 
 // x * sigmoid(x) = x * (0.5 + 0.5 tanh(x/2)): ONE MUFU op.  tanh.approx has ~2^-11 relative error, invisible after the
 // bf16 rounding of the result (2^-9) but not acceptable for the fp32 path, which keeps the exp + rcp form.
 __device__ __forceinline__ float silu_tanh(float x) {
+  // x sigmoid(x) = h + h tanh(h), h = x / 2: three instructions (FMUL, MUFU.TANH, FFMA) instead of four -- the in-place
+  // GroupNorm transform of the fused operands is issue-bound (~70 instructions per 16-byte bf16 vector)
+  const float h = 0.5f * x;
   float t;
-  asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(0.5f * x));
-  return x * fmaf(0.5f, t, 0.5f);
+  asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(h));
+  return fmaf(h, t, h);
 }
 template <typename T> __device__ __forceinline__ float silu_act(float x) {
   if constexpr (DT<T>::kIsBf16) return silu_tanh(x);
